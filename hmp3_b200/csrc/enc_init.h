@@ -1,0 +1,10 @@
+// Host-side control resolution and table generation (see enc_init.cpp).
+#pragma once
+#include "../../include/hmp3_b200.h"
+#include "enc_tables.h"
+
+namespace hmp3 {
+void control_defaults(hmp3_control *ec);
+// Returns bytes_in (nchan*4*1152) or 0 when the control block is rejected.
+int build_tables(const hmp3_control *ec, EncTables *T, int *unsupported);
+}  // namespace hmp3

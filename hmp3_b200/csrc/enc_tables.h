@@ -1,0 +1,132 @@
+// Resolved per-configuration constants and look-up tables of the Layer III encode path.
+// One EncTables object is built on the host per distinct control block (enc_init.cpp), uploaded
+// once to HBM, and read by every kernel through a const pointer.  Layout is ours; the numbers
+// follow the reference's init (file:line cited at each generator in enc_init.cpp).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HMP3_HD __host__ __device__ __forceinline__
+#define HMP3_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define HMP3_HD inline
+#define HMP3_HD_NOINLINE
+#endif
+
+namespace hmp3 {
+
+enum FrameDriver { FD_VBR_MPEG1 = 0, FD_CBR_MPEG1 = 1, FD_VBR_MPEG2 = 2, FD_CBR_MPEG2 = 3 };
+
+// Number of candidate-table classes of the Huffman bit counter (see build_count_luts()).
+constexpr int kCountClasses = 20;
+
+struct EncConfig {
+    // stream shape
+    int nchan, h_id, sr_index, samprate, h_mode, totbitrate, br_index;
+    int nband, nsb, nsb_limit, nsb_hybrid /* nsb_limitMS[0] */, nsb_limit_ms1, band_limit, band_limit_stereo;
+    // frame geometry / reservoir
+    int frame_driver, framebytes, main_framebytes, side_bytes, pad_remainder, pad_divisor;
+    int ave_target_bits, sf_bit_max, reservoir_back /* 511 MPEG-1, 255 MPEG-2 */;
+    int vbr_flag, ivbr_min, ivbr_max, vbr_pool_target;
+    int vbr_main_framebytes[16];
+    int ms_flag, is_flag, hf_flag, nsf_stereo;
+    int short_block_threshold, filter_select, mono;
+    float dc_alpha;
+    // rate-loop constants (CBitAllo3::BitAlloInit / CBitAlloShort::BitAlloInit)
+    int initial_mnr, initial_mnr_short, nt_flatten /* test1 */;
+    int nsf[2], nsf2[2], nsf3[2], nbmax[2], nbmax2[2], nbmax3[2];
+    int nsf_s[2], nbmax_s[2];
+    int ill_is_pos;
+    unsigned char head[4];
+    int granules_per_frame;  // 2 MPEG-1, 1 MPEG-2
+    // info (ec_global, mp3enc.cpp:841-866)
+    int info_freq_limit, info_nsbstereo, vbr_mnr, vbr_delta_mnr, hf_flag_user;
+};
+
+struct EncTables {
+    EncConfig cfg;
+    // ---- polyphase (window folded into 32 sums + 32-point fast DCT)
+    float polyA[32][8], polyB[32][8];
+    int polyIa[32], polyIb[32];
+    float dct32[31];
+    // ---- hybrid windows / MDCT / alias
+    float win[4][36];
+    float csa[2][8];
+    float m18_w[18], m18_w2[9], m18_c[9][4];
+    float m6_v[6], m6_v2[3], m6_c;
+    // ---- integer-indexed log / exp / pow(3/4)
+    int logmb[256];
+    float exp_hi[256], exp_lo[256];
+    int logsub[84];
+    float p34_exp[256], p34_seg[32];
+    // ---- psychoacoustic partitions and spreading
+    int psy_npart_l, psy_npart_s;      // partitions the spreading loop visits (cntl[64].count)
+    int psy_emap_n_l, psy_emap_n_s;    // partitions the energy map fills (nsum[66])
+    int psy_nsum_l[64], psy_nsum_s[64];
+    int psy_start_l[65], psy_start_s[65];
+    int spd_cnt_l[64], spd_off_l[64], spd_w0_l[64];  // w0 = first weight index of partition i
+    int spd_cnt_s[64], spd_off_s[64], spd_w0_s[64];
+    float w_spd_l[2200], w_spd_s[1000];
+    // ---- scale-factor bands
+    int nBand_l[22], startBand_l[24], nBand_s[13], startBand_s[14];
+    int nBand_l_iso[22];               // ISO widths (nBand_l[21] becomes 100 when -HF is active)
+    int log_cbw_l[22], log_cbw_s[16];
+    float rnBand_l[22];
+    int taperNT[22];
+    // ---- quantiser
+    float gain[128], igain34[128], ix43[256];
+    float quantB_round[32];
+    // ---- Huffman
+    uint32_t huff_book[16][256];  // (len << 24) | code, [book][x*16+y]
+    int huff_sel_book[32], huff_linbits[32];
+    // bit-count LUTs: per class two packed words per (x,y): lo16/hi16 = candidate tables 0/1 and 2/3
+    uint32_t cnt_lut[kCountClasses][256][2];
+    int cnt_class_of_max[24];          // ixmax 0..22 -> class (23.. handled by thresholds)
+    int cnt_tables[kCountClasses][4];  // candidate Huffman table numbers (0 = none)
+    int cnt_tmax[kCountClasses];       // largest value the class can code
+    int cnt_ncand[kCountClasses];      // 2 or 4 (0 for the null class)
+};
+
+// ------------------------------------------------------------------ scalar table functions
+HMP3_HD unsigned f2u(float x) {
+    union { float f; unsigned u; } v;
+    v.f = x;
+    return v.u;
+}
+HMP3_HD float u2f(unsigned x) {
+    union { float f; unsigned u; } v;
+    v.u = x;
+    return v.f;
+}
+
+// millibel log: table on the top 8 mantissa bits + 301 per exponent step (l3math.c:227-243, IEEE_FLOAT branch)
+HMP3_HD int mb_log(const EncTables *T, float x) {
+    unsigned u = f2u(x);
+    return T->logmb[(u >> 15) & 255] + 301 * (int)(u >> 23);
+}
+// millibel antilog (l3math.c:341-357, IEEE_FLOAT branch)
+HMP3_HD float mb_exp(const EncTables *T, int x) {
+    float t = T->exp_lo[(unsigned)x & 0xff] * T->exp_hi[((unsigned)x & 0xff00) >> 8];
+    if (x > 32000) return 1.0E32f;
+    if (x < -32000) return 1.0E-32f;
+    return t;
+}
+// round half away from zero (l3math.c:360-364)
+HMP3_HD int round_away(float x) { return (int)(x + ((f2u(x) >> 31) ? -0.5f : 0.5f)); }
+// 2*antilog(a) - antilog(b) in millibels (l3math.c:367-382)
+HMP3_HD int mb_logsub(const EncTables *T, int a, int b) {
+    int k = (a - b) >> 4;
+    if (k > 83) k = 83;
+    return a + T->logsub[k];
+}
+// |x|^(3/4), piecewise linear in the mantissa (pow34.c:131-156, IEEE_FLOAT branch); x >= 0
+HMP3_HD float pow34(const EncTables *T, float x) {
+    unsigned u = f2u(x);
+    float mant = u2f((u & 0x7FFFFFu) | (127u << 23));
+    unsigned e = u >> 19;
+    unsigned e2 = (e >> 4) & 255u;
+    e &= 15u;
+    return (mant * T->p34_seg[2 * e + 1] + T->p34_seg[2 * e]) * T->p34_exp[e2];
+}
+
+}  // namespace hmp3

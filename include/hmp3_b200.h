@@ -1,0 +1,183 @@
+/*
+ * hmp3_b200 -- C ABI of the B200-native Helix-MP3 Layer III encode path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types cross this boundary.  Every entry point
+ * names the reference interface it replaces (paths relative to the maikmerten/hmp3 tree).
+ *
+ * The reference has no C ABI today (the old C prototypes are commented out, hmp3/src/pub/encapp.h:172-197);
+ * its surface is the C++ class CMp3Enc (hmp3/src/pub/mp3enc.h:74-141) used by the CLI
+ * (hmp3/src/test/tomp3.cpp:664, 818-820, 942-943, 1025-1026).  This header exports
+ *   (1) a batch entry -- N independent streams in, N MP3 byte streams out -- which is what reaches the GPU;
+ *   (2) opaque-handle mirrors of the CMp3Enc init/encode/info calls for tomp3-style callers;
+ *   (3) error reporting.
+ * There is NO CPU fallback: every encode entry fails with HMP3_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef HMP3_B200_H_
+#define HMP3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Mirror of E_CONTROL (hmp3/src/pub/encapp.h:42-72): same field order, same meaning, same defaults. */
+typedef struct hmp3_control {
+    int mode;          /* 0 stereo, 1 joint stereo, 2 dual, 3 mono                                  */
+    int bitrate;       /* CBR per-channel kbit/s; -1 lets the encoder choose                        */
+    int samprate;      /* 16000, 22050, 24000, 32000, 44100 or 48000                                */
+    int nsbstereo;     /* -1 = encoder default                                                      */
+    int filter_select; /* -1 default, 0 none, 1 DC-blocking filter                                  */
+    int freq_limit;    /* 24000 = off                                                               */
+    int nsb_limit;     /* -1 = off                                                                  */
+    int layer;         /* 3                                                                         */
+    int cr_bit;
+    int original;
+    int hf_flag;       /* MPEG-1 high-frequency coding: 1 = M/S granules, 3 = all granules          */
+    int vbr_flag;      /* 1 = VBR, 0 = CBR                                                          */
+    int vbr_mnr;       /* 0..150                                                                    */
+    int vbr_br_limit;  /* per-channel VBR bitrate cap (160)                                         */
+    int vbr_delta_mnr;
+    int chan_add_f0;
+    int chan_add_f1;
+    int sparse_scale;
+    int mnr_adjust[21];
+    int cpu_select;
+    int quick;
+    int test1;
+    int test2;
+    int test3;
+    int short_block_threshold;
+} hmp3_control;
+
+/* Mirror of IN_OUT (hmp3/src/pub/encapp.h:159-165). */
+typedef struct hmp3_in_out {
+    int in_bytes;
+    int out_bytes;
+} hmp3_in_out;
+
+/* Mirror of MPEG_HEAD (hmp3/src/pub/encapp.h:141-157). */
+typedef struct hmp3_mpeg_head {
+    int sync, id, option, prot, br_index, sr_index, pad, private_bit, mode, mode_ext, cr, original, emphasis;
+} hmp3_mpeg_head;
+
+enum {
+    HMP3_OK = 0,
+    HMP3_ERR_NO_DEVICE = -1,   /* no usable CUDA device: there is no CPU path                       */
+    HMP3_ERR_BAD_CONTROL = -2, /* init rejected the control block (reference init returns 0)        */
+    HMP3_ERR_UNSUPPORTED = -3, /* configuration outside the built path (intensity stereo, dual)     */
+    HMP3_ERR_OUT_SPACE = -4,   /* caller's output buffer too small                                  */
+    HMP3_ERR_CUDA = -5,
+    HMP3_ERR_ARG = -6
+};
+
+/* Fill `ec` with the CLI defaults (hmp3/src/test/tomp3.cpp:357-387). */
+void hmp3_control_defaults(hmp3_control *ec);
+
+/* Apply one hmp3 command-line option ("-B64", "-V100", "-HF2", "-F19000", "-M0", ...) to `ec` with the
+ * CLI's semantics (hmp3/src/test/tomp3.cpp:390-566; -B => CBR, no -B => VBR).  Returns 0, or -1 for an
+ * option this build does not know. */
+int hmp3_control_apply_option(hmp3_control *ec, const char *opt);
+
+/* Last error text of the calling thread. */
+const char *hmp3_get_last_error(void);
+
+/* Number of usable CUDA devices (0 => every encode call fails). */
+int hmp3_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Batch entry: the GPU path.  Replaces one `hmp3 in.wav out.mp3 [opts]` process per clip
+ * (ff_encode, hmp3/src/test/tomp3.cpp:640-1090, minus WAV parsing and the Xing/Info frame):
+ * for every stream the output is the exact frame sequence CMp3Enc::MP3_audio_encode emits for
+ * that PCM with four zero frames appended at EOF and the tail flush (tomp3.cpp:923-931, 1015-1036).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct hmp3_stream_desc {
+    const hmp3_control *control; /* per-stream control (streams with equal controls share tables) */
+    const int16_t *pcm;          /* interleaved int16 PCM, HOST memory (pinned is faster)         */
+    int64_t num_samples;         /* samples per channel                                           */
+    uint8_t *out;                /* HOST buffer for the MP3 frames                                */
+    int64_t out_capacity;        /* bytes available at `out` (see hmp3_batch_out_bound)           */
+    int64_t out_bytes;           /* [out] bytes written                                           */
+    int32_t out_frames;          /* [out] frames written                                          */
+    int32_t status;              /* [out] HMP3_OK or an error for this stream                     */
+} hmp3_stream_desc;
+
+/* Upper bound of the output size for a stream. */
+int64_t hmp3_batch_out_bound(const hmp3_control *control, int64_t num_samples);
+
+/* Encode `n` independent streams on CUDA device `device`.  Host buffers in, host buffers out
+ * (H2D/D2H copies are inside).  Returns HMP3_OK if the batch ran; per-stream results in status. */
+int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device);
+
+/* Device-resident variant used by the benchmark's kernel-only leg: PCM already in HBM
+ * (`d_pcm[i]` device pointers), output left in HBM (`d_out[i]`), sizes returned to the host. */
+typedef struct hmp3_batch hmp3_batch; /* opaque, reusable plan: buffers sized for a batch shape */
+hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_samples, int n, int device);
+void hmp3_batch_destroy(hmp3_batch *b);
+/* bytes of device output region reserved per stream (stride of the device output buffer) */
+int64_t hmp3_batch_out_stride(const hmp3_batch *b);
+/* device pointers owned by the plan */
+int16_t *hmp3_batch_device_pcm(hmp3_batch *b);   /* [n][max_samples * nch] int16, stream-major   */
+uint8_t *hmp3_batch_device_out(hmp3_batch *b);   /* [n][out_stride]                              */
+int64_t hmp3_batch_pcm_stride(const hmp3_batch *b); /* int16 elements per stream                 */
+/* run all kernels on the plan's stream; inputs are whatever is in device_pcm.  Synchronous unless
+ * `async` != 0 (then hmp3_batch_sync must be called before reading results). */
+int hmp3_batch_run(hmp3_batch *b, int async);
+int hmp3_batch_sync(hmp3_batch *b);
+/* per-stream results of the last run (host arrays of n) */
+int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames);
+/* copy helpers for the host-to-host path through a plan */
+int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples);
+int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap);
+/* number of kernel launches issued by the last hmp3_batch_run */
+int hmp3_batch_last_launches(const hmp3_batch *b);
+/* device time of named phases of the last synchronous run, in ms (for bench.py's roofline leg):
+ * fills up to `cap` entries, returns the count; names[i] points to static strings. */
+int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) CMp3Enc mirrors (hmp3/src/pub/mp3enc.h:74-141).  A handle is one stream; calls buffer PCM and
+ * run the same device pipeline as the batch entry.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct hmp3_encoder hmp3_encoder;
+hmp3_encoder *hmp3_encoder_new(int device);
+void hmp3_encoder_delete(hmp3_encoder *e);
+
+/* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns the bytes the caller must
+ * supply per call, 0 = failure.  Only 16-bit integer PCM at a native MPEG rate is in scope
+ * (source_bits = 16, source_is_float = 0; no sample-rate conversion -- SURVEY.md section 8f). */
+int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
+                               int mpeg_select, int mono_convert);
+/* CMp3Enc::MP3_audio_encode (hmp3/src/mp3enc.cpp:2812-2828). */
+hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out);
+/* CMp3Enc::L3_audio_encode_init / L3_audio_encode, float PCM scaled to +-32768
+ * (hmp3/src/mp3enc.cpp:220-870, 2031-2047). */
+int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec);
+hmp3_in_out hmp3_L3_audio_encode(hmp3_encoder *e, const float *pcm, unsigned char *bs_out);
+/* Info getters (hmp3/src/mp3enc.cpp:3444-3527). */
+void hmp3_L3_audio_encode_info_ec(hmp3_encoder *e, hmp3_control *ec);
+void hmp3_L3_audio_encode_info_head(hmp3_encoder *e, hmp3_mpeg_head *head);
+void hmp3_L3_audio_encode_info_string(hmp3_encoder *e, char *s);
+unsigned int hmp3_L3_audio_encode_get_frames(hmp3_encoder *e);
+int hmp3_L3_audio_encode_get_bitrate(hmp3_encoder *e);
+float hmp3_L3_audio_encode_get_bitrate_float(hmp3_encoder *e);
+
+/* ---------------------------------------------------------------------------------------------
+ * Resolved configuration, for boundary tests (what L3_audio_encode_init computes,
+ * hmp3/src/mp3enc.cpp:289-870).  Pure host logic, needs no device.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct hmp3_resolved {
+    int nchan, h_id, sr_index, nband, band_limit, nsb, nsb_limit, nsb_limit_ms0, nsb_limit_ms1, ave_target_bits;
+    int framebytes, main_framebytes, side_bytes, remainder, divisor, ms_flag, is_flag, frame_driver,
+        granule_driver, ivbr_min, ivbr_max, vbr_pool_target, short_block_threshold, h_mode, br_index,
+        totbitrate, samprate, band_limit_stereo, sf_bit_max, nsf_stereo;
+    int head[4];
+    int hf_flag, filter_select, bytes_in;
+} hmp3_resolved;
+int hmp3_resolve_control(const hmp3_control *ec, hmp3_resolved *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMP3_B200_H_ */

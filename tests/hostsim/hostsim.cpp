@@ -1,0 +1,131 @@
+// TEST INFRASTRUCTURE ONLY.  Host build of the kernel bodies (hmp3_b200/csrc/*.h compiled by g++ with
+// -ffp-contract=off) so that parity against the oracle can be checked in a container without a GPU.
+// The product library never links or loads this file; the shipped path is CUDA-only.
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../hmp3_b200/csrc/enc_init.h"
+#include "../../hmp3_b200/csrc/analysis.h"
+
+using namespace hmp3;
+
+extern "C" {
+
+int sim_resolve(const hmp3_control *ec, int *out /*40*/) {
+    EncTables *T = new EncTables;
+    int unsup = 0;
+    int r = build_tables(ec, T, &unsup);
+    const EncConfig &C = T->cfg;
+    int v[] = {C.nchan, C.h_id, C.sr_index, C.nband, C.band_limit, C.nsb, C.nsb_limit, C.nsb_hybrid, C.nsb_limit_ms1,
+               C.ave_target_bits, C.framebytes, C.main_framebytes, C.side_bytes, C.pad_remainder, C.pad_divisor,
+               C.ms_flag, C.is_flag, C.frame_driver, 0, C.ivbr_min, C.ivbr_max, C.vbr_pool_target,
+               C.short_block_threshold, C.h_mode, C.br_index, C.totbitrate, C.samprate, C.band_limit_stereo,
+               C.sf_bit_max, C.nsf_stereo, C.head[0], C.head[1], C.head[2], C.head[3], C.hf_flag,
+               C.filter_select * 2 + (C.nchan - 1)};
+    for (unsigned i = 0; i < sizeof(v) / sizeof(int); i++) out[i] = v[i];
+    out[38] = unsup;
+    out[39] = r;
+    delete T;
+    return r;
+}
+
+// named table copy-out for boundary tests
+int sim_table(const hmp3_control *ec, const char *name, void *dst, int nbytes) {
+    EncTables *T = new EncTables;
+    int r = build_tables(ec, T, nullptr);
+    if (!r) { delete T; return -1; }
+    struct { const char *n; const void *p; int sz; } tabs[] = {
+        {"win", T->win, sizeof(T->win)}, {"csa", T->csa, sizeof(T->csa)}, {"m18_w", T->m18_w, sizeof(T->m18_w)},
+        {"m18_w2", T->m18_w2, sizeof(T->m18_w2)}, {"m18_c", T->m18_c, sizeof(T->m18_c)},
+        {"m6_v", T->m6_v, sizeof(T->m6_v)}, {"m6_v2", T->m6_v2, sizeof(T->m6_v2)}, {"m6_c", &T->m6_c, 4},
+        {"psy_nsum_l", T->psy_nsum_l, sizeof(T->psy_nsum_l)}, {"psy_nsum_s", T->psy_nsum_s, sizeof(T->psy_nsum_s)},
+        {"spd_cnt_l", T->spd_cnt_l, sizeof(T->spd_cnt_l)}, {"spd_off_l", T->spd_off_l, sizeof(T->spd_off_l)},
+        {"spd_cnt_s", T->spd_cnt_s, sizeof(T->spd_cnt_s)}, {"spd_off_s", T->spd_off_s, sizeof(T->spd_off_s)},
+        {"w_spd_l", T->w_spd_l, sizeof(T->w_spd_l)}, {"w_spd_s", T->w_spd_s, sizeof(T->w_spd_s)},
+        {"psy_n", &T->psy_npart_l, 16}, {"vbr_main_framebytes", T->cfg.vbr_main_framebytes, 64},
+        {"cnt_lut", T->cnt_lut, sizeof(T->cnt_lut)}, {"gain", T->gain, sizeof(T->gain)},
+        {"igain34", T->igain34, sizeof(T->igain34)}, {"ix43", T->ix43, sizeof(T->ix43)},
+    };
+    int ret = -2;
+    for (auto &t : tabs)
+        if (!strcmp(t.n, name)) {
+            int n = t.sz < nbytes ? t.sz : nbytes;
+            memcpy(dst, t.p, n);
+            ret = n;
+        }
+    delete T;
+    return ret;
+}
+
+// Phase A over a whole clip, sequential reference driver of the per-item routines.
+// Encode granules K = 0..ngran-1.  Outputs (any may be null):
+//   sbt    [ngran][nch][576]   P[K] (frequency-inverted, band-major)
+//   ginfo  [ngran][4]          block_type, block_type_prev, short_cur, short_next
+//   xr     [ngran][nch][576]
+//   sigmask[ngran][nch][36][2] {sig,mask}
+//   ms_raw [ngran]             M/S measure without hysteresis (long) / short measure
+//   att    [ngran][nch][9]     attack energies of P[K]
+int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int ngran, float *sbt_out, int *ginfo,
+                 float *xr_out, float *sigmask, int *ms_raw, int *att) {
+    EncTables *T = new EncTables;
+    if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
+    const int nch = T->cfg.nchan;
+    const int mpeg2 = T->cfg.h_id == 0;
+    // P[j] for j = -3 .. ngran-1 (index j+3)
+    std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
+    std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
+    for (long j = -3; j < ngran; j++)
+        for (int c = 0; c < nch; c++) {
+            float *o = &P[((j + 3) * nch + c) * 576];
+            for (int t = 0; t < 18; t++) polyphase_item(T, pcm, nsamples, nch, c, j, t, o);
+            for (int k = 0; k < 9; k++) E[((j + 3) * nch + c) * 9 + k] = attack_energy(T, o, k, mpeg2);
+        }
+    SwitchState sw;
+    switch_state_init(&sw);
+    float echo[2][64];
+    for (int c = 0; c < 2; c++)
+        for (int i = 0; i < 64; i++) echo[c][i] = 1.0e20f;
+    SigMask sm[2][36];
+    for (int c = 0; c < 2; c++)
+        for (int i = 0; i < 36; i++) sm[c][i].sig = sm[c][i].mask = 100.0f;
+    std::vector<float> xr((size_t)nch * 576);
+    PsyRaw raw;
+    for (int K = 0; K < ngran; K++) {
+        const int *e0 = &E[((K - 1 + 3) * nch + 0) * 9];
+        const int *e1 = &E[((K - 1 + 3) * nch + (nch - 1)) * 9];
+        GranuleInfo g = switch_step(T, &sw, e0, e1);
+        if (ginfo) {
+            ginfo[4 * K + 0] = g.block_type; ginfo[4 * K + 1] = g.block_type_prev;
+            ginfo[4 * K + 2] = g.short_cur;  ginfo[4 * K + 3] = g.short_next;
+        }
+        for (int c = 0; c < nch; c++) {
+            const float *prev = &P[((K - 3 + 3) * nch + c) * 576];
+            const float *cur = &P[((K - 2 + 3) * nch + c) * 576];
+            float *x = &xr[c * 576];
+            for (int sb = 0; sb < 32; sb++) hybrid_item(T, prev, cur, g.block_type, sb, x);
+            if (g.block_type != 2)
+                for (int sb = 0; sb < 32; sb++) alias_item(T, sb, x);
+            if (g.block_type != 2) {
+                psy_long_stage1(T, x, &raw);
+                psy_long_stage2(T, &raw, echo[c], g.block_type, sm[c]);
+            } else {
+                psy_short_stage1(T, x, &raw);
+                psy_short_stage2(T, &raw, echo[c], g.block_type_prev, sm[c]);
+            }
+            if (xr_out) memcpy(xr_out + ((size_t)K * nch + c) * 576, x, 576 * sizeof(float));
+            if (sbt_out) memcpy(sbt_out + ((size_t)K * nch + c) * 576, &P[((K + 3) * nch + c) * 576], 576 * sizeof(float));
+            if (sigmask) memcpy(sigmask + ((size_t)K * nch + c) * 72, sm[c], 72 * sizeof(float));
+            if (att) memcpy(att + ((size_t)K * nch + c) * 9, &E[((K + 3) * nch + c) * 9], 9 * sizeof(int));
+        }
+        if (ms_raw) {
+            if (nch == 2)
+                ms_raw[K] = (g.block_type != 2) ? ms_measure_long(T, &xr[0], &xr[576]) : ms_measure_short(T, &xr[0], &xr[576]);
+            else ms_raw[K] = 0;
+        }
+    }
+    delete T;
+    return 0;
+}
+
+}  // extern "C"
