@@ -1,0 +1,146 @@
+// Phase A CUDA kernels (sm_100a): one thread (or warp) per independent work item of analysis.h.
+// All are launched over a *chunk* of encode granules [K0, K0+NG) of every stream of the batch.
+#pragma once
+#include <cuda_runtime.h>
+#include "analysis.h"
+
+namespace hmp3 {
+
+// One stream of the batch, device view.
+struct StreamDev {
+    int cfg;             // index into the tables array
+    int nch;
+    long long pcm_off;   // offset (int16 elements) of this stream's interleaved PCM in the batch buffer
+    long long nsamples;  // per channel
+    int ngran;           // encode granules to run, including the flush allowance
+    int ngran_real;      // granules that belong to real encode calls (2 * calls)
+    long long out_off;   // byte offset of this stream's output region
+    long long out_cap;
+};
+
+// Chunk work buffers (device).  G = NG + 3 polyphase granules are kept per chunk: P[K0-3 .. K0+NG-1].
+struct ChunkBufs {
+    float *P;        // [n][NG+3][2][576]
+    int *E;          // [n][NG+3][2][9]   attack energies of P
+    GranuleInfo *gi; // [n][NG]
+    float *xr;       // [n][NG][2][576]
+    PsyRaw *raw;     // [n][NG][2]
+    int *ms_raw;     // [n][NG]
+    int NG;
+};
+
+// ---- K1: polyphase analysis, one thread per (stream, polyphase granule, channel, time slot)
+__global__ void __launch_bounds__(128) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,
+                                                   ChunkBufs cb, int K0, int nstreams) {
+    const int G = cb.NG + 3;
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)nstreams * G * 2 * 18;
+    if (id >= total) return;
+    int t = (int)(id % 18);
+    long long r = id / 18;
+    int ch = (int)(r & 1);
+    r >>= 1;
+    int jj = (int)(r % G);
+    int s = (int)(r / G);
+    const StreamDev sd = st[s];
+    if (ch >= sd.nch) return;
+    long long j = (long long)K0 - 3 + jj;
+    if (j >= sd.ngran) return;
+    const EncTables *T = tabs + sd.cfg;
+    float *out = cb.P + (((long long)s * G + jj) * 2 + ch) * 576;
+    polyphase_item(T, pcm + sd.pcm_off, (long)sd.nsamples, sd.nch, ch, (long)j, t, out);
+}
+
+// ---- K2: attack energies, one thread per (stream, polyphase granule, channel, slot pair)
+__global__ void k_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int nstreams) {
+    const int G = cb.NG + 3;
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)nstreams * G * 2 * 9;
+    if (id >= total) return;
+    int k = (int)(id % 9);
+    long long r = id / 9;
+    int ch = (int)(r & 1);
+    r >>= 1;
+    int jj = (int)(r % G);
+    int s = (int)(r / G);
+    const StreamDev sd = st[s];
+    if (ch >= sd.nch) return;
+    long long j = (long long)K0 - 3 + jj;
+    if (j >= sd.ngran) return;
+    const EncTables *T = tabs + sd.cfg;
+    const float *p = cb.P + (((long long)s * G + jj) * 2 + ch) * 576;
+    cb.E[(((long long)s * G + jj) * 2 + ch) * 9 + k] = attack_energy(T, p, k, T->cfg.h_id == 0);
+}
+
+// ---- K3: block-type decision scan, one thread per stream, sequential over the chunk
+__global__ void k_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState *sw, ChunkBufs cb, int K0,
+                              int nstreams) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    const EncTables *T = tabs + sd.cfg;
+    const int G = cb.NG + 3;
+    SwitchState state = sw[s];
+    for (int q = 0; q < cb.NG; q++) {
+        int K = K0 + q;
+        if (K >= sd.ngran) break;
+        int jj = q + 2;  // P[K-1]
+        const int *e0 = cb.E + (((long long)s * G + jj) * 2 + 0) * 9;
+        const int *e1 = cb.E + (((long long)s * G + jj) * 2 + (sd.nch - 1)) * 9;
+        cb.gi[(long long)s * cb.NG + q] = switch_step(T, &state, e0, e1);
+    }
+    sw[s] = state;
+}
+
+// ---- K4: hybrid window + MDCT + alias reduction, one warp per (stream, granule, channel), lane = sub-band
+__global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
+                                                int nstreams) {
+    const int G = cb.NG + 3;
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    long long total = (long long)nstreams * cb.NG * 2;
+    if (wid >= total) return;
+    int ch = (int)(wid & 1);
+    long long r = wid >> 1;
+    int q = (int)(r % cb.NG);
+    int s = (int)(r / cb.NG);
+    const StreamDev sd = st[s];
+    if (ch >= sd.nch || K0 + q >= sd.ngran) return;
+    const EncTables *T = tabs + sd.cfg;
+    const int bt = cb.gi[(long long)s * cb.NG + q].block_type;
+    const float *prev = cb.P + (((long long)s * G + q) * 2 + ch) * 576;      // P[K-3]
+    const float *cur = cb.P + (((long long)s * G + q + 1) * 2 + ch) * 576;   // P[K-2]
+    float *xr = cb.xr + (((long long)s * cb.NG + q) * 2 + ch) * 576;
+    hybrid_item(T, prev, cur, bt, lane, xr);
+    __syncwarp();
+    if (bt != 2) alias_item(T, lane, xr);
+}
+
+// ---- K5: psychoacoustic stage 1 (one thread per granule-channel) and M/S measure (one per granule)
+__global__ void __launch_bounds__(64) k_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
+                                                   int nstreams) {
+    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)nstreams * cb.NG * 3;
+    if (id >= total) return;
+    int job = (int)(id % 3);
+    long long r = id / 3;
+    int q = (int)(r % cb.NG);
+    int s = (int)(r / cb.NG);
+    const StreamDev sd = st[s];
+    if (K0 + q >= sd.ngran) return;
+    const EncTables *T = tabs + sd.cfg;
+    const int bt = cb.gi[(long long)s * cb.NG + q].block_type;
+    const float *x0 = cb.xr + (((long long)s * cb.NG + q) * 2) * 576;
+    if (job < 2) {
+        if (job >= sd.nch) return;
+        PsyRaw *R = cb.raw + ((long long)s * cb.NG + q) * 2 + job;
+        if (bt != 2) psy_long_stage1(T, x0 + 576 * job, R);
+        else psy_short_stage1(T, x0 + 576 * job, R);
+    } else {
+        int m = 0;
+        if (sd.nch == 2) m = (bt != 2) ? ms_measure_long(T, x0, x0 + 576) : ms_measure_short(T, x0, x0 + 576);
+        cb.ms_raw[(long long)s * cb.NG + q] = m;
+    }
+}
+
+}  // namespace hmp3

@@ -1,0 +1,23 @@
+/* Stage taps of the device pipeline, used only by the parity tests (tests/test_gpu_*.py). */
+#ifndef HMP3_B200_DEBUG_H_
+#define HMP3_B200_DEBUG_H_
+#include "hmp3_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* Phase A (polyphase -> block switching -> hybrid MDCT -> psychoacoustic stage 1 / M-S measure) of one
+ * stream on device `device`.  Any output pointer may be NULL.  Shapes (nch = channels of the stream):
+ *   sbt   [ngran][nch][576]  frequency-inverted polyphase granules P[K] (entry ngran-1 is not filled)
+ *   ginfo [ngran][4]         block_type, block_type_prev, short_flag_current, short_flag_next
+ *   xr    [ngran][nch][576]  MDCT spectra handed to the rate loop
+ *   raw   [ngran][nch][92]   psychoacoustic stage-1 record (PsyRaw)
+ *   ms_raw[ngran]            M/S correlation measure without hysteresis
+ *   att   [ngran][nch][9]    attack energies of P[K] (entry ngran-1 is not filled)
+ * Replaces, for testing: sbt_L3 (sbt.c:293), attack_detectSBT_igr (detect.c:53), hybridLong/Short +
+ * antialias (hwin.c:147-319), emap* (emap.c:61-121), spd_smr* (spdsmr.c:64-319). */
+int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long nsamples, int ngran, int device,
+                        float *sbt, int *ginfo, float *xr, float *raw, int *ms_raw, int *att);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -66,8 +66,9 @@ int sim_table(const hmp3_control *ec, const char *name, void *dst, int nbytes) {
 //   sigmask[ngran][nch][36][2] {sig,mask}
 //   ms_raw [ngran]             M/S measure without hysteresis (long) / short measure
 //   att    [ngran][nch][9]     attack energies of P[K]
+//   raw    [ngran][nch][92]    psychoacoustic stage-1 record
 int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int ngran, float *sbt_out, int *ginfo,
-                 float *xr_out, float *sigmask, int *ms_raw, int *att) {
+                 float *xr_out, float *sigmask, int *ms_raw, int *att, float *raw_out) {
     EncTables *T = new EncTables;
     if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
     const int nch = T->cfg.nchan;
@@ -113,6 +114,7 @@ int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int 
                 psy_short_stage1(T, x, &raw);
                 psy_short_stage2(T, &raw, echo[c], g.block_type_prev, sm[c]);
             }
+            if (raw_out) memcpy(raw_out + ((size_t)K * nch + c) * 92, &raw, sizeof(PsyRaw));
             if (xr_out) memcpy(xr_out + ((size_t)K * nch + c) * 576, x, 576 * sizeof(float));
             if (sbt_out) memcpy(sbt_out + ((size_t)K * nch + c) * 576, &P[((K + 3) * nch + c) * 576], 576 * sizeof(float));
             if (sigmask) memcpy(sigmask + ((size_t)K * nch + c) * 72, sm[c], 72 * sizeof(float));

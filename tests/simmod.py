@@ -50,10 +50,11 @@ def analysis(ec, pcm_i16, ngran, nch):
     pcm = np.ascontiguousarray(pcm_i16)
     out = dict(sbt=np.zeros((ngran, nch, 576), np.float32), ginfo=np.zeros((ngran, 4), np.int32),
                xr=np.zeros((ngran, nch, 576), np.float32), sigmask=np.zeros((ngran, nch, 36, 2), np.float32),
-               ms_raw=np.zeros(ngran, np.int32), att=np.zeros((ngran, nch, 9), np.int32))
+               ms_raw=np.zeros(ngran, np.int32), att=np.zeros((ngran, nch, 9), np.int32),
+               raw=np.zeros((ngran, nch, 92), np.float32))
     f = lib().sim_analysis
-    f.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int] + [C.c_void_p] * 6
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int] + [C.c_void_p] * 7
     r = f(vp(ec), vp(pcm), pcm.shape[0], ngran, vp(out["sbt"]), vp(out["ginfo"]), vp(out["xr"]),
-          vp(out["sigmask"]), vp(out["ms_raw"]), vp(out["att"]))
+          vp(out["sigmask"]), vp(out["ms_raw"]), vp(out["att"]), vp(out["raw"]))
     assert r == 0
     return out
