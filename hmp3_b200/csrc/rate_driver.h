@@ -1,0 +1,647 @@
+// Phase B of the pipeline: the per-stream serial part.  For every encode granule, in order:
+// psychoacoustic stage 2 (pre-echo memory), M/S decision with hysteresis, the rate loop (long or
+// short), scale-factor and Huffman packing into the stream's main-data byte stream, and the bit
+// reservoir / frame bookkeeping.  Follows CMp3Enc::encode_{jointB,singleB}[_MPEG2] and
+// L3_audio_encode_[vbr_]MPEG{1,2} (mp3enc.cpp:1492-2027, 2106-2593), CBitAllo3::BitAllo
+// (bitallo3.cpp:484-678) and l3pack.c.  Output is bit-exact with the reference.
+#pragma once
+#include "analysis.h"
+#include "rate_short.h"
+
+namespace hmp3 {
+
+// One emitted frame, as recorded by the serial stage; the final byte layout (header | side | slice of the
+// main-data stream) is produced by a separate, parallel assembly pass.
+struct FrameRec {
+    unsigned main_start;  // offset in the stream's main-data stream where this frame's slot begins
+    int mf_bytes;         // bytes of main-data slot in this frame
+    unsigned char head[4];
+    unsigned char side[32];
+};
+
+// MSB-first bit writer appending to a byte buffer (same bit order as l3pack.c:98-153).
+struct BitSink {
+    unsigned char *p;
+    unsigned long long acc;
+    int nacc;
+    long long total_bits;
+};
+HMP3_HD void sink_open(BitSink *b, unsigned char *dst) { b->p = dst; b->acc = 0; b->nacc = 0; b->total_bits = 0; }
+HMP3_HD void sink_put(BitSink *b, unsigned x, int n) {
+    if (n <= 0) return;
+    b->acc = (b->acc << n) | (unsigned long long)(x & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u)));
+    b->nacc += n;
+    b->total_bits += n;
+    while (b->nacc >= 8) {
+        *b->p++ = (unsigned char)(b->acc >> (b->nacc - 8));
+        b->nacc -= 8;
+    }
+}
+HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros; returns bytes written
+    if (b->nacc > 0) {
+        *b->p++ = (unsigned char)(b->acc << (8 - b->nacc));
+        b->nacc = 0;
+    }
+    return (b->total_bits + 7) >> 3;
+}
+
+// Persistent per-stream state of the serial stage.
+struct RateState {
+    LongRate L;
+    ShortRate S;
+    float echo[2][64];        // psychoacoustic pre-echo memory (CMp3Enc::ecsave[ch][0])
+    SigMask sig_mask[2][36];
+    int ix[2][576];           // quantised lines in transmission order (persist between granules)
+    unsigned char signx[2][576];
+    GrSide gr[2][2];          // [granule][channel]
+    ScaleFac sf[2][2];
+    int scfsi[2];
+    int sf_save[2][21];       // granule-0 scale factors for scfsi (l3pack.c:429)
+    // reservoir / frame bookkeeping
+    unsigned main_tot, mf_tot;
+    int padcount;
+    int frames;               // frames recorded so far
+    int frames_done;          // frames whose main-data slot is completely filled
+    int byte_pool, byte_min, byte_max;
+    int next_granule;         // encode granule to process next
+    int finished;             // all real frames are complete
+    BitSink sink;
+};
+
+HMP3_HD void rate_state_init(const EncTables *T, RateState *R) {
+    unsigned char *p = (unsigned char *)R;
+    for (unsigned i = 0; i < sizeof(RateState); i++) p[i] = 0;
+    long_rate_init(T, &R->L);
+    short_rate_init(&R->S);
+    for (int c = 0; c < 2; c++) {
+        for (int i = 0; i < 64; i++) R->echo[c][i] = 1.0e20f;
+        for (int i = 0; i < 36; i++) R->sig_mask[c][i].sig = R->sig_mask[c][i].mask = 100.0f;
+    }
+    R->padcount = T->cfg.pad_divisor;
+}
+
+// ------------------------------------------------------------------ scale-factor packing (l3pack.c:157-933)
+HMP3_HD int slen_for(int maxval, int cap) {
+    int n = 1, s;
+    maxval++;
+    for (s = 0; s < cap; s++) {
+        if (maxval <= n) break;
+        n += n;
+    }
+    return s;
+}
+HMP3_HD int sfc_index(int slen1, int slen2) {  // ISO scalefac_compress from (slen1, slen2)
+    const unsigned char t[5][4] = {{0, 1, 2, 3}, {5, 5, 6, 7}, {8, 8, 9, 10}, {4, 11, 12, 13}, {14, 14, 14, 15}};
+    return t[slen1][slen2];
+}
+HMP3_HD void sfc_slens(int sfc, int *s1, int *s2) {
+    const unsigned char t[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
+                                    {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
+    *s1 = t[sfc][0];
+    *s2 = t[sfc][1];
+}
+
+// MPEG-1, frame contains a short block: no scfsi (l3pack.c:157-281)
+HMP3_HD int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) {
+    int m1 = 0, m2 = 0, s1, s2;
+    if (block_type == 2) {
+        for (int i = 0; i < 6; i++)
+            for (int w = 0; w < 3; w++) m1 = imax_(m1, sf->s[w][i]);
+        for (int i = 6; i < 12; i++)
+            for (int w = 0; w < 3; w++) m2 = imax_(m2, sf->s[w][i]);
+        int sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
+        sfc_slens(sfc, &s1, &s2);
+        for (int i = 0; i < 6; i++)
+            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], s1);
+        for (int i = 6; i < 12; i++)
+            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], s2);
+        return sfc;
+    }
+    for (int i = 0; i < 11; i++) m1 = imax_(m1, sf->l[i]);
+    for (int i = 11; i < 21; i++) m2 = imax_(m2, sf->l[i]);
+    int sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
+    sfc_slens(sfc, &s1, &s2);
+    for (int i = 0; i < 11; i++) sink_put(b, sf->l[i], s1);
+    for (int i = 11; i < 21; i++) sink_put(b, sf->l[i], s2);
+    return sfc;
+}
+// MPEG-1, all-long frame: granule 1 may share scale-factor groups with granule 0 (l3pack.c:421-557)
+HMP3_HD int pack_sf_mpeg1_scfsi(BitSink *b, const ScaleFac *sf, int *save /*[21]*/, int igr, int *scfsi_out,
+                                int not_null) {
+    const int edge[5] = {0, 6, 11, 16, 21};
+    int scfsi = 0;
+    if (igr == 0) {
+        for (int i = 0; i < 21; i++) save[i] = sf->l[i];
+    } else {
+        for (int g = 0; g < 4; g++) {
+            int t = 0;
+            for (int i = edge[g]; i < edge[g + 1]; i++) t |= (save[i] - sf->l[i]);
+            scfsi <<= 1;
+            if (t == 0) scfsi |= 1;
+        }
+    }
+    int sfc = 0;
+    if (not_null) {
+        int m1 = 0, m2 = 0, s1, s2;
+        for (int g = 0; g < 4; g++)
+            if ((scfsi & (8 >> g)) == 0)
+                for (int i = edge[g]; i < edge[g + 1]; i++) {
+                    if (g < 2) m1 = imax_(m1, sf->l[i]);
+                    else m2 = imax_(m2, sf->l[i]);
+                }
+        sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
+        sfc_slens(sfc, &s1, &s2);
+        for (int g = 0; g < 4; g++)
+            if ((scfsi & (8 >> g)) == 0)
+                for (int i = edge[g]; i < edge[g + 1]; i++) sink_put(b, sf->l[i], g < 2 ? s1 : s2);
+    }
+    *scfsi_out = scfsi;
+    return sfc;
+}
+// MPEG-2 (LSF), no intensity stereo: four partitions with their own lengths (l3pack.c:561-933)
+HMP3_HD int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
+    int m[4] = {0, 0, 0, 0}, sl[4];
+    if (block_type == 2) {
+        for (int w = 0; w < 3; w++)
+            for (int i = 0; i < 12; i++) m[i / 3] = imax_(m[i / 3], sf->s[w][i]);
+    } else {
+        const int edge[5] = {0, 6, 11, 16, 21};
+        for (int g = 0; g < 4; g++)
+            for (int i = edge[g]; i < edge[g + 1]; i++) m[g] = imax_(m[g], sf->l[i]);
+    }
+    sl[0] = slen_for(m[0], 4);
+    sl[1] = slen_for(m[1], 4);
+    sl[2] = slen_for(m[2], 3);
+    sl[3] = slen_for(m[3], 3);
+    const int sfc = sl[3] + (sl[2] << 2) + ((sl[1] + 5 * sl[0]) << 4);
+    if (block_type == 2) {
+        for (int i = 0; i < 12; i++)
+            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], sl[i / 3]);
+    } else {
+        const int edge[5] = {0, 6, 11, 16, 21};
+        for (int g = 0; g < 4; g++)
+            for (int i = edge[g]; i < edge[g + 1]; i++) sink_put(b, sf->l[i], sl[g]);
+    }
+    return sfc;
+}
+
+// ------------------------------------------------------------------ Huffman packing (l3pack.c:946-1119)
+HMP3_HD void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+    for (int r = 0; r < 3; r++) {
+        const int n = g->aux_nreg[r];
+        const int t = g->table_select[r];
+        const int book = T->huff_sel_book[t];
+        if (book == 0) {
+            ix += 2 * n;
+            sg += 2 * n;
+            continue;
+        }
+        const uint32_t *bk = T->huff_book[book];
+        const int lb = T->huff_linbits[t];
+        const bool esc = t >= 16;
+        for (int j = 0; j < n; j++) {
+            int x = ix[2 * j], y = ix[2 * j + 1];
+            if (esc) {
+                if (x > 15) x = 15;
+                if (y > 15) y = 15;
+            }
+            const uint32_t e = bk[(x & 15) * 16 + (y & 15)];
+            sink_put(b, e & 0xFFFFFFu, (int)(e >> 24));
+            if (esc && x >= 15) sink_put(b, (unsigned)(ix[2 * j] - 15), lb);
+            if (x) sink_put(b, sg[2 * j], 1);
+            if (esc && y >= 15) sink_put(b, (unsigned)(ix[2 * j + 1] - 15), lb);
+            if (y) sink_put(b, sg[2 * j + 1], 1);
+        }
+        ix += 2 * n;
+        sg += 2 * n;
+    }
+    const int nq = g->aux_nquads;
+    if (g->count1table_select == 1) {
+        for (int j = 0; j < nq; j++) {
+            unsigned x = (unsigned)(((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) ^ 15);
+            sink_put(b, x, 4);
+            for (int k = 0; k < 4; k++)
+                if ((x & (8u >> k)) == 0) sink_put(b, sg[4 * j + k], 1);
+        }
+    } else {
+        const unsigned char codeA[16] = {1, 5, 4, 5, 6, 5, 4, 4, 7, 3, 6, 0, 7, 2, 3, 1};
+        const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
+        for (int j = 0; j < nq; j++) {
+            unsigned x = (unsigned)((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) & 15u;
+            sink_put(b, codeA[x], lenA[x]);
+            for (int k = 0; k < 4; k++)
+                if (x & (8u >> k)) sink_put(b, sg[4 * j + k], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
+HMP3_HD void pack_side(const EncTables *T, const RateState *R, int main_data_begin, int igr_only, unsigned char *out) {
+    BitSink b;
+    sink_open(&b, out);
+    const int nch = T->cfg.nchan;
+    const bool m1 = T->cfg.h_id == 1;
+    if (m1) {
+        sink_put(&b, (unsigned)main_data_begin, 9);
+        sink_put(&b, 0, T->cfg.h_mode == 3 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) sink_put(&b, (unsigned)R->scfsi[ch], 4);
+    } else {
+        sink_put(&b, (unsigned)main_data_begin, 8);
+        sink_put(&b, 0, T->cfg.h_mode == 3 ? 1 : 2);
+    }
+    for (int igr = m1 ? 0 : igr_only; igr < (m1 ? 2 : igr_only + 1); igr++)
+        for (int ch = 0; ch < nch; ch++) {
+            const GrSide *g = &R->gr[igr][ch];
+            sink_put(&b, (unsigned)g->part2_3_length, 12);
+            sink_put(&b, (unsigned)g->big_values, 9);
+            sink_put(&b, (unsigned)g->global_gain, 8);
+            sink_put(&b, (unsigned)g->scalefac_compress, m1 ? 4 : 9);
+            sink_put(&b, (unsigned)g->window_switching_flag, 1);
+            if (g->window_switching_flag) {
+                sink_put(&b, (unsigned)g->block_type, 2);
+                sink_put(&b, (unsigned)g->mixed_block_flag, 1);
+                sink_put(&b, (unsigned)g->table_select[0], 5);
+                sink_put(&b, (unsigned)g->table_select[1], 5);
+                sink_put(&b, (unsigned)g->subblock_gain[0], 3);
+                sink_put(&b, (unsigned)g->subblock_gain[1], 3);
+                sink_put(&b, (unsigned)g->subblock_gain[2], 3);
+            } else {
+                sink_put(&b, (unsigned)g->table_select[0], 5);
+                sink_put(&b, (unsigned)g->table_select[1], 5);
+                sink_put(&b, (unsigned)g->table_select[2], 5);
+                sink_put(&b, (unsigned)g->region0_count, 4);
+                sink_put(&b, (unsigned)g->region1_count, 3);
+            }
+            if (m1) sink_put(&b, (unsigned)g->preflag, 1);
+            sink_put(&b, (unsigned)g->scalefac_scale, 1);
+            sink_put(&b, (unsigned)g->count1table_select, 1);
+        }
+    sink_close(&b);
+}
+
+// ------------------------------------------------------------------ the rate loop of one granule
+// CBitAllo3::BitAllo (bitallo3.cpp:484-678).  xr is this granule's spectrum [2][576], consumed in place.
+HMP3_HD void granule_allocate(const EncTables *T, RateState *R, float *xr, int igr, int nchan, int min_bits,
+                              int target_bits, int max_bits, int pool_bits, int ms) {
+    LongRate *L = &R->L;
+    GrSide *gr = R->gr[igr];
+    ScaleFac *sf_out = R->sf[igr];
+    int *ix = &R->ix[0][0];
+    unsigned char *sg = &R->signx[0][0];
+    const SigMask *sm = &R->sig_mask[0][0];
+    const int bt = gr[0].block_type;
+    const int init = T->cfg.initial_mnr;
+    L->block_type = bt;
+    L->calls++;
+    L->delta_mnr = 0;
+    if (bt == 1) {
+        if (L->mnr > init) {
+            L->mnr = (L->mnr + init) >> 1;
+            L->mnr = imin_(L->mnr, init + 500);
+        }
+    } else if (bt == 3) {
+        L->mnr = (L->mnr + init) >> 1;
+        L->mnr = imin_(L->mnr, init + 500);
+        for (int k = 0; k < nchan * 576; k++) ix[k] = 0;
+    }
+    if (bt == 2) {
+        int mnr0;
+        if (T->cfg.vbr_flag == 0) {
+            mnr0 = L->mnr - (imax_(L->mnr - init, 0) >> 1) - (imax_(L->mnr - init - 400, 0) >> 2);
+            mnr0 = imax_(init + 400, mnr0);
+        } else mnr0 = init + 400;
+        short_granule(T, &R->S, xr, sm, nchan, min_bits, target_bits, max_bits, pool_bits, sf_out, gr, ix, sg, ms, mnr0);
+        return;  // (the CBR feedback is a no-op for short blocks, bitallo3.cpp:2905-2909)
+    }
+    L->ms = ms;
+    L->nchan = nchan;
+    L->max_bits = imin_(4000 * nchan, max_bits);
+    L->min_target = min_bits < 0 ? 0 : min_bits;
+    L->target = target_bits;
+    L->pool_bits = pool_bits;
+    if (T->cfg.vbr_flag == 0) {
+        L->pool_fraction = imin_(L->pool_fraction + 50, 614);
+        if (bt != 0) L->pool_fraction = 0;
+    }
+    int tbits = ((L->pool_fraction * L->pool_bits) >> 10);
+    if (T->cfg.vbr_flag == 0) tbits = imin_(tbits, imax_((2050 - 500) + init - L->mnr, 200));
+    L->max_target = imin_(L->max_bits, L->target + tbits);
+    if (L->mnr < -200) L->min_target = imax_(L->min_target, (3 * L->target) >> 2);
+    L->max_target = imax_(L->min_target, L->max_target);
+    L->min_target = imin_(L->min_target, L->max_target - 100);
+    if (ms) long_startup_ms(T, L, xr, sm, sg);
+    else long_startup_lr(T, L, xr, sm, sg);
+    if (L->active_lines <= 0) {  // digital silence
+        for (int ch = 0; ch < nchan; ch++) {
+            GrSide *g = gr + ch;
+            g->global_gain = 0;
+            g->window_switching_flag = (bt != 0);
+            g->block_type = bt;
+            g->mixed_block_flag = 0;
+            g->preflag = 0;
+            g->scalefac_scale = 0;
+            g->table_select[0] = g->table_select[1] = g->table_select[2] = 0;
+            g->big_values = 0;
+            g->region0_count = g->region1_count = 0;
+            g->count1table_select = 0;
+            g->aux_nquads = 0;
+            g->aux_bits = 0;
+            g->aux_not_null = 0;
+            g->aux_nreg[0] = g->aux_nreg[1] = g->aux_nreg[2] = 0;
+            for (int j = 0; j < 21; j++) sf_out[ch].l[j] = 0;
+        }
+        return;
+    }
+    const int fb = long_allocate(T, L, xr, ix, ms != 0);
+    if (T->cfg.vbr_flag == 0) long_mnr_feedback(T, L, L->active_lines, fb, bt);
+    // scale factors on the coded grid (bitallo3.cpp:763-812)
+    for (int ch = 0; ch < nchan; ch++) {
+        const int sh = L->sf_scale[ch] == 0 ? 1 : 2;
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) L->sf[ch][i] >>= sh;
+        if (L->preemp[ch])
+            for (int i = 11; i < T->cfg.nsf[ch]; i++) L->sf[ch][i] -= sf_pre_amount(i);
+        for (int i = 0; i < 21; i++) sf_out[ch].l[i] = L->sf[ch][i];
+    }
+    if (ms) {  // the mid/side rotation carried no 1/sqrt(2)
+        L->G[0] -= 2;
+        L->G[1] -= 2;
+    }
+    for (int ch = 0; ch < nchan; ch++) {
+        GrSide *g = gr + ch;
+        g->global_gain = imin_(L->G[ch] + (4 * 32 + 14), 255);
+        g->window_switching_flag = (bt != 0);
+        g->block_type = bt;
+        g->mixed_block_flag = 0;
+        g->preflag = L->preemp[ch];
+        g->scalefac_scale = L->sf_scale[ch];
+        g->aux_bits = L->huff_bits[ch];
+        g->aux_not_null = L->huff_bits[ch];
+        plan_to_side(T, &L->plan[ch], g);
+    }
+}
+
+// Per-granule inputs produced by Phase A.
+struct GranuleIn {
+    GranuleInfo info;
+    float *xr;            // [2][576], consumed in place
+    const PsyRaw *raw;    // [2]
+    int ms_raw;
+};
+
+// M/S correlation with hysteresis (bitallo3.cpp:691-696, 745-753)
+HMP3_HD int ms_correlation(LongRate *L, const GranuleIn *g) {
+    if (g->info.block_type == 2) {
+        L->ms_memory = 0;
+        return g->ms_raw;
+    }
+    int cm = g->ms_raw + L->ms_memory;
+    L->ms_memory = (cm > 0) ? 5000 : -5000;
+    return cm;
+}
+
+HMP3_HD void psy_stage2(const EncTables *T, RateState *R, const GranuleIn *g) {  // mp3enc.cpp:2597-2617
+    for (int ch = 0; ch < T->cfg.nchan; ch++) {
+        if (g->info.block_type != 2) psy_long_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type, R->sig_mask[ch]);
+        else psy_short_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type_prev, R->sig_mask[ch]);
+    }
+}
+
+HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const GranuleIn *g) {
+    // mp3enc.cpp:1429-1438: both channels carry the same decision; the aux fields live in channel 0
+    R->gr[igr][0].short_flag_next = g->info.short_next;
+    R->gr[igr][0].short_flag_current = g->info.short_cur;
+    R->gr[igr][0].block_type_prev = g->info.block_type_prev;
+    R->gr[igr][0].block_type = R->gr[igr][1].block_type = g->info.block_type;
+}
+
+// One encode call worth of granules for MPEG-1 (two granules of one frame; mp3enc.cpp:1492-1749).
+// Returns the ms flag of the frame.
+HMP3_HD int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, GranuleIn *g1) {
+    const EncConfig &C = T->cfg;
+    const int nch = C.nchan;
+    GranuleIn *gs[2] = {g0, g1};
+    const int bit_pool = R->byte_pool << 2;
+    const int bit_max = R->byte_max << 2, bit_min = R->byte_min << 2;
+    int ba_bit_max, ba_bit_min, ba_min, ba_max, dba_max = 0, target;
+    const int sf_bits = nch * C.sf_bit_max;
+    if (nch == 2) {
+        ba_bit_max = bit_max - sf_bits;
+        ba_bit_min = bit_min - sf_bits;
+        dba_max = bit_pool >> 2;
+        ba_min = ba_bit_min;
+        ba_max = ba_bit_max + dba_max;
+        target = C.ave_target_bits + C.ave_target_bits;
+    } else {
+        ba_bit_max = bit_max;
+        if (ba_bit_max > 4095) ba_bit_max = 4095;
+        ba_bit_min = bit_min;
+        ba_bit_max -= C.sf_bit_max;
+        ba_bit_min -= C.sf_bit_max;
+        ba_min = ba_bit_min;
+        ba_max = ba_bit_max;
+        target = C.ave_target_bits;
+    }
+    set_block_info(T, R, 0, g0);
+    set_block_info(T, R, 1, g1);
+    const int short_frame = (g0->info.block_type == 2) | (g1->info.block_type == 2);
+    int ms = 0;
+    if (nch == 2 && C.ms_flag) {
+        int m1 = ms_correlation(&R->L, g0);
+        int m2 = ms_correlation(&R->L, g1);
+        if ((m1 + m2) >= 0) ms = 1;
+    }
+    for (int igr = 0; igr < 2; igr++) {
+        psy_stage2(T, R, gs[igr]);
+        granule_allocate(T, R, gs[igr]->xr, igr, nch, ba_min, target, ba_max, bit_pool, ms);
+        for (int ch = 0; ch < nch; ch++) {
+            GrSide *g = &R->gr[igr][ch];
+            const long long start_bits = R->sink.total_bits;
+            g->scalefac_compress = 0;
+            if (short_frame) {
+                R->scfsi[ch] = 0;
+                if (g->aux_not_null) g->scalefac_compress = pack_sf_mpeg1_plain(&R->sink, &R->sf[igr][ch], g->block_type);
+            } else {
+                g->scalefac_compress =
+                    pack_sf_mpeg1_scfsi(&R->sink, &R->sf[igr][ch], R->sf_save[ch], igr, &R->scfsi[ch], g->aux_not_null);
+            }
+            int bits = 0;
+            if (g->aux_not_null) {
+                pack_huffman(T, &R->sink, g, R->ix[ch], R->signx[ch]);
+                bits = (int)(R->sink.total_bits - start_bits);
+            }
+            if (nch == 2) {
+                ba_min -= bits;
+                ba_max -= bits;
+            } else {
+                ba_min += ba_bit_min + C.sf_bit_max - bits;
+                ba_max += ba_bit_max + C.sf_bit_max - bits;
+            }
+            g->part2_3_length = bits;
+        }
+        if (nch == 2) {
+            ba_min += ba_bit_min + sf_bits;
+            ba_max = ba_max - dba_max;
+            ba_max += ba_bit_max + sf_bits;
+        }
+    }
+    return ms;
+}
+
+// One MPEG-2 frame = one granule (mp3enc.cpp:1832-2027)
+HMP3_HD int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, GranuleIn *g0) {
+    const EncConfig &C = T->cfg;
+    const int nch = C.nchan;
+    const int bit_pool = R->byte_pool << 3;
+    int bit_max = (R->byte_max << 3), bit_min = (R->byte_min << 3);
+    if (nch == 2 && R->byte_pool > 245) bit_min += 40;
+    int ba_bit_max = bit_max;
+    if (ba_bit_max > 4095) ba_bit_max = 4095;
+    int ba_bit_min = bit_min;
+    ba_bit_max -= nch * C.sf_bit_max;
+    ba_bit_min -= nch * C.sf_bit_max;
+    set_block_info(T, R, igr, g0);
+    int ms = 0;
+    if (nch == 2 && C.ms_flag) {
+        int m1 = ms_correlation(&R->L, g0);
+        if (m1 >= 0) ms = 1;
+    }
+    psy_stage2(T, R, g0);
+    granule_allocate(T, R, g0->xr, igr, nch, ba_bit_min, nch * C.ave_target_bits, ba_bit_max, bit_pool,
+                     nch == 2 ? ms : C.ms_flag);
+    for (int ch = 0; ch < nch; ch++) {
+        GrSide *g = &R->gr[igr][ch];
+        const long long start_bits = R->sink.total_bits;
+        int bits = 0;
+        g->scalefac_compress = 0;
+        if (g->aux_not_null) {
+            g->scalefac_compress = pack_sf_mpeg2(&R->sink, &R->sf[igr][ch], R->gr[igr][0].block_type);
+            pack_huffman(T, &R->sink, g, R->ix[ch], R->signx[ch]);
+            bits = (int)(R->sink.total_bits - start_bits);
+        }
+        g->part2_3_length = bits;
+    }
+    return ms;
+}
+
+// ------------------------------------------------------------------ frame driver + reservoir
+// Records one frame: header, side info and its main-data slot; appends this frame's main data to the
+// stream's main-data stream (mp3enc.cpp:2106-2593).  `main` is the stream's main-data buffer.
+HMP3_HD void frame_header(const EncTables *T, unsigned char *h, int pad, int mode_ext, int br_index) {
+    h[0] = T->cfg.head[0];
+    h[1] = T->cfg.head[1];
+    h[2] = T->cfg.head[2];
+    h[3] = T->cfg.head[3];
+    if (T->cfg.vbr_flag) h[2] = (unsigned char)((h[2] & 0x0F) | (br_index << 4));
+    else if (pad) h[2] |= 2;
+    h[3] = (unsigned char)((h[3] & 0xCF) | (mode_ext << 4));
+}
+
+// Encode the granules of one frame (MPEG-1: g0,g1; MPEG-2: g0 with granule parity igr).
+HMP3_HD void encode_one_frame(const EncTables *T, RateState *R, unsigned char *main, FrameRec *frames, int igr,
+                              GranuleIn *g0, GranuleIn *g1) {
+    const EncConfig &C = T->cfg;
+    const bool m1 = C.h_id == 1;
+    int pad = 0;
+    int mf_bytes = 0;
+    if (!C.vbr_flag) {
+        R->padcount -= C.pad_remainder;
+        if (R->padcount <= 0) {
+            R->padcount += C.pad_divisor;
+            pad = 1;
+        }
+        mf_bytes = C.main_framebytes + pad;
+    }
+    FrameRec *fr = frames + R->frames;
+    fr->main_start = R->mf_tot;
+    R->byte_pool = (int)(R->mf_tot - R->main_tot);
+    if (C.vbr_flag) {
+        R->byte_max = C.vbr_main_framebytes[C.ivbr_max] + R->byte_pool;
+        R->byte_min = C.vbr_main_framebytes[C.ivbr_min] + R->byte_pool - C.reservoir_back;
+    } else {
+        R->byte_max = C.main_framebytes + pad + R->byte_pool;
+        R->byte_min = R->byte_max - C.reservoir_back;
+    }
+    const int main_data_begin = R->byte_pool;
+    sink_open(&R->sink, main + R->main_tot);
+    const int ms = m1 ? encode_frame_mpeg1(T, R, g0, g1) : encode_frame_mpeg2(T, R, igr, g0);
+    const int mode_ext = ms + ms + C.is_flag;
+    int bytes = (int)sink_close(&R->sink);
+    int ibr = 0;
+    if (C.vbr_flag) {
+        const int bytes2 = bytes - R->byte_pool;
+        const int bytes3 = bytes2 + C.vbr_pool_target;
+        for (ibr = C.ivbr_min; ibr <= C.ivbr_max; ibr++)
+            if (bytes2 <= C.vbr_main_framebytes[ibr]) break;
+        bool grow = true;
+        if (!m1) {  // MPEG-2: keep the number of frames spanned by the reservoir bounded (mp3enc.cpp:2390-2413)
+            const int side_dp = (R->frames - R->frames_done) & 31;
+            grow = side_dp < 10;
+            if (side_dp > 15) {
+                if (side_dp > 24) R->byte_min = C.vbr_main_framebytes[C.ivbr_min] + R->byte_pool;
+                else R->byte_min = C.vbr_main_framebytes[C.ivbr_min] + (R->byte_pool >> 4);
+            }
+        }
+        if (grow)
+            for (; ibr <= C.ivbr_max; ibr++)
+                if (bytes3 < C.vbr_main_framebytes[ibr + 1]) break;
+        if (ibr > C.ivbr_max) ibr = C.ivbr_max;
+        mf_bytes = C.vbr_main_framebytes[ibr];
+    }
+    if (bytes < R->byte_min) {
+        for (int k = bytes; k < R->byte_min; k++) main[R->main_tot + k] = 0;
+        bytes = R->byte_min;
+    }
+    fr->mf_bytes = mf_bytes;
+    frame_header(T, fr->head, pad, mode_ext, ibr);
+    pack_side(T, R, main_data_begin, igr, fr->side);
+    R->main_tot += bytes;
+    R->mf_tot += mf_bytes;
+    R->frames++;
+    // frames whose slot is now completely covered by produced main data
+    while (R->frames_done < R->frames) {
+        const FrameRec *f = frames + R->frames_done;
+        if ((long long)R->main_tot - (long long)f->main_start < f->mf_bytes) break;
+        R->frames_done++;
+    }
+}
+
+}  // namespace hmp3
+
+namespace hmp3 {
+
+// Run the serial stage of one stream over the encode granules [K0, K0+NG) that Phase A has prepared.
+// gi/xr/raw/ms_raw point at this stream's slice of the chunk buffers (index 0 == granule K0).
+// ngran_real = granules of real encode calls (2 per call); after them the stream keeps consuming
+// zero-PCM granules until every real frame's main-data slot is filled (the CLI's tail flush,
+// test/tomp3.cpp:1015-1036), checked at call boundaries.
+HMP3_HD void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
+                            const GranuleInfo *gi, float *xr, const PsyRaw *raw, const int *ms_raw,
+                            unsigned char *main, FrameRec *frames) {
+    const bool m1 = T->cfg.h_id == 1;
+    const int frames_real = m1 ? ngran_real / 2 : ngran_real;
+    for (int K = K0; K + 1 < K0 + NG && K + 1 < ngran; K += 2) {
+        if (R->finished) return;
+        if (K < R->next_granule) continue;
+        GranuleIn g[2];
+        for (int q = 0; q < 2; q++) {
+            const int o = K - K0 + q;
+            g[q].info = gi[o];
+            g[q].xr = xr + (long long)o * 2 * 576;
+            g[q].raw = raw + (long long)o * 2;
+            g[q].ms_raw = ms_raw[o];
+        }
+        if (m1) encode_one_frame(T, R, main, frames, 0, &g[0], &g[1]);
+        else {
+            encode_one_frame(T, R, main, frames, 0, &g[0], nullptr);
+            encode_one_frame(T, R, main, frames, 1, &g[1], nullptr);
+        }
+        R->next_granule = K + 2;
+        if (K + 2 >= ngran_real && R->frames_done >= frames_real) R->finished = 1;
+    }
+}
+
+// Final byte layout of frame f of a stream: header | side info | slice of the main-data stream.
+// Returns the frame's size; `out` may be null to only measure.
+HMP3_HD int frame_bytes(const EncTables *T, const FrameRec *f) { return 4 + T->cfg.side_bytes + f->mf_bytes; }
+
+}  // namespace hmp3

@@ -1,0 +1,821 @@
+// Rate loop for long block types (0, 1, 3): noise-target computation, per-band step search, scale
+// factor selection, quantisation, Huffman region planning and the bit-budget control loops.
+// Behaviour follows CBitAllo3 (bitallo3.cpp:484-3149); integer outputs are bit-exact given identical
+// inputs.  All state of one stream lives in a LongRate object (persistent fields keep their value
+// from granule to granule exactly as the reference object does).
+#pragma once
+#include "rate_common.h"
+#include "psy_core.h"
+
+namespace hmp3 {
+
+constexpr int kGminOffset = 70;   // bitallos.h:61
+constexpr int kPart23Max = 4021;  // bitallo3.h:61
+
+struct LongRate {
+    // ---- carried from granule to granule
+    int mnr, pool_fraction, calls, delta_mnr, ms_memory;
+    int hf_quant, hf_quant_ch[2], gsf_hf, gsf_hf_ch[2];
+    int huff_bits[2];
+    int nt_adjust[2][22];
+    int ixmax[2][22];
+    int sf[2][22], active[2][22];
+    // ---- per call
+    int nchan, ms, block_type;
+    int max_bits, max_target, min_target, target, pool_bits, active_lines;
+    float xsxx[2][22], x34max[2][22];
+    int snr[2][22], noise0[2][22], noise[2][22], nt[2][22];
+    int gzero[2][22], gmin[2][22], gsf[2][22];
+    int G[2], preemp[2], sf_scale[2];
+    RegionPlan plan[2];
+    float x34[2][576];
+};
+
+HMP3_HD void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
+    L->mnr = T->cfg.initial_mnr;
+    L->pool_fraction = T->cfg.vbr_flag ? 614 : 0;
+    L->calls = 0;
+    L->delta_mnr = 0;
+    L->ms_memory = 0;
+    L->hf_quant = 0;
+    L->hf_quant_ch[0] = L->hf_quant_ch[1] = 0;
+    L->gsf_hf = -1;
+    L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
+    L->huff_bits[0] = L->huff_bits[1] = 0;
+    for (int c = 0; c < 2; c++) {
+        for (int i = 0; i < 22; i++) {
+            L->nt_adjust[c][i] = 0;
+            L->ixmax[c][i] = 0;
+            L->sf[c][i] = 0;
+            L->active[c][i] = 0;
+            L->gzero[c][i] = L->gmin[c][i] = L->gsf[c][i] = 0;
+            L->noise[c][i] = L->noise0[c][i] = L->nt[c][i] = L->snr[c][i] = 0;
+            L->x34max[c][i] = L->xsxx[c][i] = 0.0f;
+        }
+        L->G[c] = L->preemp[c] = L->sf_scale[c] = 0;
+        L->plan[c].bits = 0;
+        L->plan[c].nbig = L->plan[c].nquads = 0;
+        for (int i = 0; i < 4; i++) L->plan[c].table[i] = 0;
+        for (int i = 0; i < 3; i++) L->plan[c].cb[i] = 0;
+    }
+}
+
+// ---- scale-factor range tables by (scalefac_scale, preflag) (bitallo3.cpp:87-161)
+HMP3_HD int sf_pre_amount(int i) {  // ISO pretab
+    const unsigned char p[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
+    return p[i];
+}
+HMP3_HD int sf_select_limit(int sel, int i) {  // limits used to choose (scale, preflag)
+    const int scale = sel >> 1, pre = sel & 1;
+    const int base = (i < 11) ? 31 : 15;
+    const int step = 2 << scale;  // 2 or 4
+    return (scale ? 2 * base : base) + (pre ? step * sf_pre_amount(i) : 0);
+}
+HMP3_HD int sf_upper(int scale, int pre, int i) {
+    const int base = (i < 11) ? 30 : 14;
+    const int step = 2 << scale;
+    return (scale ? 2 * base : base) + (pre ? step * sf_pre_amount(i) : 0);
+}
+HMP3_HD int sf_lower(int scale, int pre, int i) {
+    const int step = 2 << scale;
+    return pre ? step * sf_pre_amount(i) : 0;
+}
+HMP3_HD int noise_gap_limit(int i) {  // bitallo3.cpp:182-188
+    return i < 15 ? 250 : (i == 15 ? 300 : (i < 18 ? 400 : (i < 20 ? 500 : 600)));
+}
+
+// ------------------------------------------------------------------ startup
+// dropout prevention applied to a band's noise target (bitallo3.cpp:858-865)
+HMP3_HD int nt_dropout_guard(int noise0, int nt) {
+    int tsnr = noise0 - nt;
+    if (tsnr < 300) {
+        tsnr = 187 + ((3 * tsnr) >> 3) - tsnr;
+        nt -= tsnr;
+    }
+    return nt;
+}
+
+// pull noise targets toward their band-weighted mean (bitallo3.cpp:1069-1126)
+HMP3_HD void long_flatten_targets(const EncTables *T, LongRate *L) {
+    const int f = T->cfg.nt_flatten;
+    if (f == 0) return;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int nsf = T->cfg.nsf[ch];
+        int na = 1, nab = 1, ab = 0;
+        for (int i = 0; i < nsf; i++) {
+            int th = i < 14 ? 0 : (i < 17 ? 100 : (i == 17 ? 200 : 300));
+            if (L->snr[ch][i] > th) {
+                na++;
+                ab += T->nBand_l[i] * L->nt[ch][i];
+                nab += T->nBand_l[i];
+            }
+        }
+        ab = ab / nab;
+        if (na < 5) continue;
+        for (int i = 0; i < nsf; i++) {
+            int th = i < 14 ? 0 : (i < 17 ? 100 : (i == 17 ? 200 : 300));
+            if (L->snr[ch][i] > th) {
+                int dmax = imax_(L->snr[ch][i] - 400, 0);
+                int d = (f * (ab - L->nt[ch][i])) >> 4;
+                d = imin_(d, dmax);
+                L->nt[ch][i] = L->nt[ch][i] + d;
+            }
+        }
+    }
+}
+
+HMP3_HD void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nbands) {
+    // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
+    const float *y = L->x34[ch];
+    for (int i = 0; i < nbands; i++) {
+        const int n = T->nBand_l[i];
+        float m = 0.0f;
+        for (int k = 0; k < n; k++)
+            if (y[k] > m) m = y[k];
+        L->x34max[ch][i] = m;
+        L->gzero[ch][i] = imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
+        L->gmin[ch][i] = imax_(0, L->gzero[ch][i] - kGminOffset);
+        y += n;
+    }
+}
+
+// left/right granule (bitallo3.cpp:816-898).  xr is modified in place (signs stripped).
+HMP3_HD void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][576]*/, const SigMask *sm /*[2][36]*/,
+                             unsigned char *signx /*[2][576]*/) {
+    const int mnr = L->mnr + 100;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        float *x = xr + 576 * ch;
+        unsigned char *s = signx + 576 * ch;
+        for (int i = 0; i < T->cfg.nsf3[ch]; i++) {
+            const int n = T->nBand_l[i];
+            float e = 0.0f;
+            for (int k = 0; k < n; k++) {
+                if (x[k] >= 0.0f) s[k] = 0;
+                else { s[k] = 1; x[k] = -x[k]; }
+                e += x[k] * x[k];
+            }
+            L->xsxx[ch][i] = e;
+            x += n;
+            s += n;
+        }
+    }
+    L->active_lines = 0;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+            const int cbw = T->log_cbw_l[i];
+            L->noise0[ch][i] = mb_log(T, L->xsxx[ch][i]) - cbw;
+            if (L->noise0[ch][i] < -2000) {
+                L->nt[ch][i] = L->noise0[ch][i] + 1000;
+            } else {
+                L->active_lines += T->nBand_l[i];
+                int mask = mb_log(T, sm[36 * ch + i].mask) - cbw;
+                L->nt[ch][i] = nt_dropout_guard(L->noise0[ch][i], mask - mnr + T->taperNT[i]);
+            }
+            L->snr[ch][i] = L->noise0[ch][i] - L->nt[ch][i];
+        }
+    }
+    long_flatten_targets(T, L);
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const float *x = xr + 576 * ch;
+        for (int k = 0; k < T->cfg.nbmax3[ch]; k++) L->x34[ch][k] = pow34(T, x[k]);
+        long_step_bounds(T, L, ch, T->cfg.nsf3[ch]);
+    }
+}
+
+// mid/side granule (bitallo3.cpp:902-1065): xr becomes |L+R|, |L-R| in place (no 1/sqrt2; the
+// global gain is lowered by 2 steps on output instead).
+HMP3_HD void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const SigMask *sm, unsigned char *signx) {
+    if (T->cfg.vbr_flag == 0 && L->calls > 10 && (L->target - L->min_target) < 100)
+        L->mnr = imin_(L->mnr + 50, 2050);
+    const int mnr = L->mnr;
+    L->active_lines = 0;
+    float *x = xr;
+    unsigned char *s = signx;
+    const int nsf0 = T->cfg.nsf[0];
+    int n = 0;
+    for (int i = 0; i < nsf0; i++) {
+        n = T->nBand_l[i];
+        float el = 0.0f, er = 0.0f;
+        for (int k = 0; k < n; k++) {
+            el += x[k] * x[k];
+            er += x[576 + k] * x[576 + k];
+        }
+        for (int k = 0; k < n; k++) {
+            float m = (x[k] + x[576 + k]);
+            float d = (x[k] - x[576 + k]);
+            s[k] = s[576 + k] = 0;
+            if (m < 0.0f) { s[k] = 1; m = -m; }
+            if (d < 0.0f) { s[576 + k] = 1; d = -d; }
+            x[k] = m;
+            x[576 + k] = d;
+        }
+        float em = 0.0f, ed = 0.0f;
+        for (int k = 0; k < n; k++) {
+            em += x[k] * x[k];
+            ed += x[576 + k] * x[576 + k];
+        }
+        L->xsxx[0][i] = el;
+        L->xsxx[1][i] = er;
+        const int cbw = T->log_cbw_l[i];
+        int ntl, ntr;
+        int n0l = mb_log(T, el) - cbw;
+        if (n0l < -2000) ntl = 10000;
+        else {
+            ntl = nt_dropout_guard(n0l, (mb_log(T, sm[i].mask) - cbw) - mnr + T->taperNT[i]);
+            L->active_lines += n;
+        }
+        int n0r = mb_log(T, er) - cbw;
+        if (n0r < -2000) ntr = 10000;
+        else {
+            ntr = nt_dropout_guard(n0r, (mb_log(T, sm[36 + i].mask) - cbw) - mnr + T->taperNT[i]);
+            L->active_lines += n;
+        }
+        L->nt[0][i] = ntl;
+        L->nt[1][i] = ntr;
+        L->snr[0][i] = n0l - ntl;
+        L->snr[1][i] = n0r - ntr;
+        L->noise0[0][i] = mb_log(T, em) - cbw;
+        L->noise0[1][i] = mb_log(T, ed) - cbw;
+        x += n;
+        s += n;
+    }
+    if (T->cfg.hf_flag) {  // the pseudo band above sfb 21 is rotated too
+        n = T->nBand_l[21];
+        for (int k = 0; k < n; k++) {
+            float m = (x[k] + x[576 + k]);
+            float d = (x[k] - x[576 + k]);
+            s[k] = s[576 + k] = 0;
+            if (m < 0.0f) { s[k] = 1; m = -m; }
+            if (d < 0.0f) { s[576 + k] = 1; d = -d; }
+            x[k] = m;
+            x[576 + k] = d;
+        }
+    }
+    long_flatten_targets(T, L);
+    for (int i = 0; i < nsf0; i++) {
+        const int nsum = L->noise0[0][i], ndiff = L->noise0[1][i];
+        const int xnt = imin_(L->nt[0][i], L->nt[1][i]) + 300;
+        L->nt[1][i] = L->nt[0][i] = xnt;
+        if (ndiff < xnt) {
+            L->nt[0][i] = mb_logsub(T, xnt, ndiff);
+            if (i < 16) L->nt[0][i] -= 200;
+        }
+        if (nsum < xnt) L->nt[1][i] = mb_logsub(T, xnt, nsum);
+        L->snr[0][i] = nsum - L->nt[0][i];
+        L->snr[1][i] = ndiff - L->nt[1][i];
+    }
+    for (int ch = 0; ch < 2; ch++)
+        for (int k = 0; k < T->cfg.nbmax2[ch]; k++) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
+    for (int ch = 0; ch < L->nchan; ch++) long_step_bounds(T, L, ch, T->cfg.nsf2[ch]);
+}
+
+// ------------------------------------------------------------------ per-band step search
+HMP3_HD void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.cpp:1130-1160
+    for (int ch = 0; ch < L->nchan; ch++)
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+            L->nt_adjust[ch][i] = imax_(L->nt_adjust[ch][i], -400);
+            L->nt_adjust[ch][i] = imin_(L->nt_adjust[ch][i], 400);
+            float g4 = 0.017716950f * mb_log(T, L->x34max[ch][i]) + (88.411238f - 100.0f + 8.0f);
+            float d = (1.00f / 110.5f) * (1800 - 8 * i - (L->noise0[ch][i] - L->nt[ch][i] + L->nt_adjust[ch][i]));
+            float g = g4 + d;
+            int v = round_away(g);
+            v = imin_(v, L->gzero[ch][i]);
+            v = imax_(v, L->gmin[ch][i]);
+            L->gsf[ch][i] = v;
+        }
+}
+
+// walk the step of one band toward the noise target, at most 20 steps (bitallo3.cpp:1164-1238)
+HMP3_HD int seek_finer(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
+                       int dn, int *noise_io) {
+    int s = s0 - 1;
+    int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
+    const int niter = imin_(s, 20);
+    for (int i = 0; i < niter; i++) {
+        int tn = band_noise(T, y34, y, s, n, logn);
+        int a = iabs(tn - target);
+        if (a < best_abs) { best_abs = a; best_noise = tn; best_s = s; }
+        if (tn <= target) break;
+        s--;
+    }
+    *noise_io = best_noise;
+    return best_s;
+}
+HMP3_HD int seek_coarser(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
+                         int dn, int *noise_io) {
+    int s = s0;
+    int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
+    for (int i = 0; i < 20; i++) {
+        s++;
+        int tn = band_noise(T, y34, y, s, n, logn);
+        int a = iabs(tn - target);
+        if (a < best_abs) { best_abs = a; best_noise = tn; best_s = s; }
+        if (tn >= target) break;
+    }
+    *noise_io = best_noise;
+    return best_s;
+}
+
+HMP3_HD void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const float *y34 = L->x34[ch];
+        const float *y = xr + 576 * ch;
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+            const int target = L->nt[ch][i];
+            const int n = T->nBand_l[i];
+            int s = L->gsf[ch][i];
+            if (L->noise0[ch][i] > target) {
+                const int logn = T->log_cbw_l[i];
+                int noise = band_noise(T, y34, y, s, n, logn);
+                int dn = noise - target;
+                L->nt_adjust[ch][i] = L->nt_adjust[ch][i] + (dn >> 3);
+                if (dn > 100) s = seek_finer(T, y34, y, s, n, logn, target, dn, &noise);
+                else if (dn < -100) s = seek_coarser(T, y34, y, s, n, logn, target, dn, &noise);
+                L->gsf[ch][i] = s;
+                L->noise[ch][i] = noise;
+            } else {
+                L->gsf[ch][i] = L->gzero[ch][i] + 5;
+                L->noise[ch][i] = L->noise0[ch][i];
+            }
+            y34 += n;
+            y += n;
+        }
+    }
+}
+
+// flatten isolated small peaks in the upper bands of L/R granules (bitallo3.cpp:2216-2299)
+HMP3_HD float db_of(float x) { return (float)(10.0 * log10((double)x)); }
+HMP3_HD void long_trade_peaks(const EncTables *T, LongRate *L) {
+    const float inv_peak[16] = {1.0f / (0.5f + 0.09460f),  1.0f / (1.5f + 0.02799f),  1.0f / (2.5f + 0.01671f),
+                                1.0f / (3.5f + 0.01192f),  1.0f / (4.5f + 0.00927f),  1.0f / (5.5f + 0.00758f),
+                                1.0f / (6.5f + 0.00641f),  1.0f / (7.5f + 0.00556f),  1.0f / (8.5f + 0.00490f),
+                                1.0f / (9.5f + 0.00439f),  1.0f / (10.5f + 0.00397f), 1.0f / (11.5f + 0.00362f),
+                                1.0f / (12.5f + 0.00333f), 1.0f / (13.5f + 0.00309f), 1.0f / (14.5f + 0.00287f),
+                                1.0f / (15.5f + 0.00269f)};
+    const unsigned char snap[16] = {0, 1, 2, 3, 3, 5, 5, 7, 7, 7, 7, 15, 15, 15, 15, 15};
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int nsf = T->cfg.nsf[ch];
+        int peak[22], peak10[22];
+        for (int i = 0; i < nsf; i++) {
+            peak[i] = quant_tuned_peak(T, L->x34max[ch][i], L->gsf[ch][i]);
+            peak10[i] = quant_tuned_peak10(T, L->x34max[ch][i], L->gsf[ch][i]);
+            L->ixmax[ch][i] = peak[i];
+        }
+        int i;
+        for (i = nsf - 1; i >= 11; i--) {
+            if (peak10[i] > 16) break;
+            if (peak[i] == 2) {
+                float xg = 1.7717f * db_of(L->x34max[ch][i] * (1.0f / (1.5f + 0.02799f)));
+                L->gsf[ch][i] = (int)(xg + 1.0f) + 8;
+            }
+        }
+        const int k1 = i + 1;
+        if (k1 < 9) continue;
+        int k0 = (3 * k1) >> 2;
+        if (k0 < 11) k0 = 11;
+        if (k0 >= k1) continue;
+        int top = 0;
+        for (i = k0; i < k1; i++) top = imax_(top, peak[i]);
+        if (top <= 2) continue;
+        float fetot = 0, fepk = 0;
+        for (i = k0; i < k1; i++) {
+            float e = T->rnBand_l[i] * L->xsxx[ch][i];
+            fetot += e;
+            fepk += e * peak10[i];
+        }
+        float mean_pk = fepk / (1.0f + fetot);
+        int tgt = (int)(0.1f * mean_pk + 0.65f);
+        if (tgt < 2) tgt = 2;
+        if (top <= tgt) continue;
+        if (tgt > 15) continue;
+        tgt = snap[tgt];
+        const float factor = inv_peak[tgt];
+        for (i = k0; i < k1; i++)
+            if (peak[i] > tgt) {
+                float xg = 1.7717f * db_of(L->x34max[ch][i] * factor);
+                L->gsf[ch][i] = (int)(xg + 1.0f) + 8;
+            }
+    }
+}
+
+// -HF: decide whether the lines above band 21 can be coded at the granule's gain
+// (bitallo3.cpp:2421-2565).  which = channel for L/R granules; -1 = the mid channel of an M/S granule.
+HMP3_HD void long_hf_decide(const EncTables *T, LongRate *L, int ch, bool ms) {
+    if (L->gzero[ch][21] <= 8) return;
+    int gmax0 = 0, gmax1 = 0;
+    for (int i = 0; i < 11; i++)
+        if (L->gsf[ch][i] < L->gzero[ch][i] && L->gsf[ch][i] > gmax0) gmax0 = L->gsf[ch][i];
+    for (int i = 11; i < T->cfg.nsf[ch]; i++)
+        if (L->gsf[ch][i] < L->gzero[ch][i] && L->gsf[ch][i] > gmax1) gmax1 = L->gsf[ch][i];
+    const int gtar = imax_(0, L->gzero[ch][21] - 5);
+    const int gtar2 = imax_(0, L->gzero[ch][21] - 7);
+    const int gmax = imax_(gmax0, gmax1);
+    if (gtar >= gmax) {
+        if (ms) { L->hf_quant = 1; L->gsf_hf = gtar2; }
+        else { L->hf_quant_ch[ch] = 1; L->gsf_hf_ch[ch] = gtar2; }
+    } else if (gmax0 > gmax1) {
+        const int gset = imax_(gtar, gmax1);
+        if (L->gzero[ch][21] > gset) {
+            for (int i = 0; i < 11; i++)
+                if (L->gsf[ch][i] < L->gzero[ch][i] && L->gsf[ch][i] > gset) L->gsf[ch][i] = gset;
+            if (ms) L->hf_quant = 1;
+            else L->hf_quant_ch[ch] = 1;
+        }
+    }
+}
+HMP3_HD void long_hf_adjust_lr(const EncTables *T, LongRate *L) {
+    L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
+    for (int ch = 0; ch < L->nchan; ch++) long_hf_decide(T, L, ch, false);
+    L->hf_quant = L->hf_quant_ch[0] | L->hf_quant_ch[1];
+}
+HMP3_HD void long_hf_reset_lr(LongRate *L) {
+    L->hf_quant = 0;
+    L->hf_quant_ch[0] = L->hf_quant_ch[1] = 0;
+    L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
+    L->ixmax[0][21] = L->ixmax[1][21] = 0;
+}
+HMP3_HD void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bitallo3.cpp:1629-1654
+    const int b = T->startBand_l[21], n = T->nBand_l[21];
+    for (int ch = 0; ch < nch; ch++)
+        for (int k = 0; k < n; k++) ix[576 * ch + b + k] = 0;
+}
+
+// ------------------------------------------------------------------ scale factors
+// choose (scalefac_scale, preflag): first combination whose ranges hold every active band
+// (bitallo3.cpp:1793-1888)
+HMP3_HD void long_pick_sf_mode(const EncTables *T, LongRate *L, int ch) {
+    const int nsf = T->cfg.nsf[ch];
+    if (T->cfg.h_id) {
+        int sp[4] = {0, 0, 0, 0};
+        for (int i = 0; i < nsf; i++)
+            if (L->active[ch][i]) {
+                const int s = L->sf[ch][i];
+                for (int m = 0; m < 4; m++) sp[m] |= (sf_select_limit(m, i) - s);
+                sp[1] |= (s - sf_lower(0, 1, i));
+                sp[3] |= (s - sf_lower(1, 1, i));
+            }
+        int scale, pre;
+        if (sp[0] >= 0) { scale = 0; pre = 0; }
+        else if (sp[1] >= 0) { scale = 0; pre = 1; }
+        else if (sp[2] >= 0) { scale = 1; pre = 0; }
+        else if (sp[3] >= 0) { scale = 1; pre = 1; }
+        else { scale = 1; pre = 0; }
+        L->preemp[ch] = pre;
+        L->sf_scale[ch] = scale;
+    } else {
+        int sp0 = 0;
+        for (int i = 0; i < nsf; i++)
+            if (L->active[ch][i]) sp0 |= (sf_select_limit(0, i) - L->sf[ch][i]);
+        L->preemp[ch] = 0;
+        L->sf_scale[ch] = (sp0 >= 0) ? 0 : 1;
+    }
+}
+
+// derive G and scale factors from the per-band steps, round them to the coded grid and recompute the
+// steps (bitallo3.cpp:1892-2169).  ms selects the mid/side flavour of the rounding rules.
+HMP3_HD int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
+    int gmin_all = 999;
+    int gtop = -1;
+    if (ms && L->hf_quant) gtop = L->gsf_hf;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int nsf = T->cfg.nsf[ch];
+        if (!ms) gtop = L->gsf_hf_ch[ch];
+        for (int i = 0; i < nsf; i++) {
+            L->gsf[ch][i] = imax_(L->gsf[ch][i], L->gmin[ch][i]);
+            L->active[ch][i] = 0;
+            if (L->gsf[ch][i] < L->gzero[ch][i]) {
+                L->active[ch][i] = -1;
+                gtop = imax_(gtop, L->gsf[ch][i]);
+            }
+        }
+        if (gtop < 0) {  // nothing to code in this channel
+            for (int i = 0; i < nsf; i++) {
+                L->sf[ch][i] = 0;
+                L->gsf[ch][i] = L->gzero[ch][i];
+                gtop = imax_(gtop, L->gsf[ch][i]);
+            }
+            L->preemp[ch] = 0;
+            L->sf_scale[ch] = 0;
+            L->G[ch] = gtop;
+            gmin_all = imin_(gmin_all, 100);
+            continue;  // note: the mid/side flavour carries gtop into the next channel here (bitallo3.cpp:2059-2074)
+        }
+        for (int i = 0; i < nsf; i++) L->sf[ch][i] = (gtop - L->gsf[ch][i]) & L->active[ch][i];
+        long_pick_sf_mode(T, L, ch);
+        int dsf;
+        if (L->sf_scale[ch] == 0) {
+            dsf = 2;
+            for (int i = 0; i < nsf; i++) {
+                if (ms) {
+                    if (L->active[ch][i]) {
+                        if ((L->gzero[ch][i] - L->gsf[ch][i]) < 5) L->sf[ch][i]++;
+                        else if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) L->sf[ch][i]++;
+                        L->sf[ch][i] &= (~1);
+                    }
+                } else {
+                    if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) L->sf[ch][i]++;
+                    L->sf[ch][i] &= (~1);
+                }
+            }
+        } else {
+            dsf = 4;
+            for (int i = 0; i < nsf; i++) {
+                if (ms && !L->active[ch][i]) continue;
+                int s = L->sf[ch][i] & (~3);
+                int d = L->sf[ch][i] - s;
+                int dN = L->noise[ch][i] - L->nt[ch][i] + 150 * d;
+                if (dN > noise_gap_limit(i)) s = s + 4;
+                else if (ms && (L->gzero[ch][i] - L->gsf[ch][i] - d) < 5) s = s + 4;
+                L->sf[ch][i] = ms ? s : (s & L->active[ch][i]);
+            }
+        }
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        for (int i = 0; i < nsf; i++) {
+            const int hi = sf_upper(scale, pre, i), lo = sf_lower(scale, pre, i);
+            if (L->sf[ch][i] > hi) L->sf[ch][i] = hi;
+            else if (L->sf[ch][i] < lo) L->sf[ch][i] = lo;
+        }
+        for (int i = 0; i < nsf; i++)
+            if (L->active[ch][i]) {
+                L->gsf[ch][i] = gtop - L->sf[ch][i];
+                if (L->gsf[ch][i] < 0) {
+                    L->gsf[ch][i] += dsf;
+                    L->sf[ch][i] -= dsf;
+                }
+                if (L->gsf[ch][i] >= L->gzero[ch][i]) {
+                    L->gsf[ch][i] = L->gzero[ch][i] + 5;
+                    L->sf[ch][i] = sf_lower(scale, pre, i);
+                }
+            }
+        L->G[ch] = gtop;
+        gmin_all = imin_(gmin_all, gtop);
+        if (ms) gtop = -1;
+    }
+    return gmin_all;
+}
+
+// try coarser steps on the low bands while the measured noise stays under target (bitallo3.cpp:1348-1399)
+HMP3_HD void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float *xr) {
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int sdelta = 2 * (1 + L->sf_scale[ch]);
+        const int GG = L->G[ch];
+        const float *y34 = L->x34[ch];
+        const float *y = xr + 576 * ch;
+        const int m = imin_(13, T->cfg.nsf[ch]);
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        for (int i = 0; i < m; i++) {
+            const int n = T->nBand_l[i];
+            if (L->active[ch][i] && (L->gsf[ch][i] < (L->gzero[ch][i] - 5))) {
+                int smin = L->sf[ch][i];
+                const int g0 = L->gzero[ch][i] - 4;
+                int s = imin_(L->sf[ch][i] - sdelta, sf_upper(scale, pre, i));
+                const int s0 = sf_lower(scale, pre, i);
+                const int logn = T->log_cbw_l[i];
+                for (; s >= s0; s -= sdelta) {
+                    const int g = GG - s;
+                    if (g >= g0) break;
+                    int nz = band_noise(T, y34, y, g, n, logn);
+                    if (nz <= L->nt[ch][i]) {
+                        L->noise[ch][i] = nz;
+                        smin = s;
+                    }
+                }
+                L->sf[ch][i] = smin;
+                L->gsf[ch][i] = imax_(GG - smin, 0);
+            }
+            y34 += n;
+            y += n;
+        }
+    }
+}
+
+// re-fit the scale factor of bands whose largest quantised value is 1 or 2 (bitallo3.cpp:1471-1536)
+HMP3_HD void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const int *ix) {
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int gscale = L->G[ch] << 13;
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        const float *y = xr + 576 * ch;
+        const int *q = ix + 576 * ch;
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+            const int n = T->nBand_l[i];
+            if ((L->ixmax[ch][i] == 1) || (L->ixmax[ch][i] == 2)) {
+                int t = band_refit_gain(T, q, y, n);
+                int s;
+                if (scale == 0) s = ((gscale - t + (1 << 13)) & (~((1 << 14) - 1))) >> 13;
+                else s = ((gscale - t + (1 << 14)) & (~((1 << 15) - 1))) >> 13;
+                s = imin_(s, sf_upper(scale, pre, i));
+                s = imax_(s, sf_lower(scale, pre, i));
+                L->sf[ch][i] = s;
+            }
+            y += n;
+            q += n;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ quantise + count
+HMP3_HD void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned) {  // bitallo3.cpp:1540-1581
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const float *x = L->x34[ch];
+        int *q = ix + 576 * ch;
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+            const int n = T->nBand_l[i];
+            L->ixmax[ch][i] = tuned ? quant_tuned(T, x, q, L->gsf[ch][i], n, false, 0.0f)
+                                    : quant_plain(T, x, q, L->gsf[ch][i], n);
+            x += n;
+            q += n;
+        }
+    }
+}
+// drop isolated single-valued quads from the top, at most level/16 of them (bitallo3.cpp:1657-1687)
+HMP3_HD void sparsify_quads(int *q, int n, int level) {
+    int c = 0;
+    for (int i = 0; i < n; i++) c += q[i];
+    c = (level * c) >> 4;
+    if (c <= 0) return;
+    int dropped = 0;
+    for (int i = n - 4; i >= 0; i -= 4)
+        if (q[i] + q[i + 1] + q[i + 2] + q[i + 3] == 1) {
+            q[i] = q[i + 1] = q[i + 2] = q[i + 3] = 0;
+            if (++dropped >= c) break;
+        }
+}
+HMP3_HD void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms) {  // bitallo3.cpp:1690-1736
+    const int b = T->startBand_l[21], n = T->nBand_l[21];
+    if (ms) {
+        L->ixmax[0][21] = quant_tuned(T, L->x34[0] + b, ix + b, L->G[0], n, true, -.30f);
+        return;
+    }
+    for (int ch = 0; ch < L->nchan; ch++)
+        if (L->hf_quant_ch[ch]) {
+            L->ixmax[ch][21] = quant_tuned(T, L->x34[ch] + b, ix + 576 * ch + b, L->G[ch], n, true, -.30f);
+            sparsify_quads(ix + 576 * ch + b, n, 4);
+        }
+}
+HMP3_HD int long_count(const EncTables *T, LongRate *L, const int *ix, const int *ncb) {  // bitallo3.cpp:1740-1779
+    int bits = 0;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        L->huff_bits[ch] = plan_regions_long(T, L->block_type, L->ixmax[ch], ix + 576 * ch, ncb[ch], &L->plan[ch]);
+        bits += L->huff_bits[ch];
+    }
+    return bits;
+}
+
+// ------------------------------------------------------------------ bit-budget control loops
+HMP3_HD int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, bool ms) {  // :2569-2721
+    const int thres = L->min_target - (L->min_target >> 4);
+    if (bits0 > thres) return bits0;
+    int g[2][21];
+    int bits = bits0;
+    for (int ch = 0; ch < L->nchan; ch++)
+        for (int i = 0; i < T->cfg.nsf[ch]; i++) g[ch][i] = L->gsf[ch][i];
+    const int hf = T->cfg.hf_flag;
+    for (int pass = 0; pass < 11; pass++) {
+        const bool undo = (pass == 10) || (pass > 0 && bits >= thres);
+        if (undo) {
+            // finished stepping down; if that overshot the ceiling go back one step
+            if (!(bits > L->max_target)) break;
+            for (int ch = 0; ch < L->nchan; ch++)
+                for (int i = 0; i < T->cfg.nsf[ch]; i++) L->gsf[ch][i] = g[ch][i] + 1;
+        } else {
+            for (int ch = 0; ch < L->nchan; ch++)
+                for (int i = 0; i < T->cfg.nsf[ch]; i++)
+                    L->gsf[ch][i] = g[ch][i] = imax_(g[ch][i] - 1, L->gmin[ch][i]);
+        }
+        if (ms) {
+            L->hf_quant = 0;
+            L->ixmax[0][21] = 0;
+            L->gsf_hf = -1;
+            long_clear_hf_lines(T, ix, 1);
+            if (hf) long_hf_decide(T, L, 0, true);
+            long_scale_factors(T, L, true);
+            long_quantise(T, L, ix, true);
+            L->ixmax[0][21] = 0;
+            if (L->hf_quant) long_quantise_hf(T, L, ix, true);
+            bits = long_count(T, L, ix, T->cfg.nsf2);
+        } else {
+            if (hf & 2) {
+                long_hf_reset_lr(L);
+                long_hf_adjust_lr(T, L);
+            }
+            long_scale_factors(T, L, false);
+            long_quantise(T, L, ix, true);
+            if (L->hf_quant) long_quantise_hf(T, L, ix, false);
+            bits = long_count(T, L, ix, T->cfg.nsf3);
+        }
+        if (undo) break;
+    }
+    return bits;
+}
+
+HMP3_HD int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, int *ix, int bits0) {  // :2814-2852
+    const int f = (250 * 1024) / (L->active_lines + 10);
+    int dN = imax_((f * (bits0 - L->max_target)) >> 10, 40);
+    int bits = bits0;
+    L->delta_mnr = 0;
+    for (int k = 0; k < 10; k++) {
+        L->delta_mnr += dN;
+        for (int ch = 0; ch < L->nchan; ch++)
+            for (int i = 0; i < T->cfg.nsf[ch]; i++) L->nt[ch][i] += dN;
+        long_seek_actual(T, L, xr);
+        long_scale_factors(T, L, false);
+        long_quantise(T, L, ix, false);
+        bits = long_count(T, L, ix, T->cfg.nsf2);
+        if (bits <= L->max_target) break;
+        dN = imax_((f * (bits - L->max_target)) >> 10, 40);
+    }
+    return bits;
+}
+HMP3_HD int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_channel) {  // :2725-2772
+    int bits = 0;
+    for (int k = 0; k < 100; k++) {
+        for (int ch = 0; ch < L->nchan; ch++)
+            if (!per_channel || L->huff_bits[ch] > kPart23Max)
+                for (int i = 0; i < T->cfg.nsf[ch]; i++) L->gsf[ch][i] = imin_(127, L->gsf[ch][i] + 1);
+        long_scale_factors(T, L, false);
+        long_quantise(T, L, ix, false);
+        bits = long_count(T, L, ix, T->cfg.nsf2);
+        if (per_channel) {
+            if ((L->huff_bits[0] <= kPart23Max) && (L->huff_bits[1] <= kPart23Max)) break;
+        } else if (bits <= L->max_bits) break;
+    }
+    return bits;
+}
+
+// the allocation of one long granule; returns the bit count before the budget loops (the CBR
+// feedback signal) (bitallo3.cpp:2948-3149)
+HMP3_HD int long_allocate(const EncTables *T, LongRate *L, float *xr, int *ix, bool ms) {
+    const int hf = T->cfg.hf_flag;
+    if (hf) {
+        if (ms) {
+            L->hf_quant = 0;
+            L->ixmax[0][21] = L->ixmax[1][21] = 0;
+            L->gsf_hf = -1;
+        } else long_hf_reset_lr(L);
+        long_clear_hf_lines(T, ix, L->nchan);
+    }
+    long_seek_initial(T, L);
+    long_seek_actual(T, L, xr);
+    if (ms) {
+        if (hf) long_hf_decide(T, L, 0, true);
+    } else {
+        long_trade_peaks(T, L);
+        if (hf & 2) long_hf_adjust_lr(T, L);
+    }
+    long_scale_factors(T, L, ms);
+    long_coarsen_low_bands(T, L, xr);
+    long_quantise(T, L, ix, true);
+    if (ms) L->ixmax[0][21] = 0;
+    if (L->hf_quant) long_quantise_hf(T, L, ix, ms);
+    int bits = long_count(T, L, ix, ms ? T->cfg.nsf2 : T->cfg.nsf3);
+    const int bits0 = bits;
+    if (bits < L->min_target && L->mnr < 2000) bits = long_more_bits(T, L, ix, bits, ms);
+    if (ms) {
+        L->hf_quant = 0;
+        L->ixmax[0][21] = 0;
+        L->gsf_hf = -1;
+    } else if (hf) long_hf_reset_lr(L);
+    const int nclr = ms ? 1 : L->nchan;
+    if (bits > L->max_target) {
+        long_clear_hf_lines(T, ix, nclr);
+        bits = long_fewer_bits(T, L, xr, ix, bits);
+    }
+    if (bits > L->max_bits) {
+        long_clear_hf_lines(T, ix, nclr);
+        bits = long_cap_bits(T, L, ix, false);
+    }
+    if (bits > kPart23Max)
+        for (int ch = 0; ch < L->nchan; ch++)
+            if (L->huff_bits[ch] > kPart23Max) {
+                long_clear_hf_lines(T, ix, nclr);
+                bits = long_cap_bits(T, L, ix, true);
+                break;
+            }
+    long_refit_sparse_bands(T, L, xr, ix);
+    return bits0;
+}
+
+// CBR quality feedback (bitallo3.cpp:2897-2944)
+HMP3_HD void long_mnr_feedback(const EncTables *T, LongRate *L, int active_lines, int bits, int block_type) {
+    if (block_type == 2) return;
+    if (L->calls > 10) {
+        const float per_band = 150.0f / (0.20f * (active_lines + 10));
+        int mnr = (int)(0.05 * per_band * (bits - L->target));
+        int mnr2 = (int)(0.05 * per_band * imax_((bits - L->max_bits), 0));
+        int dpool = imax_(L->target - bits, 0);
+        int dbits = (((2044 + 8 * 5) - L->pool_bits) >> 4) - dpool;
+        dbits = imax_(dbits, 0);
+        dbits = imin_(dbits, 200);
+        int mnrp = (int)(per_band * dbits);
+        int mnr0 = (int)(0.2 * per_band * imax_((L->min_target - bits), 0));
+        int dmnr = mnr + mnr2 + mnrp - mnr0;
+        int maxd = imax_(L->mnr - T->cfg.initial_mnr, L->target >> 3);
+        dmnr = imin_(dmnr, maxd);
+        if (L->delta_mnr) dmnr = imax_(dmnr, (L->delta_mnr >> 1));
+        L->mnr = L->mnr - dmnr;
+        L->mnr = imin_(L->mnr, 2000);
+        if (bits > (L->target + 2000)) L->mnr = imin_(L->mnr, T->cfg.initial_mnr);
+    }
+}
+
+}  // namespace hmp3

@@ -131,3 +131,97 @@ int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int 
 }
 
 }  // extern "C"
+
+#include "../../hmp3_b200/csrc/rate_driver.h"
+
+extern "C" {
+
+// Whole-clip encode on the host build of the kernel bodies (Phase A sequential + Phase B), CLI
+// semantics.  Returns bytes written to `out`, or <0.  `trace` (optional) receives per granule:
+// 27 GR ints x2 ch, sf_l 23 x2, sf_s 39 x2, ix 576 x2, ms flag, = 1333 ints per granule? (see tests/simmod.py)
+long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, unsigned char *out, long out_cap,
+                     int *trace, int max_trace_granules, int *nframes_out) {
+    EncTables *T = new EncTables;
+    if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
+    const int nch = T->cfg.nchan;
+    const int mpeg2 = T->cfg.h_id == 0;
+    long calls = (nsamples + 4 * 1152) / 1152;
+    int ngran_real = (int)(2 * calls);
+    int ngran = ngran_real + 2 * 12;
+    std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
+    std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
+    for (long j = -3; j < ngran; j++)
+        for (int c = 0; c < nch; c++) {
+            float *o = &P[((j + 3) * nch + c) * 576];
+            for (int t = 0; t < 18; t++) polyphase_item(T, pcm, nsamples, nch, c, j, t, o);
+            for (int k = 0; k < 9; k++) E[((j + 3) * nch + c) * 9 + k] = attack_energy(T, o, k, mpeg2);
+        }
+    SwitchState sw;
+    switch_state_init(&sw);
+    std::vector<GranuleInfo> gi(ngran);
+    std::vector<float> xr((size_t)ngran * 2 * 576, 0.0f);
+    std::vector<PsyRaw> raw((size_t)ngran * 2);
+    std::vector<int> msr(ngran, 0);
+    for (int K = 0; K < ngran; K++) {
+        const int *e0 = &E[((K - 1 + 3) * nch + 0) * 9];
+        const int *e1 = &E[((K - 1 + 3) * nch + (nch - 1)) * 9];
+        gi[K] = switch_step(T, &sw, e0, e1);
+        for (int c = 0; c < nch; c++) {
+            const float *prev = &P[((K - 3 + 3) * nch + c) * 576];
+            const float *cur = &P[((K - 2 + 3) * nch + c) * 576];
+            float *x = &xr[((size_t)K * 2 + c) * 576];
+            for (int sb = 0; sb < 32; sb++) hybrid_item(T, prev, cur, gi[K].block_type, sb, x);
+            if (gi[K].block_type != 2) {
+                for (int sb = 0; sb < 32; sb++) alias_item(T, sb, x);
+                psy_long_stage1(T, x, &raw[(size_t)K * 2 + c]);
+            } else psy_short_stage1(T, x, &raw[(size_t)K * 2 + c]);
+        }
+        if (nch == 2) {
+            const float *x0 = &xr[((size_t)K * 2) * 576];
+            msr[K] = gi[K].block_type != 2 ? ms_measure_long(T, x0, x0 + 576) : ms_measure_short(T, x0, x0 + 576);
+        }
+    }
+    RateState *R = new RateState;
+    rate_state_init(T, R);
+    std::vector<unsigned char> mainbuf((size_t)(ngran + 4) * 2100, 0);
+    std::vector<FrameRec> frames(ngran + 4);
+    // run granule pair by pair so that traces can be taken after each call
+    for (int K = 0; K + 1 < ngran && !R->finished; K += 2) {
+        rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &raw[(size_t)K * 2], &msr[K],
+                       mainbuf.data(), frames.data());
+        if (trace)
+            for (int q = 0; q < 2; q++) {
+                int Kq = K + q;
+                if (Kq >= max_trace_granules) continue;
+                int *t = trace + (size_t)Kq * 1400;
+                memset(t, 0, 1400 * sizeof(int));
+                for (int c = 0; c < nch; c++) {
+                    memcpy(t + 27 * c, &R->gr[q][c], 27 * sizeof(int));
+                    memcpy(t + 54 + 23 * c, R->sf[q][c].l, 23 * sizeof(int));
+                    memcpy(t + 100 + 39 * c, R->sf[q][c].s, 39 * sizeof(int));
+                }
+                // ix is shared by both granules of the call: only meaningful for the last granule processed
+                memcpy(t + 200, R->ix, 2 * 576 * sizeof(int));
+                t[1360] = R->L.mnr;
+                t[1361] = R->byte_pool;
+                t[1362] = frames[R->frames - 1].head[3];
+            }
+    }
+    long total = 0;
+    const int nf = R->frames_done;
+    for (int f = 0; f < nf; f++) {
+        const FrameRec &fr = frames[f];
+        int sz = frame_bytes(T, &fr);
+        if (total + sz > out_cap) { total = -2; break; }
+        memcpy(out + total, fr.head, 4);
+        memcpy(out + total + 4, fr.side, T->cfg.side_bytes);
+        memcpy(out + total + 4 + T->cfg.side_bytes, mainbuf.data() + fr.main_start, fr.mf_bytes);
+        total += sz;
+    }
+    if (nframes_out) *nframes_out = nf;
+    delete R;
+    delete T;
+    return total;
+}
+
+}  // extern "C"

@@ -58,3 +58,20 @@ def analysis(ec, pcm_i16, ngran, nch):
           vp(out["sigmask"]), vp(out["ms_raw"]), vp(out["att"]), vp(out["raw"]))
     assert r == 0
     return out
+
+
+def encode_clip(ec, pcm_i16, max_trace_granules=0):
+    """Whole-clip encode through the host build of the kernel bodies. Returns (mp3 bytes, nframes, trace)."""
+    pcm = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+    n = pcm.shape[0]
+    cap = 4096 + int(n / 1152 + 80) * 2100
+    out = np.zeros(cap, np.uint8)
+    tr = np.zeros((max_trace_granules, 1400), np.int32) if max_trace_granules else None
+    nf = C.c_int(0)
+    f = lib().sim_encode_clip
+    f.restype = C.c_long
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
+    r = f(vp(ec), vp(pcm), n, vp(out), cap, vp(tr), max_trace_granules, C.byref(nf))
+    if r < 0:
+        raise RuntimeError("sim_encode_clip failed %d" % r)
+    return out[:r].copy(), nf.value, tr
