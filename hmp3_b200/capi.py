@@ -71,3 +71,115 @@ def debug_analysis(ec, pcm_i16, ngran, nch, device=0):
     if r != 0:
         raise Hmp3Error("hmp3_debug_analysis failed (%d): %s" % (r, last_error()))
     return out
+
+
+class Batch:
+    """Reusable batch plan (hmp3_batch_*): n streams of fixed control + length on one device."""
+
+    def __init__(self, controls, num_samples, device=0):
+        L = lib()
+        self.n = len(controls)
+        self.ctl = np.ascontiguousarray(np.stack(controls).astype(np.int32))
+        self.ns = np.ascontiguousarray(np.asarray(num_samples, dtype=np.int64))
+        L.hmp3_batch_create.restype = C.c_void_p
+        L.hmp3_batch_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        self.h = L.hmp3_batch_create(vp(self.ctl), vp(self.ns), self.n, device)
+        if not self.h:
+            raise Hmp3Error("hmp3_batch_create failed: " + last_error())
+        L.hmp3_batch_out_bound.restype = C.c_int64
+        L.hmp3_batch_out_bound.argtypes = [C.c_void_p, C.c_int64]
+        self.bound = np.array([L.hmp3_batch_out_bound(vp(self.ctl[i]), int(self.ns[i])) for i in range(self.n)],
+                              dtype=np.int64)
+        for name in ("hmp3_batch_destroy", "hmp3_batch_sync"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.hmp3_batch_run.argtypes = [C.c_void_p, C.c_int]
+        L.hmp3_batch_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.hmp3_batch_last_launches.argtypes = [C.c_void_p]
+        L.hmp3_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.hmp3_batch_results.argtypes = [C.c_void_p] * 5
+        L.hmp3_batch_download_all.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.hmp3_batch_encode_host.argtypes = [C.c_void_p] * 7
+        L.hmp3_batch_phase_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hmp3_batch_device_pcm.restype = C.c_void_p
+        L.hmp3_batch_device_pcm.argtypes = [C.c_void_p]
+
+    def close(self):
+        if self.h:
+            lib().hmp3_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, r, what):
+        if r != 0:
+            raise Hmp3Error("%s failed (%d): %s" % (what, r, last_error()))
+
+    def upload(self, i, pcm_i16):
+        a = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+        self._ck(lib().hmp3_batch_upload(self.h, i, vp(a), a.shape[0]), "upload")
+
+    def upload_ptr(self, i, ptr, nsamples):
+        self._ck(lib().hmp3_batch_upload(self.h, i, C.c_void_p(ptr), nsamples), "upload")
+
+    def run(self, async_=False):
+        self._ck(lib().hmp3_batch_run(self.h, 1 if async_ else 0), "run")
+
+    def sync(self):
+        self._ck(lib().hmp3_batch_sync(self.h), "sync")
+
+    def set_timing(self, on):
+        lib().hmp3_batch_set_timing(self.h, 1 if on else 0)
+
+    def launches(self):
+        return lib().hmp3_batch_last_launches(self.h)
+
+    def results(self):
+        nb, nf = np.zeros(self.n, np.int64), np.zeros(self.n, np.int32)
+        off, st = np.zeros(self.n, np.int64), np.zeros(self.n, np.int32)
+        self._ck(lib().hmp3_batch_results(self.h, vp(nb), vp(nf), vp(off), vp(st)), "results")
+        return nb, nf, off, st
+
+    def download_all(self, out=None):
+        nb, nf, off, st = self.results()
+        total = int(nb.sum())
+        if out is None:
+            out = np.zeros(max(total, 1), np.uint8)
+        tot = C.c_int64(0)
+        self._ck(lib().hmp3_batch_download_all(self.h, vp(out), out.size, C.byref(tot)), "download_all")
+        return out, off, nb, nf, st
+
+    def phase_ms(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        ln = (C.c_int * 16)()
+        k = lib().hmp3_batch_phase_ms(self.h, names, ms, ln, 16)
+        return {names[i].decode(): (ms[i], ln[i]) for i in range(k)}
+
+    def encode_host_ptrs(self, pcm_ptrs, out_ptrs, out_caps):
+        """pcm_ptrs/out_ptrs: uint64 arrays of host addresses; returns (out_bytes, out_frames, status)."""
+        nb, nf, st = np.zeros(self.n, np.int64), np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self._ck(lib().hmp3_batch_encode_host(self.h, vp(pcm_ptrs), vp(out_ptrs), vp(out_caps), vp(nb), vp(nf),
+                                              vp(st)), "encode_host")
+        return nb, nf, st
+
+    def encode_host(self, pcms):
+        pcms = [np.ascontiguousarray(p, dtype=np.int16) for p in pcms]
+        outs = [np.zeros(int(b), np.uint8) for b in self.bound]
+        pp = np.array([p.ctypes.data for p in pcms], dtype=np.uint64)
+        op = np.array([o.ctypes.data for o in outs], dtype=np.uint64)
+        nb, nf, st = self.encode_host_ptrs(pp, op, self.bound)
+        for i in range(self.n):
+            if st[i] != 0:
+                raise Hmp3Error("stream %d failed with status %d" % (i, st[i]))
+        return [outs[i][:nb[i]].copy() for i in range(self.n)], nf
+
+
+def encode_batch(controls, pcms, device=0):
+    """Encode a list of int16 PCM arrays (nsamples, nch) -> list of MP3 byte arrays (no Xing/Info frame)."""
+    b = Batch(controls, [p.shape[0] for p in pcms], device)
+    try:
+        outs, _ = b.encode_host(pcms)
+    finally:
+        b.close()
+    return outs

@@ -7,10 +7,10 @@
 
 #if defined(__CUDACC__)
 #define HMP3_HD __host__ __device__ __forceinline__
-#define HMP3_HD_NOINLINE __host__ __device__ __noinline__
+#define HMP3_FN static __host__ __device__ __noinline__
 #else
 #define HMP3_HD inline
-#define HMP3_HD_NOINLINE
+#define HMP3_FN static inline
 #endif
 
 namespace hmp3 {

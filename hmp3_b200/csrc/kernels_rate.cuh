@@ -1,0 +1,80 @@
+// Phase B CUDA kernels (sm_100a): the per-stream serial stage (psychoacoustic stage 2, M/S decision,
+// rate loop, scale-factor/Huffman packing, reservoir) and the parallel frame assembly.
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels_analysis.cuh"
+#include "rate_driver.h"
+
+namespace hmp3 {
+
+// Per-stream placement of the serial stage's buffers (device view).
+struct StreamOut {
+    long long main_off;    // byte offset of this stream's main-data stream in the main buffer
+    long long frames_off;  // first FrameRec of this stream
+    int frames_cap;
+};
+
+struct StreamResult {
+    long long out_bytes;
+    int frames;
+    int finished;
+};
+
+// ---- K6: state reset, one thread per stream
+__global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int nstreams) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    rate_state_init(tabs + st[s].cfg, rs + s);
+}
+
+// ---- K6: the serial stage over one chunk of granules, one thread per stream
+__global__ void __launch_bounds__(32) k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so,
+                                             RateState *rs, ChunkBufs cb, unsigned char *main_buf,
+                                             FrameRec *frames, int K0, int nstreams) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    if (K0 >= sd.ngran) return;
+    const StreamOut o = so[s];
+    const long long q0 = (long long)s * cb.NG;
+    rate_run_chunk(tabs + sd.cfg, rs + s, K0, cb.NG, sd.ngran, sd.ngran_real, cb.gi + q0, cb.xr + q0 * 2 * 576,
+                   cb.raw + q0 * 2, cb.ms_raw + q0, main_buf + o.main_off, frames + o.frames_off);
+}
+
+// ---- per-stream totals after the last chunk
+__global__ void k_results(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
+                          const FrameRec *frames, StreamResult *res, int nstreams) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const RateState *R = rs + s;
+    StreamResult r;
+    r.frames = R->frames_done;
+    r.finished = R->finished;
+    r.out_bytes = 0;
+    if (r.frames > 0) {
+        const FrameRec *f = frames + so[s].frames_off + (r.frames - 1);
+        r.out_bytes = (long long)f->out_off + frame_bytes(tabs + st[s].cfg, f);
+    }
+    res[s] = r;
+}
+
+// ---- K7: frame assembly, one warp per frame: header | side info | slice of the main-data stream
+__global__ void __launch_bounds__(256) k_assemble(const EncTables *tabs, const StreamDev *st, const StreamOut *so,
+                                                  const StreamResult *res, const long long *out_off,
+                                                  const unsigned char *main_buf, const FrameRec *frames,
+                                                  unsigned char *out, int max_frames, int nstreams) {
+    long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)(wid / max_frames), f = (int)(wid % max_frames);
+    if (s >= nstreams || f >= res[s].frames) return;
+    const int side = tabs[st[s].cfg].cfg.side_bytes;
+    const FrameRec *fr = frames + so[s].frames_off + f;
+    unsigned char *dst = out + out_off[s] + fr->out_off;
+    if (lane < 4) dst[lane] = fr->head[lane];
+    if (lane < side) dst[4 + lane] = fr->side[lane];
+    const unsigned char *src = main_buf + so[s].main_off + fr->main_start;
+    dst += 4 + side;
+    for (int k = lane; k < fr->mf_bytes; k += 32) dst[k] = src[k];
+}
+
+}  // namespace hmp3

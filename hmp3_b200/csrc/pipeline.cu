@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,7 @@
 #include "../../include/hmp3_b200_debug.h"
 #include "enc_init.h"
 #include "kernels_analysis.cuh"
+#include "kernels_rate.cuh"
 
 using namespace hmp3;
 
@@ -34,6 +36,34 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
+// exclusive scan of the per-stream output sizes -> compact output offsets (single block)
+__global__ void k_out_offsets(const StreamResult *res, long long *out_off, int n) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = t * per, hi = min(n, lo + per);
+    long long sum = 0;
+    for (int i = lo; i < hi; i++) sum += res[i].out_bytes;
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        long long v = (t >= d) ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - sum;
+    for (int i = lo; i < hi; i++) {
+        out_off[i] = run;
+        run += res[i].out_bytes;
+    }
+    if (t == 1023) out_off[n] = part[1023];
+}
+
+enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_RATE, PH_ASSEMBLE, PH_COUNT };
+const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "rate_loop",
+                                     "assemble"};
+
 }  // namespace
 
 struct hmp3_batch {
@@ -41,31 +71,65 @@ struct hmp3_batch {
     int n = 0;
     int NG = 0;
     int max_gran = 0;
+    int max_frames = 0;
     std::vector<hmp3_control> controls;  // distinct
     std::vector<EncTables> tabs_h;
     std::vector<StreamDev> st_h;
+    std::vector<StreamOut> so_h;
+    std::vector<StreamResult> res_h;
+    std::vector<long long> out_off_h;
     EncTables *d_tabs = nullptr;
     StreamDev *d_st = nullptr;
+    StreamOut *d_so = nullptr;
     int16_t *d_pcm = nullptr;
     long long pcm_elems = 0;
     SwitchState *d_sw = nullptr;
+    SwitchState *d_sw_init = nullptr;
+    RateState *d_rs = nullptr;
+    unsigned char *d_main = nullptr;
+    FrameRec *d_frames = nullptr;
+    StreamResult *d_res = nullptr;
+    long long *d_out_off = nullptr;
+    unsigned char *d_out = nullptr;
+    long long out_cap = 0;
     ChunkBufs cb{};
     cudaStream_t stream = nullptr;
     int launches = 0;
+    bool results_valid = false;
     std::vector<int> status;
+    // optional per-kernel timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> ev_phase;
+    size_t ev_used = 0;
+    float phase_ms[PH_COUNT] = {0};
+    int phase_launches[PH_COUNT] = {0};
+    // pinned staging for the host-buffer entry
+    unsigned char *h_stage = nullptr;
+    long long h_stage_bytes = 0;
 
     ~hmp3_batch() {
         cudaSetDevice(device);
         cudaFree(d_tabs);
         cudaFree(d_st);
+        cudaFree(d_so);
         cudaFree(d_pcm);
         cudaFree(d_sw);
+        cudaFree(d_sw_init);
+        cudaFree(d_rs);
+        cudaFree(d_main);
+        cudaFree(d_frames);
+        cudaFree(d_res);
+        cudaFree(d_out_off);
+        cudaFree(d_out);
         cudaFree(cb.P);
         cudaFree(cb.E);
         cudaFree(cb.gi);
         cudaFree(cb.xr);
         cudaFree(cb.raw);
         cudaFree(cb.ms_raw);
+        for (auto e : ev) cudaEventDestroy(e);
+        if (h_stage) cudaFreeHost(h_stage);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -77,8 +141,12 @@ namespace {
 long long calls_for(long long nsamples) { return (nsamples + 4 * 1152) / 1152; }
 const int kFlushCalls = 12;  // upper bound of the tail-flush calls we provision analysis data for
 
+int max_main_frame_bytes(const EncConfig &C) {
+    return C.vbr_flag ? C.vbr_main_framebytes[C.ivbr_max] : C.main_framebytes + 1;
+}
+
 int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *nsamples, int n, int device,
-                int chunk_granules) {
+                int chunk_granules, bool analysis_only) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
         set_err("no usable CUDA device (this library has no CPU path)");
@@ -89,8 +157,9 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     b->n = n;
     b->status.assign(n, HMP3_OK);
     b->st_h.resize(n);
-    long long pcm_off = 0;
-    int max_gran = 0;
+    b->so_h.resize(n);
+    long long pcm_off = 0, main_off = 0, frames_off = 0, out_cap = 0;
+    int max_gran = 0, max_frames = 0;
     for (int i = 0; i < n; i++) {
         int cfg = -1;
         for (size_t c = 0; c < b->controls.size(); c++)
@@ -101,13 +170,12 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
             int r = build_tables(&controls[i], T, &unsup);
             if (!r) {
                 b->status[i] = unsup ? HMP3_ERR_UNSUPPORTED : HMP3_ERR_BAD_CONTROL;
-                delete T;
             } else {
                 cfg = (int)b->controls.size();
                 b->controls.push_back(controls[i]);
                 b->tabs_h.push_back(*T);
-                delete T;
             }
+            delete T;
         }
         StreamDev &sd = b->st_h[i];
         memset(&sd, 0, sizeof(sd));
@@ -121,6 +189,19 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         pcm_off += nsamples[i] * (sd.nch ? sd.nch : 1);
         pcm_off = (pcm_off + 7) & ~7LL;
         max_gran = std::max(max_gran, sd.ngran);
+        StreamOut &so = b->so_h[i];
+        so.main_off = main_off;
+        so.frames_off = frames_off;
+        so.frames_cap = 0;
+        if (cfg >= 0) {
+            const EncConfig &C = b->tabs_h[cfg].cfg;
+            const int nfr = sd.ngran / C.granules_per_frame + 2;
+            so.frames_cap = nfr;
+            main_off += ((long long)nfr * max_main_frame_bytes(C) + 4096 + 15) & ~15LL;
+            frames_off += nfr;
+            out_cap += (long long)nfr * (4 + C.side_bytes + max_main_frame_bytes(C));
+            max_frames = std::max(max_frames, nfr);
+        }
     }
     if (b->tabs_h.empty()) {
         set_err("no stream has a valid control block");
@@ -128,14 +209,23 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     }
     b->pcm_elems = pcm_off;
     b->max_gran = max_gran;
+    b->max_frames = max_frames;
     b->NG = chunk_granules;
+    b->out_cap = out_cap;
     CK(cudaStreamCreate(&b->stream));
     CK(cudaMalloc(&b->d_tabs, sizeof(EncTables) * b->tabs_h.size()));
     CK(cudaMemcpy(b->d_tabs, b->tabs_h.data(), sizeof(EncTables) * b->tabs_h.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b->d_st, sizeof(StreamDev) * n));
     CK(cudaMemcpy(b->d_st, b->st_h.data(), sizeof(StreamDev) * n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b->d_pcm, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
+    CK(cudaMemset(b->d_pcm, 0, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
     CK(cudaMalloc(&b->d_sw, sizeof(SwitchState) * n));
+    CK(cudaMalloc(&b->d_sw_init, sizeof(SwitchState) * n));
+    {
+        std::vector<SwitchState> sw(n);
+        for (auto &s : sw) switch_state_init(&s);
+        CK(cudaMemcpy(b->d_sw_init, sw.data(), sizeof(SwitchState) * n, cudaMemcpyHostToDevice));
+    }
     const long long NG = b->NG, G = NG + 3;
     b->cb.NG = (int)NG;
     CK(cudaMalloc(&b->cb.P, sizeof(float) * n * G * 2 * 576));
@@ -144,29 +234,110 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     CK(cudaMalloc(&b->cb.xr, sizeof(float) * n * NG * 2 * 576));
     CK(cudaMalloc(&b->cb.raw, sizeof(PsyRaw) * n * NG * 2));
     CK(cudaMalloc(&b->cb.ms_raw, sizeof(int) * n * NG));
+    if (!analysis_only) {
+        CK(cudaMalloc(&b->d_so, sizeof(StreamOut) * n));
+        CK(cudaMemcpy(b->d_so, b->so_h.data(), sizeof(StreamOut) * n, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&b->d_rs, sizeof(RateState) * n));
+        CK(cudaMalloc(&b->d_main, std::max<long long>(main_off, 16)));
+        CK(cudaMalloc(&b->d_frames, sizeof(FrameRec) * std::max<long long>(frames_off, 1)));
+        CK(cudaMalloc(&b->d_res, sizeof(StreamResult) * n));
+        CK(cudaMalloc(&b->d_out_off, sizeof(long long) * (n + 1)));
+        CK(cudaMalloc(&b->d_out, std::max<long long>(out_cap, 16)));
+        b->res_h.resize(n);
+        b->out_off_h.resize(n + 1);
+    }
     return HMP3_OK;
 }
 
 int plan_reset_state(hmp3_batch *b) {
-    std::vector<SwitchState> sw(b->n);
-    for (auto &s : sw) switch_state_init(&s);
-    CK(cudaMemcpyAsync(b->d_sw, sw.data(), sizeof(SwitchState) * b->n, cudaMemcpyHostToDevice, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpyAsync(b->d_sw, b->d_sw_init, sizeof(SwitchState) * b->n, cudaMemcpyDeviceToDevice, b->stream));
     return HMP3_OK;
+}
+
+void mark(hmp3_batch *b, int phase) {  // record an event pair boundary when timing is on
+    if (!b->timing) return;
+    if (b->ev_used == b->ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        b->ev.push_back(e);
+        b->ev_phase.push_back(-1);
+    }
+    b->ev_phase[b->ev_used] = phase;
+    cudaEventRecord(b->ev[b->ev_used++], b->stream);
 }
 
 // Phase A for the chunk starting at encode granule K0.
 int launch_analysis(hmp3_batch *b, int K0) {
     const int n = b->n;
     const long long NG = b->NG, G = NG + 3;
+    mark(b, PH_POLY);
     k_polyphase<<<blocks_for((long long)n * G * 2 * 18, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_pcm, b->cb,
                                                                                      K0, n);
+    mark(b, PH_ATTACK);
     k_attack<<<blocks_for((long long)n * G * 2 * 9, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    mark(b, PH_SWITCH);
     k_switch_scan<<<blocks_for(n, 32), 32, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_sw, b->cb, K0, n);
+    mark(b, PH_HYBRID);
     k_hybrid<<<blocks_for((long long)n * NG * 2 * 32, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    mark(b, PH_PSY);
     k_psy_stage1<<<blocks_for((long long)n * NG * 3, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    mark(b, -1);
     b->launches += 5;
     CK(cudaGetLastError());
+    return HMP3_OK;
+}
+
+int run_plan(hmp3_batch *b) {
+    const int n = b->n;
+    CK(cudaSetDevice(b->device));
+    b->launches = 0;
+    b->ev_used = 0;
+    b->results_valid = false;
+    int r = plan_reset_state(b);
+    if (r != HMP3_OK) return r;
+    k_rate_init<<<blocks_for(n, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_rs, n);
+    b->launches++;
+    for (int K0 = 0; K0 < b->max_gran; K0 += b->NG) {
+        r = launch_analysis(b, K0);
+        if (r != HMP3_OK) return r;
+        mark(b, PH_RATE);
+        k_rate<<<blocks_for(n, 32), 32, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main,
+                                                        b->d_frames, K0, n);
+        mark(b, -1);
+        b->launches++;
+    }
+    k_results<<<blocks_for(n, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, n);
+    k_out_offsets<<<1, 1024, 0, b->stream>>>(b->d_res, b->d_out_off, n);
+    mark(b, PH_ASSEMBLE);
+    k_assemble<<<blocks_for((long long)n * b->max_frames * 32, 256), 256, 0, b->stream>>>(
+        b->d_tabs, b->d_st, b->d_so, b->d_res, b->d_out_off, b->d_main, b->d_frames, b->d_out, b->max_frames, n);
+    mark(b, -1);
+    b->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult) * n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->out_off_h.data(), b->d_out_off, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost,
+                       b->stream));
+    return HMP3_OK;
+}
+
+int sync_plan(hmp3_batch *b) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    b->results_valid = true;
+    if (b->timing) {
+        for (int p = 0; p < PH_COUNT; p++) {
+            b->phase_ms[p] = 0;
+            b->phase_launches[p] = 0;
+        }
+        for (size_t i = 0; i + 1 < b->ev_used; i++) {
+            const int p = b->ev_phase[i];
+            if (p < 0) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]);
+            b->phase_ms[p] += ms;
+            b->phase_launches[p]++;
+        }
+    }
     return HMP3_OK;
 }
 
@@ -184,12 +355,258 @@ int hmp3_device_count(void) {
 
 void hmp3_control_defaults(hmp3_control *ec) { control_defaults(ec); }
 
+int hmp3_resolve_control(const hmp3_control *ec, hmp3_resolved *out) {
+    EncTables *T = new EncTables;
+    int unsup = 0;
+    const int r = build_tables(ec, T, &unsup);
+    if (!r) {
+        delete T;
+        set_err(unsup ? "configuration outside the built path" : "control block rejected");
+        return unsup ? HMP3_ERR_UNSUPPORTED : HMP3_ERR_BAD_CONTROL;
+    }
+    const EncConfig &C = T->cfg;
+    memset(out, 0, sizeof(*out));
+    out->nchan = C.nchan;
+    out->h_id = C.h_id;
+    out->sr_index = C.sr_index;
+    out->nband = C.nband;
+    out->band_limit = C.band_limit;
+    out->nsb = C.nsb;
+    out->nsb_limit = C.nsb_limit;
+    out->nsb_limit_ms0 = C.nsb_hybrid;
+    out->nsb_limit_ms1 = C.nsb_limit_ms1;
+    out->ave_target_bits = C.ave_target_bits;
+    out->framebytes = C.framebytes;
+    out->main_framebytes = C.main_framebytes;
+    out->side_bytes = C.side_bytes;
+    out->remainder = C.pad_remainder;
+    out->divisor = C.pad_divisor;
+    out->ms_flag = C.ms_flag;
+    out->is_flag = C.is_flag;
+    out->frame_driver = C.frame_driver;
+    out->granule_driver = 0;
+    out->ivbr_min = C.ivbr_min;
+    out->ivbr_max = C.ivbr_max;
+    out->vbr_pool_target = C.vbr_pool_target;
+    out->short_block_threshold = C.short_block_threshold;
+    out->h_mode = C.h_mode;
+    out->br_index = C.br_index;
+    out->totbitrate = C.totbitrate;
+    out->samprate = C.samprate;
+    out->band_limit_stereo = C.band_limit_stereo;
+    out->sf_bit_max = C.sf_bit_max;
+    out->nsf_stereo = C.nsf_stereo;
+    for (int i = 0; i < 4; i++) out->head[i] = C.head[i];
+    out->hf_flag = C.hf_flag;
+    out->filter_select = C.filter_select;
+    out->bytes_in = r;
+    delete T;
+    return HMP3_OK;
+}
+
+int64_t hmp3_batch_out_bound(const hmp3_control *control, int64_t num_samples) {
+    EncTables *T = new EncTables;
+    if (!build_tables(control, T, nullptr)) {
+        delete T;
+        return 0;
+    }
+    const EncConfig &C = T->cfg;
+    const long long nfr = 2 * (calls_for(num_samples) + kFlushCalls) / C.granules_per_frame + 2;
+    const int64_t r = nfr * (4 + C.side_bytes + max_main_frame_bytes(C));
+    delete T;
+    return r;
+}
+
+hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_samples, int n, int device) {
+    if (n <= 0 || !controls || !num_samples) {
+        set_err("bad arguments");
+        return nullptr;
+    }
+    hmp3_batch *b = new hmp3_batch;
+    std::vector<long long> ns(num_samples, num_samples + n);
+    int r = plan_create(b, controls, ns.data(), n, device, 32, false);
+    if (r != HMP3_OK) {
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+
+void hmp3_batch_destroy(hmp3_batch *b) { delete b; }
+
+int16_t *hmp3_batch_device_pcm(hmp3_batch *b) { return b->d_pcm; }
+int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i) { return b->st_h[i].pcm_off; }
+uint8_t *hmp3_batch_device_out(hmp3_batch *b) { return b->d_out; }
+int64_t hmp3_batch_out_capacity(const hmp3_batch *b) { return b->out_cap; }
+
+int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples) {
+    if (i < 0 || i >= b->n || num_samples != b->st_h[i].nsamples) {
+        set_err("upload: stream index or length does not match the plan");
+        return HMP3_ERR_ARG;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(b->d_pcm + b->st_h[i].pcm_off, pcm, sizeof(int16_t) * num_samples * b->st_h[i].nch,
+                       cudaMemcpyHostToDevice, b->stream));
+    return HMP3_OK;
+}
+
+int hmp3_batch_set_timing(hmp3_batch *b, int on) {
+    b->timing = on != 0;
+    return HMP3_OK;
+}
+
+int hmp3_batch_run(hmp3_batch *b, int async) {
+    int r = run_plan(b);
+    if (r != HMP3_OK) return r;
+    return async ? HMP3_OK : sync_plan(b);
+}
+
+int hmp3_batch_sync(hmp3_batch *b) { return sync_plan(b); }
+
+int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames, int64_t *out_offsets,
+                       int32_t *status) {
+    if (!b->results_valid) {
+        set_err("results: no completed run");
+        return HMP3_ERR_ARG;
+    }
+    for (int i = 0; i < b->n; i++) {
+        int st = b->status[i];
+        if (st == HMP3_OK && !b->res_h[i].finished) st = HMP3_ERR_OUT_SPACE;
+        if (out_bytes) out_bytes[i] = b->status[i] == HMP3_OK ? b->res_h[i].out_bytes : 0;
+        if (out_frames) out_frames[i] = b->status[i] == HMP3_OK ? b->res_h[i].frames : 0;
+        if (out_offsets) out_offsets[i] = b->out_off_h[i];
+        if (status) status[i] = st;
+    }
+    return HMP3_OK;
+}
+
+int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap) {
+    if (!b->results_valid || i < 0 || i >= b->n) {
+        set_err("download: no completed run or bad index");
+        return HMP3_ERR_ARG;
+    }
+    const long long nb = b->res_h[i].out_bytes;
+    if (nb > cap) {
+        set_err("download: output buffer too small");
+        return HMP3_ERR_OUT_SPACE;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpy(out, b->d_out + b->out_off_h[i], nb, cudaMemcpyDeviceToHost));
+    return HMP3_OK;
+}
+
+int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *total) {
+    if (!b->results_valid) {
+        set_err("download: no completed run");
+        return HMP3_ERR_ARG;
+    }
+    const long long nb = b->out_off_h[b->n];
+    if (total) *total = nb;
+    if (nb > cap) {
+        set_err("download: output buffer too small");
+        return HMP3_ERR_OUT_SPACE;
+    }
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpyAsync(out, b->d_out, nb, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return HMP3_OK;
+}
+
+int hmp3_batch_last_launches(const hmp3_batch *b) { return b->launches; }
+
+int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap) {
+    int k = 0;
+    for (int p = 0; p < PH_COUNT && k < cap; p++, k++) {
+        if (names) names[k] = kPhaseNames[p];
+        if (ms) ms[k] = b->phase_ms[p];
+        if (launches) launches[k] = b->phase_launches[p];
+    }
+    return k;
+}
+
+// Host buffers in, host buffers out: upload every stream's PCM, run, copy each stream's frames back.
+int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+                           int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
+    CK(cudaSetDevice(b->device));
+    for (int i = 0; i < b->n; i++) {
+        if (b->status[i] != HMP3_OK) continue;
+        int r = hmp3_batch_upload(b, i, pcm[i], b->st_h[i].nsamples);
+        if (r != HMP3_OK) return r;
+    }
+    int r = run_plan(b);
+    if (r != HMP3_OK) return r;
+    r = sync_plan(b);
+    if (r != HMP3_OK) return r;
+    // one bulk D2H into pinned staging, then scatter to the callers' buffers
+    const long long total = b->out_off_h[b->n];
+    if (b->h_stage_bytes < total) {
+        if (b->h_stage) cudaFreeHost(b->h_stage);
+        b->h_stage = nullptr;
+        b->h_stage_bytes = 0;
+        CK(cudaMallocHost(&b->h_stage, total + (total >> 3) + 4096));
+        b->h_stage_bytes = total + (total >> 3) + 4096;
+    }
+    CK(cudaMemcpyAsync(b->h_stage, b->d_out, total, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < b->n; i++) {
+        int st = b->status[i];
+        long long nb = st == HMP3_OK ? b->res_h[i].out_bytes : 0;
+        if (st == HMP3_OK && !b->res_h[i].finished) st = HMP3_ERR_OUT_SPACE;
+        if (st == HMP3_OK && nb > out_cap[i]) {
+            st = HMP3_ERR_OUT_SPACE;
+            nb = 0;
+        }
+        if (nb) memcpy(out[i], b->h_stage + b->out_off_h[i], nb);
+        if (out_bytes) out_bytes[i] = nb;
+        if (out_frames) out_frames[i] = st == HMP3_OK ? b->res_h[i].frames : 0;
+        if (status) status[i] = st;
+    }
+    return HMP3_OK;
+}
+
+int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
+    if (n <= 0 || !streams) {
+        set_err("bad arguments");
+        return HMP3_ERR_ARG;
+    }
+    std::vector<hmp3_control> ctl(n);
+    std::vector<int64_t> ns(n), cap(n), nb(n);
+    std::vector<const int16_t *> pcm(n);
+    std::vector<uint8_t *> out(n);
+    std::vector<int32_t> nf(n), st(n);
+    for (int i = 0; i < n; i++) {
+        if (!streams[i].control) {
+            set_err("stream without a control block");
+            return HMP3_ERR_ARG;
+        }
+        ctl[i] = *streams[i].control;
+        ns[i] = streams[i].num_samples;
+        pcm[i] = streams[i].pcm;
+        out[i] = streams[i].out;
+        cap[i] = streams[i].out_capacity;
+    }
+    hmp3_batch *b = hmp3_batch_create(ctl.data(), ns.data(), n, device);
+    if (!b) {
+        int ndev = hmp3_device_count();
+        return ndev <= device ? HMP3_ERR_NO_DEVICE : HMP3_ERR_BAD_CONTROL;
+    }
+    int r = hmp3_batch_encode_host(b, pcm.data(), out.data(), cap.data(), nb.data(), nf.data(), st.data());
+    if (r == HMP3_OK)
+        for (int i = 0; i < n; i++) {
+            streams[i].out_bytes = nb[i];
+            streams[i].out_frames = nf[i];
+            streams[i].status = st[i];
+        }
+    hmp3_batch_destroy(b);
+    return r;
+}
+
 // Debug / parity entry: Phase A of ONE stream on the device, stage outputs copied back to the host.
 // Same argument meaning as the host simulator's sim_analysis (tests/hostsim/hostsim.cpp).
 int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long nsamples, int ngran, int device,
                         float *sbt_out, int *ginfo, float *xr_out, float *raw_out, int *ms_raw, int *att) {
     hmp3_batch b;
-    int r = plan_create(&b, ec, &nsamples, 1, device, 32);
+    int r = plan_create(&b, ec, &nsamples, 1, device, 32, true);
     if (r != HMP3_OK) return r;
     if (b.status[0] != HMP3_OK) return b.status[0];
     const int nch = b.st_h[0].nch;

@@ -33,7 +33,7 @@ HMP3_HD int imax_(int a, int b) { return a > b ? a : b; }
 
 // ------------------------------------------------------------------ quantiser passes (l3math.c)
 // plain rounding quantiser (l3math.c:655-671)
-HMP3_HD int quant_plain(const EncTables *T, const float *x34, int *ix, int g, int n) {
+HMP3_FN int quant_plain(const EncTables *T, const float *x34, int *ix, int g, int n) {
     const float ig = T->igain34[g];
     int m = 0;
     for (int i = 0; i < n; i++) {
@@ -45,7 +45,7 @@ HMP3_HD int quant_plain(const EncTables *T, const float *x34, int *ix, int g, in
 }
 // RD-tuned quantiser: magnitude-dependent rounding offset (l3math.c:674-694); `r0` replaces the offset of
 // magnitude class 0 (l3math.c:697-725 when given), clamp_lo mirrors the extra lower clamp of that variant.
-HMP3_HD int quant_tuned(const EncTables *T, const float *x34, int *ix, int g, int n, bool alt, float r0) {
+HMP3_FN int quant_tuned(const EncTables *T, const float *x34, int *ix, int g, int n, bool alt, float r0) {
     const float ig = T->igain34[g];
     int m = 0;
     for (int i = 0; i < n; i++) {
@@ -81,7 +81,7 @@ HMP3_HD float dequant43(const EncTables *T, int q) {
 }
 
 // quantisation noise of one band at step g, in millibels relative to the band width (l3math.c:511-544)
-HMP3_HD int band_noise(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
+HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
     const float ig = T->igain34[g], gn = T->gain[g];
     float acc = 0.0f;
     for (int i = 0; i < n; i++) {
@@ -97,7 +97,7 @@ HMP3_HD int band_noise(const EncTables *T, const float *x34, const float *x, int
 }
 
 // gain (scaled by 2^13) that best maps quantised values back onto the spectrum (l3math.c:1087-1114)
-HMP3_HD int band_refit_gain(const EncTables *T, const int *q, const float *x, int n) {
+HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, int n) {
     float sqq = 0, sxx = 0;
     for (int i = 0; i < n; i++) {
         float v;
@@ -127,7 +127,7 @@ HMP3_HD int count_class_of(const EncTables *T, int m) {
 
 // bits of n values (n/2 pairs) under the candidate tables of class c; ties go to the higher candidate
 // (cnt.c:96-292)
-HMP3_HD CountResult count_pairs(const EncTables *T, int c, const int *ix, int n) {
+HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n) {
     CountResult r;
     r.bits = r.index = 0;
     const int nc = T->cnt_ncand[c];
@@ -161,7 +161,7 @@ HMP3_HD CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
 }
 
 // count1 region: table A (variable length) against table B (4 bits), sign bits included (cnt.c:295-326)
-HMP3_HD CountResult count_quads(const int *ix, int nquads) {
+HMP3_FN CountResult count_quads(const int *ix, int nquads) {
     CountResult r;
     r.bits = r.index = 0;
     if (nquads <= 0) return r;
@@ -189,7 +189,7 @@ HMP3_HD void region_split_rule(int nbands, int *r0, int *r1) {
 // Region planning + bit count for a long-block granule channel (block types 0 / 1,3).
 // ixmax[] = per-band maxima, ix[] = the persistent quantised-line buffer (lines past the last coded band
 // keep whatever earlier granules left there, as in the reference).  bitalloc.cpp:470-754.
-HMP3_HD int plan_regions_long(const EncTables *T, int block_type, const int *ixmax, const int *ix, int ncb,
+HMP3_FN int plan_regions_long(const EncTables *T, int block_type, const int *ixmax, const int *ix, int ncb,
                               RegionPlan *P) {
     const int *start = T->startBand_l, *width = T->nBand_l;
     int i, j, n;
@@ -284,7 +284,7 @@ HMP3_HD int plan_regions_long(const EncTables *T, int block_type, const int *ixm
 }
 
 // side-info fields that follow from a region plan (bitalloc.cpp:758-811)
-HMP3_HD void plan_to_side(const EncTables *T, const RegionPlan *P, GrSide *g) {
+HMP3_FN void plan_to_side(const EncTables *T, const RegionPlan *P, GrSide *g) {
     if (P->bits <= 0) {
         g->table_select[0] = g->table_select[1] = g->table_select[2] = 0;
         g->big_values = 0;

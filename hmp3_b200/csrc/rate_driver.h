@@ -15,6 +15,7 @@ namespace hmp3 {
 struct FrameRec {
     unsigned main_start;  // offset in the stream's main-data stream where this frame's slot begins
     int mf_bytes;         // bytes of main-data slot in this frame
+    unsigned out_off;     // byte offset of this frame in the stream's output
     unsigned char head[4];
     unsigned char side[32];
 };
@@ -58,7 +59,7 @@ struct RateState {
     int scfsi[2];
     int sf_save[2][21];       // granule-0 scale factors for scfsi (l3pack.c:429)
     // reservoir / frame bookkeeping
-    unsigned main_tot, mf_tot;
+    unsigned main_tot, mf_tot, out_tot;
     int padcount;
     int frames;               // frames recorded so far
     int frames_done;          // frames whose main-data slot is completely filled
@@ -68,7 +69,7 @@ struct RateState {
     BitSink sink;
 };
 
-HMP3_HD void rate_state_init(const EncTables *T, RateState *R) {
+HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {
     unsigned char *p = (unsigned char *)R;
     for (unsigned i = 0; i < sizeof(RateState); i++) p[i] = 0;
     long_rate_init(T, &R->L);
@@ -102,7 +103,7 @@ HMP3_HD void sfc_slens(int sfc, int *s1, int *s2) {
 }
 
 // MPEG-1, frame contains a short block: no scfsi (l3pack.c:157-281)
-HMP3_HD int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) {
+HMP3_FN int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) {
     int m1 = 0, m2 = 0, s1, s2;
     if (block_type == 2) {
         for (int i = 0; i < 6; i++)
@@ -126,7 +127,7 @@ HMP3_HD int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) 
     return sfc;
 }
 // MPEG-1, all-long frame: granule 1 may share scale-factor groups with granule 0 (l3pack.c:421-557)
-HMP3_HD int pack_sf_mpeg1_scfsi(BitSink *b, const ScaleFac *sf, int *save /*[21]*/, int igr, int *scfsi_out,
+HMP3_FN int pack_sf_mpeg1_scfsi(BitSink *b, const ScaleFac *sf, int *save /*[21]*/, int igr, int *scfsi_out,
                                 int not_null) {
     const int edge[5] = {0, 6, 11, 16, 21};
     int scfsi = 0;
@@ -159,7 +160,7 @@ HMP3_HD int pack_sf_mpeg1_scfsi(BitSink *b, const ScaleFac *sf, int *save /*[21]
     return sfc;
 }
 // MPEG-2 (LSF), no intensity stereo: four partitions with their own lengths (l3pack.c:561-933)
-HMP3_HD int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
+HMP3_FN int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
     int m[4] = {0, 0, 0, 0}, sl[4];
     if (block_type == 2) {
         for (int w = 0; w < 3; w++)
@@ -186,7 +187,7 @@ HMP3_HD int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
 }
 
 // ------------------------------------------------------------------ Huffman packing (l3pack.c:946-1119)
-HMP3_HD void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
     for (int r = 0; r < 3; r++) {
         const int n = g->aux_nreg[r];
         const int t = g->table_select[r];
@@ -236,7 +237,7 @@ HMP3_HD void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
 }
 
 // ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
-HMP3_HD void pack_side(const EncTables *T, const RateState *R, int main_data_begin, int igr_only, unsigned char *out) {
+HMP3_FN void pack_side(const EncTables *T, const RateState *R, int main_data_begin, int igr_only, unsigned char *out) {
     BitSink b;
     sink_open(&b, out);
     const int nch = T->cfg.nchan;
@@ -281,7 +282,7 @@ HMP3_HD void pack_side(const EncTables *T, const RateState *R, int main_data_beg
 
 // ------------------------------------------------------------------ the rate loop of one granule
 // CBitAllo3::BitAllo (bitallo3.cpp:484-678).  xr is this granule's spectrum [2][576], consumed in place.
-HMP3_HD void granule_allocate(const EncTables *T, RateState *R, float *xr, int igr, int nchan, int min_bits,
+HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int igr, int nchan, int min_bits,
                               int target_bits, int max_bits, int pool_bits, int ms) {
     LongRate *L = &R->L;
     GrSide *gr = R->gr[igr];
@@ -399,7 +400,7 @@ HMP3_HD int ms_correlation(LongRate *L, const GranuleIn *g) {
     return cm;
 }
 
-HMP3_HD void psy_stage2(const EncTables *T, RateState *R, const GranuleIn *g) {  // mp3enc.cpp:2597-2617
+HMP3_FN void psy_stage2(const EncTables *T, RateState *R, const GranuleIn *g) {  // mp3enc.cpp:2597-2617
     for (int ch = 0; ch < T->cfg.nchan; ch++) {
         if (g->info.block_type != 2) psy_long_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type, R->sig_mask[ch]);
         else psy_short_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type_prev, R->sig_mask[ch]);
@@ -416,7 +417,7 @@ HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const Gra
 
 // One encode call worth of granules for MPEG-1 (two granules of one frame; mp3enc.cpp:1492-1749).
 // Returns the ms flag of the frame.
-HMP3_HD int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, GranuleIn *g1) {
+HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, GranuleIn *g1) {
     const EncConfig &C = T->cfg;
     const int nch = C.nchan;
     GranuleIn *gs[2] = {g0, g1};
@@ -488,7 +489,7 @@ HMP3_HD int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
 }
 
 // One MPEG-2 frame = one granule (mp3enc.cpp:1832-2027)
-HMP3_HD int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, GranuleIn *g0) {
+HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, GranuleIn *g0) {
     const EncConfig &C = T->cfg;
     const int nch = C.nchan;
     const int bit_pool = R->byte_pool << 3;
@@ -537,7 +538,7 @@ HMP3_HD void frame_header(const EncTables *T, unsigned char *h, int pad, int mod
 }
 
 // Encode the granules of one frame (MPEG-1: g0,g1; MPEG-2: g0 with granule parity igr).
-HMP3_HD void encode_one_frame(const EncTables *T, RateState *R, unsigned char *main, FrameRec *frames, int igr,
+HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, unsigned char *main, FrameRec *frames, int igr,
                               GranuleIn *g0, GranuleIn *g1) {
     const EncConfig &C = T->cfg;
     const bool m1 = C.h_id == 1;
@@ -592,6 +593,8 @@ HMP3_HD void encode_one_frame(const EncTables *T, RateState *R, unsigned char *m
         bytes = R->byte_min;
     }
     fr->mf_bytes = mf_bytes;
+    fr->out_off = R->out_tot;
+    R->out_tot += (unsigned)(4 + C.side_bytes + mf_bytes);
     frame_header(T, fr->head, pad, mode_ext, ibr);
     pack_side(T, R, main_data_begin, igr, fr->side);
     R->main_tot += bytes;
@@ -614,7 +617,7 @@ namespace hmp3 {
 // ngran_real = granules of real encode calls (2 per call); after them the stream keeps consuming
 // zero-PCM granules until every real frame's main-data slot is filled (the CLI's tail flush,
 // test/tomp3.cpp:1015-1036), checked at call boundaries.
-HMP3_HD void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
+HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
                             const GranuleInfo *gi, float *xr, const PsyRaw *raw, const int *ms_raw,
                             unsigned char *main, FrameRec *frames) {
     const bool m1 = T->cfg.h_id == 1;

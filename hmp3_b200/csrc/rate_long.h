@@ -31,7 +31,7 @@ struct LongRate {
     float x34[2][576];
 };
 
-HMP3_HD void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
+HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
     L->mnr = T->cfg.initial_mnr;
     L->pool_fraction = T->cfg.vbr_flag ? 614 : 0;
     L->calls = 0;
@@ -96,7 +96,7 @@ HMP3_HD int nt_dropout_guard(int noise0, int nt) {
 }
 
 // pull noise targets toward their band-weighted mean (bitallo3.cpp:1069-1126)
-HMP3_HD void long_flatten_targets(const EncTables *T, LongRate *L) {
+HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
     const int f = T->cfg.nt_flatten;
     if (f == 0) return;
     for (int ch = 0; ch < L->nchan; ch++) {
@@ -124,7 +124,7 @@ HMP3_HD void long_flatten_targets(const EncTables *T, LongRate *L) {
     }
 }
 
-HMP3_HD void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nbands) {
+HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nbands) {
     // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
     const float *y = L->x34[ch];
     for (int i = 0; i < nbands; i++) {
@@ -140,7 +140,7 @@ HMP3_HD void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nband
 }
 
 // left/right granule (bitallo3.cpp:816-898).  xr is modified in place (signs stripped).
-HMP3_HD void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][576]*/, const SigMask *sm /*[2][36]*/,
+HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][576]*/, const SigMask *sm /*[2][36]*/,
                              unsigned char *signx /*[2][576]*/) {
     const int mnr = L->mnr + 100;
     for (int ch = 0; ch < L->nchan; ch++) {
@@ -184,7 +184,7 @@ HMP3_HD void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
 
 // mid/side granule (bitallo3.cpp:902-1065): xr becomes |L+R|, |L-R| in place (no 1/sqrt2; the
 // global gain is lowered by 2 steps on output instead).
-HMP3_HD void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const SigMask *sm, unsigned char *signx) {
+HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const SigMask *sm, unsigned char *signx) {
     if (T->cfg.vbr_flag == 0 && L->calls > 10 && (L->target - L->min_target) < 100)
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
@@ -270,7 +270,7 @@ HMP3_HD void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
 }
 
 // ------------------------------------------------------------------ per-band step search
-HMP3_HD void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.cpp:1130-1160
+HMP3_FN void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.cpp:1130-1160
     for (int ch = 0; ch < L->nchan; ch++)
         for (int i = 0; i < T->cfg.nsf[ch]; i++) {
             L->nt_adjust[ch][i] = imax_(L->nt_adjust[ch][i], -400);
@@ -286,7 +286,7 @@ HMP3_HD void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.c
 }
 
 // walk the step of one band toward the noise target, at most 20 steps (bitallo3.cpp:1164-1238)
-HMP3_HD int seek_finer(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
+HMP3_FN int seek_finer(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
                        int dn, int *noise_io) {
     int s = s0 - 1;
     int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
@@ -301,7 +301,7 @@ HMP3_HD int seek_finer(const EncTables *T, const float *y34, const float *y, int
     *noise_io = best_noise;
     return best_s;
 }
-HMP3_HD int seek_coarser(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
+HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
                          int dn, int *noise_io) {
     int s = s0;
     int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
@@ -316,7 +316,7 @@ HMP3_HD int seek_coarser(const EncTables *T, const float *y34, const float *y, i
     return best_s;
 }
 
-HMP3_HD void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
+HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *y34 = L->x34[ch];
         const float *y = xr + 576 * ch;
@@ -345,7 +345,7 @@ HMP3_HD void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
 
 // flatten isolated small peaks in the upper bands of L/R granules (bitallo3.cpp:2216-2299)
 HMP3_HD float db_of(float x) { return (float)(10.0 * log10((double)x)); }
-HMP3_HD void long_trade_peaks(const EncTables *T, LongRate *L) {
+HMP3_FN void long_trade_peaks(const EncTables *T, LongRate *L) {
     const float inv_peak[16] = {1.0f / (0.5f + 0.09460f),  1.0f / (1.5f + 0.02799f),  1.0f / (2.5f + 0.01671f),
                                 1.0f / (3.5f + 0.01192f),  1.0f / (4.5f + 0.00927f),  1.0f / (5.5f + 0.00758f),
                                 1.0f / (6.5f + 0.00641f),  1.0f / (7.5f + 0.00556f),  1.0f / (8.5f + 0.00490f),
@@ -400,7 +400,7 @@ HMP3_HD void long_trade_peaks(const EncTables *T, LongRate *L) {
 
 // -HF: decide whether the lines above band 21 can be coded at the granule's gain
 // (bitallo3.cpp:2421-2565).  which = channel for L/R granules; -1 = the mid channel of an M/S granule.
-HMP3_HD void long_hf_decide(const EncTables *T, LongRate *L, int ch, bool ms) {
+HMP3_FN void long_hf_decide(const EncTables *T, LongRate *L, int ch, bool ms) {
     if (L->gzero[ch][21] <= 8) return;
     int gmax0 = 0, gmax1 = 0;
     for (int i = 0; i < 11; i++)
@@ -423,7 +423,7 @@ HMP3_HD void long_hf_decide(const EncTables *T, LongRate *L, int ch, bool ms) {
         }
     }
 }
-HMP3_HD void long_hf_adjust_lr(const EncTables *T, LongRate *L) {
+HMP3_FN void long_hf_adjust_lr(const EncTables *T, LongRate *L) {
     L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
     for (int ch = 0; ch < L->nchan; ch++) long_hf_decide(T, L, ch, false);
     L->hf_quant = L->hf_quant_ch[0] | L->hf_quant_ch[1];
@@ -434,7 +434,7 @@ HMP3_HD void long_hf_reset_lr(LongRate *L) {
     L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
     L->ixmax[0][21] = L->ixmax[1][21] = 0;
 }
-HMP3_HD void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bitallo3.cpp:1629-1654
+HMP3_FN void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bitallo3.cpp:1629-1654
     const int b = T->startBand_l[21], n = T->nBand_l[21];
     for (int ch = 0; ch < nch; ch++)
         for (int k = 0; k < n; k++) ix[576 * ch + b + k] = 0;
@@ -443,7 +443,7 @@ HMP3_HD void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bit
 // ------------------------------------------------------------------ scale factors
 // choose (scalefac_scale, preflag): first combination whose ranges hold every active band
 // (bitallo3.cpp:1793-1888)
-HMP3_HD void long_pick_sf_mode(const EncTables *T, LongRate *L, int ch) {
+HMP3_FN void long_pick_sf_mode(const EncTables *T, LongRate *L, int ch) {
     const int nsf = T->cfg.nsf[ch];
     if (T->cfg.h_id) {
         int sp[4] = {0, 0, 0, 0};
@@ -473,7 +473,7 @@ HMP3_HD void long_pick_sf_mode(const EncTables *T, LongRate *L, int ch) {
 
 // derive G and scale factors from the per-band steps, round them to the coded grid and recompute the
 // steps (bitallo3.cpp:1892-2169).  ms selects the mid/side flavour of the rounding rules.
-HMP3_HD int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
+HMP3_FN int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
     int gmin_all = 999;
     int gtop = -1;
     if (ms && L->hf_quant) gtop = L->gsf_hf;
@@ -555,7 +555,7 @@ HMP3_HD int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
 }
 
 // try coarser steps on the low bands while the measured noise stays under target (bitallo3.cpp:1348-1399)
-HMP3_HD void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float *xr) {
+HMP3_FN void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float *xr) {
     for (int ch = 0; ch < L->nchan; ch++) {
         const int sdelta = 2 * (1 + L->sf_scale[ch]);
         const int GG = L->G[ch];
@@ -590,7 +590,7 @@ HMP3_HD void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float
 }
 
 // re-fit the scale factor of bands whose largest quantised value is 1 or 2 (bitallo3.cpp:1471-1536)
-HMP3_HD void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const int *ix) {
+HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const int *ix) {
     for (int ch = 0; ch < L->nchan; ch++) {
         const int gscale = L->G[ch] << 13;
         const int scale = L->sf_scale[ch], pre = L->preemp[ch];
@@ -614,7 +614,7 @@ HMP3_HD void long_refit_sparse_bands(const EncTables *T, LongRate *L, const floa
 }
 
 // ------------------------------------------------------------------ quantise + count
-HMP3_HD void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned) {  // bitallo3.cpp:1540-1581
+HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned) {  // bitallo3.cpp:1540-1581
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *x = L->x34[ch];
         int *q = ix + 576 * ch;
@@ -628,7 +628,7 @@ HMP3_HD void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
     }
 }
 // drop isolated single-valued quads from the top, at most level/16 of them (bitallo3.cpp:1657-1687)
-HMP3_HD void sparsify_quads(int *q, int n, int level) {
+HMP3_FN void sparsify_quads(int *q, int n, int level) {
     int c = 0;
     for (int i = 0; i < n; i++) c += q[i];
     c = (level * c) >> 4;
@@ -640,7 +640,7 @@ HMP3_HD void sparsify_quads(int *q, int n, int level) {
             if (++dropped >= c) break;
         }
 }
-HMP3_HD void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms) {  // bitallo3.cpp:1690-1736
+HMP3_FN void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms) {  // bitallo3.cpp:1690-1736
     const int b = T->startBand_l[21], n = T->nBand_l[21];
     if (ms) {
         L->ixmax[0][21] = quant_tuned(T, L->x34[0] + b, ix + b, L->G[0], n, true, -.30f);
@@ -652,7 +652,7 @@ HMP3_HD void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms)
             sparsify_quads(ix + 576 * ch + b, n, 4);
         }
 }
-HMP3_HD int long_count(const EncTables *T, LongRate *L, const int *ix, const int *ncb) {  // bitallo3.cpp:1740-1779
+HMP3_FN int long_count(const EncTables *T, LongRate *L, const int *ix, const int *ncb) {  // bitallo3.cpp:1740-1779
     int bits = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
         L->huff_bits[ch] = plan_regions_long(T, L->block_type, L->ixmax[ch], ix + 576 * ch, ncb[ch], &L->plan[ch]);
@@ -662,7 +662,7 @@ HMP3_HD int long_count(const EncTables *T, LongRate *L, const int *ix, const int
 }
 
 // ------------------------------------------------------------------ bit-budget control loops
-HMP3_HD int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, bool ms) {  // :2569-2721
+HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, bool ms) {  // :2569-2721
     const int thres = L->min_target - (L->min_target >> 4);
     if (bits0 > thres) return bits0;
     int g[2][21];
@@ -708,7 +708,7 @@ HMP3_HD int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, 
     return bits;
 }
 
-HMP3_HD int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, int *ix, int bits0) {  // :2814-2852
+HMP3_FN int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, int *ix, int bits0) {  // :2814-2852
     const int f = (250 * 1024) / (L->active_lines + 10);
     int dN = imax_((f * (bits0 - L->max_target)) >> 10, 40);
     int bits = bits0;
@@ -726,7 +726,7 @@ HMP3_HD int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, in
     }
     return bits;
 }
-HMP3_HD int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_channel) {  // :2725-2772
+HMP3_FN int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_channel) {  // :2725-2772
     int bits = 0;
     for (int k = 0; k < 100; k++) {
         for (int ch = 0; ch < L->nchan; ch++)
@@ -744,7 +744,7 @@ HMP3_HD int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_cha
 
 // the allocation of one long granule; returns the bit count before the budget loops (the CBR
 // feedback signal) (bitallo3.cpp:2948-3149)
-HMP3_HD int long_allocate(const EncTables *T, LongRate *L, float *xr, int *ix, bool ms) {
+HMP3_FN int long_allocate(const EncTables *T, LongRate *L, float *xr, int *ix, bool ms) {
     const int hf = T->cfg.hf_flag;
     if (hf) {
         if (ms) {
@@ -796,7 +796,7 @@ HMP3_HD int long_allocate(const EncTables *T, LongRate *L, float *xr, int *ix, b
 }
 
 // CBR quality feedback (bitallo3.cpp:2897-2944)
-HMP3_HD void long_mnr_feedback(const EncTables *T, LongRate *L, int active_lines, int bits, int block_type) {
+HMP3_FN void long_mnr_feedback(const EncTables *T, LongRate *L, int active_lines, int bits, int block_type) {
     if (block_type == 2) return;
     if (L->calls > 10) {
         const float per_band = 150.0f / (0.20f * (active_lines + 10));

@@ -22,13 +22,13 @@ struct ShortRate {
     int quad_scratch[580];
 };
 
-HMP3_HD void short_rate_init(ShortRate *S) {
+HMP3_FN void short_rate_init(ShortRate *S) {
     // everything the allocator reads before writing starts at zero (bitallos.cpp:85-110, 128-198)
     unsigned char *p = (unsigned char *)S;
     for (unsigned i = 0; i < sizeof(ShortRate); i++) p[i] = 0;
 }
 
-HMP3_HD void short_step_bounds(const EncTables *T, ShortRate *S) {
+HMP3_FN void short_step_bounds(const EncTables *T, ShortRate *S) {
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++) {
             const float *y = S->x34[ch][w];
@@ -47,7 +47,7 @@ HMP3_HD void short_step_bounds(const EncTables *T, ShortRate *S) {
 }
 
 // pull targets of audible bands halfway to their mean when the mean is high (bitallos.cpp:700-745)
-HMP3_HD void short_flatten_targets(const EncTables *T, ShortRate *S) {
+HMP3_FN void short_flatten_targets(const EncTables *T, ShortRate *S) {
     int na = 1, a = 0;
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++)
@@ -62,7 +62,7 @@ HMP3_HD void short_flatten_targets(const EncTables *T, ShortRate *S) {
 }
 
 // xr: [2][3][192] (window-major within the channel); sm: [2][3][12]
-HMP3_HD void short_startup_lr(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:455-546
+HMP3_FN void short_startup_lr(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:455-546
     const int mnr = S->mnr;
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++) {
@@ -104,7 +104,7 @@ HMP3_HD void short_startup_lr(const EncTables *T, ShortRate *S, float *xr, const
     short_step_bounds(T, S);
 }
 
-HMP3_HD void short_startup_ms(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:549-697
+HMP3_FN void short_startup_ms(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:549-697
     S->active_lines = 0;
     const int nsf0 = T->cfg.nsf_s[0];
     for (int w = 0; w < 3; w++) {
@@ -168,7 +168,7 @@ HMP3_HD void short_startup_ms(const EncTables *T, ShortRate *S, float *xr, const
     short_step_bounds(T, S);
 }
 
-HMP3_HD void short_seek_initial(const EncTables *T, ShortRate *S) {  // bitallos.cpp:748-776
+HMP3_FN void short_seek_initial(const EncTables *T, ShortRate *S) {  // bitallos.cpp:748-776
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++)
             for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
@@ -182,7 +182,7 @@ HMP3_HD void short_seek_initial(const EncTables *T, ShortRate *S) {  // bitallos
             }
 }
 
-HMP3_HD void short_seek_actual(const EncTables *T, ShortRate *S, const float *xr) {  // bitallos.cpp:841-886
+HMP3_FN void short_seek_actual(const EncTables *T, ShortRate *S, const float *xr) {  // bitallos.cpp:841-886
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++) {
             const float *y34 = S->x34[ch][w];
@@ -209,7 +209,7 @@ HMP3_HD void short_seek_actual(const EncTables *T, ShortRate *S, const float *xr
         }
 }
 
-HMP3_HD void short_quantise(const EncTables *T, ShortRate *S, bool tuned) {  // bitallos.cpp:889-936
+HMP3_FN void short_quantise(const EncTables *T, ShortRate *S, bool tuned) {  // bitallos.cpp:889-936
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++) {
             const float *x = S->x34[ch][w];
@@ -225,7 +225,7 @@ HMP3_HD void short_quantise(const EncTables *T, ShortRate *S, bool tuned) {  // 
 }
 
 // per-window gains, scale factors on the coded grid, steps recomputed (bitallos.cpp:1195-1317)
-HMP3_HD void short_scale_factors(const EncTables *T, ShortRate *S) {
+HMP3_FN void short_scale_factors(const EncTables *T, ShortRate *S) {
     for (int ch = 0; ch < S->nchan; ch++) {
         const int nsf = T->cfg.nsf_s[ch];
         S->sf_scale[ch] = 0;
@@ -314,7 +314,7 @@ HMP3_HD void short_scale_factors(const EncTables *T, ShortRate *S) {
 
 // fixed regions: region 0 = first three short bands (of all windows), one big region after it, count1
 // region = whole bands in transmission order padded to quads (bitallosc.cpp:296-420)
-HMP3_HD int short_plan_regions(const EncTables *T, ShortRate *S, int ch) {
+HMP3_FN int short_plan_regions(const EncTables *T, ShortRate *S, int ch) {
     const int ncb = T->cfg.nsf_s[ch];
     const int(*ixmax)[16] = S->ixmax[ch];
     const int *start = T->startBand_s;
@@ -394,7 +394,7 @@ HMP3_HD int short_plan_regions(const EncTables *T, ShortRate *S, int ch) {
     P->bits = bits;
     return bits;
 }
-HMP3_HD int short_count(const EncTables *T, ShortRate *S) {
+HMP3_FN int short_count(const EncTables *T, ShortRate *S) {
     int bits = 0;
     for (int ch = 0; ch < S->nchan; ch++) {
         S->huff_bits[ch] = short_plan_regions(T, S, ch);
@@ -402,7 +402,7 @@ HMP3_HD int short_count(const EncTables *T, ShortRate *S) {
     }
     return bits;
 }
-HMP3_HD void short_plan_to_side(const EncTables *T, const RegionPlan *P, GrSide *g) {  // bitallosc.cpp:423-487
+HMP3_FN void short_plan_to_side(const EncTables *T, const RegionPlan *P, GrSide *g) {  // bitallosc.cpp:423-487
     if (P->bits <= 0) {
         g->table_select[0] = g->table_select[1] = g->table_select[2] = 0;
         g->big_values = 0;
@@ -432,7 +432,7 @@ HMP3_HD void short_plan_to_side(const EncTables *T, const RegionPlan *P, GrSide 
 }
 
 // one short granule (bitallos.cpp:1455-1503 with the control loops :1320-1452)
-HMP3_HD void short_allocate(const EncTables *T, ShortRate *S, const float *xr) {
+HMP3_FN void short_allocate(const EncTables *T, ShortRate *S, const float *xr) {
     if (S->mnr < -200) S->min_target = imax_(S->min_target, (3 * S->target) >> 2);
     short_seek_initial(T, S);
     short_seek_actual(T, S, xr);
@@ -501,7 +501,7 @@ HMP3_HD void short_allocate(const EncTables *T, ShortRate *S, const float *xr) {
 // Full short-block granule: returns the feedback bit count.  gr/sf_out are the persistent side-info
 // records of this granule; ix_out/sign_out receive the lines in transmission order
 // (bitallos.cpp:202-372).
-HMP3_HD int short_granule(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm, int nchan, int min_bits,
+HMP3_FN int short_granule(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm, int nchan, int min_bits,
                           int target_bits, int max_bits, int pool_bits, ScaleFac *sf_out, GrSide *gr, int *ix_out,
                           unsigned char *sign_out, int ms, int mnr) {
     S->mnr = mnr;

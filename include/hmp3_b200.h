@@ -110,30 +110,35 @@ int64_t hmp3_batch_out_bound(const hmp3_control *control, int64_t num_samples);
  * (H2D/D2H copies are inside).  Returns HMP3_OK if the batch ran; per-stream results in status. */
 int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device);
 
-/* Device-resident variant used by the benchmark's kernel-only leg: PCM already in HBM
- * (`d_pcm[i]` device pointers), output left in HBM (`d_out[i]`), sizes returned to the host. */
-typedef struct hmp3_batch hmp3_batch; /* opaque, reusable plan: buffers sized for a batch shape */
+/* Reusable batch plan: device buffers sized once for a batch shape (controls + clip lengths), then
+ * any number of encodes of that shape.  hmp3_encode_batch is create + encode_host + destroy. */
+typedef struct hmp3_batch hmp3_batch; /* opaque */
 hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_samples, int n, int device);
 void hmp3_batch_destroy(hmp3_batch *b);
-/* bytes of device output region reserved per stream (stride of the device output buffer) */
-int64_t hmp3_batch_out_stride(const hmp3_batch *b);
-/* device pointers owned by the plan */
-int16_t *hmp3_batch_device_pcm(hmp3_batch *b);   /* [n][max_samples * nch] int16, stream-major   */
-uint8_t *hmp3_batch_device_out(hmp3_batch *b);   /* [n][out_stride]                              */
-int64_t hmp3_batch_pcm_stride(const hmp3_batch *b); /* int16 elements per stream                 */
-/* run all kernels on the plan's stream; inputs are whatever is in device_pcm.  Synchronous unless
- * `async` != 0 (then hmp3_batch_sync must be called before reading results). */
+/* Host buffers in, host buffers out through a plan: uploads every stream's PCM (H2D), runs all kernels,
+ * copies the frames back (D2H) into out[i].  Arrays have n entries; out_bytes/out_frames/status may be NULL. */
+int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+                           int64_t *out_bytes, int32_t *out_frames, int32_t *status);
+/* Device-resident legs (the benchmark's kernel-only measurement and custom feeders): */
+int16_t *hmp3_batch_device_pcm(hmp3_batch *b);          /* all streams' interleaved int16 PCM           */
+int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i); /* int16 element offset of stream i in it    */
+uint8_t *hmp3_batch_device_out(hmp3_batch *b);          /* compact output: stream i at out_offsets[i]   */
+int64_t hmp3_batch_out_capacity(const hmp3_batch *b);
+int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples); /* async H2D      */
+/* run all kernels on the plan's stream over whatever PCM is resident.  Synchronous unless `async` != 0
+ * (then hmp3_batch_sync must be called before reading results). */
 int hmp3_batch_run(hmp3_batch *b, int async);
 int hmp3_batch_sync(hmp3_batch *b);
-/* per-stream results of the last run (host arrays of n) */
-int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames);
-/* copy helpers for the host-to-host path through a plan */
-int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples);
+/* per-stream results of the last completed run (host arrays of n; any may be NULL) */
+int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames, int64_t *out_offsets,
+                       int32_t *status);
 int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap);
+int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *total);
 /* number of kernel launches issued by the last hmp3_batch_run */
 int hmp3_batch_last_launches(const hmp3_batch *b);
-/* device time of named phases of the last synchronous run, in ms (for bench.py's roofline leg):
- * fills up to `cap` entries, returns the count; names[i] points to static strings. */
+/* per-kernel device time (CUDA events on the plan's stream) of the last synchronous run made after
+ * hmp3_batch_set_timing(b, 1): fills up to `cap` entries, returns the count; names[i] are static. */
+int hmp3_batch_set_timing(hmp3_batch *b, int on);
 int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap);
 
 /* ---------------------------------------------------------------------------------------------
