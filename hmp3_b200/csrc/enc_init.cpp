@@ -663,6 +663,9 @@ int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
         for (i = 0; i < 22; i++) { T.startBand_l[i] = kk; kk += T.nBand_l[i]; }
         T.startBand_l[22] = kk;
         T.startBand_l[23] = 576;
+        for (i = 0; i < 576; i++) T.line_band_l[i] = 22;
+        for (i = 0; i < 22; i++)
+            for (int k = T.startBand_l[i]; k < T.startBand_l[i + 1] && k < 576; k++) T.line_band_l[k] = (unsigned char)i;
         kk = 0;
         for (i = 0; i < 13; i++) { T.startBand_s[i] = kk; kk += T.nBand_s[i]; }
         T.startBand_s[13] = kk;

@@ -13,7 +13,23 @@
 #define HMP3_FN static inline
 #endif
 
+// Device code runs one stream per warp: scalar control flow is executed uniformly by all 32 lanes and
+// the per-line / per-band loops are split over the lanes (HMP3_COOP).  The host build (test-only
+// simulator) runs the plain sequential loops.
+#if defined(__CUDA_ARCH__)
+#define HMP3_COOP 1
+#define HMP3_LANE ((int)(threadIdx.x & 31u))
+#define HMP3_SYNC() __syncwarp()
+#else
+#define HMP3_COOP 0
+#define HMP3_LANE 0
+#define HMP3_SYNC()
+#endif
+
 namespace hmp3 {
+
+// warps (= streams) per thread block of the serial-stage kernel
+constexpr int kRateWarpsPerBlock = 4;
 
 enum FrameDriver { FD_VBR_MPEG1 = 0, FD_CBR_MPEG1 = 1, FD_VBR_MPEG2 = 2, FD_CBR_MPEG2 = 3 };
 
@@ -85,6 +101,8 @@ struct EncTables {
     int cnt_tables[kCountClasses][4];  // candidate Huffman table numbers (0 = none)
     int cnt_tmax[kCountClasses];       // largest value the class can code
     int cnt_ncand[kCountClasses];      // 2 or 4 (0 for the null class)
+    // ---- line -> scale-factor band (long blocks), 22 = above the last band
+    unsigned char line_band_l[576];
 };
 
 // ------------------------------------------------------------------ scalar table functions

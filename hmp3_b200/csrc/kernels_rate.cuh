@@ -27,11 +27,13 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
     rate_state_init(tabs + st[s].cfg, rs + s);
 }
 
-// ---- K6: the serial stage over one chunk of granules, one thread per stream
-__global__ void __launch_bounds__(32) k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so,
-                                             RateState *rs, ChunkBufs cb, unsigned char *main_buf,
-                                             FrameRec *frames, int K0, int nstreams) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- K6: the serial stage over one chunk of granules, ONE WARP per stream: the scalar control flow of the
+// rate loop runs uniformly on all 32 lanes, the per-line / per-band loops are split across the lanes
+// (HMP3_COOP sections of rate_*.h).
+__global__ void __launch_bounds__(32 * kRateWarpsPerBlock)
+    k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+           unsigned char *main_buf, FrameRec *frames, int K0, int nstreams) {
+    const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (s >= nstreams) return;
     const StreamDev sd = st[s];
     if (K0 >= sd.ngran) return;

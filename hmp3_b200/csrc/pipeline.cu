@@ -3,6 +3,7 @@
 // every entry point fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -301,8 +302,8 @@ int run_plan(hmp3_batch *b) {
         r = launch_analysis(b, K0);
         if (r != HMP3_OK) return r;
         mark(b, PH_RATE);
-        k_rate<<<blocks_for(n, 32), 32, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main,
-                                                        b->d_frames, K0, n);
+        k_rate<<<blocks_for((long long)n * 32, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, b->stream>>>(
+            b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main, b->d_frames, K0, n);
         mark(b, -1);
         b->launches++;
     }

@@ -84,6 +84,25 @@ HMP3_HD float dequant43(const EncTables *T, int q) {
 HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
     const float ig = T->igain34[g], gn = T->gain[g];
     float acc = 0.0f;
+#if HMP3_COOP
+    // lanes square the errors of 32 lines at a time; the sum is then taken in line order by every lane
+    const int lane = HMP3_LANE;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        float dd = 0.0f;
+        if (i < n) {
+            float t = (ig * x34[i] + (0.0f - 0.0946f));
+            int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
+            float xh;
+            if (q >= 0 && q < 256) xh = gn * T->ix43[q];
+            else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
+            float d = x[i] - xh;
+            dd = d * d;
+        }
+        const int m = (n - i0) < 32 ? (n - i0) : 32;
+        for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, dd, k);
+    }
+#else
     for (int i = 0; i < n; i++) {
         float t = (ig * x34[i] + (0.0f - 0.0946f));
         int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
@@ -93,12 +112,32 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
         float d = x[i] - xh;
         acc += d * d;
     }
+#endif
     return mb_log(T, 1.0e-12f + acc) - logn;
 }
 
 // gain (scaled by 2^13) that best maps quantised values back onto the spectrum (l3math.c:1087-1114)
 HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, int n) {
     float sqq = 0, sxx = 0;
+#if HMP3_COOP
+    const int lane = HMP3_LANE;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        float vv = 0.0f, xx = 0.0f;
+        if (i < n) {
+            float v;
+            if (q[i] < 256) v = T->ix43[q[i]];
+            else v = (float)(pow((double)q[i], (4.0 / 3.0)));
+            vv = v * v;
+            xx = x[i] * x[i];
+        }
+        const int m = (n - i0) < 32 ? (n - i0) : 32;
+        for (int k = 0; k < m; k++) {
+            sqq += __shfl_sync(0xffffffffu, vv, k);
+            sxx += __shfl_sync(0xffffffffu, xx, k);
+        }
+    }
+#else
     for (int i = 0; i < n; i++) {
         float v;
         if (q[i] < 256) v = T->ix43[q[i]];
@@ -106,6 +145,7 @@ HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, in
         sqq += v * v;
         sxx += x[i] * x[i];
     }
+#endif
     return 54 * mb_log(T, sxx / sqq) + (8 << 13);
 }
 
@@ -134,20 +174,29 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
     if (nc == 0 || n <= 0) return r;
     const uint32_t(*lut)[2] = T->cnt_lut[c];
     unsigned s0 = 0, s1 = 0;
+#if HMP3_COOP
+    const int i_first = 2 * HMP3_LANE, i_step = 64;
+#else
+    const int i_first = 0, i_step = 2;
+#endif
     if (c >= 7) {  // escape tables: values above 15 use the row/column of 15
-        for (int i = 0; i < n; i += 2) {
+        for (int i = i_first; i < n; i += i_step) {
             int a = ix[i] > 15 ? 15 : ix[i], b = ix[i + 1] > 15 ? 15 : ix[i + 1];
             s0 += lut[a * 16 + b][0];
         }
     } else if (nc == 2) {
-        for (int i = 0; i < n; i += 2) s0 += lut[(ix[i] & 15) * 16 + (ix[i + 1] & 15)][0];
+        for (int i = i_first; i < n; i += i_step) s0 += lut[(ix[i] & 15) * 16 + (ix[i + 1] & 15)][0];
     } else {
-        for (int i = 0; i < n; i += 2) {
+        for (int i = i_first; i < n; i += i_step) {
             const uint32_t *e = lut[(ix[i] & 15) * 16 + (ix[i + 1] & 15)];
             s0 += e[0];
             s1 += e[1];
         }
     }
+#if HMP3_COOP
+    s0 = __reduce_add_sync(0xffffffffu, s0);
+    s1 = __reduce_add_sync(0xffffffffu, s1);
+#endif
     int b0 = (int)(s0 & 0xFFFF), b1 = (int)((s0 >> 16) & 0xFFFF);
     if (b0 < b1) { r.bits = b0; r.index = 0; }
     else { r.bits = b1; r.index = 1; }
@@ -167,12 +216,21 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
     if (nquads <= 0) return r;
     const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
     int a = 0, b = 0;
+#if HMP3_COOP
+    for (int i = HMP3_LANE; i < nquads; i += 32) {
+        const int k = 4 * i;
+#else
     for (int i = 0, k = 0; i < nquads; i++, k += 4) {
+#endif
         int j = ((ix[k] << 3) + (ix[k + 1] << 2) + (ix[k + 2] << 1) + ix[k + 3]) & 15;
         int ones = (j & 1) + ((j >> 1) & 1) + ((j >> 2) & 1) + ((j >> 3) & 1);
         a += lenA[j] + ones;
         b += 4 + ones;
     }
+#if HMP3_COOP
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+#endif
     if (a < b) { r.bits = a; r.index = 0; }
     else { r.bits = b; r.index = 1; }
     return r;

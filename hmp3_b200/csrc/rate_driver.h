@@ -187,7 +187,7 @@ HMP3_FN int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
 }
 
 // ------------------------------------------------------------------ Huffman packing (l3pack.c:946-1119)
-HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+HMP3_FN void pack_huffman_seq(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
     for (int r = 0; r < 3; r++) {
         const int n = g->aux_nreg[r];
         const int t = g->table_select[r];
@@ -235,6 +235,127 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
         }
     }
 }
+
+
+#if HMP3_COOP
+// Warp-parallel Huffman packing: each lane builds the bit field of one pair (or quad), a warp scan of the
+// field lengths gives its position, and the fields are OR-ed into a per-warp shared-memory bit buffer that
+// is then streamed out in whole bytes.  Produces exactly the bits of the sequential writer below.
+constexpr int kPackWords = 168;  // 5376 bits: part2_3_length can never exceed 4095 + the scale factors
+__device__ __forceinline__ void bitbuf_or(unsigned *W, int pos, unsigned long long v, int len) {
+    if (len <= 0) return;
+    const unsigned long long V = v << (64 - len);
+    const unsigned hi = (unsigned)(V >> 32), lo = (unsigned)V;
+    const int w = pos >> 5, o = pos & 31;
+    const unsigned w0 = hi >> o;
+    const unsigned w1 = __funnelshift_r(lo, hi, o);
+    const unsigned w2 = __funnelshift_r(0u, lo, o);
+    if (w0) atomicOr(W + w, w0);
+    if (w1) atomicOr(W + w + 1, w1);
+    if (w2) atomicOr(W + w + 2, w2);
+}
+__device__ __forceinline__ int warp_scan_excl(int v, int *total) {
+    const int lane = HMP3_LANE;
+    int s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += t;
+    }
+    *total = __shfl_sync(0xffffffffu, s, 31);
+    return s - v;
+}
+HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+    __shared__ unsigned s_bits[kRateWarpsPerBlock][kPackWords];
+    unsigned *W = s_bits[(threadIdx.x >> 5) % kRateWarpsPerBlock];
+    const int lane = HMP3_LANE;
+    HMP3_SYNC();
+    const int p0 = b->nacc;  // bits pending in the writer (< 8)
+    if (p0 + g->aux_bits > kPackWords * 32 - 160) {  // cannot happen within the part2_3 limits; stay correct anyway
+        pack_huffman_seq(T, b, g, ix, sg);
+        return;
+    }
+    const int nwords = imin_(kPackWords, ((p0 + g->aux_bits + 31) >> 5) + 3);
+    for (int k = lane; k < nwords; k += 32) W[k] = 0;
+    HMP3_SYNC();
+    if (lane == 0 && p0 > 0) W[0] = ((unsigned)b->acc & ((1u << p0) - 1u)) << (32 - p0);
+    HMP3_SYNC();
+    int pos = p0;
+    for (int r = 0; r < 3; r++) {
+        const int n = g->aux_nreg[r];
+        const int t = g->table_select[r];
+        const int book = T->huff_sel_book[t];
+        if (book != 0) {
+            const uint32_t *bk = T->huff_book[book];
+            const int lb = T->huff_linbits[t];
+            const bool esc = t >= 16;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                unsigned long long v = 0;
+                int len = 0;
+                if (j < n) {
+                    const int x0 = ix[2 * j], y0 = ix[2 * j + 1];
+                    int x = x0, y = y0;
+                    if (esc) {
+                        if (x > 15) x = 15;
+                        if (y > 15) y = 15;
+                    }
+                    const uint32_t e = bk[(x & 15) * 16 + (y & 15)];
+                    v = e & 0xFFFFFFu;
+                    len = (int)(e >> 24);
+                    if (esc && x >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(x0 - 15) & ((1u << lb) - 1u)); len += lb; }
+                    if (x) { v = (v << 1) | (sg[2 * j] & 1u); len++; }
+                    if (esc && y >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(y0 - 15) & ((1u << lb) - 1u)); len += lb; }
+                    if (y) { v = (v << 1) | (sg[2 * j + 1] & 1u); len++; }
+                }
+                int tot;
+                const int off = warp_scan_excl(len, &tot);
+                bitbuf_or(W, pos + off, v, len);
+                pos += tot;
+            }
+        }
+        ix += 2 * n;
+        sg += 2 * n;
+    }
+    {
+        const int nq = g->aux_nquads;
+        const bool tabB = g->count1table_select == 1;
+        const unsigned char codeA[16] = {1, 5, 4, 5, 6, 5, 4, 4, 7, 3, 6, 0, 7, 2, 3, 1};
+        const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
+        for (int j0 = 0; j0 < nq; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned long long v = 0;
+            int len = 0;
+            if (j < nq) {
+                const unsigned x = (unsigned)((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) & 15u;
+                if (tabB) { v = x ^ 15u; len = 4; }
+                else { v = codeA[x]; len = lenA[x]; }
+                for (int k = 0; k < 4; k++)
+                    if (x & (8u >> k)) { v = (v << 1) | (sg[4 * j + k] & 1u); len++; }
+            }
+            int tot;
+            const int off = warp_scan_excl(len, &tot);
+            bitbuf_or(W, pos + off, v, len);
+            pos += tot;
+        }
+    }
+    HMP3_SYNC();
+    const int nbytes = pos >> 3, rem = pos & 7;
+    unsigned char *dst = b->p;
+    for (int k = lane; k < nbytes; k += 32) dst[k] = (unsigned char)(W[k >> 2] >> (24 - 8 * (k & 3)));
+    const unsigned last = (W[nbytes >> 2] >> (24 - 8 * (nbytes & 3))) & 0xffu;
+    HMP3_SYNC();
+    b->p = dst + nbytes;
+    b->acc = rem ? (unsigned long long)(last >> (8 - rem)) : 0ull;
+    b->nacc = rem;
+    b->total_bits += pos - p0;
+    HMP3_SYNC();
+}
+#else
+HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+    pack_huffman_seq(T, b, g, ix, sg);
+}
+#endif
 
 // ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
 HMP3_FN void pack_side(const EncTables *T, const RateState *R, int main_data_begin, int igr_only, unsigned char *out) {
@@ -303,7 +424,12 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int i
     } else if (bt == 3) {
         L->mnr = (L->mnr + init) >> 1;
         L->mnr = imin_(L->mnr, init + 500);
+#if HMP3_COOP
+        for (int k = HMP3_LANE; k < nchan * 576; k += 32) ix[k] = 0;
+        HMP3_SYNC();
+#else
         for (int k = 0; k < nchan * 576; k++) ix[k] = 0;
+#endif
     }
     if (bt == 2) {
         int mnr0;

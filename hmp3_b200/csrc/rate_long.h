@@ -126,6 +126,21 @@ HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
 
 HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nbands) {
     // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
+#if HMP3_COOP
+    HMP3_SYNC();
+    const int i = HMP3_LANE;  // one band per lane
+    if (i < nbands) {
+        const float *y = L->x34[ch] + T->startBand_l[i];
+        const int n = T->nBand_l[i];
+        float m = 0.0f;
+        for (int k = 0; k < n; k++)
+            if (y[k] > m) m = y[k];
+        L->x34max[ch][i] = m;
+        L->gzero[ch][i] = imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
+        L->gmin[ch][i] = imax_(0, L->gzero[ch][i] - kGminOffset);
+    }
+    HMP3_SYNC();
+#else
     const float *y = L->x34[ch];
     for (int i = 0; i < nbands; i++) {
         const int n = T->nBand_l[i];
@@ -137,12 +152,44 @@ HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nband
         L->gmin[ch][i] = imax_(0, L->gzero[ch][i] - kGminOffset);
         y += n;
     }
+#endif
 }
+
+#if HMP3_COOP
+// sums of v[] over each of the first nbands bands, accumulated in line order: one band per lane
+HMP3_HD void long_band_sums(const EncTables *T, const float *v, int nbands, float *out) {
+    HMP3_SYNC();
+    const int i = HMP3_LANE;
+    if (i < nbands) {
+        const float *y = v + T->startBand_l[i];
+        const int n = T->nBand_l[i];
+        float e = 0.0f;
+        for (int k = 0; k < n; k++) e += y[k];
+        out[i] = e;
+    }
+    HMP3_SYNC();
+}
+#endif
 
 // left/right granule (bitallo3.cpp:816-898).  xr is modified in place (signs stripped).
 HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][576]*/, const SigMask *sm /*[2][36]*/,
                              unsigned char *signx /*[2][576]*/) {
     const int mnr = L->mnr + 100;
+#if HMP3_COOP
+    for (int ch = 0; ch < L->nchan; ch++) {
+        float *x = xr + 576 * ch;
+        unsigned char *s = signx + 576 * ch;
+        float *sq = L->x34[ch];  // scratch until the 3/4 powers are taken below
+        const int nl = T->startBand_l[T->cfg.nsf3[ch]];
+        for (int k = HMP3_LANE; k < nl; k += 32) {
+            float v = x[k];
+            if (v >= 0.0f) s[k] = 0;
+            else { s[k] = 1; v = -v; x[k] = v; }
+            sq[k] = v * v;
+        }
+        long_band_sums(T, sq, T->cfg.nsf3[ch], L->xsxx[ch]);
+    }
+#else
     for (int ch = 0; ch < L->nchan; ch++) {
         float *x = xr + 576 * ch;
         unsigned char *s = signx + 576 * ch;
@@ -159,6 +206,7 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
             s += n;
         }
     }
+#endif
     L->active_lines = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
         for (int i = 0; i < T->cfg.nsf[ch]; i++) {
@@ -177,7 +225,12 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
     long_flatten_targets(T, L);
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *x = xr + 576 * ch;
+#if HMP3_COOP
+        HMP3_SYNC();
+        for (int k = HMP3_LANE; k < T->cfg.nbmax3[ch]; k += 32) L->x34[ch][k] = pow34(T, x[k]);
+#else
         for (int k = 0; k < T->cfg.nbmax3[ch]; k++) L->x34[ch][k] = pow34(T, x[k]);
+#endif
         long_step_bounds(T, L, ch, T->cfg.nsf3[ch]);
     }
 }
@@ -189,9 +242,40 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
     L->active_lines = 0;
+    const int nsf0 = T->cfg.nsf[0];
+#if HMP3_COOP
+    {
+        float *sq0 = L->x34[0], *sq1 = L->x34[1];  // scratch until the 3/4 powers are taken below
+        const int nl = T->startBand_l[nsf0];
+        const int nrot = nl + (T->cfg.hf_flag ? T->nBand_l[21] : 0);  // the pseudo band above sfb 21 is rotated too
+        for (int k = HMP3_LANE; k < nl; k += 32) {
+            sq0[k] = xr[k] * xr[k];
+            sq1[k] = xr[576 + k] * xr[576 + k];
+        }
+        long_band_sums(T, sq0, nsf0, L->xsxx[0]);
+        long_band_sums(T, sq1, nsf0, L->xsxx[1]);
+        for (int k = HMP3_LANE; k < nrot; k += 32) {
+            float m = (xr[k] + xr[576 + k]);
+            float d = (xr[k] - xr[576 + k]);
+            unsigned char sm_ = 0, sd_ = 0;
+            if (m < 0.0f) { sm_ = 1; m = -m; }
+            if (d < 0.0f) { sd_ = 1; d = -d; }
+            signx[k] = sm_;
+            signx[576 + k] = sd_;
+            xr[k] = m;
+            xr[576 + k] = d;
+            sq0[k] = m * m;
+            sq1[k] = d * d;
+        }
+        long_band_sums(T, sq0, nsf0, L->x34max[0]);  // mid / side energies, parked until the step bounds are set
+        long_band_sums(T, sq1, nsf0, L->x34max[1]);
+    }
+    for (int i = 0; i < nsf0; i++) {
+        const int n = T->nBand_l[i];
+        const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = L->x34max[0][i], ed = L->x34max[1][i];
+#else
     float *x = xr;
     unsigned char *s = signx;
-    const int nsf0 = T->cfg.nsf[0];
     int n = 0;
     for (int i = 0; i < nsf0; i++) {
         n = T->nBand_l[i];
@@ -216,6 +300,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         }
         L->xsxx[0][i] = el;
         L->xsxx[1][i] = er;
+#endif
         const int cbw = T->log_cbw_l[i];
         int ntl, ntr;
         int n0l = mb_log(T, el) - cbw;
@@ -236,9 +321,12 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         L->snr[1][i] = n0r - ntr;
         L->noise0[0][i] = mb_log(T, em) - cbw;
         L->noise0[1][i] = mb_log(T, ed) - cbw;
+#if !HMP3_COOP
         x += n;
         s += n;
+#endif
     }
+#if !HMP3_COOP
     if (T->cfg.hf_flag) {  // the pseudo band above sfb 21 is rotated too
         n = T->nBand_l[21];
         for (int k = 0; k < n; k++) {
@@ -251,6 +339,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
             x[576 + k] = d;
         }
     }
+#endif
     long_flatten_targets(T, L);
     for (int i = 0; i < nsf0; i++) {
         const int nsum = L->noise0[0][i], ndiff = L->noise0[1][i];
@@ -264,8 +353,13 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         L->snr[0][i] = nsum - L->nt[0][i];
         L->snr[1][i] = ndiff - L->nt[1][i];
     }
+    HMP3_SYNC();
     for (int ch = 0; ch < 2; ch++)
+#if HMP3_COOP
+        for (int k = HMP3_LANE; k < T->cfg.nbmax2[ch]; k += 32) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
+#else
         for (int k = 0; k < T->cfg.nbmax2[ch]; k++) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
+#endif
     for (int ch = 0; ch < L->nchan; ch++) long_step_bounds(T, L, ch, T->cfg.nsf2[ch]);
 }
 
@@ -615,6 +709,37 @@ HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const floa
 
 // ------------------------------------------------------------------ quantise + count
 HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned) {  // bitallo3.cpp:1540-1581
+#if HMP3_COOP
+    // every lane quantises every 32nd line with its band's step; band maxima are then gathered one band per lane
+    HMP3_SYNC();
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const float *x = L->x34[ch];
+        int *q = ix + 576 * ch;
+        const int nb = T->cfg.nsf[ch], nl = T->startBand_l[nb];
+        for (int k = HMP3_LANE; k < nl; k += 32) {
+            const float ig = T->igain34[L->gsf[ch][T->line_band_l[k]]];
+            int v;
+            if (tuned) {
+                float t = ig * x[k] + (0.5f - 0.4375f);
+                int c = (int)t;
+                if (c > 31) c = 31;
+                v = (int)(t - T->quantB_round[c]);
+            } else v = (int)(ig * x[k] + (0.5f - 0.0946f));
+            q[k] = v;
+        }
+        HMP3_SYNC();
+        const int i = HMP3_LANE;
+        if (i < nb) {
+            const int *qb = q + T->startBand_l[i];
+            const int n = T->nBand_l[i];
+            int m = 0;
+            for (int k = 0; k < n; k++)
+                if (qb[k] > m) m = qb[k];
+            L->ixmax[ch][i] = m;
+        }
+    }
+    HMP3_SYNC();
+#else
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *x = L->x34[ch];
         int *q = ix + 576 * ch;
@@ -626,6 +751,7 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
             q += n;
         }
     }
+#endif
 }
 // drop isolated single-valued quads from the top, at most level/16 of them (bitallo3.cpp:1657-1687)
 HMP3_FN void sparsify_quads(int *q, int n, int level) {

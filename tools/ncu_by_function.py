@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Aggregate an ncu source-page capture of a kernel per (noinline) device function.
+
+usage: ncu_by_function.py <report.ncu-rep> <library.so> <kernel-substring>
+Joins `ncu --page source --print-source sass` (per-instruction samples / executed counts) with the
+function symbol table of the cubin extracted from the library."""
+import csv, subprocess, sys, os, re, tempfile, collections
+
+rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+syms = []
+for f in os.listdir(tmp):
+    if not f.endswith(".cubin"):
+        continue
+    out = subprocess.run(["readelf", "-sW", os.path.join(tmp, f)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    for line in out.splitlines():
+        p = line.split()
+        if len(p) >= 8 and p[3] == "FUNC" and ("$" + "_Z") in p[7] and re.search(r"\d" + kern + "E", p[7].split("$")[1]):
+            name = p[7].split("$")[2]
+            m = re.search(r"hmp3(\d+)([A-Za-z_0-9]+)", name)
+            short = m.group(2)[:int(m.group(1))] if m else name
+            syms.append((int(p[1], 16), int(p[2]), short))
+syms.sort()
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE,
+                     stderr=subprocess.DEVNULL, text=True).stdout
+rows = list(csv.reader(src.splitlines()))
+hdr = None
+base = None
+agg = collections.defaultdict(lambda: [0, 0, 0])
+for r in rows:
+    if r and r[0] == "Address":
+        hdr = r
+        continue
+    if not hdr or len(r) != len(hdr):
+        continue
+    d = dict(zip(hdr, r))
+    a = int(d["Address"], 16)
+    if base is None:
+        base = a
+    off = a - base
+    fn = "(kernel body)"
+    for s0, sz, nm in syms:
+        if s0 <= off < s0 + sz:
+            fn = nm
+            break
+    agg[fn][0] += int(d["# Samples"] or 0)
+    agg[fn][1] += int(d["Instructions Executed"] or 0)
+    agg[fn][2] += int(d["Thread Instructions Executed"] or 0)
+ts = sum(v[0] for v in agg.values()) or 1
+ti = sum(v[1] for v in agg.values()) or 1
+print("%-28s %8s %8s %14s %8s" % ("function", "samples%", "instr%", "warp-instr", "thr/inst"))
+for fn, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print("%-28s %7.2f%% %7.2f%% %14d %8.1f" % (fn, 100 * v[0] / ts, 100 * v[1] / ti, v[1], v[2] / max(v[1], 1)))
+print("total warp instructions", ti, "samples", ts)
