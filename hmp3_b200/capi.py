@@ -90,11 +90,13 @@ class Batch:
         L.hmp3_batch_out_bound.argtypes = [C.c_void_p, C.c_int64]
         self.bound = np.array([L.hmp3_batch_out_bound(vp(self.ctl[i]), int(self.ns[i])) for i in range(self.n)],
                               dtype=np.int64)
-        for name in ("hmp3_batch_destroy", "hmp3_batch_sync"):
+        for name in ("hmp3_batch_destroy", "hmp3_batch_sync", "hmp3_batch_wait_uploads"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.hmp3_batch_run.argtypes = [C.c_void_p, C.c_int]
         L.hmp3_batch_set_timing.argtypes = [C.c_void_p, C.c_int]
         L.hmp3_batch_last_launches.argtypes = [C.c_void_p]
+        L.hmp3_batch_last_run_ms.argtypes = [C.c_void_p]
+        L.hmp3_batch_last_run_ms.restype = C.c_float
         L.hmp3_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         L.hmp3_batch_results.argtypes = [C.c_void_p] * 5
         L.hmp3_batch_download_all.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
@@ -128,11 +130,17 @@ class Batch:
     def sync(self):
         self._ck(lib().hmp3_batch_sync(self.h), "sync")
 
+    def sync_stream(self):
+        self._ck(lib().hmp3_batch_wait_uploads(self.h), "wait_uploads")
+
     def set_timing(self, on):
         lib().hmp3_batch_set_timing(self.h, 1 if on else 0)
 
     def launches(self):
         return lib().hmp3_batch_last_launches(self.h)
+
+    def last_run_ms(self):
+        return float(lib().hmp3_batch_last_run_ms(self.h))
 
     def results(self):
         nb, nf = np.zeros(self.n, np.int64), np.zeros(self.n, np.int32)

@@ -1,0 +1,71 @@
+// Device-side views of a batch and the host-callable kernel launchers.  The kernels live in two
+// translation units (kernels_analysis.cu: Phase A, kernels_rate.cu: the serial stage) so that each can
+// be compiled with the flags that suit it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hmp3 {
+
+struct EncTables;
+struct GranuleInfo;
+struct PsyRaw;
+struct SwitchState;
+struct RateState;
+struct FrameRec;
+
+// One stream of the batch, device view.
+struct StreamDev {
+    int cfg;             // index into the tables array
+    int nch;
+    long long pcm_off;   // offset (int16 elements) of this stream's interleaved PCM in the batch buffer
+    long long nsamples;  // per channel
+    int ngran;           // encode granules to run, including the flush allowance
+    int ngran_real;      // granules that belong to real encode calls (2 * calls)
+    long long out_off;   // byte offset of this stream's output region
+    long long out_cap;
+};
+
+// Chunk work buffers (device).  G = NG + 3 polyphase granules are kept per chunk: P[K0-3 .. K0+NG-1].
+struct ChunkBufs {
+    float *P;        // [n][NG+3][2][576]
+    int *E;          // [n][NG+3][2][9]   attack energies of P
+    GranuleInfo *gi; // [n][NG]
+    float *xr;       // [n][NG][2][576]
+    PsyRaw *raw;     // [n][NG][2]
+    int *ms_raw;     // [n][NG]
+    int NG;
+};
+
+// Per-stream placement of the serial stage's buffers (device view).
+struct StreamOut {
+    long long main_off;    // byte offset of this stream's main-data stream in the main buffer
+    long long frames_off;  // first FrameRec of this stream
+    int frames_cap;
+};
+
+struct StreamResult {
+    long long out_bytes;
+    int frames;
+    int finished;
+};
+
+// ---- launchers (all asynchronous on `stream`)
+void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
+                      cudaStream_t stream);
+void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+void launch_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState *sw, ChunkBufs cb, int K0, int n,
+                        cudaStream_t stream);
+void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream);
+void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);
+// per-stream totals, compact output offsets (out_off[n] = total) and frame assembly
+void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
+                   const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
+                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble);
+size_t sizeof_rate_state();
+size_t sizeof_frame_rec();
+
+}  // namespace hmp3

@@ -1,0 +1,26 @@
+// Phase A kernels + launchers (see kernels_analysis.cuh).
+#include "kernels_analysis.cuh"
+
+namespace hmp3 {
+static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
+
+void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
+                      cudaStream_t stream) {
+    const long long G = cb.NG + 3;
+    k_polyphase<<<blocks_for((long long)n * G * 2 * 18, 128), 128, 0, stream>>>(tabs, st, pcm, cb, K0, n);
+}
+void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
+    const long long G = cb.NG + 3;
+    k_attack<<<blocks_for((long long)n * G * 2 * 9, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
+}
+void launch_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState *sw, ChunkBufs cb, int K0, int n,
+                        cudaStream_t stream) {
+    k_switch_scan<<<blocks_for(n, 32), 32, 0, stream>>>(tabs, st, sw, cb, K0, n);
+}
+void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
+    k_hybrid<<<blocks_for((long long)n * cb.NG * 2 * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
+}
+void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
+    k_psy_stage1<<<blocks_for((long long)n * cb.NG * 3, 64), 64, 0, stream>>>(tabs, st, cb, K0, n);
+}
+}  // namespace hmp3

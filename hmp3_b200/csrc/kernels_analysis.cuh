@@ -3,31 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "analysis.h"
+#include "batch_types.h"
 
 namespace hmp3 {
-
-// One stream of the batch, device view.
-struct StreamDev {
-    int cfg;             // index into the tables array
-    int nch;
-    long long pcm_off;   // offset (int16 elements) of this stream's interleaved PCM in the batch buffer
-    long long nsamples;  // per channel
-    int ngran;           // encode granules to run, including the flush allowance
-    int ngran_real;      // granules that belong to real encode calls (2 * calls)
-    long long out_off;   // byte offset of this stream's output region
-    long long out_cap;
-};
-
-// Chunk work buffers (device).  G = NG + 3 polyphase granules are kept per chunk: P[K0-3 .. K0+NG-1].
-struct ChunkBufs {
-    float *P;        // [n][NG+3][2][576]
-    int *E;          // [n][NG+3][2][9]   attack energies of P
-    GranuleInfo *gi; // [n][NG]
-    float *xr;       // [n][NG][2][576]
-    PsyRaw *raw;     // [n][NG][2]
-    int *ms_raw;     // [n][NG]
-    int NG;
-};
 
 // ---- K1: polyphase analysis, one thread per (stream, polyphase granule, channel, time slot)
 __global__ void __launch_bounds__(128) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,

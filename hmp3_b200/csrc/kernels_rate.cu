@@ -1,0 +1,53 @@
+// Serial-stage kernels + launchers (see kernels_rate.cuh).  This translation unit is compiled for code
+// SIZE (the rate loop is tens of thousands of instructions of branchy scalar code executed once per
+// granule: instruction fetch, not arithmetic, bounds it).
+#include "kernels_rate.cuh"
+
+namespace hmp3 {
+static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
+
+// exclusive scan of the per-stream output sizes -> compact output offsets (single block)
+__global__ void k_out_offsets(const StreamResult *res, long long *out_off, int n) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024;
+    const int lo = t * per, hi = min(n, lo + per);
+    long long sum = 0;
+    for (int i = lo; i < hi; i++) sum += res[i].out_bytes;
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        long long v = (t >= d) ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - sum;
+    for (int i = lo; i < hi; i++) {
+        out_off[i] = run;
+        run += res[i].out_bytes;
+    }
+    if (t == 1023) out_off[n] = part[1023];
+}
+
+
+void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream) {
+    k_rate_init<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, rs, n);
+}
+void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream) {
+    k_rate<<<blocks_for((long long)n * 32, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
+        tabs, st, so, rs, cb, main_buf, frames, K0, n);
+}
+void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
+                   const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
+                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble) {
+    k_results<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, so, rs, frames, res, n);
+    k_out_offsets<<<1, 1024, 0, stream>>>(res, out_off, n);
+    if (before_assemble) cudaEventRecord(before_assemble, stream);
+    k_assemble<<<blocks_for((long long)n * max_frames * 32, 256), 256, 0, stream>>>(tabs, st, so, res, out_off, main_buf,
+                                                                                     frames, out, max_frames, n);
+}
+size_t sizeof_rate_state() { return sizeof(RateState); }
+size_t sizeof_frame_rec() { return sizeof(FrameRec); }
+}  // namespace hmp3

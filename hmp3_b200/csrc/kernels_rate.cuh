@@ -2,23 +2,15 @@
 // rate loop, scale-factor/Huffman packing, reservoir) and the parallel frame assembly.
 #pragma once
 #include <cuda_runtime.h>
-#include "kernels_analysis.cuh"
+#include "analysis.h"
+#include "batch_types.h"
 #include "rate_driver.h"
 
+#ifndef HMP3_RATE_MIN_BLOCKS
+#define HMP3_RATE_MIN_BLOCKS 8
+#endif
+
 namespace hmp3 {
-
-// Per-stream placement of the serial stage's buffers (device view).
-struct StreamOut {
-    long long main_off;    // byte offset of this stream's main-data stream in the main buffer
-    long long frames_off;  // first FrameRec of this stream
-    int frames_cap;
-};
-
-struct StreamResult {
-    long long out_bytes;
-    int frames;
-    int finished;
-};
 
 // ---- K6: state reset, one thread per stream
 __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int nstreams) {
@@ -30,7 +22,7 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
 // ---- K6: the serial stage over one chunk of granules, ONE WARP per stream: the scalar control flow of the
 // rate loop runs uniformly on all 32 lanes, the per-line / per-band loops are split across the lanes
 // (HMP3_COOP sections of rate_*.h).
-__global__ void __launch_bounds__(32 * kRateWarpsPerBlock)
+__global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
            unsigned char *main_buf, FrameRec *frames, int K0, int nstreams) {
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);

@@ -14,8 +14,8 @@
 #include "../../include/hmp3_b200.h"
 #include "../../include/hmp3_b200_debug.h"
 #include "enc_init.h"
-#include "kernels_analysis.cuh"
-#include "kernels_rate.cuh"
+#include "analysis.h"
+#include "batch_types.h"
 
 using namespace hmp3;
 
@@ -36,30 +36,6 @@ void set_err(const std::string &s) { g_err = s; }
 bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
-
-// exclusive scan of the per-stream output sizes -> compact output offsets (single block)
-__global__ void k_out_offsets(const StreamResult *res, long long *out_off, int n) {
-    __shared__ long long part[1024];
-    const int t = threadIdx.x;
-    const int per = (n + 1023) / 1024;
-    const int lo = t * per, hi = min(n, lo + per);
-    long long sum = 0;
-    for (int i = lo; i < hi; i++) sum += res[i].out_bytes;
-    part[t] = sum;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        long long v = (t >= d) ? part[t - d] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - sum;
-    for (int i = lo; i < hi; i++) {
-        out_off[i] = run;
-        run += res[i].out_bytes;
-    }
-    if (t == 1023) out_off[n] = part[1023];
-}
 
 enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_RATE, PH_ASSEMBLE, PH_COUNT };
 const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "rate_loop",
@@ -105,6 +81,8 @@ struct hmp3_batch {
     size_t ev_used = 0;
     float phase_ms[PH_COUNT] = {0};
     int phase_launches[PH_COUNT] = {0};
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;  // device time of the last run
+    float last_run_ms = 0;
     // pinned staging for the host-buffer entry
     unsigned char *h_stage = nullptr;
     long long h_stage_bytes = 0;
@@ -130,6 +108,8 @@ struct hmp3_batch {
         cudaFree(cb.raw);
         cudaFree(cb.ms_raw);
         for (auto e : ev) cudaEventDestroy(e);
+        if (ev_run0) cudaEventDestroy(ev_run0);
+        if (ev_run1) cudaEventDestroy(ev_run1);
         if (h_stage) cudaFreeHost(h_stage);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -238,9 +218,9 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     if (!analysis_only) {
         CK(cudaMalloc(&b->d_so, sizeof(StreamOut) * n));
         CK(cudaMemcpy(b->d_so, b->so_h.data(), sizeof(StreamOut) * n, cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&b->d_rs, sizeof(RateState) * n));
+        CK(cudaMalloc(&b->d_rs, sizeof_rate_state() * n));
         CK(cudaMalloc(&b->d_main, std::max<long long>(main_off, 16)));
-        CK(cudaMalloc(&b->d_frames, sizeof(FrameRec) * std::max<long long>(frames_off, 1)));
+        CK(cudaMalloc(&b->d_frames, sizeof_frame_rec() * std::max<long long>(frames_off, 1)));
         CK(cudaMalloc(&b->d_res, sizeof(StreamResult) * n));
         CK(cudaMalloc(&b->d_out_off, sizeof(long long) * (n + 1)));
         CK(cudaMalloc(&b->d_out, std::max<long long>(out_cap, 16)));
@@ -272,16 +252,15 @@ int launch_analysis(hmp3_batch *b, int K0) {
     const int n = b->n;
     const long long NG = b->NG, G = NG + 3;
     mark(b, PH_POLY);
-    k_polyphase<<<blocks_for((long long)n * G * 2 * 18, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_pcm, b->cb,
-                                                                                     K0, n);
+    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, b->cb, K0, n, b->stream);
     mark(b, PH_ATTACK);
-    k_attack<<<blocks_for((long long)n * G * 2 * 9, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    launch_attack(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
     mark(b, PH_SWITCH);
-    k_switch_scan<<<blocks_for(n, 32), 32, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_sw, b->cb, K0, n);
+    launch_switch_scan(b->d_tabs, b->d_st, b->d_sw, b->cb, K0, n, b->stream);
     mark(b, PH_HYBRID);
-    k_hybrid<<<blocks_for((long long)n * NG * 2 * 32, 128), 128, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    launch_hybrid(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
     mark(b, PH_PSY);
-    k_psy_stage1<<<blocks_for((long long)n * NG * 3, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->cb, K0, n);
+    launch_psy_stage1(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
     mark(b, -1);
     b->launches += 5;
     CK(cudaGetLastError());
@@ -294,27 +273,35 @@ int run_plan(hmp3_batch *b) {
     b->launches = 0;
     b->ev_used = 0;
     b->results_valid = false;
+    if (!b->ev_run0) {
+        CK(cudaEventCreate(&b->ev_run0));
+        CK(cudaEventCreate(&b->ev_run1));
+    }
+    CK(cudaEventRecord(b->ev_run0, b->stream));
     int r = plan_reset_state(b);
     if (r != HMP3_OK) return r;
-    k_rate_init<<<blocks_for(n, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_rs, n);
+    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, n, b->stream);
     b->launches++;
     for (int K0 = 0; K0 < b->max_gran; K0 += b->NG) {
         r = launch_analysis(b, K0);
         if (r != HMP3_OK) return r;
         mark(b, PH_RATE);
-        k_rate<<<blocks_for((long long)n * 32, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, b->stream>>>(
-            b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main, b->d_frames, K0, n);
+        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main, b->d_frames, K0, n, b->stream);
         mark(b, -1);
         b->launches++;
     }
-    k_results<<<blocks_for(n, 64), 64, 0, b->stream>>>(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, n);
-    k_out_offsets<<<1, 1024, 0, b->stream>>>(b->d_res, b->d_out_off, n);
-    mark(b, PH_ASSEMBLE);
-    k_assemble<<<blocks_for((long long)n * b->max_frames * 32, 256), 256, 0, b->stream>>>(
-        b->d_tabs, b->d_st, b->d_so, b->d_res, b->d_out_off, b->d_main, b->d_frames, b->d_out, b->max_frames, n);
+    cudaEvent_t ev_asm = nullptr;
+    if (b->timing) {
+        mark(b, -1);  // reserve an event that launch_finish records right before the assembly kernel
+        ev_asm = b->ev[b->ev_used - 1];
+        b->ev_phase[b->ev_used - 1] = PH_ASSEMBLE;
+    }
+    launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out,
+                  b->max_frames, n, b->stream, ev_asm);
     mark(b, -1);
     b->launches += 3;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(b->ev_run1, b->stream));
     CK(cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult) * n, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->out_off_h.data(), b->d_out_off, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost,
                        b->stream));
@@ -325,6 +312,7 @@ int sync_plan(hmp3_batch *b) {
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
     b->results_valid = true;
+    cudaEventElapsedTime(&b->last_run_ms, b->ev_run0, b->ev_run1);
     if (b->timing) {
         for (int p = 0; p < PH_COUNT; p++) {
             b->phase_ms[p] = 0;
@@ -451,6 +439,12 @@ int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samp
     return HMP3_OK;
 }
 
+int hmp3_batch_wait_uploads(hmp3_batch *b) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return HMP3_OK;
+}
+
 int hmp3_batch_set_timing(hmp3_batch *b, int on) {
     b->timing = on != 0;
     return HMP3_OK;
@@ -514,6 +508,7 @@ int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *t
 }
 
 int hmp3_batch_last_launches(const hmp3_batch *b) { return b->launches; }
+float hmp3_batch_last_run_ms(const hmp3_batch *b) { return b->last_run_ms; }
 
 int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap) {
     int k = 0;

@@ -125,6 +125,7 @@ int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i); /* int16 element offs
 uint8_t *hmp3_batch_device_out(hmp3_batch *b);          /* compact output: stream i at out_offsets[i]   */
 int64_t hmp3_batch_out_capacity(const hmp3_batch *b);
 int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples); /* async H2D      */
+int hmp3_batch_wait_uploads(hmp3_batch *b);             /* block until queued uploads have landed       */
 /* run all kernels on the plan's stream over whatever PCM is resident.  Synchronous unless `async` != 0
  * (then hmp3_batch_sync must be called before reading results). */
 int hmp3_batch_run(hmp3_batch *b, int async);
@@ -136,6 +137,8 @@ int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap);
 int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *total);
 /* number of kernel launches issued by the last hmp3_batch_run */
 int hmp3_batch_last_launches(const hmp3_batch *b);
+/* device time (CUDA events on the plan's stream, first kernel to last kernel) of the last completed run, ms */
+float hmp3_batch_last_run_ms(const hmp3_batch *b);
 /* per-kernel device time (CUDA events on the plan's stream) of the last synchronous run made after
  * hmp3_batch_set_timing(b, 1): fills up to `cap` entries, returns the count; names[i] are static. */
 int hmp3_batch_set_timing(hmp3_batch *b, int on);
