@@ -280,7 +280,7 @@ def run_gpu(args, rank, local_rank, world):
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        gran_per_launch = 32                                     # chunk length of the plan (granules)
+        gran_per_launch = plan.chunk_granules()                  # granules per stream per k_rate launch
         bytes_per_launch = K6_BYTES_PER_GC * B * gran_per_launch * NCH
         avg_launch_s = rate_ms / max(rate_launches, 1) / 1e3
         achieved = bytes_per_launch / avg_launch_s / 1e9

@@ -139,6 +139,11 @@ class Batch:
     def launches(self):
         return lib().hmp3_batch_last_launches(self.h)
 
+    def chunk_granules(self):
+        f = lib().hmp3_batch_chunk_granules
+        f.argtypes = [C.c_void_p]
+        return int(f(self.h))
+
     def last_run_ms(self):
         return float(lib().hmp3_batch_last_run_ms(self.h))
 

@@ -69,8 +69,12 @@ struct hmp3_batch {
     long long *d_out_off = nullptr;
     unsigned char *d_out = nullptr;
     long long out_cap = 0;
-    ChunkBufs cb{};
-    cudaStream_t stream = nullptr;
+    ChunkBufs cb2[2]{};                 // double-buffered chunk work areas: Phase A of chunk c+1 overlaps the serial stage of c
+    ChunkBufs &cb = cb2[0];
+    cudaStream_t stream = nullptr;      // serial stage, finish, copies
+    cudaStream_t stream_a = nullptr;    // Phase A
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_start = nullptr;
+    int nbuf = 2;
     int launches = 0;
     bool results_valid = false;
     std::vector<int> status;
@@ -101,12 +105,18 @@ struct hmp3_batch {
         cudaFree(d_res);
         cudaFree(d_out_off);
         cudaFree(d_out);
-        cudaFree(cb.P);
-        cudaFree(cb.E);
-        cudaFree(cb.gi);
-        cudaFree(cb.xr);
-        cudaFree(cb.raw);
-        cudaFree(cb.ms_raw);
+        for (int k = 0; k < 2; k++) {
+            cudaFree(cb2[k].P);
+            cudaFree(cb2[k].E);
+            cudaFree(cb2[k].gi);
+            cudaFree(cb2[k].xr);
+            cudaFree(cb2[k].raw);
+            cudaFree(cb2[k].ms_raw);
+            if (ev_a[k]) cudaEventDestroy(ev_a[k]);
+            if (ev_r[k]) cudaEventDestroy(ev_r[k]);
+        }
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (stream_a) cudaStreamDestroy(stream_a);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_run0) cudaEventDestroy(ev_run0);
         if (ev_run1) cudaEventDestroy(ev_run1);
@@ -208,13 +218,21 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMemcpy(b->d_sw_init, sw.data(), sizeof(SwitchState) * n, cudaMemcpyHostToDevice));
     }
     const long long NG = b->NG, G = NG + 3;
-    b->cb.NG = (int)NG;
-    CK(cudaMalloc(&b->cb.P, sizeof(float) * n * G * 2 * 576));
-    CK(cudaMalloc(&b->cb.E, sizeof(int) * n * G * 2 * 9));
-    CK(cudaMalloc(&b->cb.gi, sizeof(GranuleInfo) * n * NG));
-    CK(cudaMalloc(&b->cb.xr, sizeof(float) * n * NG * 2 * 576));
-    CK(cudaMalloc(&b->cb.raw, sizeof(PsyRaw) * n * NG * 2));
-    CK(cudaMalloc(&b->cb.ms_raw, sizeof(int) * n * NG));
+    b->nbuf = analysis_only ? 1 : 2;
+    CK(cudaStreamCreate(&b->stream_a));
+    CK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < b->nbuf; k++) {
+        ChunkBufs &cb = b->cb2[k];
+        cb.NG = (int)NG;
+        CK(cudaMalloc(&cb.P, sizeof(float) * n * G * 2 * 576));
+        CK(cudaMalloc(&cb.E, sizeof(int) * n * G * 2 * 9));
+        CK(cudaMalloc(&cb.gi, sizeof(GranuleInfo) * n * NG));
+        CK(cudaMalloc(&cb.xr, sizeof(float) * n * NG * 2 * 576));
+        CK(cudaMalloc(&cb.raw, sizeof(PsyRaw) * n * NG * 2));
+        CK(cudaMalloc(&cb.ms_raw, sizeof(int) * n * NG));
+        CK(cudaEventCreateWithFlags(&b->ev_a[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_r[k], cudaEventDisableTiming));
+    }
     if (!analysis_only) {
         CK(cudaMalloc(&b->d_so, sizeof(StreamOut) * n));
         CK(cudaMemcpy(b->d_so, b->so_h.data(), sizeof(StreamOut) * n, cudaMemcpyHostToDevice));
@@ -235,7 +253,9 @@ int plan_reset_state(hmp3_batch *b) {
     return HMP3_OK;
 }
 
-void mark(hmp3_batch *b, int phase) {  // record an event pair boundary when timing is on
+// Per-kernel timing (when enabled): events are recorded in (begin, end) pairs on the launching stream;
+// mark(phase >= 0) opens a pair, mark(-1) closes it.
+void mark(hmp3_batch *b, int phase, cudaStream_t st) {
     if (!b->timing) return;
     if (b->ev_used == b->ev.size()) {
         cudaEvent_t e;
@@ -244,24 +264,28 @@ void mark(hmp3_batch *b, int phase) {  // record an event pair boundary when tim
         b->ev_phase.push_back(-1);
     }
     b->ev_phase[b->ev_used] = phase;
-    cudaEventRecord(b->ev[b->ev_used++], b->stream);
+    cudaEventRecord(b->ev[b->ev_used++], st);
 }
 
-// Phase A for the chunk starting at encode granule K0.
-int launch_analysis(hmp3_batch *b, int K0) {
+// Phase A for the chunk starting at encode granule K0, into chunk buffer set `k`, on stream `st`.
+int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st) {
     const int n = b->n;
-    const long long NG = b->NG, G = NG + 3;
-    mark(b, PH_POLY);
-    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, b->cb, K0, n, b->stream);
-    mark(b, PH_ATTACK);
-    launch_attack(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
-    mark(b, PH_SWITCH);
-    launch_switch_scan(b->d_tabs, b->d_st, b->d_sw, b->cb, K0, n, b->stream);
-    mark(b, PH_HYBRID);
-    launch_hybrid(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
-    mark(b, PH_PSY);
-    launch_psy_stage1(b->d_tabs, b->d_st, b->cb, K0, n, b->stream);
-    mark(b, -1);
+    const ChunkBufs &cb = b->cb2[k];
+    mark(b, PH_POLY, st);
+    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, cb, K0, n, st);
+    mark(b, -1, st);
+    mark(b, PH_ATTACK, st);
+    launch_attack(b->d_tabs, b->d_st, cb, K0, n, st);
+    mark(b, -1, st);
+    mark(b, PH_SWITCH, st);
+    launch_switch_scan(b->d_tabs, b->d_st, b->d_sw, cb, K0, n, st);
+    mark(b, -1, st);
+    mark(b, PH_HYBRID, st);
+    launch_hybrid(b->d_tabs, b->d_st, cb, K0, n, st);
+    mark(b, -1, st);
+    mark(b, PH_PSY, st);
+    launch_psy_stage1(b->d_tabs, b->d_st, cb, K0, n, st);
+    mark(b, -1, st);
     b->launches += 5;
     CK(cudaGetLastError());
     return HMP3_OK;
@@ -282,23 +306,32 @@ int run_plan(hmp3_batch *b) {
     if (r != HMP3_OK) return r;
     launch_rate_init(b->d_tabs, b->d_st, b->d_rs, n, b->stream);
     b->launches++;
-    for (int K0 = 0; K0 < b->max_gran; K0 += b->NG) {
-        r = launch_analysis(b, K0);
+    // Phase A runs on its own stream one chunk ahead of the serial stage (two chunk buffer sets):
+    //   analysis(c) -> ev_a[c&1] -> serial(c) -> ev_r[c&1] -> analysis(c+2) may reuse the buffers
+    CK(cudaEventRecord(b->ev_start, b->stream));
+    CK(cudaStreamWaitEvent(b->stream_a, b->ev_start, 0));
+    int c = 0;
+    for (int K0 = 0; K0 < b->max_gran; K0 += b->NG, c++) {
+        const int k = c & 1;
+        if (c >= 2) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
+        r = launch_analysis(b, K0, k, b->stream_a);
         if (r != HMP3_OK) return r;
-        mark(b, PH_RATE);
-        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb, b->d_main, b->d_frames, K0, n, b->stream);
-        mark(b, -1);
+        CK(cudaEventRecord(b->ev_a[k], b->stream_a));
+        CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
+        mark(b, PH_RATE, b->stream);
+        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[k], b->d_main, b->d_frames, K0, n, b->stream);
+        mark(b, -1, b->stream);
+        CK(cudaEventRecord(b->ev_r[k], b->stream));
         b->launches++;
     }
     cudaEvent_t ev_asm = nullptr;
     if (b->timing) {
-        mark(b, -1);  // reserve an event that launch_finish records right before the assembly kernel
+        mark(b, PH_ASSEMBLE, b->stream);  // re-recorded by launch_finish right before the assembly kernel
         ev_asm = b->ev[b->ev_used - 1];
-        b->ev_phase[b->ev_used - 1] = PH_ASSEMBLE;
     }
     launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out,
                   b->max_frames, n, b->stream, ev_asm);
-    mark(b, -1);
+    mark(b, -1, b->stream);
     b->launches += 3;
     CK(cudaGetLastError());
     CK(cudaEventRecord(b->ev_run1, b->stream));
@@ -318,7 +351,7 @@ int sync_plan(hmp3_batch *b) {
             b->phase_ms[p] = 0;
             b->phase_launches[p] = 0;
         }
-        for (size_t i = 0; i + 1 < b->ev_used; i++) {
+        for (size_t i = 0; i + 1 < b->ev_used; i += 2) {  // (begin, end) pairs
             const int p = b->ev_phase[i];
             if (p < 0) continue;
             float ms = 0;
@@ -413,7 +446,10 @@ hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_s
     }
     hmp3_batch *b = new hmp3_batch;
     std::vector<long long> ns(num_samples, num_samples + n);
-    int r = plan_create(b, controls, ns.data(), n, device, 32, false);
+    int ng = getenv("HMP3_CHUNK_GRANULES") ? atoi(getenv("HMP3_CHUNK_GRANULES")) : 64;
+    if (ng < 2) ng = 2;
+    ng &= ~1;
+    int r = plan_create(b, controls, ns.data(), n, device, ng, false);
     if (r != HMP3_OK) {
         delete b;
         return nullptr;
@@ -508,6 +544,7 @@ int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *t
 }
 
 int hmp3_batch_last_launches(const hmp3_batch *b) { return b->launches; }
+int hmp3_batch_chunk_granules(const hmp3_batch *b) { return b->NG; }
 float hmp3_batch_last_run_ms(const hmp3_batch *b) { return b->last_run_ms; }
 
 int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap) {
@@ -617,7 +654,7 @@ int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long ns
     std::vector<GranuleInfo> GI(NG);
     std::vector<PsyRaw> RW((size_t)NG * 2);
     for (int K0 = 0; K0 < ngran; K0 += NG) {
-        r = launch_analysis(&b, K0);
+        r = launch_analysis(&b, K0, 0, b.stream);
         if (r != HMP3_OK) return r;
         CK(cudaStreamSynchronize(b.stream));
         CK(cudaMemcpy(P.data(), b.cb.P, P.size() * 4, cudaMemcpyDeviceToHost));

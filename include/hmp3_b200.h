@@ -137,6 +137,8 @@ int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap);
 int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *total);
 /* number of kernel launches issued by the last hmp3_batch_run */
 int hmp3_batch_last_launches(const hmp3_batch *b);
+/* encode granules each stream advances per launch of the serial-stage kernel (the chunk length) */
+int hmp3_batch_chunk_granules(const hmp3_batch *b);
 /* device time (CUDA events on the plan's stream, first kernel to last kernel) of the last completed run, ms */
 float hmp3_batch_last_run_ms(const hmp3_batch *b);
 /* per-kernel device time (CUDA events on the plan's stream) of the last synchronous run made after
