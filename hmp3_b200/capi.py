@@ -196,3 +196,76 @@ def encode_batch(controls, pcms, device=0):
     finally:
         b.close()
     return outs
+
+
+class Encoder:
+    """CMp3Enc-style handle (hmp3_encoder_*): init, then one call per 1152 samples per channel."""
+
+    def __init__(self, device=0, capacity_seconds=None):
+        L = lib()
+        L.hmp3_encoder_new.restype = C.c_void_p
+        L.hmp3_encoder_new.argtypes = [C.c_int]
+        L.hmp3_encoder_delete.argtypes = [C.c_void_p]
+        L.hmp3_encoder_set_capacity_seconds.argtypes = [C.c_void_p, C.c_int]
+        L.hmp3_MP3_audio_encode_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.hmp3_L3_audio_encode_init.argtypes = [C.c_void_p, C.c_void_p]
+        L.hmp3_MP3_audio_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmp3_MP3_audio_encode.restype = C.c_uint64      # struct {int in_bytes; int out_bytes;} by value
+        L.hmp3_L3_audio_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hmp3_L3_audio_encode.restype = C.c_uint64
+        L.hmp3_L3_audio_encode_get_frames.argtypes = [C.c_void_p]
+        L.hmp3_L3_audio_encode_get_frames.restype = C.c_uint
+        L.hmp3_L3_audio_encode_get_bitrate_float.argtypes = [C.c_void_p]
+        L.hmp3_L3_audio_encode_get_bitrate_float.restype = C.c_float
+        L.hmp3_L3_audio_encode_info_string.argtypes = [C.c_void_p, C.c_char_p]
+        L.hmp3_L3_audio_encode_info_ec.argtypes = [C.c_void_p, C.c_void_p]
+        self.h = L.hmp3_encoder_new(device)
+        if not self.h:
+            raise Hmp3Error("hmp3_encoder_new failed: " + last_error())
+        if capacity_seconds:
+            L.hmp3_encoder_set_capacity_seconds(self.h, int(capacity_seconds))
+        self.out = np.zeros(1 << 17, np.uint8)
+
+    def close(self):
+        if self.h:
+            lib().hmp3_encoder_delete(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def init_mp3(self, ec, source_bits=16, source_is_float=0, mpeg_select=0, mono_convert=0):
+        return lib().hmp3_MP3_audio_encode_init(self.h, vp(ec), source_bits, source_is_float, mpeg_select, mono_convert)
+
+    def init_l3(self, ec):
+        return lib().hmp3_L3_audio_encode_init(self.h, vp(ec))
+
+    @staticmethod
+    def _io(v):
+        return int(v & 0xFFFFFFFF), int(v >> 32)
+
+    def encode_mp3(self, pcm_i16):
+        a = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+        i, o = self._io(lib().hmp3_MP3_audio_encode(self.h, vp(a), vp(self.out)))
+        return i, self.out[:o].copy()
+
+    def encode_l3(self, pcm_f32):
+        a = np.ascontiguousarray(pcm_f32, dtype=np.float32)
+        i, o = self._io(lib().hmp3_L3_audio_encode(self.h, vp(a), vp(self.out)))
+        return i, self.out[:o].copy()
+
+    def frames(self):
+        return int(lib().hmp3_L3_audio_encode_get_frames(self.h))
+
+    def bitrate(self):
+        return float(lib().hmp3_L3_audio_encode_get_bitrate_float(self.h))
+
+    def info_string(self):
+        buf = C.create_string_buffer(256)
+        lib().hmp3_L3_audio_encode_info_string(self.h, buf)
+        return buf.value.decode()
+
+    def info_ec(self):
+        a = np.zeros(len(EC_FIELDS), np.int32)
+        lib().hmp3_L3_audio_encode_info_ec(self.h, vp(a))
+        return dict(zip(EC_FIELDS, a.tolist()))

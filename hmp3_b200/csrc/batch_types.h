@@ -64,7 +64,8 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
 // per-stream totals, compact output offsets (out_off[n] = total) and frame assembly
 void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
-                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble);
+                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble,
+                   int frame_lo = 0, long long out_base = 0);
 size_t sizeof_rate_state();
 size_t sizeof_frame_rec();
 

@@ -369,6 +369,53 @@ void control_defaults(hmp3_control *ec) {  // test/tomp3.cpp:357-387
 // L3_audio_encode_init (mp3enc.cpp:220-870) + BitAlloInit (bitallo3.cpp:288-480, bitallos.cpp:128-198).
 // Returns bytes_in (nchan*4*1152) or 0 on rejection; *unsupported is set when the control selects
 // the intensity-stereo / dual-channel allocator that is outside the built path.
+// One command-line option with the reference CLI's meaning (test/tomp3.cpp:390-558).  Options that do not
+// touch E_CONTROL (-D -EC -X -IL -A -P -Z, file names) are accepted and ignored.  Returns 0, or -1 if the
+// option is not one the reference knows (the reference prints its usage for those).
+int control_apply_option(hmp3_control *ec, const char *opt) {
+    if (!opt || opt[0] != '-') return -1;
+    auto lc = [](char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; };
+    const char c1 = lc(opt[1]), c2 = opt[1] ? lc(opt[2]) : 0, c3 = (opt[1] && opt[2]) ? lc(opt[3]) : 0;
+    switch (c1) {
+        case 'e': return 0;                                    // -EC: display only
+        case 'h':
+            if (c2 == 'f') { ec->hf_flag = 1 | atoi(opt + 3); return 0; }
+            return -1;                                         // -h: usage
+        case 'q': ec->quick = atoi(opt + 2); return 0;
+        case 'd': return 0;
+        case 'u': ec->cpu_select = atoi(opt + 2); return 0;
+        case 'x': return 0;                                    // Xing/Info header: host post-pass, not this path
+        case 'b': ec->bitrate = atoi(opt + 2); break;
+        case 'c': ec->cr_bit = atoi(opt + 2); return 0;
+        case 'o': ec->original = atoi(opt + 2); return 0;
+        case 'p': return 0;
+        case 'm': ec->mode = atoi(opt + 2); return 0;
+        case 'n': ec->nsbstereo = atoi(opt + 2); return 0;
+        case 's':
+            if (c2 == 'b') { if (c3 == 't') ec->short_block_threshold = atoi(opt + 4); }
+            else ec->filter_select = atoi(opt + 2);
+            return 0;
+        case 'f': ec->freq_limit = atoi(opt + 2); return 0;
+        case 'z': return 0;
+        case 't':
+            if (c2 == 'x') ec->test1 = atoi(opt + 3);
+            else ec->vbr_delta_mnr = atoi(opt + 2);
+            return 0;
+        case 'i':
+            if (c2 != 'l') ec->chan_add_f0 = atoi(opt + 2);
+            return 0;
+        case 'j': ec->chan_add_f1 = atoi(opt + 2); return 0;
+        case 'v': ec->vbr_flag = 1; ec->vbr_mnr = atoi(opt + 2); break;
+        case 'l': ec->vbr_br_limit = atoi(opt + 2); return 0;
+        case 'a': return 0;                                    // mpeg_select is an init argument, not E_CONTROL
+        case 'w': return 0;                                    // mnr_adjust file: parsed but unused by the live path
+        default: return -1;
+    }
+    // the CLI derives vbr_flag from the final bitrate after all options (test/tomp3.cpp:563-566)
+    ec->vbr_flag = (ec->bitrate < 0) ? 1 : 0;
+    return 0;
+}
+
 int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
     EncTables &T = *Tp;
     memset(&T, 0, sizeof(T));
@@ -816,6 +863,19 @@ int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
     C.vbr_mnr = ec.vbr_mnr;
     C.vbr_delta_mnr = ec.vbr_delta_mnr;
     C.hf_flag_user = ec.hf_flag;
+    {
+        hmp3_control g = ec;
+        g.mode = C.h_mode;
+        g.bitrate = C.totbitrate;
+        if (C.h_mode != 3) g.bitrate /= 2;
+        g.samprate = samprate;
+        g.nsbstereo = C.info_nsbstereo;
+        g.freq_limit = C.info_freq_limit;
+        g.nsb_limit = nsb_limit;
+        g.layer = 3;
+        static_assert(sizeof(hmp3_control) == sizeof(C.info_ec), "E_CONTROL image size");
+        memcpy(C.info_ec, &g, sizeof(g));
+    }
     return C.nchan * 4 * 1152;
 }
 

@@ -5,6 +5,7 @@
 
 namespace hmp3 {
 void control_defaults(hmp3_control *ec);
+int control_apply_option(hmp3_control *ec, const char *opt);
 // Returns bytes_in (nchan*4*1152) or 0 when the control block is rejected.
 int build_tables(const hmp3_control *ec, EncTables *T, int *unsupported);
 }  // namespace hmp3

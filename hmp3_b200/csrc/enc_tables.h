@@ -57,6 +57,7 @@ struct EncConfig {
     int granules_per_frame;  // 2 MPEG-1, 1 MPEG-2
     // info (ec_global, mp3enc.cpp:841-866)
     int info_freq_limit, info_nsbstereo, vbr_mnr, vbr_delta_mnr, hf_flag_user;
+    int info_ec[45];  // image of the effective E_CONTROL (ec_global)
 };
 
 struct EncTables {

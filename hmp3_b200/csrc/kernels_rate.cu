@@ -41,12 +41,14 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
 }
 void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
-                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble) {
+                   unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble,
+                   int frame_lo, long long out_base) {
     k_results<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, so, rs, frames, res, n);
     k_out_offsets<<<1, 1024, 0, stream>>>(res, out_off, n);
     if (before_assemble) cudaEventRecord(before_assemble, stream);
     k_assemble<<<blocks_for((long long)n * max_frames * 32, 256), 256, 0, stream>>>(tabs, st, so, res, out_off, main_buf,
-                                                                                     frames, out, max_frames, n);
+                                                                                     frames, out, max_frames, n, frame_lo,
+                                                                                     out_base);
 }
 size_t sizeof_rate_state() { return sizeof(RateState); }
 size_t sizeof_frame_rec() { return sizeof(FrameRec); }

@@ -56,14 +56,16 @@ __global__ void k_results(const EncTables *tabs, const StreamDev *st, const Stre
 __global__ void __launch_bounds__(256) k_assemble(const EncTables *tabs, const StreamDev *st, const StreamOut *so,
                                                   const StreamResult *res, const long long *out_off,
                                                   const unsigned char *main_buf, const FrameRec *frames,
-                                                  unsigned char *out, int max_frames, int nstreams) {
+                                                  unsigned char *out, int max_frames, int nstreams, int frame_lo,
+                                                  long long out_base) {
+    // frames [frame_lo, res.frames) of every stream; byte `out_base` of a stream's output lands at out_off[s]
     long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int s = (int)(wid / max_frames), f = (int)(wid % max_frames);
+    const int s = (int)(wid / max_frames), f = frame_lo + (int)(wid % max_frames);
     if (s >= nstreams || f >= res[s].frames) return;
     const int side = tabs[st[s].cfg].cfg.side_bytes;
     const FrameRec *fr = frames + so[s].frames_off + f;
-    unsigned char *dst = out + out_off[s] + fr->out_off;
+    unsigned char *dst = out + out_off[s] + ((long long)fr->out_off - out_base);
     if (lane < 4) dst[lane] = fr->head[lane];
     if (lane < side) dst[4 + lane] = fr->side[lane];
     const unsigned char *src = main_buf + so[s].main_off + fr->main_start;

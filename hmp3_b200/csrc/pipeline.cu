@@ -137,7 +137,7 @@ int max_main_frame_bytes(const EncConfig &C) {
 }
 
 int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *nsamples, int n, int device,
-                int chunk_granules, bool analysis_only) {
+                int chunk_granules, bool analysis_only, bool streaming = false) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
         set_err("no usable CUDA device (this library has no CPU path)");
@@ -177,6 +177,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         long long calls = calls_for(nsamples[i]);
         sd.ngran_real = cfg < 0 ? 0 : (int)(2 * calls);
         sd.ngran = cfg < 0 ? 0 : (int)(2 * (calls + kFlushCalls));
+        if (streaming) sd.ngran_real = sd.ngran;  // a handle never decides by itself that the stream has ended
         pcm_off += nsamples[i] * (sd.nch ? sd.nch : 1);
         pcm_off = (pcm_off + 7) & ~7LL;
         max_gran = std::max(max_gran, sd.ngran);
@@ -446,7 +447,7 @@ hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_s
     }
     hmp3_batch *b = new hmp3_batch;
     std::vector<long long> ns(num_samples, num_samples + n);
-    int ng = getenv("HMP3_CHUNK_GRANULES") ? atoi(getenv("HMP3_CHUNK_GRANULES")) : 64;
+    int ng = getenv("HMP3_CHUNK_GRANULES") ? atoi(getenv("HMP3_CHUNK_GRANULES")) : 128;
     if (ng < 2) ng = 2;
     ng &= ~1;
     int r = plan_create(b, controls, ns.data(), n, device, ng, false);
@@ -633,6 +634,215 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
     hmp3_batch_destroy(b);
     return r;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// (2) CMp3Enc mirrors: one stream per handle, two granules per call through the same kernels.
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct hmp3_encoder {
+    int device = 0;
+    hmp3_batch *b = nullptr;
+    int nch = 0, calls = 0, max_calls = 0;
+    int frames_out = 0;
+    long long bytes_out = 0;
+    double ave_bytes = 0;
+    bool float_in = false;
+    int capacity_seconds = 1200;
+    std::vector<int16_t> stage;
+    ~hmp3_encoder() { delete b; }
+};
+
+namespace {
+int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
+    delete e->b;
+    e->b = nullptr;
+    e->calls = e->frames_out = 0;
+    e->bytes_out = 0;
+    e->ave_bytes = 0;
+    e->float_in = float_in;
+    EncTables *T = new EncTables;
+    int unsup = 0;
+    const int bytes_in = build_tables(ec, T, &unsup);
+    const int samprate = T->cfg.samprate;
+    delete T;
+    if (!bytes_in) {
+        set_err(unsup ? "configuration outside the built path" : "control block rejected");
+        return 0;
+    }
+    e->b = new hmp3_batch;
+    long long ns = (long long)e->capacity_seconds * samprate;
+    ns -= ns % 1152;
+    if (plan_create(e->b, ec, &ns, 1, e->device, 2, false, true) != HMP3_OK) {
+        delete e->b;
+        e->b = nullptr;
+        return 0;
+    }
+    hmp3_batch *b = e->b;
+    e->nch = b->st_h[0].nch;
+    e->max_calls = b->st_h[0].ngran / 2;
+    e->stage.assign((size_t)1152 * e->nch, 0);
+    cudaSetDevice(e->device);
+    if (plan_reset_state(b) != HMP3_OK) return 0;
+    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, 1, b->stream);
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+        set_err("device initialisation failed");
+        return 0;
+    }
+    return bytes_in;
+}
+
+// one encode call: 1152 samples per channel in, whatever frames became complete out
+hmp3_in_out encoder_step(hmp3_encoder *e, const int16_t *pcm, unsigned char *bs_out) {
+    hmp3_in_out io = {0, 0};
+    hmp3_batch *b = e->b;
+    if (!b) {
+        set_err("encoder not initialised");
+        return io;
+    }
+    if (e->calls >= e->max_calls) {
+        set_err("stream longer than the handle's capacity (hmp3_encoder_set_capacity_seconds)");
+        return io;
+    }
+    cudaSetDevice(e->device);
+    const int K0 = 2 * e->calls;
+    const size_t nb_in = sizeof(int16_t) * 1152 * e->nch;
+    if (cudaMemcpyAsync(b->d_pcm + (size_t)e->calls * 1152 * e->nch, pcm, nb_in, cudaMemcpyHostToDevice, b->stream) !=
+        cudaSuccess) {
+        set_err("H2D copy failed");
+        return io;
+    }
+    if (launch_analysis(b, K0, 0, b->stream) != HMP3_OK) return io;
+    launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
+    launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out, 48, 1,
+                  b->stream, nullptr, e->frames_out, e->bytes_out);
+    cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult), cudaMemcpyDeviceToHost, b->stream);
+    if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+        set_err(std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
+        return io;
+    }
+    const StreamResult &r = b->res_h[0];
+    const long long nb = r.out_bytes - e->bytes_out;
+    if (nb > 0) cudaMemcpy(bs_out, b->d_out, nb, cudaMemcpyDeviceToHost);
+    e->frames_out = r.frames;
+    e->bytes_out = r.out_bytes;
+    e->ave_bytes += ((256.0 * nb) - e->ave_bytes) / 64.0;  // tracks CMp3Enc::ave_tot_bytes_out (mp3enc.cpp:2315-2317)
+    e->calls++;
+    io.in_bytes = (int)nb_in;
+    io.out_bytes = (int)nb;
+    return io;
+}
+}  // namespace
+
+extern "C" {
+
+hmp3_encoder *hmp3_encoder_new(int device) {
+    if (hmp3_device_count() <= device) {
+        set_err("no usable CUDA device (this library has no CPU path)");
+        return nullptr;
+    }
+    hmp3_encoder *e = new hmp3_encoder;
+    e->device = device;
+    return e;
+}
+void hmp3_encoder_delete(hmp3_encoder *e) { delete e; }
+int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds) {
+    if (!e || seconds < 1) return HMP3_ERR_ARG;
+    e->capacity_seconds = seconds;
+    return HMP3_OK;
+}
+
+int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
+                               int mpeg_select, int mono_convert) {
+    if (!e || !ec) return 0;
+    // only what the hot path covers: 16-bit integer PCM at a native MPEG rate, no down-mix, no resampling
+    const int rates[6] = {16000, 22050, 24000, 32000, 44100, 48000};
+    bool native = false;
+    for (int r : rates) native |= (ec->samprate == r);
+    if (source_bits != 16 || source_is_float || !native || (mono_convert && ec->mode != 3) ||
+        (mpeg_select > 2 && mpeg_select != ec->samprate) || (mpeg_select == 1 && ec->samprate < 32000) ||
+        (mpeg_select == 2 && ec->samprate > 24000)) {
+        set_err("MP3_audio_encode_init: only 16-bit PCM at a native MPEG rate without conversion is in scope");
+        return 0;
+    }
+    const int bytes_in = encoder_init(e, ec, false);
+    return bytes_in ? bytes_in / 2 : 0;  // 2 bytes per sample instead of 4
+}
+hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
+    return encoder_step(e, (const int16_t *)pcm, bs_out);
+}
+int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec) {
+    if (!e || !ec) return 0;
+    return encoder_init(e, ec, true);
+}
+hmp3_in_out hmp3_L3_audio_encode(hmp3_encoder *e, const float *pcm, unsigned char *bs_out) {
+    hmp3_in_out io = {0, 0};
+    if (!e || !e->b) {
+        set_err("encoder not initialised");
+        return io;
+    }
+    // the kernels take 16-bit PCM: the float entry accepts exactly the values the reference's own front end
+    // produces from 16-bit input (integers in [-32768, 32767], srcc.cpp:804-834)
+    const int n = 1152 * e->nch;
+    for (int i = 0; i < n; i++) {
+        const float v = pcm[i];
+        const int q = (int)v;
+        if ((float)q != v || q < -32768 || q > 32767) {
+            set_err("L3_audio_encode: sample is not a 16-bit integer value");
+            return io;
+        }
+        e->stage[i] = (int16_t)q;
+    }
+    io = encoder_step(e, e->stage.data(), bs_out);
+    if (io.in_bytes) io.in_bytes = n * 4;
+    return io;
+}
+void hmp3_L3_audio_encode_info_ec(hmp3_encoder *e, hmp3_control *ec) {
+    if (e && e->b && ec) memcpy(ec, e->b->tabs_h[0].cfg.info_ec, sizeof(*ec));
+}
+void hmp3_L3_audio_encode_info_head(hmp3_encoder *e, hmp3_mpeg_head *h) {
+    if (!e || !e->b || !h) return;
+    const EncConfig &C = e->b->tabs_h[0].cfg;
+    memset(h, 0, sizeof(*h));
+    h->sync = 1;  // setup_header (setup.c:191-289)
+    h->id = C.h_id;
+    h->option = 1;
+    h->prot = 1;
+    h->br_index = C.br_index;
+    h->sr_index = C.sr_index;
+    h->mode = C.h_mode;
+    h->mode_ext = (C.head[3] >> 4) & 3;
+    h->cr = (C.head[3] >> 3) & 1;
+    h->original = (C.head[3] >> 2) & 1;
+}
+void hmp3_L3_audio_encode_info_string(hmp3_encoder *e, char *s) {  // mpeg_info_string (setup.c:336-366)
+    if (!e || !e->b || !s) return;
+    const EncConfig &C = e->b->tabs_h[0].cfg;
+    const char *mode_msg[] = {"mode 0 STEREO", "mode 1 STEREO", "DUAL", "MONO"};
+    s += sprintf(s, "Layer %s ", "III");
+    s += sprintf(s, "  %s ", mode_msg[C.h_mode & 3]);
+    if (C.h_mode == 1 && C.info_nsbstereo < 32) s += sprintf(s, " IS-%d ", C.info_nsbstereo);
+    s += sprintf(s, "  %ldHz ", (long)C.samprate);
+    if (!C.vbr_flag) s += sprintf(s, "  %dkbps ", C.totbitrate);
+    else {
+        s += sprintf(s, " VBR-%d", C.vbr_mnr);
+        if (C.vbr_delta_mnr) s += sprintf(s, "(%d)", C.vbr_delta_mnr);
+    }
+    if (C.hf_flag) {
+        s += sprintf(s, "  hf");
+        if (C.hf_flag & 2) s += sprintf(s, "2");
+    }
+}
+unsigned int hmp3_L3_audio_encode_get_frames(hmp3_encoder *e) { return e ? (unsigned)e->frames_out : 0; }
+float hmp3_L3_audio_encode_get_bitrate_float(hmp3_encoder *e) {  // mp3enc.cpp:3450-3463
+    if (!e || !e->b || e->frames_out <= 0) return 0.0f;
+    const EncConfig &C = e->b->tabs_h[0].cfg;
+    const float samples = (C.h_id == 1) ? 1152.0f : 576.0f;
+    return ((0.001f * 8.0f) * e->bytes_out * C.samprate / (samples * e->frames_out));
+}
+int hmp3_L3_audio_encode_get_bitrate(hmp3_encoder *e) { return (int)(hmp3_L3_audio_encode_get_bitrate_float(e) + 0.5f); }
+int hmp3_control_apply_option(hmp3_control *ec, const char *opt) { return control_apply_option(ec, opt); }
 
 // Debug / parity entry: Phase A of ONE stream on the device, stage outputs copied back to the host.
 // Same argument meaning as the host simulator's sim_analysis (tests/hostsim/hostsim.cpp).

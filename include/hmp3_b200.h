@@ -153,6 +153,8 @@ int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int 
 typedef struct hmp3_encoder hmp3_encoder;
 hmp3_encoder *hmp3_encoder_new(int device);
 void hmp3_encoder_delete(hmp3_encoder *e);
+/* A handle reserves device buffers for a bounded stream length at init (default 1200 s); call before init. */
+int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds);
 
 /* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns the bytes the caller must
  * supply per call, 0 = failure.  Only 16-bit integer PCM at a native MPEG rate is in scope

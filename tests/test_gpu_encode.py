@@ -63,3 +63,53 @@ def test_bad_control_is_rejected():
     ec = capi.control(samprate=44100, nch=2, bitrate=16)   # below the MPEG-1 minimum: reference init returns 0
     with pytest.raises(capi.Hmp3Error):
         capi.encode_batch([ec], [synth_pcm(1, 0.5, 44100, 2)])
+
+
+@pytest.mark.parametrize("name,seed,sr,nch,kw", [CONFIGS[0], CONFIGS[3], CONFIGS[4]])
+def test_encoder_handle_matches_reference_call_by_call(name, seed, sr, nch, kw):
+    """The CMp3Enc mirror: same bytes per call as CMp3Enc::L3_audio_encode, same flush protocol, same getters."""
+    pcm = synth_pcm(seed + 7, 4.0, sr, nch)
+    ref_bytes, tr = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, max_trace_calls=4000)
+    enc = capi.Encoder(capacity_seconds=30)
+    per_call = enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw))
+    assert per_call == 2304 * nch
+    ncalls_real = (pcm.shape[0] + 4 * 1152) // 1152
+    padded = np.zeros(((ncalls_real + 40) * 1152, nch), np.int16)
+    padded[:pcm.shape[0]] = pcm
+    out, c = [], 0
+    frames_expected = ncalls_real * (1 if sr >= 32000 else 2)
+    # the CLI's protocol: real calls, then zero PCM until every expected frame has been written
+    while c < ncalls_real or enc.frames() < frames_expected:
+        used, b = enc.encode_mp3(padded[c * 1152:(c + 1) * 1152])
+        assert used == per_call
+        if c < len(tr):
+            assert b.size == tr["out_bytes"][c], "call %d" % c
+        out.append(b)
+        c += 1
+    got = np.concatenate(out)
+    assert got.size == ref_bytes.size and np.array_equal(got, ref_bytes)
+    assert enc.frames() >= frames_expected
+    assert abs(enc.bitrate() - 8e-3 * got.size * sr / ((1152 if sr >= 32000 else 576) * enc.frames())) < 1e-3
+    assert "Layer III" in enc.info_string()
+    enc.close()
+
+
+def test_encoder_handle_float_entry_and_rejections():
+    enc = capi.Encoder(capacity_seconds=10)
+    assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=64), source_bits=24) == 0   # out of scope
+    assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=16)) == 0                    # reference rejects
+    assert enc.init_l3(capi.control(samprate=44100, nch=2, bitrate=64)) == 2 * 4 * 1152
+    pcm = synth_pcm(3, 1.0, 44100, 2)
+    ref_bytes, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=44100, nch=2, bitrate=64), pcm[:20 * 1152])
+    out = []
+    for c in range(20 + 4 + 6):
+        blk = pcm[c * 1152:(c + 1) * 1152].astype(np.float32) if c < 20 else np.zeros((1152, 2), np.float32)
+        used, b = enc.encode_l3(blk)
+        assert used == 2 * 4 * 1152
+        out.append(b)
+    got = np.concatenate(out)
+    assert np.array_equal(got[:ref_bytes.size], ref_bytes)
+    used, _ = enc.encode_l3(np.full((1152, 2), 0.5, np.float32))                                # not 16-bit PCM
+    assert used == 0
+    assert enc.info_ec()["bitrate"] == 64
+    enc.close()
