@@ -28,6 +28,45 @@
 
 namespace hmp3 {
 
+#if HMP3_COOP
+// Warp intrinsics as inline PTX: the serial-stage translation unit is compiled at a low front-end optimisation
+// level (for code size), where the CUDA header wrappers of these would become real function calls.
+__device__ __forceinline__ float wshfl(float v, int src) {
+    float r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(v), "r"(src));
+    return r;
+}
+__device__ __forceinline__ int wshfl(int v, int src) {
+    int r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src));
+    return r;
+}
+__device__ __forceinline__ int wshfl_up(int v, int d) {
+    int r;
+    asm volatile("shfl.sync.up.b32 %0, %1, %2, 0x0, 0xffffffff;" : "=r"(r) : "r"(v), "r"(d));
+    return r;
+}
+__device__ __forceinline__ unsigned wsum(unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ int wsum(int v) { return (int)wsum((unsigned)v); }
+__device__ __forceinline__ int wmax(int v) {
+    int r;
+    asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void smem_or(unsigned *p, unsigned v) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned funnel_r(unsigned lo, unsigned hi, unsigned sh) {
+    unsigned r;
+    asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sh));
+    return r;
+}
+#endif
+
 // warps (= streams) per thread block of the serial-stage kernel
 constexpr int kRateWarpsPerBlock = 4;
 

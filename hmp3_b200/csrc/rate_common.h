@@ -100,7 +100,7 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
             dd = d * d;
         }
         const int m = (n - i0) < 32 ? (n - i0) : 32;
-        for (int k = 0; k < m; k++) acc += __shfl_sync(0xffffffffu, dd, k);
+        for (int k = 0; k < m; k++) acc += wshfl(dd, k);
     }
 #else
     for (int i = 0; i < n; i++) {
@@ -133,8 +133,8 @@ HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, in
         }
         const int m = (n - i0) < 32 ? (n - i0) : 32;
         for (int k = 0; k < m; k++) {
-            sqq += __shfl_sync(0xffffffffu, vv, k);
-            sxx += __shfl_sync(0xffffffffu, xx, k);
+            sqq += wshfl(vv, k);
+            sxx += wshfl(xx, k);
         }
     }
 #else
@@ -194,8 +194,8 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
         }
     }
 #if HMP3_COOP
-    s0 = __reduce_add_sync(0xffffffffu, s0);
-    s1 = __reduce_add_sync(0xffffffffu, s1);
+    s0 = wsum(s0);
+    s1 = wsum(s1);
 #endif
     int b0 = (int)(s0 & 0xFFFF), b1 = (int)((s0 >> 16) & 0xFFFF);
     if (b0 < b1) { r.bits = b0; r.index = 0; }
@@ -228,8 +228,8 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
         b += 4 + ones;
     }
 #if HMP3_COOP
-    a = __reduce_add_sync(0xffffffffu, a);
-    b = __reduce_add_sync(0xffffffffu, b);
+    a = wsum(a);
+    b = wsum(b);
 #endif
     if (a < b) { r.bits = a; r.index = 0; }
     else { r.bits = b; r.index = 1; }

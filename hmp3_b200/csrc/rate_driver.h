@@ -248,21 +248,21 @@ __device__ __forceinline__ void bitbuf_or(unsigned *W, int pos, unsigned long lo
     const unsigned hi = (unsigned)(V >> 32), lo = (unsigned)V;
     const int w = pos >> 5, o = pos & 31;
     const unsigned w0 = hi >> o;
-    const unsigned w1 = __funnelshift_r(lo, hi, o);
-    const unsigned w2 = __funnelshift_r(0u, lo, o);
-    if (w0) atomicOr(W + w, w0);
-    if (w1) atomicOr(W + w + 1, w1);
-    if (w2) atomicOr(W + w + 2, w2);
+    const unsigned w1 = funnel_r(lo, hi, (unsigned)o);
+    const unsigned w2 = funnel_r(0u, lo, (unsigned)o);
+    if (w0) smem_or(W + w, w0);
+    if (w1) smem_or(W + w + 1, w1);
+    if (w2) smem_or(W + w + 2, w2);
 }
 __device__ __forceinline__ int warp_scan_excl(int v, int *total) {
     const int lane = HMP3_LANE;
     int s = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, s, d);
+        int t = wshfl_up(s, d);
         if (lane >= d) s += t;
     }
-    *total = __shfl_sync(0xffffffffu, s, 31);
+    *total = wshfl(s, 31);
     return s - v;
 }
 HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
