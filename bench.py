@@ -42,6 +42,10 @@ METRIC = "encoded audio sec/sec (x realtime), 44.1k stereo CBR128"
 # algorithmic bytes of the serial stage per granule-channel (DESIGN.md "K6"): MDCT lines in (2304 B) +
 # psychoacoustic record in (368 B) + packed main data out (CBR128: 381 B / 4 granule-channels = 95 B)
 K6_BYTES_PER_GC = 2304 + 368 + 95
+# DRAM traffic of the same kernel per granule-channel, from the committed `ncu --set full` capture
+# (profiles/r1_rate_ncu_details.txt: dram read 2.202 GB + write 5.145 GB for a launch of 2368 streams x 128
+# granules x 2 channels); per-launch traffic = this x the granule-channels one launch processes
+K6_NCU_DRAM_BYTES_PER_GC = (2.202276e9 + 5.144660e9) / (2368 * 128 * 2)
 
 
 def base_clips():
@@ -286,7 +290,10 @@ def run_gpu(args, rank, local_rank, world):
         achieved = bytes_per_launch / avg_launch_s / 1e9
         roof = {"kernel": "k_rate (serial stage: rate loop + Huffman packing, one warp per stream)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": args.rate_traffic,
+                "frac": achieved / hbm_peak,
+                "traffic": args.rate_traffic if args.rate_traffic is not None
+                else K6_NCU_DRAM_BYTES_PER_GC * B * gran_per_launch * NCH,
+                "traffic_source": "ncu --set full capture in profiles/r1_rate_ncu_details.txt, scaled per granule-channel",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": rate_ms / total_phase_ms,
                 "note": "latency/instruction-fetch bound serial code, not a bandwidth kernel: see DESIGN.md"}
@@ -332,7 +339,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips-per-gpu", type=int, default=2500)
+    ap.add_argument("--clips-per-gpu", type=int, default=4736,
+                    help="streams per GPU (default: one full wave of the serial-stage kernel, 148 SMs x 32 warps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rate-traffic", type=float, default=None,
                     help="dram bytes per k_rate launch from the committed ncu capture (profiles/), if known")
