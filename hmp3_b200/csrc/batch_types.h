@@ -13,6 +13,7 @@ struct PsyRaw;
 struct SwitchState;
 struct RateState;
 struct FrameRec;
+struct PackGc;
 
 // One stream of the batch, device view.
 struct StreamDev {
@@ -34,6 +35,8 @@ struct ChunkBufs {
     float *xr;       // [n][NG][2][576]
     PsyRaw *raw;     // [n][NG][2]
     int *ms_raw;     // [n][NG]
+    PackGc *pack;    // [n][NG][2]  granule-channel records for the packing pass
+    int *fr0, *fr1;  // [n] frames recorded by each stream before / after this chunk's serial stage
     int NG;
 };
 
@@ -61,6 +64,10 @@ void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb,
 void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream);
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);
+// packing pass of the frames the serial stage recorded in this chunk; `flags[s]` is set if a frame's written
+// bits ever differ from the accounted ones
+void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
+                 FrameRec *frames, int *flags, int K0, int n, cudaStream_t stream);
 // per-stream totals, compact output offsets (out_off[n] = total) and frame assembly
 void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
@@ -68,5 +75,6 @@ void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *
                    int frame_lo = 0, long long out_base = 0);
 size_t sizeof_rate_state();
 size_t sizeof_frame_rec();
+size_t sizeof_pack_gc();
 
 }  // namespace hmp3

@@ -26,7 +26,26 @@
 #define HMP3_SYNC()
 #endif
 
+// Small constant look-up tables live at namespace scope in device memory (a function-local array would be
+// rebuilt on the stack at every call and bloat the code).
+#if defined(__CUDACC__)
+#define HMP3_CONST_TABLE __device__ const
+#else
+#define HMP3_CONST_TABLE static const
+#endif
+
 namespace hmp3 {
+
+HMP3_CONST_TABLE unsigned char kPretab[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};  // ISO pretab
+HMP3_CONST_TABLE unsigned char kQuadLenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};   // count1 table A lengths
+HMP3_CONST_TABLE unsigned char kQuadCodeA[16] = {1, 5, 4, 5, 6, 5, 4, 4, 7, 3, 6, 0, 7, 2, 3, 1};  // ... and codes
+HMP3_CONST_TABLE unsigned char kRegion0[24] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7};
+HMP3_CONST_TABLE unsigned char kRegion1[24] = {1, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5, 5, 5, 5, 6, 6, 7, 7, 7, 8, 8, 8, 8};
+HMP3_CONST_TABLE unsigned char kSfcIndex[5][4] = {{0, 1, 2, 3}, {5, 5, 6, 7}, {8, 8, 9, 10}, {4, 11, 12, 13}, {14, 14, 14, 15}};
+HMP3_CONST_TABLE unsigned char kSfcSlen[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
+                                                  {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
+HMP3_CONST_TABLE int kSfGroupEdge[5] = {0, 6, 11, 16, 21};
+HMP3_CONST_TABLE unsigned char kPeakSnap[16] = {0, 1, 2, 3, 3, 5, 5, 7, 7, 7, 7, 15, 15, 15, 15, 15};
 
 #if HMP3_COOP
 // Warp intrinsics as inline PTX: the serial-stage translation unit is compiled at a low front-end optimisation
@@ -57,6 +76,11 @@ __device__ __forceinline__ int wmax(int v) {
     asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
     return r;
 }
+__device__ __forceinline__ unsigned wballot(int pred) {
+    unsigned r;
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; }" : "=r"(r) : "r"(pred));
+    return r;
+}
 __device__ __forceinline__ void smem_or(unsigned *p, unsigned v) {
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
@@ -69,6 +93,8 @@ __device__ __forceinline__ unsigned funnel_r(unsigned lo, unsigned hi, unsigned 
 
 // warps (= streams) per thread block of the serial-stage kernel
 constexpr int kRateWarpsPerBlock = 4;
+// warps (= frames) per thread block of the packing kernel
+constexpr int kPackWarpsPerBlock = 8;
 
 enum FrameDriver { FD_VBR_MPEG1 = 0, FD_CBR_MPEG1 = 1, FD_VBR_MPEG2 = 2, FD_CBR_MPEG2 = 3 };
 

@@ -39,6 +39,11 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
     k_rate<<<blocks_for((long long)n * 32, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
         tabs, st, so, rs, cb, main_buf, frames, K0, n);
 }
+void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
+                 FrameRec *frames, int *flags, int K0, int n, cudaStream_t stream) {
+    k_pack<<<blocks_for((long long)n * cb.NG * 32, 32 * kPackWarpsPerBlock), 32 * kPackWarpsPerBlock, 0, stream>>>(
+        tabs, st, so, cb, main_buf, frames, flags, K0, n);
+}
 void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
                    unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble,
@@ -52,4 +57,5 @@ void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *
 }
 size_t sizeof_rate_state() { return sizeof(RateState); }
 size_t sizeof_frame_rec() { return sizeof(FrameRec); }
+size_t sizeof_pack_gc() { return sizeof(PackGc); }
 }  // namespace hmp3

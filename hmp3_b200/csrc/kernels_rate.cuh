@@ -28,11 +28,29 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (s >= nstreams) return;
     const StreamDev sd = st[s];
+    cb.fr0[s] = cb.fr1[s] = rs[s].frames;  // nothing recorded in this chunk unless the loop below runs
     if (K0 >= sd.ngran) return;
     const StreamOut o = so[s];
     const long long q0 = (long long)s * cb.NG;
     rate_run_chunk(tabs + sd.cfg, rs + s, K0, cb.NG, sd.ngran, sd.ngran_real, cb.gi + q0, cb.xr + q0 * 2 * 576,
-                   cb.raw + q0 * 2, cb.ms_raw + q0, main_buf + o.main_off, frames + o.frames_off);
+                   cb.raw + q0 * 2, cb.ms_raw + q0, cb.pack + q0 * 2, frames + o.frames_off);
+    cb.fr1[s] = rs[s].frames;
+}
+
+// ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)
+__global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
+    k_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
+           FrameRec *frames, int *flags, int K0, int nstreams) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int s = (int)(wid / cb.NG), j = (int)(wid % cb.NG);  // at most NG frames per stream per chunk (MPEG-2)
+    if (s >= nstreams) return;
+    const int f = cb.fr0[s] + j;
+    if (f >= cb.fr1[s]) return;
+    const StreamOut o = so[s];
+    FrameRec *fr = frames + o.frames_off + f;
+    const EncTables *T = tabs + st[s].cfg;
+    const PackGc *gc = cb.pack + ((long long)s * cb.NG + (fr->granule0 - K0)) * 2;
+    if (pack_frame(T, fr, gc, main_buf + o.main_off) && (threadIdx.x & 31) == 0) flags[s] = 1;
 }
 
 // ---- per-stream totals after the last chunk

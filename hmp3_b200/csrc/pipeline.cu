@@ -37,9 +37,9 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_RATE, PH_ASSEMBLE, PH_COUNT };
+enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
 const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "rate_loop",
-                                     "assemble"};
+                                     "pack", "assemble"};
 
 }  // namespace
 
@@ -73,7 +73,11 @@ struct hmp3_batch {
     ChunkBufs &cb = cb2[0];
     cudaStream_t stream = nullptr;      // serial stage, finish, copies
     cudaStream_t stream_a = nullptr;    // Phase A
-    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_start = nullptr;
+    cudaStream_t stream_p = nullptr;    // packing pass
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr},
+                ev_start = nullptr;
+    int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
+    std::vector<int> flags_h;
     int nbuf = 2;
     int launches = 0;
     bool results_valid = false;
@@ -112,11 +116,17 @@ struct hmp3_batch {
             cudaFree(cb2[k].xr);
             cudaFree(cb2[k].raw);
             cudaFree(cb2[k].ms_raw);
+            cudaFree(cb2[k].pack);
+            cudaFree(cb2[k].fr0);
+            cudaFree(cb2[k].fr1);
             if (ev_a[k]) cudaEventDestroy(ev_a[k]);
             if (ev_r[k]) cudaEventDestroy(ev_r[k]);
+            if (ev_p[k]) cudaEventDestroy(ev_p[k]);
         }
         if (ev_start) cudaEventDestroy(ev_start);
+        cudaFree(d_flags);
         if (stream_a) cudaStreamDestroy(stream_a);
+        if (stream_p) cudaStreamDestroy(stream_p);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_run0) cudaEventDestroy(ev_run0);
         if (ev_run1) cudaEventDestroy(ev_run1);
@@ -221,6 +231,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     const long long NG = b->NG, G = NG + 3;
     b->nbuf = analysis_only ? 1 : 2;
     CK(cudaStreamCreate(&b->stream_a));
+    CK(cudaStreamCreate(&b->stream_p));
     CK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
     for (int k = 0; k < b->nbuf; k++) {
         ChunkBufs &cb = b->cb2[k];
@@ -231,8 +242,14 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMalloc(&cb.xr, sizeof(float) * n * NG * 2 * 576));
         CK(cudaMalloc(&cb.raw, sizeof(PsyRaw) * n * NG * 2));
         CK(cudaMalloc(&cb.ms_raw, sizeof(int) * n * NG));
+        if (!analysis_only) {
+            CK(cudaMalloc(&cb.pack, sizeof_pack_gc() * n * NG * 2));
+            CK(cudaMalloc(&cb.fr0, sizeof(int) * n));
+            CK(cudaMalloc(&cb.fr1, sizeof(int) * n));
+        }
         CK(cudaEventCreateWithFlags(&b->ev_a[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_r[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b->ev_p[k], cudaEventDisableTiming));
     }
     if (!analysis_only) {
         CK(cudaMalloc(&b->d_so, sizeof(StreamOut) * n));
@@ -241,6 +258,8 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMalloc(&b->d_main, std::max<long long>(main_off, 16)));
         CK(cudaMalloc(&b->d_frames, sizeof_frame_rec() * std::max<long long>(frames_off, 1)));
         CK(cudaMalloc(&b->d_res, sizeof(StreamResult) * n));
+        CK(cudaMalloc(&b->d_flags, sizeof(int) * n));
+        b->flags_h.assign(n, 0);
         CK(cudaMalloc(&b->d_out_off, sizeof(long long) * (n + 1)));
         CK(cudaMalloc(&b->d_out, std::max<long long>(out_cap, 16)));
         b->res_h.resize(n);
@@ -307,10 +326,13 @@ int run_plan(hmp3_batch *b) {
     if (r != HMP3_OK) return r;
     launch_rate_init(b->d_tabs, b->d_st, b->d_rs, n, b->stream);
     b->launches++;
-    // Phase A runs on its own stream one chunk ahead of the serial stage (two chunk buffer sets):
-    //   analysis(c) -> ev_a[c&1] -> serial(c) -> ev_r[c&1] -> analysis(c+2) may reuse the buffers
+    // Phase A runs on its own stream one chunk ahead of the serial stage, the packing pass on a third stream
+    // one chunk behind it (two chunk buffer sets):
+    //   analysis(c) -> ev_a -> serial(c) -> ev_r -> pack(c) -> ev_p ;  analysis(c+2) waits ev_r(c), serial(c+2) waits ev_p(c)
+    CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * n, b->stream));
     CK(cudaEventRecord(b->ev_start, b->stream));
     CK(cudaStreamWaitEvent(b->stream_a, b->ev_start, 0));
+    CK(cudaStreamWaitEvent(b->stream_p, b->ev_start, 0));
     int c = 0;
     for (int K0 = 0; K0 < b->max_gran; K0 += b->NG, c++) {
         const int k = c & 1;
@@ -319,12 +341,19 @@ int run_plan(hmp3_batch *b) {
         if (r != HMP3_OK) return r;
         CK(cudaEventRecord(b->ev_a[k], b->stream_a));
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
+        if (c >= 2) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
         launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[k], b->d_main, b->d_frames, K0, n, b->stream);
         mark(b, -1, b->stream);
         CK(cudaEventRecord(b->ev_r[k], b->stream));
-        b->launches++;
+        CK(cudaStreamWaitEvent(b->stream_p, b->ev_r[k], 0));
+        mark(b, PH_PACK, b->stream_p);
+        launch_pack(b->d_tabs, b->d_st, b->d_so, b->cb2[k], b->d_main, b->d_frames, b->d_flags, K0, n, b->stream_p);
+        mark(b, -1, b->stream_p);
+        CK(cudaEventRecord(b->ev_p[k], b->stream_p));
+        b->launches += 2;
     }
+    for (int k = 0; k < 2 && k < c; k++) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
     cudaEvent_t ev_asm = nullptr;
     if (b->timing) {
         mark(b, PH_ASSEMBLE, b->stream);  // re-recorded by launch_finish right before the assembly kernel
@@ -339,6 +368,7 @@ int run_plan(hmp3_batch *b) {
     CK(cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult) * n, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->out_off_h.data(), b->d_out_off, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost,
                        b->stream));
+    CK(cudaMemcpyAsync(b->flags_h.data(), b->d_flags, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream));
     return HMP3_OK;
 }
 
@@ -504,6 +534,7 @@ int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames, i
     for (int i = 0; i < b->n; i++) {
         int st = b->status[i];
         if (st == HMP3_OK && !b->res_h[i].finished) st = HMP3_ERR_OUT_SPACE;
+        if (st == HMP3_OK && b->flags_h[i]) st = HMP3_ERR_INTERNAL;
         if (out_bytes) out_bytes[i] = b->status[i] == HMP3_OK ? b->res_h[i].out_bytes : 0;
         if (out_frames) out_frames[i] = b->status[i] == HMP3_OK ? b->res_h[i].frames : 0;
         if (out_offsets) out_offsets[i] = b->out_off_h[i];
@@ -586,6 +617,7 @@ int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *co
         int st = b->status[i];
         long long nb = st == HMP3_OK ? b->res_h[i].out_bytes : 0;
         if (st == HMP3_OK && !b->res_h[i].finished) st = HMP3_ERR_OUT_SPACE;
+        if (st == HMP3_OK && b->flags_h[i]) st = HMP3_ERR_INTERNAL;
         if (st == HMP3_OK && nb > out_cap[i]) {
             st = HMP3_ERR_OUT_SPACE;
             nb = 0;
@@ -685,6 +717,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     e->stage.assign((size_t)1152 * e->nch, 0);
     cudaSetDevice(e->device);
     if (plan_reset_state(b) != HMP3_OK) return 0;
+    cudaMemsetAsync(b->d_flags, 0, sizeof(int), b->stream);
     launch_rate_init(b->d_tabs, b->d_st, b->d_rs, 1, b->stream);
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
         set_err("device initialisation failed");
@@ -715,6 +748,7 @@ hmp3_in_out encoder_step(hmp3_encoder *e, const int16_t *pcm, unsigned char *bs_
     }
     if (launch_analysis(b, K0, 0, b->stream) != HMP3_OK) return io;
     launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
+    launch_pack(b->d_tabs, b->d_st, b->d_so, b->cb2[0], b->d_main, b->d_frames, b->d_flags, K0, 1, b->stream);
     launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out, 48, 1,
                   b->stream, nullptr, e->frames_out, e->bytes_out);
     cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult), cudaMemcpyDeviceToHost, b->stream);

@@ -214,7 +214,6 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
     CountResult r;
     r.bits = r.index = 0;
     if (nquads <= 0) return r;
-    const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
     int a = 0, b = 0;
 #if HMP3_COOP
     for (int i = HMP3_LANE; i < nquads; i += 32) {
@@ -224,7 +223,7 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
 #endif
         int j = ((ix[k] << 3) + (ix[k + 1] << 2) + (ix[k + 2] << 1) + ix[k + 3]) & 15;
         int ones = (j & 1) + ((j >> 1) & 1) + ((j >> 2) & 1) + ((j >> 3) & 1);
-        a += lenA[j] + ones;
+        a += kQuadLenA[j] + ones;
         b += 4 + ones;
     }
 #if HMP3_COOP
@@ -238,10 +237,8 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
 
 // region lengths in bands as a function of the number of big-value bands (bitalloc.cpp:124-203)
 HMP3_HD void region_split_rule(int nbands, int *r0, int *r1) {
-    const unsigned char t0[24] = {1, 1, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 6, 7, 7, 7};
-    const unsigned char t1[24] = {1, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5, 5, 5, 5, 6, 6, 7, 7, 7, 8, 8, 8, 8};
-    *r0 = t0[nbands];
-    *r1 = t1[nbands];
+    *r0 = kRegion0[nbands];
+    *r1 = kRegion1[nbands];
 }
 
 // Region planning + bit count for a long-block granule channel (block types 0 / 1,3).

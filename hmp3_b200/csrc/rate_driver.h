@@ -10,14 +10,31 @@
 
 namespace hmp3 {
 
-// One emitted frame, as recorded by the serial stage; the final byte layout (header | side | slice of the
-// main-data stream) is produced by a separate, parallel assembly pass.
+// One emitted frame, as recorded by the serial stage.  The serial stage only does the bit ACCOUNTING; the bits
+// themselves (scale factors, Huffman codes, side info) are written afterwards by the packing pass
+// (pack_frame: one warp per frame, all frames in parallel) and the final byte layout (header | side | slice of
+// the main-data stream) by the assembly pass.
 struct FrameRec {
-    unsigned main_start;  // offset in the stream's main-data stream where this frame's slot begins
+    unsigned main_start;  // offset in the stream's main-data stream where this frame's SLOT begins
     int mf_bytes;         // bytes of main-data slot in this frame
     unsigned out_off;     // byte offset of this frame in the stream's output
+    unsigned data_start;  // offset in the main-data stream where this frame's OWN data begins
+    int data_bits;        // bits of scale factors + Huffman data of this frame
+    int data_bytes;       // bytes the frame's data occupies (rounded up, zero-padded to the reservoir minimum)
+    int granule0;         // first encode granule of the frame
+    short ngr, igr0;      // granules in the frame (2 MPEG-1, 1 MPEG-2) and granule parity of the first
+    short main_data_begin, short_frame;
+    short scfsi[2];
     unsigned char head[4];
     unsigned char side[32];
+};
+
+// What the packing pass needs of one granule-channel.
+struct PackGc {
+    short ix[576];          // quantised magnitudes, transmission order
+    unsigned sign[18];      // sign bit of line k = bit (k & 31) of word (k >> 5)
+    unsigned char sf[64];   // long: l[0..22]; short: s[w][i] at 23 + 13*w + i
+    GrSide gr;
 };
 
 // MSB-first bit writer appending to a byte buffer (same bit order as l3pack.c:98-153).
@@ -66,7 +83,6 @@ struct RateState {
     int byte_pool, byte_min, byte_max;
     int next_granule;         // encode granule to process next
     int finished;             // all real frames are complete
-    BitSink sink;
 };
 
 HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {
@@ -92,18 +108,20 @@ HMP3_HD int slen_for(int maxval, int cap) {
     return s;
 }
 HMP3_HD int sfc_index(int slen1, int slen2) {  // ISO scalefac_compress from (slen1, slen2)
-    const unsigned char t[5][4] = {{0, 1, 2, 3}, {5, 5, 6, 7}, {8, 8, 9, 10}, {4, 11, 12, 13}, {14, 14, 14, 15}};
-    return t[slen1][slen2];
+    return kSfcIndex[slen1][slen2];
 }
 HMP3_HD void sfc_slens(int sfc, int *s1, int *s2) {
-    const unsigned char t[16][2] = {{0, 0}, {0, 1}, {0, 2}, {0, 3}, {3, 0}, {1, 1}, {1, 2}, {1, 3},
-                                    {2, 1}, {2, 2}, {2, 3}, {3, 1}, {3, 2}, {3, 3}, {4, 2}, {4, 3}};
-    *s1 = t[sfc][0];
-    *s2 = t[sfc][1];
+    *s1 = kSfcSlen[sfc][0];
+    *s2 = kSfcSlen[sfc][1];
 }
 
+// Scale-factor coding is split in two: plan_sf_* (serial stage) takes the decisions -- scalefac_compress, scfsi
+// -- and returns the number of bits; write_sf_* (packing pass) emits the bits those decisions imply.
+HMP3_HD int sf_byte(const unsigned char *sf, int i) { return sf[i]; }                       // long band i
+HMP3_HD int sf_byte_s(const unsigned char *sf, int w, int i) { return sf[23 + 13 * w + i]; }  // short window w band i
+
 // MPEG-1, frame contains a short block: no scfsi (l3pack.c:157-281)
-HMP3_FN int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) {
+HMP3_FN int plan_sf_mpeg1_plain(const ScaleFac *sf, int block_type, int *bits) {
     int m1 = 0, m2 = 0, s1, s2;
     if (block_type == 2) {
         for (int i = 0; i < 6; i++)
@@ -112,135 +130,147 @@ HMP3_FN int pack_sf_mpeg1_plain(BitSink *b, const ScaleFac *sf, int block_type) 
             for (int w = 0; w < 3; w++) m2 = imax_(m2, sf->s[w][i]);
         int sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
         sfc_slens(sfc, &s1, &s2);
-        for (int i = 0; i < 6; i++)
-            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], s1);
-        for (int i = 6; i < 12; i++)
-            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], s2);
+        *bits = 18 * s1 + 18 * s2;
         return sfc;
     }
     for (int i = 0; i < 11; i++) m1 = imax_(m1, sf->l[i]);
     for (int i = 11; i < 21; i++) m2 = imax_(m2, sf->l[i]);
     int sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
     sfc_slens(sfc, &s1, &s2);
-    for (int i = 0; i < 11; i++) sink_put(b, sf->l[i], s1);
-    for (int i = 11; i < 21; i++) sink_put(b, sf->l[i], s2);
+    *bits = 11 * s1 + 10 * s2;
     return sfc;
 }
+HMP3_FN void write_sf_mpeg1_plain(BitSink *b, const unsigned char *sf, int block_type, int sfc) {
+    int s1, s2;
+    sfc_slens(sfc, &s1, &s2);
+    if (block_type == 2) {
+        for (int i = 0; i < 6; i++)
+            for (int w = 0; w < 3; w++) sink_put(b, sf_byte_s(sf, w, i), s1);
+        for (int i = 6; i < 12; i++)
+            for (int w = 0; w < 3; w++) sink_put(b, sf_byte_s(sf, w, i), s2);
+        return;
+    }
+    for (int i = 0; i < 11; i++) sink_put(b, sf_byte(sf, i), s1);
+    for (int i = 11; i < 21; i++) sink_put(b, sf_byte(sf, i), s2);
+}
 // MPEG-1, all-long frame: granule 1 may share scale-factor groups with granule 0 (l3pack.c:421-557)
-HMP3_FN int pack_sf_mpeg1_scfsi(BitSink *b, const ScaleFac *sf, int *save /*[21]*/, int igr, int *scfsi_out,
-                                int not_null) {
-    const int edge[5] = {0, 6, 11, 16, 21};
+HMP3_FN int plan_sf_mpeg1_scfsi(const ScaleFac *sf, int *save /*[21]*/, int igr, int *scfsi_out, int not_null,
+                                int *bits) {
     int scfsi = 0;
     if (igr == 0) {
         for (int i = 0; i < 21; i++) save[i] = sf->l[i];
     } else {
         for (int g = 0; g < 4; g++) {
             int t = 0;
-            for (int i = edge[g]; i < edge[g + 1]; i++) t |= (save[i] - sf->l[i]);
+            for (int i = kSfGroupEdge[g]; i < kSfGroupEdge[g + 1]; i++) t |= (save[i] - sf->l[i]);
             scfsi <<= 1;
             if (t == 0) scfsi |= 1;
         }
     }
     int sfc = 0;
+    *bits = 0;
     if (not_null) {
         int m1 = 0, m2 = 0, s1, s2;
         for (int g = 0; g < 4; g++)
             if ((scfsi & (8 >> g)) == 0)
-                for (int i = edge[g]; i < edge[g + 1]; i++) {
+                for (int i = kSfGroupEdge[g]; i < kSfGroupEdge[g + 1]; i++) {
                     if (g < 2) m1 = imax_(m1, sf->l[i]);
                     else m2 = imax_(m2, sf->l[i]);
                 }
         sfc = sfc_index(slen_for(m1, 4), slen_for(m2, 3));
         sfc_slens(sfc, &s1, &s2);
         for (int g = 0; g < 4; g++)
-            if ((scfsi & (8 >> g)) == 0)
-                for (int i = edge[g]; i < edge[g + 1]; i++) sink_put(b, sf->l[i], g < 2 ? s1 : s2);
+            if ((scfsi & (8 >> g)) == 0) *bits += (kSfGroupEdge[g + 1] - kSfGroupEdge[g]) * (g < 2 ? s1 : s2);
     }
     *scfsi_out = scfsi;
     return sfc;
 }
+HMP3_FN void write_sf_mpeg1_scfsi(BitSink *b, const unsigned char *sf, int scfsi, int sfc) {
+    int s1, s2;
+    sfc_slens(sfc, &s1, &s2);
+    for (int g = 0; g < 4; g++)
+        if ((scfsi & (8 >> g)) == 0)
+            for (int i = kSfGroupEdge[g]; i < kSfGroupEdge[g + 1]; i++) sink_put(b, sf_byte(sf, i), g < 2 ? s1 : s2);
+}
 // MPEG-2 (LSF), no intensity stereo: four partitions with their own lengths (l3pack.c:561-933)
-HMP3_FN int pack_sf_mpeg2(BitSink *b, const ScaleFac *sf, int block_type) {
+HMP3_FN int plan_sf_mpeg2(const ScaleFac *sf, int block_type, int *bits) {
     int m[4] = {0, 0, 0, 0}, sl[4];
     if (block_type == 2) {
         for (int w = 0; w < 3; w++)
             for (int i = 0; i < 12; i++) m[i / 3] = imax_(m[i / 3], sf->s[w][i]);
     } else {
-        const int edge[5] = {0, 6, 11, 16, 21};
         for (int g = 0; g < 4; g++)
-            for (int i = edge[g]; i < edge[g + 1]; i++) m[g] = imax_(m[g], sf->l[i]);
+            for (int i = kSfGroupEdge[g]; i < kSfGroupEdge[g + 1]; i++) m[g] = imax_(m[g], sf->l[i]);
     }
     sl[0] = slen_for(m[0], 4);
     sl[1] = slen_for(m[1], 4);
     sl[2] = slen_for(m[2], 3);
     sl[3] = slen_for(m[3], 3);
-    const int sfc = sl[3] + (sl[2] << 2) + ((sl[1] + 5 * sl[0]) << 4);
+    if (block_type == 2) *bits = 9 * (sl[0] + sl[1] + sl[2] + sl[3]);
+    else *bits = 6 * sl[0] + 5 * (sl[1] + sl[2] + sl[3]);
+    return sl[3] + (sl[2] << 2) + ((sl[1] + 5 * sl[0]) << 4);
+}
+HMP3_FN void write_sf_mpeg2(BitSink *b, const unsigned char *sf, int block_type, int sfc) {
+    int sl[4];
+    sl[3] = sfc & 3;
+    sl[2] = (sfc >> 2) & 3;
+    sl[1] = (sfc >> 4) % 5;
+    sl[0] = (sfc >> 4) / 5;
     if (block_type == 2) {
         for (int i = 0; i < 12; i++)
-            for (int w = 0; w < 3; w++) sink_put(b, sf->s[w][i], sl[i / 3]);
+            for (int w = 0; w < 3; w++) sink_put(b, sf_byte_s(sf, w, i), sl[i / 3]);
     } else {
-        const int edge[5] = {0, 6, 11, 16, 21};
         for (int g = 0; g < 4; g++)
-            for (int i = edge[g]; i < edge[g + 1]; i++) sink_put(b, sf->l[i], sl[g]);
+            for (int i = kSfGroupEdge[g]; i < kSfGroupEdge[g + 1]; i++) sink_put(b, sf_byte(sf, i), sl[g]);
     }
-    return sfc;
 }
 
 // ------------------------------------------------------------------ Huffman packing (l3pack.c:946-1119)
-HMP3_FN void pack_huffman_seq(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
+HMP3_HD unsigned sign_bit(const unsigned *sign, int k) { return (sign[k >> 5] >> (k & 31)) & 1u; }
+
+HMP3_FN void pack_huffman_seq(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
+    int k0 = 0;  // first line of the current region
     for (int r = 0; r < 3; r++) {
         const int n = g->aux_nreg[r];
         const int t = g->table_select[r];
         const int book = T->huff_sel_book[t];
-        if (book == 0) {
-            ix += 2 * n;
-            sg += 2 * n;
-            continue;
-        }
-        const uint32_t *bk = T->huff_book[book];
-        const int lb = T->huff_linbits[t];
-        const bool esc = t >= 16;
-        for (int j = 0; j < n; j++) {
-            int x = ix[2 * j], y = ix[2 * j + 1];
-            if (esc) {
-                if (x > 15) x = 15;
-                if (y > 15) y = 15;
+        if (book != 0) {
+            const uint32_t *bk = T->huff_book[book];
+            const int lb = T->huff_linbits[t];
+            const bool esc = t >= 16;
+            for (int j = 0; j < n; j++) {
+                const int k = k0 + 2 * j;
+                int x = ix[k], y = ix[k + 1];
+                if (esc) {
+                    if (x > 15) x = 15;
+                    if (y > 15) y = 15;
+                }
+                const uint32_t e = bk[(x & 15) * 16 + (y & 15)];
+                sink_put(b, e & 0xFFFFFFu, (int)(e >> 24));
+                if (esc && x >= 15) sink_put(b, (unsigned)(ix[k] - 15), lb);
+                if (x) sink_put(b, sign_bit(sign, k), 1);
+                if (esc && y >= 15) sink_put(b, (unsigned)(ix[k + 1] - 15), lb);
+                if (y) sink_put(b, sign_bit(sign, k + 1), 1);
             }
-            const uint32_t e = bk[(x & 15) * 16 + (y & 15)];
-            sink_put(b, e & 0xFFFFFFu, (int)(e >> 24));
-            if (esc && x >= 15) sink_put(b, (unsigned)(ix[2 * j] - 15), lb);
-            if (x) sink_put(b, sg[2 * j], 1);
-            if (esc && y >= 15) sink_put(b, (unsigned)(ix[2 * j + 1] - 15), lb);
-            if (y) sink_put(b, sg[2 * j + 1], 1);
         }
-        ix += 2 * n;
-        sg += 2 * n;
+        k0 += 2 * n;
     }
     const int nq = g->aux_nquads;
-    if (g->count1table_select == 1) {
-        for (int j = 0; j < nq; j++) {
-            unsigned x = (unsigned)(((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) ^ 15);
-            sink_put(b, x, 4);
-            for (int k = 0; k < 4; k++)
-                if ((x & (8u >> k)) == 0) sink_put(b, sg[4 * j + k], 1);
-        }
-    } else {
-        const unsigned char codeA[16] = {1, 5, 4, 5, 6, 5, 4, 4, 7, 3, 6, 0, 7, 2, 3, 1};
-        const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
-        for (int j = 0; j < nq; j++) {
-            unsigned x = (unsigned)((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) & 15u;
-            sink_put(b, codeA[x], lenA[x]);
-            for (int k = 0; k < 4; k++)
-                if (x & (8u >> k)) sink_put(b, sg[4 * j + k], 1);
-        }
+    const bool tabB = g->count1table_select == 1;
+    for (int j = 0; j < nq; j++) {
+        const int k = k0 + 4 * j;
+        const unsigned x = (unsigned)((ix[k] << 3) + (ix[k + 1] << 2) + (ix[k + 2] << 1) + ix[k + 3]) & 15u;
+        if (tabB) sink_put(b, x ^ 15u, 4);
+        else sink_put(b, kQuadCodeA[x], kQuadLenA[x]);
+        for (int q = 0; q < 4; q++)
+            if (x & (8u >> q)) sink_put(b, sign_bit(sign, k + q), 1);
     }
 }
-
 
 #if HMP3_COOP
 // Warp-parallel Huffman packing: each lane builds the bit field of one pair (or quad), a warp scan of the
 // field lengths gives its position, and the fields are OR-ed into a per-warp shared-memory bit buffer that
-// is then streamed out in whole bytes.  Produces exactly the bits of the sequential writer below.
+// is then streamed out in whole bytes.  Produces exactly the bits of the sequential writer above.
 constexpr int kPackWords = 168;  // 5376 bits: part2_3_length can never exceed 4095 + the scale factors
 __device__ __forceinline__ void bitbuf_or(unsigned *W, int pos, unsigned long long v, int len) {
     if (len <= 0) return;
@@ -265,14 +295,14 @@ __device__ __forceinline__ int warp_scan_excl(int v, int *total) {
     *total = wshfl(s, 31);
     return s - v;
 }
-HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
-    __shared__ unsigned s_bits[kRateWarpsPerBlock][kPackWords];
-    unsigned *W = s_bits[(threadIdx.x >> 5) % kRateWarpsPerBlock];
+HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
+    __shared__ unsigned s_bits[kPackWarpsPerBlock][kPackWords];
+    unsigned *W = s_bits[(threadIdx.x >> 5) % kPackWarpsPerBlock];
     const int lane = HMP3_LANE;
     HMP3_SYNC();
     const int p0 = b->nacc;  // bits pending in the writer (< 8)
     if (p0 + g->aux_bits > kPackWords * 32 - 160) {  // cannot happen within the part2_3 limits; stay correct anyway
-        pack_huffman_seq(T, b, g, ix, sg);
+        pack_huffman_seq(T, b, g, ix, sign);
         return;
     }
     const int nwords = imin_(kPackWords, ((p0 + g->aux_bits + 31) >> 5) + 3);
@@ -281,6 +311,7 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
     if (lane == 0 && p0 > 0) W[0] = ((unsigned)b->acc & ((1u << p0) - 1u)) << (32 - p0);
     HMP3_SYNC();
     int pos = p0;
+    int k0 = 0;
     for (int r = 0; r < 3; r++) {
         const int n = g->aux_nreg[r];
         const int t = g->table_select[r];
@@ -294,7 +325,8 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
                 unsigned long long v = 0;
                 int len = 0;
                 if (j < n) {
-                    const int x0 = ix[2 * j], y0 = ix[2 * j + 1];
+                    const int k = k0 + 2 * j;
+                    const int x0 = ix[k], y0 = ix[k + 1];
                     int x = x0, y = y0;
                     if (esc) {
                         if (x > 15) x = 15;
@@ -304,9 +336,9 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
                     v = e & 0xFFFFFFu;
                     len = (int)(e >> 24);
                     if (esc && x >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(x0 - 15) & ((1u << lb) - 1u)); len += lb; }
-                    if (x) { v = (v << 1) | (sg[2 * j] & 1u); len++; }
+                    if (x) { v = (v << 1) | sign_bit(sign, k); len++; }
                     if (esc && y >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(y0 - 15) & ((1u << lb) - 1u)); len += lb; }
-                    if (y) { v = (v << 1) | (sg[2 * j + 1] & 1u); len++; }
+                    if (y) { v = (v << 1) | sign_bit(sign, k + 1); len++; }
                 }
                 int tot;
                 const int off = warp_scan_excl(len, &tot);
@@ -314,24 +346,22 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
                 pos += tot;
             }
         }
-        ix += 2 * n;
-        sg += 2 * n;
+        k0 += 2 * n;
     }
     {
         const int nq = g->aux_nquads;
         const bool tabB = g->count1table_select == 1;
-        const unsigned char codeA[16] = {1, 5, 4, 5, 6, 5, 4, 4, 7, 3, 6, 0, 7, 2, 3, 1};
-        const unsigned char lenA[16] = {1, 4, 4, 5, 4, 6, 5, 6, 4, 5, 5, 6, 5, 6, 6, 6};
         for (int j0 = 0; j0 < nq; j0 += 32) {
             const int j = j0 + lane;
             unsigned long long v = 0;
             int len = 0;
             if (j < nq) {
-                const unsigned x = (unsigned)((ix[4 * j] << 3) + (ix[4 * j + 1] << 2) + (ix[4 * j + 2] << 1) + ix[4 * j + 3]) & 15u;
+                const int k = k0 + 4 * j;
+                const unsigned x = (unsigned)((ix[k] << 3) + (ix[k + 1] << 2) + (ix[k + 2] << 1) + ix[k + 3]) & 15u;
                 if (tabB) { v = x ^ 15u; len = 4; }
-                else { v = codeA[x]; len = lenA[x]; }
-                for (int k = 0; k < 4; k++)
-                    if (x & (8u >> k)) { v = (v << 1) | (sg[4 * j + k] & 1u); len++; }
+                else { v = kQuadCodeA[x]; len = kQuadLenA[x]; }
+                for (int q = 0; q < 4; q++)
+                    if (x & (8u >> q)) { v = (v << 1) | sign_bit(sign, k + q); len++; }
             }
             int tot;
             const int off = warp_scan_excl(len, &tot);
@@ -352,53 +382,85 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
     HMP3_SYNC();
 }
 #else
-HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const int *ix, const unsigned char *sg) {
-    pack_huffman_seq(T, b, g, ix, sg);
+HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
+    pack_huffman_seq(T, b, g, ix, sign);
 }
 #endif
 
 // ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
-HMP3_FN void pack_side(const EncTables *T, const RateState *R, int main_data_begin, int igr_only, unsigned char *out) {
+// gc = the frame's granule-channel records in (granule, channel) order
+HMP3_FN void pack_side(const EncTables *T, const FrameRec *fr, const PackGc *gc, unsigned char *out) {
     BitSink b;
     sink_open(&b, out);
     const int nch = T->cfg.nchan;
     const bool m1 = T->cfg.h_id == 1;
     if (m1) {
-        sink_put(&b, (unsigned)main_data_begin, 9);
+        sink_put(&b, (unsigned)fr->main_data_begin, 9);
         sink_put(&b, 0, T->cfg.h_mode == 3 ? 5 : 3);
-        for (int ch = 0; ch < nch; ch++) sink_put(&b, (unsigned)R->scfsi[ch], 4);
+        for (int ch = 0; ch < nch; ch++) sink_put(&b, (unsigned)fr->scfsi[ch], 4);
     } else {
-        sink_put(&b, (unsigned)main_data_begin, 8);
+        sink_put(&b, (unsigned)fr->main_data_begin, 8);
         sink_put(&b, 0, T->cfg.h_mode == 3 ? 1 : 2);
     }
-    for (int igr = m1 ? 0 : igr_only; igr < (m1 ? 2 : igr_only + 1); igr++)
-        for (int ch = 0; ch < nch; ch++) {
-            const GrSide *g = &R->gr[igr][ch];
-            sink_put(&b, (unsigned)g->part2_3_length, 12);
-            sink_put(&b, (unsigned)g->big_values, 9);
-            sink_put(&b, (unsigned)g->global_gain, 8);
-            sink_put(&b, (unsigned)g->scalefac_compress, m1 ? 4 : 9);
-            sink_put(&b, (unsigned)g->window_switching_flag, 1);
-            if (g->window_switching_flag) {
-                sink_put(&b, (unsigned)g->block_type, 2);
-                sink_put(&b, (unsigned)g->mixed_block_flag, 1);
-                sink_put(&b, (unsigned)g->table_select[0], 5);
-                sink_put(&b, (unsigned)g->table_select[1], 5);
-                sink_put(&b, (unsigned)g->subblock_gain[0], 3);
-                sink_put(&b, (unsigned)g->subblock_gain[1], 3);
-                sink_put(&b, (unsigned)g->subblock_gain[2], 3);
-            } else {
-                sink_put(&b, (unsigned)g->table_select[0], 5);
-                sink_put(&b, (unsigned)g->table_select[1], 5);
-                sink_put(&b, (unsigned)g->table_select[2], 5);
-                sink_put(&b, (unsigned)g->region0_count, 4);
-                sink_put(&b, (unsigned)g->region1_count, 3);
-            }
-            if (m1) sink_put(&b, (unsigned)g->preflag, 1);
-            sink_put(&b, (unsigned)g->scalefac_scale, 1);
-            sink_put(&b, (unsigned)g->count1table_select, 1);
+    for (int k = 0; k < fr->ngr * nch; k++) {
+        const GrSide *g = &gc[k].gr;
+        sink_put(&b, (unsigned)g->part2_3_length, 12);
+        sink_put(&b, (unsigned)g->big_values, 9);
+        sink_put(&b, (unsigned)g->global_gain, 8);
+        sink_put(&b, (unsigned)g->scalefac_compress, m1 ? 4 : 9);
+        sink_put(&b, (unsigned)g->window_switching_flag, 1);
+        if (g->window_switching_flag) {
+            sink_put(&b, (unsigned)g->block_type, 2);
+            sink_put(&b, (unsigned)g->mixed_block_flag, 1);
+            sink_put(&b, (unsigned)g->table_select[0], 5);
+            sink_put(&b, (unsigned)g->table_select[1], 5);
+            sink_put(&b, (unsigned)g->subblock_gain[0], 3);
+            sink_put(&b, (unsigned)g->subblock_gain[1], 3);
+            sink_put(&b, (unsigned)g->subblock_gain[2], 3);
+        } else {
+            sink_put(&b, (unsigned)g->table_select[0], 5);
+            sink_put(&b, (unsigned)g->table_select[1], 5);
+            sink_put(&b, (unsigned)g->table_select[2], 5);
+            sink_put(&b, (unsigned)g->region0_count, 4);
+            sink_put(&b, (unsigned)g->region1_count, 3);
         }
+        if (m1) sink_put(&b, (unsigned)g->preflag, 1);
+        sink_put(&b, (unsigned)g->scalefac_scale, 1);
+        sink_put(&b, (unsigned)g->count1table_select, 1);
+    }
     sink_close(&b);
+}
+
+// The packing pass for one frame (one warp on the device): scale factors + Huffman data of every granule-
+// channel into the stream's main-data stream at the position the serial stage reserved, zero padding up to
+// the reservoir minimum, then the side information.  Returns 0, or 1 if the bits written differ from the
+// serial stage's accounting (which would be a bug: the counter and the packer use the same tables).
+HMP3_FN int pack_frame(const EncTables *T, FrameRec *fr, const PackGc *gc, unsigned char *main) {
+    const int nch = T->cfg.nchan;
+    const bool m1 = T->cfg.h_id == 1;
+    BitSink b;
+    sink_open(&b, main + fr->data_start);
+    int bad = 0;
+    for (int k = 0; k < fr->ngr * nch; k++) {
+        const PackGc *p = gc + k;
+        const GrSide *g = &p->gr;
+        const long long start = b.total_bits;
+        if (g->aux_not_null) {
+            if (!m1) write_sf_mpeg2(&b, p->sf, g->block_type, g->scalefac_compress);
+            else if (fr->short_frame) write_sf_mpeg1_plain(&b, p->sf, g->block_type, g->scalefac_compress);
+            else write_sf_mpeg1_scfsi(&b, p->sf, (k / nch) ? fr->scfsi[k % nch] : 0, g->scalefac_compress);
+            pack_huffman(T, &b, g, p->ix, p->sign);
+        }
+        if ((int)(b.total_bits - start) != g->part2_3_length) bad = 1;
+    }
+    const int bytes = (int)sink_close(&b);
+#if HMP3_COOP
+    for (int k = bytes + HMP3_LANE; k < fr->data_bytes; k += 32) main[fr->data_start + k] = 0;
+#else
+    for (int k = bytes; k < fr->data_bytes; k++) main[fr->data_start + k] = 0;
+#endif
+    pack_side(T, fr, gc, fr->side);
+    return bad;
 }
 
 // ------------------------------------------------------------------ the rate loop of one granule
@@ -541,9 +603,45 @@ HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const Gra
     R->gr[igr][0].block_type = R->gr[igr][1].block_type = g->info.block_type;
 }
 
+// Record what the packing pass needs of granule-channel (igr, ch): quantised lines, signs, scale factors, side info.
+HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
+    const int *ix = R->ix[ch];
+    const unsigned char *sg = R->signx[ch];
+#if HMP3_COOP
+    const int lane = HMP3_LANE;
+    HMP3_SYNC();
+    for (int w = 0; w < 18; w++) {
+        const int k = 32 * w + lane;
+        out->ix[k] = (short)ix[k];
+        const unsigned bal = wballot(sg[k] & 1);
+        if (lane == 0) out->sign[w] = bal;
+    }
+    const ScaleFac *sf = &R->sf[igr][ch];
+    if (lane < 23) out->sf[lane] = (unsigned char)sf->l[lane];
+    for (int k = lane; k < 39; k += 32) out->sf[23 + k] = (unsigned char)sf->s[k / 13][k % 13];
+    const int *gs = (const int *)&R->gr[igr][ch];
+    int *gd = (int *)&out->gr;
+    if (lane < (int)(sizeof(GrSide) / sizeof(int))) gd[lane] = gs[lane];
+    HMP3_SYNC();
+#else
+    for (int k = 0; k < 576; k++) out->ix[k] = (short)ix[k];
+    for (int w = 0; w < 18; w++) {
+        unsigned m = 0;
+        for (int k = 0; k < 32; k++) m |= (unsigned)(sg[32 * w + k] & 1) << k;
+        out->sign[w] = m;
+    }
+    const ScaleFac *sf = &R->sf[igr][ch];
+    for (int i = 0; i < 23; i++) out->sf[i] = (unsigned char)sf->l[i];
+    for (int w = 0; w < 3; w++)
+        for (int i = 0; i < 13; i++) out->sf[23 + 13 * w + i] = (unsigned char)sf->s[w][i];
+    out->gr = R->gr[igr][ch];
+#endif
+}
+
 // One encode call worth of granules for MPEG-1 (two granules of one frame; mp3enc.cpp:1492-1749).
-// Returns the ms flag of the frame.
-HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, GranuleIn *g1) {
+// Returns the ms flag of the frame; *frame_bits receives the bits of the frame's main data.
+HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, GranuleIn *g1, PackGc *pack,
+                               int *frame_bits) {
     const EncConfig &C = T->cfg;
     const int nch = C.nchan;
     GranuleIn *gs[2] = {g0, g1};
@@ -577,25 +675,23 @@ HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
         int m2 = ms_correlation(&R->L, g1);
         if ((m1 + m2) >= 0) ms = 1;
     }
+    int total = 0;
     for (int igr = 0; igr < 2; igr++) {
         psy_stage2(T, R, gs[igr]);
         granule_allocate(T, R, gs[igr]->xr, igr, nch, ba_min, target, ba_max, bit_pool, ms);
         for (int ch = 0; ch < nch; ch++) {
             GrSide *g = &R->gr[igr][ch];
-            const long long start_bits = R->sink.total_bits;
+            int sfb = 0;
             g->scalefac_compress = 0;
             if (short_frame) {
                 R->scfsi[ch] = 0;
-                if (g->aux_not_null) g->scalefac_compress = pack_sf_mpeg1_plain(&R->sink, &R->sf[igr][ch], g->block_type);
+                if (g->aux_not_null) g->scalefac_compress = plan_sf_mpeg1_plain(&R->sf[igr][ch], g->block_type, &sfb);
             } else {
                 g->scalefac_compress =
-                    pack_sf_mpeg1_scfsi(&R->sink, &R->sf[igr][ch], R->sf_save[ch], igr, &R->scfsi[ch], g->aux_not_null);
+                    plan_sf_mpeg1_scfsi(&R->sf[igr][ch], R->sf_save[ch], igr, &R->scfsi[ch], g->aux_not_null, &sfb);
             }
-            int bits = 0;
-            if (g->aux_not_null) {
-                pack_huffman(T, &R->sink, g, R->ix[ch], R->signx[ch]);
-                bits = (int)(R->sink.total_bits - start_bits);
-            }
+            // the Huffman bits are exactly the counted ones (the counter and the packer share their tables)
+            const int bits = g->aux_not_null ? sfb + g->aux_bits : 0;
             if (nch == 2) {
                 ba_min -= bits;
                 ba_max -= bits;
@@ -604,6 +700,8 @@ HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
                 ba_max += ba_bit_max + C.sf_bit_max - bits;
             }
             g->part2_3_length = bits;
+            total += bits;
+            record_gc(R, igr, ch, pack + (igr * nch + ch));
         }
         if (nch == 2) {
             ba_min += ba_bit_min + sf_bits;
@@ -611,11 +709,12 @@ HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
             ba_max += ba_bit_max + sf_bits;
         }
     }
+    *frame_bits = total;
     return ms;
 }
 
 // One MPEG-2 frame = one granule (mp3enc.cpp:1832-2027)
-HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, GranuleIn *g0) {
+HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, GranuleIn *g0, PackGc *pack, int *frame_bits) {
     const EncConfig &C = T->cfg;
     const int nch = C.nchan;
     const int bit_pool = R->byte_pool << 3;
@@ -635,24 +734,27 @@ HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, Granul
     psy_stage2(T, R, g0);
     granule_allocate(T, R, g0->xr, igr, nch, ba_bit_min, nch * C.ave_target_bits, ba_bit_max, bit_pool,
                      nch == 2 ? ms : C.ms_flag);
+    int total = 0;
     for (int ch = 0; ch < nch; ch++) {
         GrSide *g = &R->gr[igr][ch];
-        const long long start_bits = R->sink.total_bits;
         int bits = 0;
         g->scalefac_compress = 0;
         if (g->aux_not_null) {
-            g->scalefac_compress = pack_sf_mpeg2(&R->sink, &R->sf[igr][ch], R->gr[igr][0].block_type);
-            pack_huffman(T, &R->sink, g, R->ix[ch], R->signx[ch]);
-            bits = (int)(R->sink.total_bits - start_bits);
+            int sfb = 0;
+            g->scalefac_compress = plan_sf_mpeg2(&R->sf[igr][ch], R->gr[igr][0].block_type, &sfb);
+            bits = sfb + g->aux_bits;
         }
         g->part2_3_length = bits;
+        total += bits;
+        record_gc(R, igr, ch, pack + ch);
     }
+    *frame_bits = total;
     return ms;
 }
 
 // ------------------------------------------------------------------ frame driver + reservoir
-// Records one frame: header, side info and its main-data slot; appends this frame's main data to the
-// stream's main-data stream (mp3enc.cpp:2106-2593).  `main` is the stream's main-data buffer.
+// Records one frame: header, its main-data slot and where its own data goes in the stream's main-data
+// stream (mp3enc.cpp:2106-2593).
 HMP3_HD void frame_header(const EncTables *T, unsigned char *h, int pad, int mode_ext, int br_index) {
     h[0] = T->cfg.head[0];
     h[1] = T->cfg.head[1];
@@ -663,9 +765,10 @@ HMP3_HD void frame_header(const EncTables *T, unsigned char *h, int pad, int mod
     h[3] = (unsigned char)((h[3] & 0xCF) | (mode_ext << 4));
 }
 
-// Encode the granules of one frame (MPEG-1: g0,g1; MPEG-2: g0 with granule parity igr).
-HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, unsigned char *main, FrameRec *frames, int igr,
-                              GranuleIn *g0, GranuleIn *g1) {
+// Encode the granules of one frame (MPEG-1: g0,g1; MPEG-2: g0 with granule parity igr).  `pack` receives the
+// frame's granule-channel records, K is the frame's first encode granule.
+HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, FrameRec *frames, int igr, GranuleIn *g0,
+                              GranuleIn *g1, PackGc *pack, int K) {
     const EncConfig &C = T->cfg;
     const bool m1 = C.h_id == 1;
     int pad = 0;
@@ -689,10 +792,10 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, unsigned char *m
         R->byte_min = R->byte_max - C.reservoir_back;
     }
     const int main_data_begin = R->byte_pool;
-    sink_open(&R->sink, main + R->main_tot);
-    const int ms = m1 ? encode_frame_mpeg1(T, R, g0, g1) : encode_frame_mpeg2(T, R, igr, g0);
+    int frame_bits = 0;
+    const int ms = m1 ? encode_frame_mpeg1(T, R, g0, g1, pack, &frame_bits) : encode_frame_mpeg2(T, R, igr, g0, pack, &frame_bits);
     const int mode_ext = ms + ms + C.is_flag;
-    int bytes = (int)sink_close(&R->sink);
+    int bytes = (frame_bits + 7) >> 3;
     int ibr = 0;
     if (C.vbr_flag) {
         const int bytes2 = bytes - R->byte_pool;
@@ -714,15 +817,21 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, unsigned char *m
         if (ibr > C.ivbr_max) ibr = C.ivbr_max;
         mf_bytes = C.vbr_main_framebytes[ibr];
     }
-    if (bytes < R->byte_min) {
-        for (int k = bytes; k < R->byte_min; k++) main[R->main_tot + k] = 0;
-        bytes = R->byte_min;
-    }
+    if (bytes < R->byte_min) bytes = R->byte_min;  // the packing pass zero-fills up to here
     fr->mf_bytes = mf_bytes;
     fr->out_off = R->out_tot;
     R->out_tot += (unsigned)(4 + C.side_bytes + mf_bytes);
+    fr->data_start = R->main_tot;
+    fr->data_bits = frame_bits;
+    fr->data_bytes = bytes;
+    fr->granule0 = K;
+    fr->ngr = (short)(m1 ? 2 : 1);
+    fr->igr0 = (short)igr;
+    fr->main_data_begin = (short)main_data_begin;
+    fr->short_frame = (short)(m1 ? ((g0->info.block_type == 2) | (g1->info.block_type == 2)) : 0);
+    fr->scfsi[0] = (short)R->scfsi[0];
+    fr->scfsi[1] = (short)R->scfsi[1];
     frame_header(T, fr->head, pad, mode_ext, ibr);
-    pack_side(T, R, main_data_begin, igr, fr->side);
     R->main_tot += bytes;
     R->mf_tot += mf_bytes;
     R->frames++;
@@ -739,13 +848,13 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, unsigned char *m
 namespace hmp3 {
 
 // Run the serial stage of one stream over the encode granules [K0, K0+NG) that Phase A has prepared.
-// gi/xr/raw/ms_raw point at this stream's slice of the chunk buffers (index 0 == granule K0).
-// ngran_real = granules of real encode calls (2 per call); after them the stream keeps consuming
-// zero-PCM granules until every real frame's main-data slot is filled (the CLI's tail flush,
+// gi/xr/raw/ms_raw/pack point at this stream's slice of the chunk buffers (index 0 == granule K0; pack holds
+// two records per granule).  ngran_real = granules of real encode calls (2 per call); after them the stream
+// keeps consuming zero-PCM granules until every real frame's main-data slot is filled (the CLI's tail flush,
 // test/tomp3.cpp:1015-1036), checked at call boundaries.
 HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
-                            const GranuleInfo *gi, float *xr, const PsyRaw *raw, const int *ms_raw,
-                            unsigned char *main, FrameRec *frames) {
+                            const GranuleInfo *gi, float *xr, const PsyRaw *raw, const int *ms_raw, PackGc *pack,
+                            FrameRec *frames) {
     const bool m1 = T->cfg.h_id == 1;
     const int frames_real = m1 ? ngran_real / 2 : ngran_real;
     for (int K = K0; K + 1 < K0 + NG && K + 1 < ngran; K += 2) {
@@ -759,10 +868,11 @@ HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, in
             g[q].raw = raw + (long long)o * 2;
             g[q].ms_raw = ms_raw[o];
         }
-        if (m1) encode_one_frame(T, R, main, frames, 0, &g[0], &g[1]);
+        PackGc *pk = pack + (long long)(K - K0) * 2;
+        if (m1) encode_one_frame(T, R, frames, 0, &g[0], &g[1], pk, K);
         else {
-            encode_one_frame(T, R, main, frames, 0, &g[0], nullptr);
-            encode_one_frame(T, R, main, frames, 1, &g[1], nullptr);
+            encode_one_frame(T, R, frames, 0, &g[0], nullptr, pk, K);
+            encode_one_frame(T, R, frames, 1, &g[1], nullptr, pk + 2, K + 1);
         }
         R->next_granule = K + 2;
         if (K + 2 >= ngran_real && R->frames_done >= frames_real) R->finished = 1;
@@ -770,7 +880,6 @@ HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, in
 }
 
 // Final byte layout of frame f of a stream: header | side info | slice of the main-data stream.
-// Returns the frame's size; `out` may be null to only measure.
 HMP3_HD int frame_bytes(const EncTables *T, const FrameRec *f) { return 4 + T->cfg.side_bytes + f->mf_bytes; }
 
 }  // namespace hmp3

@@ -62,8 +62,7 @@ HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:
 
 // ---- scale-factor range tables by (scalefac_scale, preflag) (bitallo3.cpp:87-161)
 HMP3_HD int sf_pre_amount(int i) {  // ISO pretab
-    const unsigned char p[22] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0};
-    return p[i];
+    return kPretab[i];
 }
 HMP3_HD int sf_select_limit(int sel, int i) {  // limits used to choose (scale, preflag)
     const int scale = sel >> 1, pre = sel & 1;
@@ -438,15 +437,15 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
 }
 
 // flatten isolated small peaks in the upper bands of L/R granules (bitallo3.cpp:2216-2299)
+// reciprocal of the value that quantises to n + 0.5 under the tuned rounding (bitallo3.cpp:2216-2232)
+HMP3_CONST_TABLE float kInvPeak[16] = {1.0f / (0.5f + 0.09460f),  1.0f / (1.5f + 0.02799f),  1.0f / (2.5f + 0.01671f),
+    1.0f / (3.5f + 0.01192f),  1.0f / (4.5f + 0.00927f),  1.0f / (5.5f + 0.00758f),
+    1.0f / (6.5f + 0.00641f),  1.0f / (7.5f + 0.00556f),  1.0f / (8.5f + 0.00490f),
+    1.0f / (9.5f + 0.00439f),  1.0f / (10.5f + 0.00397f), 1.0f / (11.5f + 0.00362f),
+    1.0f / (12.5f + 0.00333f), 1.0f / (13.5f + 0.00309f), 1.0f / (14.5f + 0.00287f),
+    1.0f / (15.5f + 0.00269f)};
 HMP3_HD float db_of(float x) { return (float)(10.0 * log10((double)x)); }
 HMP3_FN void long_trade_peaks(const EncTables *T, LongRate *L) {
-    const float inv_peak[16] = {1.0f / (0.5f + 0.09460f),  1.0f / (1.5f + 0.02799f),  1.0f / (2.5f + 0.01671f),
-                                1.0f / (3.5f + 0.01192f),  1.0f / (4.5f + 0.00927f),  1.0f / (5.5f + 0.00758f),
-                                1.0f / (6.5f + 0.00641f),  1.0f / (7.5f + 0.00556f),  1.0f / (8.5f + 0.00490f),
-                                1.0f / (9.5f + 0.00439f),  1.0f / (10.5f + 0.00397f), 1.0f / (11.5f + 0.00362f),
-                                1.0f / (12.5f + 0.00333f), 1.0f / (13.5f + 0.00309f), 1.0f / (14.5f + 0.00287f),
-                                1.0f / (15.5f + 0.00269f)};
-    const unsigned char snap[16] = {0, 1, 2, 3, 3, 5, 5, 7, 7, 7, 7, 15, 15, 15, 15, 15};
     for (int ch = 0; ch < L->nchan; ch++) {
         const int nsf = T->cfg.nsf[ch];
         int peak[22], peak10[22];
@@ -482,8 +481,8 @@ HMP3_FN void long_trade_peaks(const EncTables *T, LongRate *L) {
         if (tgt < 2) tgt = 2;
         if (top <= tgt) continue;
         if (tgt > 15) continue;
-        tgt = snap[tgt];
-        const float factor = inv_peak[tgt];
+        tgt = kPeakSnap[tgt];
+        const float factor = kInvPeak[tgt];
         for (i = k0; i < k1; i++)
             if (peak[i] > tgt) {
                 float xg = 1.7717f * db_of(L->x34max[ch][i] * factor);

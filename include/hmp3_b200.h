@@ -69,7 +69,8 @@ enum {
     HMP3_ERR_UNSUPPORTED = -3, /* configuration outside the built path (intensity stereo, dual)     */
     HMP3_ERR_OUT_SPACE = -4,   /* caller's output buffer too small                                  */
     HMP3_ERR_CUDA = -5,
-    HMP3_ERR_ARG = -6
+    HMP3_ERR_ARG = -6,
+    HMP3_ERR_INTERNAL = -7     /* the packing pass disagreed with the bit accounting (a bug)      */
 };
 
 /* Fill `ec` with the CLI defaults (hmp3/src/test/tomp3.cpp:357-387). */

@@ -185,10 +185,16 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
     rate_state_init(T, R);
     std::vector<unsigned char> mainbuf((size_t)(ngran + 4) * 2100, 0);
     std::vector<FrameRec> frames(ngran + 4);
-    // run granule pair by pair so that traces can be taken after each call
+    // run granule pair by pair so that traces can be taken after each call; the packing pass of the frames a
+    // call recorded follows it immediately (on the device it is a separate kernel over all frames of a chunk)
+    std::vector<PackGc> pack(4);
+    int bad = 0;
     for (int K = 0; K + 1 < ngran && !R->finished; K += 2) {
+        const int f0 = R->frames;
         rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &raw[(size_t)K * 2], &msr[K],
-                       mainbuf.data(), frames.data());
+                       pack.data(), frames.data());
+        for (int f = f0; f < R->frames; f++)
+            bad |= pack_frame(T, &frames[f], pack.data() + (size_t)(frames[f].granule0 - K) * 2, mainbuf.data());
         if (trace)
             for (int q = 0; q < 2; q++) {
                 int Kq = K + q;
@@ -207,6 +213,7 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
                 t[1362] = frames[R->frames - 1].head[3];
             }
     }
+    if (bad) { delete R; delete T; return -3; }
     long total = 0;
     const int nf = R->frames_done;
     for (int f = 0; f < nf; f++) {
