@@ -76,6 +76,20 @@ __device__ __forceinline__ int wmax(int v) {
     asm volatile("redux.sync.max.s32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(v));
     return r;
 }
+// acc + v[0] + v[1] + ... + v[m-1] in lane order (m <= 32, uniform), v[k] = lane k's value; every lane gets the
+// result.  Shuffles are issued four at a time so their latencies overlap; the additions stay strictly ordered.
+__device__ __forceinline__ float wsum_ordered(float acc, float v, int m) {
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+        const float a0 = wshfl(v, k), a1 = wshfl(v, k + 1), a2 = wshfl(v, k + 2), a3 = wshfl(v, k + 3);
+        acc += a0;
+        acc += a1;
+        acc += a2;
+        acc += a3;
+    }
+    for (; k < m; k++) acc += wshfl(v, k);
+    return acc;
+}
 __device__ __forceinline__ unsigned wballot(int pred) {
     unsigned r;
     asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; }" : "=r"(r) : "r"(pred));

@@ -99,8 +99,7 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
             float d = x[i] - xh;
             dd = d * d;
         }
-        const int m = (n - i0) < 32 ? (n - i0) : 32;
-        for (int k = 0; k < m; k++) acc += wshfl(dd, k);
+        acc = wsum_ordered(acc, dd, (n - i0) < 32 ? (n - i0) : 32);
     }
 #else
     for (int i = 0; i < n; i++) {
@@ -132,10 +131,8 @@ HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, in
             xx = x[i] * x[i];
         }
         const int m = (n - i0) < 32 ? (n - i0) : 32;
-        for (int k = 0; k < m; k++) {
-            sqq += wshfl(vv, k);
-            sxx += wshfl(xx, k);
-        }
+        sqq = wsum_ordered(sqq, vv, m);
+        sxx = wsum_ordered(sxx, xx, m);
     }
 #else
     for (int i = 0; i < n; i++) {

@@ -29,6 +29,7 @@ struct LongRate {
     int G[2], preemp[2], sf_scale[2];
     RegionPlan plan[2];
     float x34[2][576];
+    float dd[2][576];  // per-line squared errors of the step search in flight (device build)
 };
 
 HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
@@ -409,6 +410,112 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
     return best_s;
 }
 
+#if HMP3_COOP
+// Device form of the per-band step search: all bands of both channels walk together.  Lane b owns band b of
+// each channel (its search state lives in that lane's registers).  Every round (1) all lanes evaluate the
+// squared error of every line whose band is still searching, at that band's current trial step, into L->dd;
+// (2) each owning lane adds up its band IN LINE ORDER (so the float result is the sequential one) and advances
+// its little state machine exactly as seek_finer / seek_coarser do.  Rounds end when no band is searching.
+HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
+    const int lane = HMP3_LANE;
+    int mode[2], s_try[2], target[2], best_abs[2], best_noise[2], best_s[2], iter[2], niter[2];
+    HMP3_SYNC();
+    for (int c = 0; c < 2; c++) {
+        mode[c] = 0;
+        s_try[c] = target[c] = best_abs[c] = best_noise[c] = best_s[c] = iter[c] = niter[c] = 0;
+        if (c < L->nchan && lane < T->cfg.nsf[c]) {
+            target[c] = L->nt[c][lane];
+            if (L->noise0[c][lane] > target[c]) {
+                mode[c] = 1;
+                s_try[c] = L->gsf[c][lane];
+            } else {
+                L->gsf[c][lane] = L->gzero[c][lane] + 5;
+                L->noise[c][lane] = L->noise0[c][lane];
+            }
+        }
+    }
+    for (;;) {
+        unsigned am[2];
+        am[0] = wballot(mode[0] != 0);
+        am[1] = wballot(mode[1] != 0);
+        if ((am[0] | am[1]) == 0) break;
+        for (int c = 0; c < L->nchan; c++) {
+            if (am[c] == 0) continue;
+            const int nl = T->startBand_l[T->cfg.nsf[c]];
+            const float *y34 = L->x34[c];
+            const float *y = xr + 576 * c;
+            float *dd = L->dd[c];
+            for (int k0 = 0; k0 < nl; k0 += 32) {
+                const int k = k0 + lane;
+                const int b = (k < nl) ? (int)T->line_band_l[k] : 0;
+                const bool act = (k < nl) && ((am[c] >> b) & 1u);
+                if (wballot(act) == 0) continue;
+                const int st = wshfl(s_try[c], b);
+                if (act) {
+                    const float ig = T->igain34[st], gn = T->gain[st];
+                    float t = (ig * y34[k] + (0.0f - 0.0946f));
+                    int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
+                    float xh;
+                    if (q >= 0 && q < 256) xh = gn * T->ix43[q];
+                    else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
+                    float d = y[k] - xh;
+                    dd[k] = d * d;
+                }
+            }
+        }
+        HMP3_SYNC();
+        for (int c = 0; c < L->nchan; c++) {
+            if (mode[c] == 0) continue;
+            const float *v = L->dd[c] + T->startBand_l[lane];
+            const int n = T->nBand_l[lane];
+            float acc = 0.0f;
+            for (int k = 0; k < n; k++) acc += v[k];
+            const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[lane];
+            bool done = false;
+            if (mode[c] == 1) {
+                const int dn = tn - target[c];
+                L->nt_adjust[c][lane] = L->nt_adjust[c][lane] + (dn >> 3);
+                best_abs[c] = iabs(dn);
+                best_noise[c] = tn;
+                best_s[c] = s_try[c];
+                iter[c] = 0;
+                if (dn > 100) {
+                    niter[c] = imin_(s_try[c] - 1, 20);
+                    s_try[c] = s_try[c] - 1;
+                    mode[c] = 2;
+                    done = niter[c] <= 0;
+                } else if (dn < -100) {
+                    niter[c] = 20;
+                    s_try[c] = s_try[c] + 1;
+                    mode[c] = 3;
+                } else done = true;
+            } else {
+                const int a = iabs(tn - target[c]);
+                if (a < best_abs[c]) {
+                    best_abs[c] = a;
+                    best_noise[c] = tn;
+                    best_s[c] = s_try[c];
+                }
+                iter[c]++;
+                if (mode[c] == 2) {
+                    if (tn <= target[c] || iter[c] >= niter[c]) done = true;
+                    else s_try[c]--;
+                } else {
+                    if (tn >= target[c] || iter[c] >= niter[c]) done = true;
+                    else s_try[c]++;
+                }
+            }
+            if (done) {
+                L->gsf[c][lane] = best_s[c];
+                L->noise[c][lane] = best_noise[c];
+                mode[c] = 0;
+            }
+        }
+        HMP3_SYNC();
+    }
+    HMP3_SYNC();
+}
+#else
 HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *y34 = L->x34[ch];
@@ -435,6 +542,8 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
         }
     }
 }
+
+#endif
 
 // flatten isolated small peaks in the upper bands of L/R granules (bitallo3.cpp:2216-2299)
 // reciprocal of the value that quantises to n + 0.5 under the tuned rounding (bitallo3.cpp:2216-2232)
