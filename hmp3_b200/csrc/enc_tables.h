@@ -5,7 +5,10 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(HMP3_NO_FORCE_INLINE)
+#define HMP3_HD __host__ __device__ inline
+#define HMP3_FN static __host__ __device__ __noinline__
+#elif defined(__CUDACC__)
 #define HMP3_HD __host__ __device__ __forceinline__
 #define HMP3_FN static __host__ __device__ __noinline__
 #else
