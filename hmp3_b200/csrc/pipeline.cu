@@ -76,6 +76,8 @@ struct hmp3_batch {
     cudaStream_t stream_p = nullptr;    // packing pass
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr},
                 ev_start = nullptr;
+    const int16_t **d_src = nullptr;    // [n] device-visible addresses of the callers' pinned PCM (staged runs)
+    bool staged = false;                // this run pulls PCM chunk by chunk with k_stage_pcm
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
     std::vector<int> flags_h;
     int nbuf = 2;
@@ -125,6 +127,7 @@ struct hmp3_batch {
         }
         if (ev_start) cudaEventDestroy(ev_start);
         cudaFree(d_flags);
+        cudaFree(d_src);
         if (stream_a) cudaStreamDestroy(stream_a);
         if (stream_p) cudaStreamDestroy(stream_p);
         for (auto e : ev) cudaEventDestroy(e);
@@ -337,6 +340,11 @@ int run_plan(hmp3_batch *b) {
     for (int K0 = 0; K0 < b->max_gran; K0 += b->NG, c++) {
         const int k = c & 1;
         if (c >= 2) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
+        if (b->staged) {  // samples first needed by this chunk's polyphase: up to the end of granule K0+NG-1
+            const long long lo = c == 0 ? 0 : 576LL * K0, hi = 576LL * (K0 + b->NG);
+            launch_stage_pcm(b->d_st, b->d_src, b->d_pcm, lo, hi, n, b->stream_a);
+            b->launches++;
+        }
         r = launch_analysis(b, K0, k, b->stream_a);
         if (r != HMP3_OK) return r;
         CK(cudaEventRecord(b->ev_a[k], b->stream_a));
@@ -590,29 +598,71 @@ int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int 
 }
 
 // Host buffers in, host buffers out: upload every stream's PCM, run, copy each stream's frames back.
+namespace {
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
     CK(cudaSetDevice(b->device));
-    for (int i = 0; i < b->n; i++) {
+    // Pinned input: the device pulls each chunk's samples itself while the previous chunk is in the serial stage
+    // (k_stage_pcm).  Pageable input: one queued copy per stream before the first kernel.
+    bool pinned_in = true, pinned_out = true;
+    for (int i = 0; i < b->n && (pinned_in || pinned_out); i++) {
         if (b->status[i] != HMP3_OK) continue;
-        int r = hmp3_batch_upload(b, i, pcm[i], b->st_h[i].nsamples);
-        if (r != HMP3_OK) return r;
+        if (pinned_in && b->st_h[i].nsamples > 0 && !is_pinned(pcm[i])) pinned_in = false;
+        if (pinned_out && !is_pinned(out[i])) pinned_out = false;
     }
+    if (pinned_in) {
+        std::vector<const int16_t *> src(b->n, nullptr);
+        for (int i = 0; i < b->n; i++) {
+            if (b->status[i] != HMP3_OK || b->st_h[i].nsamples == 0) continue;
+            void *dp = nullptr;
+            if (cudaHostGetDevicePointer(&dp, (void *)pcm[i], 0) != cudaSuccess) {
+                cudaGetLastError();
+                pinned_in = false;
+                break;
+            }
+            src[i] = (const int16_t *)dp;
+        }
+        if (pinned_in) {
+            if (!b->d_src) CK(cudaMalloc(&b->d_src, sizeof(int16_t *) * b->n));
+            CK(cudaMemcpyAsync(b->d_src, src.data(), sizeof(int16_t *) * b->n, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaStreamSynchronize(b->stream));  // src is a local
+        }
+    }
+    if (!pinned_in) {
+        for (int i = 0; i < b->n; i++) {
+            if (b->status[i] != HMP3_OK) continue;
+            int r = hmp3_batch_upload(b, i, pcm[i], b->st_h[i].nsamples);
+            if (r != HMP3_OK) return r;
+        }
+    }
+    b->staged = pinned_in;
     int r = run_plan(b);
+    b->staged = false;
     if (r != HMP3_OK) return r;
     r = sync_plan(b);
     if (r != HMP3_OK) return r;
-    // one bulk D2H into pinned staging, then scatter to the callers' buffers
     const long long total = b->out_off_h[b->n];
-    if (b->h_stage_bytes < total) {
-        if (b->h_stage) cudaFreeHost(b->h_stage);
-        b->h_stage = nullptr;
-        b->h_stage_bytes = 0;
-        CK(cudaMallocHost(&b->h_stage, total + (total >> 3) + 4096));
-        b->h_stage_bytes = total + (total >> 3) + 4096;
+    if (!pinned_out) {  // one bulk D2H into pinned staging, then scatter to the callers' pageable buffers
+        if (b->h_stage_bytes < total) {
+            if (b->h_stage) cudaFreeHost(b->h_stage);
+            b->h_stage = nullptr;
+            b->h_stage_bytes = 0;
+            CK(cudaMallocHost(&b->h_stage, total + (total >> 3) + 4096));
+            b->h_stage_bytes = total + (total >> 3) + 4096;
+        }
+        CK(cudaMemcpyAsync(b->h_stage, b->d_out, total, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
     }
-    CK(cudaMemcpyAsync(b->h_stage, b->d_out, total, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
     for (int i = 0; i < b->n; i++) {
         int st = b->status[i];
         long long nb = st == HMP3_OK ? b->res_h[i].out_bytes : 0;
@@ -622,11 +672,16 @@ int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *co
             st = HMP3_ERR_OUT_SPACE;
             nb = 0;
         }
-        if (nb) memcpy(out[i], b->h_stage + b->out_off_h[i], nb);
+        if (nb) {
+            if (pinned_out)  // straight into the caller's pinned buffer
+                CK(cudaMemcpyAsync(out[i], b->d_out + b->out_off_h[i], nb, cudaMemcpyDeviceToHost, b->stream));
+            else memcpy(out[i], b->h_stage + b->out_off_h[i], nb);
+        }
         if (out_bytes) out_bytes[i] = nb;
         if (out_frames) out_frames[i] = st == HMP3_OK ? b->res_h[i].frames : 0;
         if (status) status[i] = st;
     }
+    if (pinned_out) CK(cudaStreamSynchronize(b->stream));
     return HMP3_OK;
 }
 

@@ -113,3 +113,29 @@ def test_encoder_handle_float_entry_and_rejections():
     assert used == 0
     assert enc.info_ec()["bitrate"] == 64
     enc.close()
+
+
+def test_pinned_host_buffers_take_the_staged_path():
+    """Pinned PCM is pulled chunk by chunk by the device (k_stage_pcm) and pinned outputs are written directly:
+    same bytes as the pageable path, for aligned and odd-aligned sources, stereo and mono."""
+    import torch
+    specs = [(44100, 2, dict(bitrate=64), 7.3, 0), (44100, 2, dict(bitrate=64), 3.1, 1), (22050, 1, dict(bitrate=32), 6.2, 1),
+             (22050, 1, dict(bitrate=32), 6.2, 2), (48000, 2, dict(vbr_mnr=100, hf=2, freq_limit=19000), 5.0, 3)]
+    ctl, pcms, pins, ptrs = [], [], [], []
+    for k, (sr, nch, kw, secs, skip) in enumerate(specs):
+        full = synth_pcm(900 + k, secs, sr, nch)
+        t = torch.from_numpy(full).pin_memory()
+        view = t[skip:]                                   # odd sample offsets: 2- or 4-byte aligned only
+        pins.append(t)
+        pcms.append(view.numpy())
+        ptrs.append(view.data_ptr())
+        ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+    want = capi.encode_batch(ctl, [np.array(p) for p in pcms])      # pageable copies
+    b = capi.Batch(ctl, [p.shape[0] for p in pcms])
+    outs = [torch.zeros(int(c), dtype=torch.uint8).pin_memory() for c in b.bound]
+    nb, nf, st = b.encode_host_ptrs(np.array(ptrs, dtype=np.uint64), np.array([o.data_ptr() for o in outs], dtype=np.uint64),
+                                    b.bound)
+    assert (st == 0).all()
+    for i in range(len(specs)):
+        assert nb[i] == want[i].size and np.array_equal(outs[i].numpy()[:nb[i]], want[i]), i
+    b.close()
