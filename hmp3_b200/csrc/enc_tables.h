@@ -16,15 +16,25 @@
 #define HMP3_FN static inline
 #endif
 
-// Device code runs one stream per warp: scalar control flow is executed uniformly by all 32 lanes and
-// the per-line / per-band loops are split over the lanes (HMP3_COOP).  The host build (test-only
-// simulator) runs the plain sequential loops.
+// Device code of the serial stage runs one stream per GROUP of HMP3_W lanes (two streams share a warp by
+// default): scalar control flow is executed uniformly by the lanes of a group and the per-line / per-band loops
+// are split over them (HMP3_COOP sections).  Two streams per warp is an instruction-FETCH optimisation: the rate
+// loop is ~190 KB of code walked once per granule, its speed is set by instruction-cache misses, and two groups
+// running the same functions in near lock-step share those misses (divergence between the groups is handled by
+// the hardware; every warp-level primitive below names only the lanes of its own group).
+// The host build (test-only simulator) runs the plain sequential loops.
 #if defined(__CUDA_ARCH__)
 #define HMP3_COOP 1
-#define HMP3_LANE ((int)(threadIdx.x & 31u))
-#define HMP3_SYNC() __syncwarp()
+#ifndef HMP3_W
+#define HMP3_W 16
+#endif
+#define HMP3_LANE ((int)(threadIdx.x & (unsigned)(HMP3_W - 1)))
+#define HMP3_GSHIFT (threadIdx.x & 31u & ~(unsigned)(HMP3_W - 1))
+#define HMP3_GMASK ((HMP3_W == 32) ? 0xffffffffu : (((1u << (HMP3_W & 31)) - 1u) << HMP3_GSHIFT))
+#define HMP3_SYNC() __syncwarp(HMP3_GMASK)
 #else
 #define HMP3_COOP 0
+#define HMP3_W 1
 #define HMP3_LANE 0
 #define HMP3_SYNC()
 #endif
@@ -106,9 +116,44 @@ __device__ __forceinline__ unsigned funnel_r(unsigned lo, unsigned hi, unsigned 
     asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sh));
     return r;
 }
+// ---- the same primitives restricted to the calling lane's GROUP of HMP3_W lanes (serial stage)
+__device__ __forceinline__ float gshfl(float v, int src) {
+    float r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, %3, %4;" : "=f"(r) : "f"(v), "r"(src), "r"(((32 - HMP3_W) << 8) | 0x1f), "r"(HMP3_GMASK));
+    return r;
+}
+__device__ __forceinline__ int gshfl(int v, int src) {
+    int r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(v), "r"(src), "r"(((32 - HMP3_W) << 8) | 0x1f), "r"(HMP3_GMASK));
+    return r;
+}
+__device__ __forceinline__ unsigned gsum(unsigned v) {
+    unsigned r;
+    asm volatile("redux.sync.add.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(HMP3_GMASK));
+    return r;
+}
+__device__ __forceinline__ int gsum(int v) { return (int)gsum((unsigned)v); }
+__device__ __forceinline__ unsigned gballot(int pred) {  // bit i = lane i of the group
+    unsigned r;
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; vote.sync.ballot.b32 %0, p, %2; }" : "=r"(r) : "r"(pred), "r"(HMP3_GMASK));
+    return r >> HMP3_GSHIFT;
+}
+// acc + v[0] + ... + v[m-1] in lane order (m <= HMP3_W, uniform in the group); every lane gets the result
+__device__ __forceinline__ float gsum_ordered(float acc, float v, int m) {
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+        const float a0 = gshfl(v, k), a1 = gshfl(v, k + 1), a2 = gshfl(v, k + 2), a3 = gshfl(v, k + 3);
+        acc += a0;
+        acc += a1;
+        acc += a2;
+        acc += a3;
+    }
+    for (; k < m; k++) acc += gshfl(v, k);
+    return acc;
+}
 #endif
 
-// warps (= streams) per thread block of the serial-stage kernel
+// warps per thread block of the serial-stage kernel (each warp carries 32 / HMP3_W streams)
 constexpr int kRateWarpsPerBlock = 4;
 // warps (= frames) per thread block of the packing kernel
 constexpr int kPackWarpsPerBlock = 8;

@@ -3,6 +3,12 @@
 // granule: instruction fetch, not arithmetic, bounds it).
 #include "kernels_rate.cuh"
 
+// lanes per stream of the serial stage (HMP3_W is only defined in device code)
+#ifndef HMP3_W_HOST_VALUE
+#define HMP3_W_HOST_VALUE 16
+#endif
+static constexpr int HMP3_W_HOST = HMP3_W_HOST_VALUE;
+
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
@@ -36,7 +42,7 @@ void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs,
 }
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream) {
-    k_rate<<<blocks_for((long long)n * 32, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
+    k_rate<<<blocks_for((long long)n * HMP3_W_HOST, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
         tabs, st, so, rs, cb, main_buf, frames, K0, n);
 }
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,

@@ -19,22 +19,24 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
     rate_state_init(tabs + st[s].cfg, rs + s);
 }
 
-// ---- K6: the serial stage over one chunk of granules, ONE WARP per stream: the scalar control flow of the
-// rate loop runs uniformly on all 32 lanes, the per-line / per-band loops are split across the lanes
-// (HMP3_COOP sections of rate_*.h).
+// ---- K6: the serial stage over one chunk of granules, one GROUP of HMP3_W lanes per stream (two streams per
+// warp): the scalar control flow of the rate loop runs uniformly on the lanes of a group, the per-line /
+// per-band loops are split across them (HMP3_COOP sections of rate_*.h).
 __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
            unsigned char *main_buf, FrameRec *frames, int K0, int nstreams) {
-    const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) / HMP3_W);
     if (s >= nstreams) return;
     const StreamDev sd = st[s];
-    cb.fr0[s] = cb.fr1[s] = rs[s].frames;  // nothing recorded in this chunk unless the loop below runs
+    if (HMP3_LANE == 0) cb.fr0[s] = cb.fr1[s] = rs[s].frames;  // nothing recorded in this chunk unless the loop below runs
+    HMP3_SYNC();
     if (K0 >= sd.ngran) return;
     const StreamOut o = so[s];
     const long long q0 = (long long)s * cb.NG;
     rate_run_chunk(tabs + sd.cfg, rs + s, K0, cb.NG, sd.ngran, sd.ngran_real, cb.gi + q0, cb.xr + q0 * 2 * 576,
                    cb.raw + q0 * 2, cb.ms_raw + q0, cb.pack + q0 * 2, frames + o.frames_off);
-    cb.fr1[s] = rs[s].frames;
+    HMP3_SYNC();
+    if (HMP3_LANE == 0) cb.fr1[s] = rs[s].frames;
 }
 
 // ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)

@@ -87,7 +87,7 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
 #if HMP3_COOP
     // lanes square the errors of 32 lines at a time; the sum is then taken in line order by every lane
     const int lane = HMP3_LANE;
-    for (int i0 = 0; i0 < n; i0 += 32) {
+    for (int i0 = 0; i0 < n; i0 += HMP3_W) {
         const int i = i0 + lane;
         float dd = 0.0f;
         if (i < n) {
@@ -99,7 +99,7 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
             float d = x[i] - xh;
             dd = d * d;
         }
-        acc = wsum_ordered(acc, dd, (n - i0) < 32 ? (n - i0) : 32);
+        acc = gsum_ordered(acc, dd, (n - i0) < HMP3_W ? (n - i0) : HMP3_W);
     }
 #else
     for (int i = 0; i < n; i++) {
@@ -120,7 +120,7 @@ HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, in
     float sqq = 0, sxx = 0;
 #if HMP3_COOP
     const int lane = HMP3_LANE;
-    for (int i0 = 0; i0 < n; i0 += 32) {
+    for (int i0 = 0; i0 < n; i0 += HMP3_W) {
         const int i = i0 + lane;
         float vv = 0.0f, xx = 0.0f;
         if (i < n) {
@@ -130,9 +130,9 @@ HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, in
             vv = v * v;
             xx = x[i] * x[i];
         }
-        const int m = (n - i0) < 32 ? (n - i0) : 32;
-        sqq = wsum_ordered(sqq, vv, m);
-        sxx = wsum_ordered(sxx, xx, m);
+        const int m = (n - i0) < HMP3_W ? (n - i0) : HMP3_W;
+        sqq = gsum_ordered(sqq, vv, m);
+        sxx = gsum_ordered(sxx, xx, m);
     }
 #else
     for (int i = 0; i < n; i++) {
@@ -172,7 +172,7 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
     const uint32_t(*lut)[2] = T->cnt_lut[c];
     unsigned s0 = 0, s1 = 0;
 #if HMP3_COOP
-    const int i_first = 2 * HMP3_LANE, i_step = 64;
+    const int i_first = 2 * HMP3_LANE, i_step = 2 * HMP3_W;
 #else
     const int i_first = 0, i_step = 2;
 #endif
@@ -191,8 +191,8 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
         }
     }
 #if HMP3_COOP
-    s0 = wsum(s0);
-    s1 = wsum(s1);
+    s0 = gsum(s0);
+    s1 = gsum(s1);
 #endif
     int b0 = (int)(s0 & 0xFFFF), b1 = (int)((s0 >> 16) & 0xFFFF);
     if (b0 < b1) { r.bits = b0; r.index = 0; }
@@ -213,7 +213,7 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
     if (nquads <= 0) return r;
     int a = 0, b = 0;
 #if HMP3_COOP
-    for (int i = HMP3_LANE; i < nquads; i += 32) {
+    for (int i = HMP3_LANE; i < nquads; i += HMP3_W) {
         const int k = 4 * i;
 #else
     for (int i = 0, k = 0; i < nquads; i++, k += 4) {
@@ -224,8 +224,8 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
         b += 4 + ones;
     }
 #if HMP3_COOP
-    a = wsum(a);
-    b = wsum(b);
+    a = gsum(a);
+    b = gsum(b);
 #endif
     if (a < b) { r.bits = a; r.index = 0; }
     else { r.bits = b; r.index = 1; }

@@ -268,6 +268,9 @@ HMP3_FN void pack_huffman_seq(const EncTables *T, BitSink *b, const GrSide *g, c
 }
 
 #if HMP3_COOP
+// (the packing pass runs one FULL warp per frame: its primitives are warp-wide, unlike the serial stage's)
+#define PK_LANE ((int)(threadIdx.x & 31u))
+#define PK_SYNC() __syncwarp()
 // Warp-parallel Huffman packing: each lane builds the bit field of one pair (or quad), a warp scan of the
 // field lengths gives its position, and the fields are OR-ed into a per-warp shared-memory bit buffer that
 // is then streamed out in whole bytes.  Produces exactly the bits of the sequential writer above.
@@ -285,7 +288,7 @@ __device__ __forceinline__ void bitbuf_or(unsigned *W, int pos, unsigned long lo
     if (w2) smem_or(W + w + 2, w2);
 }
 __device__ __forceinline__ int warp_scan_excl(int v, int *total) {
-    const int lane = HMP3_LANE;
+    const int lane = PK_LANE;
     int s = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -298,8 +301,8 @@ __device__ __forceinline__ int warp_scan_excl(int v, int *total) {
 HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
     __shared__ unsigned s_bits[kPackWarpsPerBlock][kPackWords];
     unsigned *W = s_bits[(threadIdx.x >> 5) % kPackWarpsPerBlock];
-    const int lane = HMP3_LANE;
-    HMP3_SYNC();
+    const int lane = PK_LANE;
+    PK_SYNC();
     const int p0 = b->nacc;  // bits pending in the writer (< 8)
     if (p0 + g->aux_bits > kPackWords * 32 - 160) {  // cannot happen within the part2_3 limits; stay correct anyway
         pack_huffman_seq(T, b, g, ix, sign);
@@ -307,9 +310,9 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
     }
     const int nwords = imin_(kPackWords, ((p0 + g->aux_bits + 31) >> 5) + 3);
     for (int k = lane; k < nwords; k += 32) W[k] = 0;
-    HMP3_SYNC();
+    PK_SYNC();
     if (lane == 0 && p0 > 0) W[0] = ((unsigned)b->acc & ((1u << p0) - 1u)) << (32 - p0);
-    HMP3_SYNC();
+    PK_SYNC();
     int pos = p0;
     int k0 = 0;
     for (int r = 0; r < 3; r++) {
@@ -369,17 +372,17 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
             pos += tot;
         }
     }
-    HMP3_SYNC();
+    PK_SYNC();
     const int nbytes = pos >> 3, rem = pos & 7;
     unsigned char *dst = b->p;
     for (int k = lane; k < nbytes; k += 32) dst[k] = (unsigned char)(W[k >> 2] >> (24 - 8 * (k & 3)));
     const unsigned last = (W[nbytes >> 2] >> (24 - 8 * (nbytes & 3))) & 0xffu;
-    HMP3_SYNC();
+    PK_SYNC();
     b->p = dst + nbytes;
     b->acc = rem ? (unsigned long long)(last >> (8 - rem)) : 0ull;
     b->nacc = rem;
     b->total_bits += pos - p0;
-    HMP3_SYNC();
+    PK_SYNC();
 }
 #else
 HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
@@ -455,7 +458,7 @@ HMP3_FN int pack_frame(const EncTables *T, FrameRec *fr, const PackGc *gc, unsig
     }
     const int bytes = (int)sink_close(&b);
 #if HMP3_COOP
-    for (int k = bytes + HMP3_LANE; k < fr->data_bytes; k += 32) main[fr->data_start + k] = 0;
+    for (int k = bytes + PK_LANE; k < fr->data_bytes; k += 32) main[fr->data_start + k] = 0;
 #else
     for (int k = bytes; k < fr->data_bytes; k++) main[fr->data_start + k] = 0;
 #endif
@@ -487,7 +490,7 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int i
         L->mnr = (L->mnr + init) >> 1;
         L->mnr = imin_(L->mnr, init + 500);
 #if HMP3_COOP
-        for (int k = HMP3_LANE; k < nchan * 576; k += 32) ix[k] = 0;
+        for (int k = HMP3_LANE; k < nchan * 576; k += HMP3_W) ix[k] = 0;
         HMP3_SYNC();
 #else
         for (int k = 0; k < nchan * 576; k++) ix[k] = 0;
@@ -611,17 +614,20 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
     const int lane = HMP3_LANE;
     HMP3_SYNC();
     for (int w = 0; w < 18; w++) {
-        const int k = 32 * w + lane;
-        out->ix[k] = (short)ix[k];
-        const unsigned bal = wballot(sg[k] & 1);
-        if (lane == 0) out->sign[w] = bal;
+        unsigned bits = 0;
+        for (int h = 0; h < 32 / HMP3_W; h++) {
+            const int k = 32 * w + HMP3_W * h + lane;
+            out->ix[k] = (short)ix[k];
+            bits |= gballot(sg[k] & 1) << (HMP3_W * h);
+        }
+        if (lane == 0) out->sign[w] = bits;
     }
     const ScaleFac *sf = &R->sf[igr][ch];
-    if (lane < 23) out->sf[lane] = (unsigned char)sf->l[lane];
-    for (int k = lane; k < 39; k += 32) out->sf[23 + k] = (unsigned char)sf->s[k / 13][k % 13];
+    for (int k = lane; k < 23; k += HMP3_W) out->sf[k] = (unsigned char)sf->l[k];
+    for (int k = lane; k < 39; k += HMP3_W) out->sf[23 + k] = (unsigned char)sf->s[k / 13][k % 13];
     const int *gs = (const int *)&R->gr[igr][ch];
     int *gd = (int *)&out->gr;
-    if (lane < (int)(sizeof(GrSide) / sizeof(int))) gd[lane] = gs[lane];
+    for (int k = lane; k < (int)(sizeof(GrSide) / sizeof(int)); k += HMP3_W) gd[k] = gs[k];
     HMP3_SYNC();
 #else
     for (int k = 0; k < 576; k++) out->ix[k] = (short)ix[k];

@@ -128,8 +128,7 @@ HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nband
     // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
 #if HMP3_COOP
     HMP3_SYNC();
-    const int i = HMP3_LANE;  // one band per lane
-    if (i < nbands) {
+    for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {  // bands dealt over the lanes
         const float *y = L->x34[ch] + T->startBand_l[i];
         const int n = T->nBand_l[i];
         float m = 0.0f;
@@ -159,8 +158,7 @@ HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nband
 // sums of v[] over each of the first nbands bands, accumulated in line order: one band per lane
 HMP3_HD void long_band_sums(const EncTables *T, const float *v, int nbands, float *out) {
     HMP3_SYNC();
-    const int i = HMP3_LANE;
-    if (i < nbands) {
+    for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {
         const float *y = v + T->startBand_l[i];
         const int n = T->nBand_l[i];
         float e = 0.0f;
@@ -181,7 +179,7 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
         unsigned char *s = signx + 576 * ch;
         float *sq = L->x34[ch];  // scratch until the 3/4 powers are taken below
         const int nl = T->startBand_l[T->cfg.nsf3[ch]];
-        for (int k = HMP3_LANE; k < nl; k += 32) {
+        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
             float v = x[k];
             if (v >= 0.0f) s[k] = 0;
             else { s[k] = 1; v = -v; x[k] = v; }
@@ -227,7 +225,7 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
         const float *x = xr + 576 * ch;
 #if HMP3_COOP
         HMP3_SYNC();
-        for (int k = HMP3_LANE; k < T->cfg.nbmax3[ch]; k += 32) L->x34[ch][k] = pow34(T, x[k]);
+        for (int k = HMP3_LANE; k < T->cfg.nbmax3[ch]; k += HMP3_W) L->x34[ch][k] = pow34(T, x[k]);
 #else
         for (int k = 0; k < T->cfg.nbmax3[ch]; k++) L->x34[ch][k] = pow34(T, x[k]);
 #endif
@@ -248,13 +246,13 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         float *sq0 = L->x34[0], *sq1 = L->x34[1];  // scratch until the 3/4 powers are taken below
         const int nl = T->startBand_l[nsf0];
         const int nrot = nl + (T->cfg.hf_flag ? T->nBand_l[21] : 0);  // the pseudo band above sfb 21 is rotated too
-        for (int k = HMP3_LANE; k < nl; k += 32) {
+        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
             sq0[k] = xr[k] * xr[k];
             sq1[k] = xr[576 + k] * xr[576 + k];
         }
         long_band_sums(T, sq0, nsf0, L->xsxx[0]);
         long_band_sums(T, sq1, nsf0, L->xsxx[1]);
-        for (int k = HMP3_LANE; k < nrot; k += 32) {
+        for (int k = HMP3_LANE; k < nrot; k += HMP3_W) {
             float m = (xr[k] + xr[576 + k]);
             float d = (xr[k] - xr[576 + k]);
             unsigned char sm_ = 0, sd_ = 0;
@@ -356,7 +354,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
     HMP3_SYNC();
     for (int ch = 0; ch < 2; ch++)
 #if HMP3_COOP
-        for (int k = HMP3_LANE; k < T->cfg.nbmax2[ch]; k += 32) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
+        for (int k = HMP3_LANE; k < T->cfg.nbmax2[ch]; k += HMP3_W) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
 #else
         for (int k = 0; k < T->cfg.nbmax2[ch]; k++) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
 #endif
@@ -417,27 +415,29 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
 // (2) each owning lane adds up its band IN LINE ORDER (so the float result is the sequential one) and advances
 // its little state machine exactly as seek_finer / seek_coarser do.  Rounds end when no band is searching.
 HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
+    constexpr int NS = (22 + HMP3_W - 1) / HMP3_W;  // band slots per lane: band = lane + HMP3_W * slot
+    constexpr int NI = 2 * NS;                      // items per lane: item = channel * NS + slot
     const int lane = HMP3_LANE;
-    int mode[2], s_try[2], target[2], best_abs[2], best_noise[2], best_s[2], iter[2], niter[2];
+    int mode[NI], s_try[NI], target[NI], best_abs[NI], best_noise[NI], best_s[NI], iter[NI], niter[NI];
     HMP3_SYNC();
-    for (int c = 0; c < 2; c++) {
-        mode[c] = 0;
-        s_try[c] = target[c] = best_abs[c] = best_noise[c] = best_s[c] = iter[c] = niter[c] = 0;
-        if (c < L->nchan && lane < T->cfg.nsf[c]) {
-            target[c] = L->nt[c][lane];
-            if (L->noise0[c][lane] > target[c]) {
-                mode[c] = 1;
-                s_try[c] = L->gsf[c][lane];
+    for (int it = 0; it < NI; it++) {
+        const int c = it / NS, bnd = lane + HMP3_W * (it % NS);
+        mode[it] = 0;
+        s_try[it] = target[it] = best_abs[it] = best_noise[it] = best_s[it] = iter[it] = niter[it] = 0;
+        if (c < L->nchan && bnd < T->cfg.nsf[c]) {
+            target[it] = L->nt[c][bnd];
+            if (L->noise0[c][bnd] > target[it]) {
+                mode[it] = 1;
+                s_try[it] = L->gsf[c][bnd];
             } else {
-                L->gsf[c][lane] = L->gzero[c][lane] + 5;
-                L->noise[c][lane] = L->noise0[c][lane];
+                L->gsf[c][bnd] = L->gzero[c][bnd] + 5;
+                L->noise[c][bnd] = L->noise0[c][bnd];
             }
         }
     }
     for (;;) {
-        unsigned am[2];
-        am[0] = wballot(mode[0] != 0);
-        am[1] = wballot(mode[1] != 0);
+        unsigned am[2] = {0u, 0u};  // bit b = band b of the channel is still searching
+        for (int it = 0; it < NI; it++) am[it / NS] |= gballot(mode[it] != 0) << (HMP3_W * (it % NS));
         if ((am[0] | am[1]) == 0) break;
         for (int c = 0; c < L->nchan; c++) {
             if (am[c] == 0) continue;
@@ -445,12 +445,16 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
             const float *y34 = L->x34[c];
             const float *y = xr + 576 * c;
             float *dd = L->dd[c];
-            for (int k0 = 0; k0 < nl; k0 += 32) {
+            for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
                 const int k = k0 + lane;
                 const int b = (k < nl) ? (int)T->line_band_l[k] : 0;
                 const bool act = (k < nl) && ((am[c] >> b) & 1u);
-                if (wballot(act) == 0) continue;
-                const int st = wshfl(s_try[c], b);
+                if (gballot(act) == 0) continue;
+                int st = gshfl(s_try[c * NS], b & (HMP3_W - 1));
+                if (NS > 1) {
+                    const int st1 = gshfl(s_try[c * NS + NS - 1], b & (HMP3_W - 1));
+                    if (b >= HMP3_W) st = st1;
+                }
                 if (act) {
                     const float ig = T->igain34[st], gn = T->gain[st];
                     float t = (ig * y34[k] + (0.0f - 0.0946f));
@@ -464,51 +468,52 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
             }
         }
         HMP3_SYNC();
-        for (int c = 0; c < L->nchan; c++) {
-            if (mode[c] == 0) continue;
-            const float *v = L->dd[c] + T->startBand_l[lane];
-            const int n = T->nBand_l[lane];
+        for (int it = 0; it < NI; it++) {
+            if (mode[it] == 0) continue;
+            const int c = it / NS, bnd = lane + HMP3_W * (it % NS);
+            const float *v = L->dd[c] + T->startBand_l[bnd];
+            const int n = T->nBand_l[bnd];
             float acc = 0.0f;
             for (int k = 0; k < n; k++) acc += v[k];
-            const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[lane];
+            const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];
             bool done = false;
-            if (mode[c] == 1) {
-                const int dn = tn - target[c];
-                L->nt_adjust[c][lane] = L->nt_adjust[c][lane] + (dn >> 3);
-                best_abs[c] = iabs(dn);
-                best_noise[c] = tn;
-                best_s[c] = s_try[c];
-                iter[c] = 0;
+            if (mode[it] == 1) {
+                const int dn = tn - target[it];
+                L->nt_adjust[c][bnd] = L->nt_adjust[c][bnd] + (dn >> 3);
+                best_abs[it] = iabs(dn);
+                best_noise[it] = tn;
+                best_s[it] = s_try[it];
+                iter[it] = 0;
                 if (dn > 100) {
-                    niter[c] = imin_(s_try[c] - 1, 20);
-                    s_try[c] = s_try[c] - 1;
-                    mode[c] = 2;
-                    done = niter[c] <= 0;
+                    niter[it] = imin_(s_try[it] - 1, 20);
+                    s_try[it] = s_try[it] - 1;
+                    mode[it] = 2;
+                    done = niter[it] <= 0;
                 } else if (dn < -100) {
-                    niter[c] = 20;
-                    s_try[c] = s_try[c] + 1;
-                    mode[c] = 3;
+                    niter[it] = 20;
+                    s_try[it] = s_try[it] + 1;
+                    mode[it] = 3;
                 } else done = true;
             } else {
-                const int a = iabs(tn - target[c]);
-                if (a < best_abs[c]) {
-                    best_abs[c] = a;
-                    best_noise[c] = tn;
-                    best_s[c] = s_try[c];
+                const int a = iabs(tn - target[it]);
+                if (a < best_abs[it]) {
+                    best_abs[it] = a;
+                    best_noise[it] = tn;
+                    best_s[it] = s_try[it];
                 }
-                iter[c]++;
-                if (mode[c] == 2) {
-                    if (tn <= target[c] || iter[c] >= niter[c]) done = true;
-                    else s_try[c]--;
+                iter[it]++;
+                if (mode[it] == 2) {
+                    if (tn <= target[it] || iter[it] >= niter[it]) done = true;
+                    else s_try[it]--;
                 } else {
-                    if (tn >= target[c] || iter[c] >= niter[c]) done = true;
-                    else s_try[c]++;
+                    if (tn >= target[it] || iter[it] >= niter[it]) done = true;
+                    else s_try[it]++;
                 }
             }
             if (done) {
-                L->gsf[c][lane] = best_s[c];
-                L->noise[c][lane] = best_noise[c];
-                mode[c] = 0;
+                L->gsf[c][bnd] = best_s[it];
+                L->noise[c][bnd] = best_noise[it];
+                mode[it] = 0;
             }
         }
         HMP3_SYNC();
@@ -824,7 +829,7 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
         const float *x = L->x34[ch];
         int *q = ix + 576 * ch;
         const int nb = T->cfg.nsf[ch], nl = T->startBand_l[nb];
-        for (int k = HMP3_LANE; k < nl; k += 32) {
+        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
             const float ig = T->igain34[L->gsf[ch][T->line_band_l[k]]];
             int v;
             if (tuned) {
@@ -836,8 +841,7 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
             q[k] = v;
         }
         HMP3_SYNC();
-        const int i = HMP3_LANE;
-        if (i < nb) {
+        for (int i = HMP3_LANE; i < nb; i += HMP3_W) {
             const int *qb = q + T->startBand_l[i];
             const int n = T->nBand_l[i];
             int m = 0;
