@@ -18,7 +18,7 @@ def parse_frames(mp3):
     off, sizes, mdb = [], [], []
     p = 0
     while p + 4 <= mp3.size:
-        h = mp3[p:p + 4]
+        h = [int(v) for v in mp3[p:p + 4]]
         assert h[0] == 0xFF and (h[1] & 0xFE) == 0xFA, "lost sync at byte %d" % p   # MPEG-1 Layer III, no CRC
         br = br_tab[h[2] >> 4]
         pad = (h[2] >> 1) & 1
