@@ -81,6 +81,33 @@ HMP3_HD float dequant43(const EncTables *T, int q) {
 }
 
 // quantisation noise of one band at step g, in millibels relative to the band width (l3math.c:511-544)
+// the plain sequential loop (host build; on the device also used one band per lane where bands are short)
+HMP3_HD int band_noise_seq(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
+    const float ig = T->igain34[g], gn = T->gain[g];
+    float acc = 0.0f;
+    for (int i = 0; i < n; i++) {
+        float t = (ig * x34[i] + (0.0f - 0.0946f));
+        int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
+        float xh;
+        if (q >= 0 && q < 256) xh = gn * T->ix43[q];
+        else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
+        float d = x[i] - xh;
+        acc += d * d;
+    }
+    return mb_log(T, 1.0e-12f + acc) - logn;
+}
+HMP3_HD int band_refit_gain_seq(const EncTables *T, const int *q, const float *x, int n) {
+    float sqq = 0, sxx = 0;
+    for (int i = 0; i < n; i++) {
+        float v;
+        if (q[i] < 256) v = T->ix43[q[i]];
+        else v = (float)(pow((double)q[i], (4.0 / 3.0)));
+        sqq += v * v;
+        sxx += x[i] * x[i];
+    }
+    return 54 * mb_log(T, sxx / sqq) + (8 << 13);
+}
+
 HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
     const float ig = T->igain34[g], gn = T->gain[g];
     float acc = 0.0f;

@@ -763,6 +763,40 @@ HMP3_FN int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
 
 // try coarser steps on the low bands while the measured noise stays under target (bitallo3.cpp:1348-1399)
 HMP3_FN void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float *xr) {
+#if HMP3_COOP
+    // the low bands are short (4..16 lines) and independent: one (channel, band) per lane, each lane walking its
+    // candidates with the plain sequential noise measurement
+    HMP3_SYNC();
+    for (int it = HMP3_LANE; it < 32; it += HMP3_W) {
+        const int ch = it >> 4, i = it & 15;
+        if (ch >= L->nchan || i >= imin_(13, T->cfg.nsf[ch])) continue;
+        if (!(L->active[ch][i] && (L->gsf[ch][i] < (L->gzero[ch][i] - 5)))) continue;
+        const int sdelta = 2 * (1 + L->sf_scale[ch]);
+        const int GG = L->G[ch];
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        const float *y34 = L->x34[ch] + T->startBand_l[i];
+        const float *y = xr + 576 * ch + T->startBand_l[i];
+        const int n = T->nBand_l[i];
+        int smin = L->sf[ch][i];
+        const int g0 = L->gzero[ch][i] - 4;
+        int s = imin_(L->sf[ch][i] - sdelta, sf_upper(scale, pre, i));
+        const int s0 = sf_lower(scale, pre, i);
+        const int logn = T->log_cbw_l[i];
+        const int nt = L->nt[ch][i];
+        for (; s >= s0; s -= sdelta) {
+            const int g = GG - s;
+            if (g >= g0) break;
+            int nz = band_noise_seq(T, y34, y, g, n, logn);
+            if (nz <= nt) {
+                L->noise[ch][i] = nz;
+                smin = s;
+            }
+        }
+        L->sf[ch][i] = smin;
+        L->gsf[ch][i] = imax_(GG - smin, 0);
+    }
+    HMP3_SYNC();
+#else
     for (int ch = 0; ch < L->nchan; ch++) {
         const int sdelta = 2 * (1 + L->sf_scale[ch]);
         const int GG = L->G[ch];
@@ -794,10 +828,29 @@ HMP3_FN void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float
             y += n;
         }
     }
+#endif
 }
 
 // re-fit the scale factor of bands whose largest quantised value is 1 or 2 (bitallo3.cpp:1471-1536)
 HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const int *ix) {
+#if HMP3_COOP
+    HMP3_SYNC();
+    for (int it = HMP3_LANE; it < 64; it += HMP3_W) {  // one (channel, band) per lane
+        const int ch = it >> 5, i = it & 31;
+        if (ch >= L->nchan || i >= T->cfg.nsf[ch]) continue;
+        if (!((L->ixmax[ch][i] == 1) || (L->ixmax[ch][i] == 2))) continue;
+        const int gscale = L->G[ch] << 13;
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        const int t = band_refit_gain_seq(T, ix + 576 * ch + T->startBand_l[i], xr + 576 * ch + T->startBand_l[i], T->nBand_l[i]);
+        int s;
+        if (scale == 0) s = ((gscale - t + (1 << 13)) & (~((1 << 14) - 1))) >> 13;
+        else s = ((gscale - t + (1 << 14)) & (~((1 << 15) - 1))) >> 13;
+        s = imin_(s, sf_upper(scale, pre, i));
+        s = imax_(s, sf_lower(scale, pre, i));
+        L->sf[ch][i] = s;
+    }
+    HMP3_SYNC();
+#else
     for (int ch = 0; ch < L->nchan; ch++) {
         const int gscale = L->G[ch] << 13;
         const int scale = L->sf_scale[ch], pre = L->preemp[ch];
@@ -818,6 +871,7 @@ HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const floa
             q += n;
         }
     }
+#endif
 }
 
 // ------------------------------------------------------------------ quantise + count

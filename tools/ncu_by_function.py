@@ -27,7 +27,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(src.splitlines()))
 hdr = None
 base = None
-agg = collections.defaultdict(lambda: [0, 0, 0])
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0])
 for r in rows:
     if r and r[0] == "Address":
         hdr = r
@@ -47,9 +47,13 @@ for r in rows:
     agg[fn][0] += int(d["# Samples"] or 0)
     agg[fn][1] += int(d["Instructions Executed"] or 0)
     agg[fn][2] += int(d["Thread Instructions Executed"] or 0)
+    agg[fn][3] += int(d.get("stall_no_inst") or 0)
+    agg[fn][4] += int(d.get("stall_long_sb") or 0)
+    agg[fn][5] += int(d.get("stall_wait") or 0)
 ts = sum(v[0] for v in agg.values()) or 1
 ti = sum(v[1] for v in agg.values()) or 1
-print("%-28s %8s %8s %14s %8s" % ("function", "samples%", "instr%", "warp-instr", "thr/inst"))
+print("%-28s %8s %8s %14s %8s %8s %8s %8s" % ("function", "samples%", "instr%", "warp-instr", "thr/inst", "no_inst%", "long_sb%", "wait%"))
 for fn, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-    print("%-28s %7.2f%% %7.2f%% %14d %8.1f" % (fn, 100 * v[0] / ts, 100 * v[1] / ti, v[1], v[2] / max(v[1], 1)))
+    print("%-28s %7.2f%% %7.2f%% %14d %8.1f %7.2f%% %7.2f%% %7.2f%%" % (fn, 100 * v[0] / ts, 100 * v[1] / ti, v[1], v[2] / max(v[1], 1),
+                                                            100 * v[3] / ts, 100 * v[4] / ts, 100 * v[5] / ts))
 print("total warp instructions", ti, "samples", ts)
