@@ -14,6 +14,9 @@ struct SwitchState;
 struct RateState;
 struct FrameRec;
 struct PackGc;
+struct PrepGranule;
+struct PsyState;
+struct SigMask;
 
 // One stream of the batch, device view.
 struct StreamDev {
@@ -35,6 +38,9 @@ struct ChunkBufs {
     float *xr;       // [n][NG][2][576]
     PsyRaw *raw;     // [n][NG][2]
     int *ms_raw;     // [n][NG]
+    signed char *ms; // [n][NG]  M/S decision of the granule's frame (after hysteresis)
+    SigMask *sm;     // [n][NG][2][36]  psychoacoustic sig/mask per granule-channel (stage 2)
+    PrepGranule *prep; // [n][NG]  state-free part of the rate-loop prologue (long blocks)
     PackGc *pack;    // [n][NG][2]  granule-channel records for the packing pass
     int *fr0, *fr1;  // [n] frames recorded by each stream before / after this chunk's serial stage
     int NG;
@@ -63,6 +69,12 @@ void launch_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState 
                         cudaStream_t stream);
 void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
 void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+// scans and prepare pass that follow psy stage 1 (carry: msmem [n], psy [n][2])
+void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
+                    cudaStream_t stream);
+void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream);
+size_t sizeof_prep_granule();
+size_t sizeof_psy_state();
 void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream);
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);

@@ -1,4 +1,5 @@
 // Phase A kernels + launchers (see kernels_analysis.cuh).
+#define HMP3_W 32  // cooperative sections in this translation unit are warp-wide
 #include "kernels_analysis.cuh"
 
 namespace hmp3 {
@@ -32,4 +33,15 @@ void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int
 void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
     k_psy_stage1<<<blocks_for((long long)n * cb.NG * 3, 64), 64, 0, stream>>>(tabs, st, cb, K0, n);
 }
+void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
+                    cudaStream_t stream) {
+    k_ms_scan<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, msmem, cb, K0, n);
+    k_psy_stage2<<<blocks_for(2LL * n, 64), 64, 0, stream>>>(tabs, st, psy, cb, K0, n);
+    k_prepare<<<blocks_for((long long)n * cb.NG * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
+}
+void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream) {
+    k_prepare_init<<<blocks_for(2LL * n, 128), 128, 0, stream>>>(msmem, psy, n);
+}
+size_t sizeof_prep_granule() { return sizeof(PrepGranule); }
+size_t sizeof_psy_state() { return sizeof(PsyState); }
 }  // namespace hmp3

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "analysis.h"
+#include "prepare.h"
 #include "batch_types.h"
 
 namespace hmp3 {
@@ -145,6 +146,81 @@ __global__ void __launch_bounds__(64) k_psy_stage1(const EncTables *tabs, const 
         if (sd.nch == 2) m = (bt != 2) ? ms_measure_long(T, x0, x0 + 576) : ms_measure_short(T, x0, x0 + 576);
         cb.ms_raw[(long long)s * cb.NG + q] = m;
     }
+}
+
+// ---- K5b: M/S decision scan (hysteresis memory), one thread per stream, sequential over the chunk.
+// Frames are pairs of granules (MPEG-1: the decision is per frame, mp3enc.cpp:1537-1546; MPEG-2: per granule).
+__global__ void k_ms_scan(const EncTables *tabs, const StreamDev *st, int *msmem, ChunkBufs cb, int K0, int nstreams) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    const EncTables *T = tabs + sd.cfg;
+    const bool stereo_ms = (sd.nch == 2 && T->cfg.ms_flag);
+    const bool m1 = T->cfg.h_id == 1;
+    int mem = msmem[s];
+    const GranuleInfo *gi = cb.gi + (long long)s * cb.NG;
+    const int *raw = cb.ms_raw + (long long)s * cb.NG;
+    signed char *out = cb.ms + (long long)s * cb.NG;
+    for (int q = 0; q + 1 < cb.NG && K0 + q + 1 < sd.ngran; q += 2) {
+        int f0 = 0, f1 = 0;
+        if (stereo_ms) {
+            const int a = ms_scan_step(&mem, gi[q].block_type, raw[q]);
+            if (m1) {
+                const int b = ms_scan_step(&mem, gi[q + 1].block_type, raw[q + 1]);
+                f0 = f1 = ((a + b) >= 0);
+            } else {
+                f0 = (a >= 0);
+                const int b = ms_scan_step(&mem, gi[q + 1].block_type, raw[q + 1]);
+                f1 = (b >= 0);
+            }
+        }
+        out[q] = (signed char)f0;
+        out[q + 1] = (signed char)f1;
+    }
+    msmem[s] = mem;
+}
+
+// ---- K5c: psychoacoustic stage 2 (pre-echo memory), one thread per (stream, channel), sequential over the chunk
+__global__ void k_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy, ChunkBufs cb, int K0,
+                             int nstreams) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = id >> 1, ch = id & 1;
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    if (ch >= sd.nch) return;
+    const EncTables *T = tabs + sd.cfg;
+    PsyState *P = psy + (long long)s * 2 + ch;
+    for (int q = 0; q < cb.NG && K0 + q < sd.ngran; q++) {
+        const GranuleInfo g = cb.gi[(long long)s * cb.NG + q];
+        const PsyRaw *R = cb.raw + ((long long)s * cb.NG + q) * 2 + ch;
+        if (g.block_type != 2) psy_long_stage2(T, R, P->echo, g.block_type, P->sm);
+        else psy_short_stage2(T, R, P->echo, g.block_type_prev, P->sm);
+        SigMask *o = cb.sm + (((long long)s * cb.NG + q) * 2 + ch) * 36;
+        for (int i = 0; i < 36; i++) o[i] = P->sm[i];
+    }
+}
+
+// ---- K5d: prepare pass, one warp per (stream, granule): state-free part of the rate-loop prologue (long blocks)
+__global__ void __launch_bounds__(128) k_prepare(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
+                                                 int nstreams) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int q = (int)(wid % cb.NG), s = (int)(wid / cb.NG);
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    if (K0 + q >= sd.ngran) return;
+    const long long o = (long long)s * cb.NG + q;
+    if (cb.gi[o].block_type == 2) return;
+    const EncTables *T = tabs + sd.cfg;
+    // the flag the allocator is called with (mp3enc.cpp:1556 / :1880: MPEG-2 mono passes the configured ms_flag)
+    const int ms = (T->cfg.h_id == 0 && sd.nch != 2) ? T->cfg.ms_flag : (int)cb.ms[o];
+    long_prepare(T, ms, cb.xr + o * 2 * 576, cb.prep + o);
+}
+
+__global__ void k_prepare_init(int *msmem, PsyState *psy, int nstreams) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * nstreams) return;
+    psy_state_init(psy + id);
+    if ((id & 1) == 0) msmem[id >> 1] = 0;
 }
 
 }  // namespace hmp3

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     const StreamOut o = so[s];
     const long long q0 = (long long)s * cb.NG;
     rate_run_chunk(tabs + sd.cfg, rs + s, K0, cb.NG, sd.ngran, sd.ngran_real, cb.gi + q0, cb.xr + q0 * 2 * 576,
-                   cb.raw + q0 * 2, cb.ms_raw + q0, cb.pack + q0 * 2, frames + o.frames_off);
+                   cb.sm + q0 * 72, cb.prep + q0, cb.ms + q0, cb.pack + q0 * 2, frames + o.frames_off);
     HMP3_SYNC();
     if (HMP3_LANE == 0) cb.fr1[s] = rs[s].frames;
 }

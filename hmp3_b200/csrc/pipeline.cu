@@ -37,9 +37,9 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
-const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "rate_loop",
-                                     "pack", "assemble"};
+enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
+const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "ms_psy2_prepare",
+                                     "rate_loop", "pack", "assemble"};
 
 }  // namespace
 
@@ -78,6 +78,8 @@ struct hmp3_batch {
                 ev_start = nullptr;
     const int16_t **d_src = nullptr;    // [n] device-visible addresses of the callers' pinned PCM (staged runs)
     bool staged = false;                // this run pulls PCM chunk by chunk with k_stage_pcm
+    int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
+    PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
     std::vector<int> flags_h;
     int nbuf = 2;
@@ -118,6 +120,9 @@ struct hmp3_batch {
             cudaFree(cb2[k].xr);
             cudaFree(cb2[k].raw);
             cudaFree(cb2[k].ms_raw);
+            cudaFree(cb2[k].ms);
+            cudaFree(cb2[k].sm);
+            cudaFree(cb2[k].prep);
             cudaFree(cb2[k].pack);
             cudaFree(cb2[k].fr0);
             cudaFree(cb2[k].fr1);
@@ -127,6 +132,8 @@ struct hmp3_batch {
         }
         if (ev_start) cudaEventDestroy(ev_start);
         cudaFree(d_flags);
+        cudaFree(d_msmem);
+        cudaFree(d_psy);
         cudaFree(d_src);
         if (stream_a) cudaStreamDestroy(stream_a);
         if (stream_p) cudaStreamDestroy(stream_p);
@@ -224,6 +231,8 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     CK(cudaMemcpy(b->d_st, b->st_h.data(), sizeof(StreamDev) * n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b->d_pcm, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
     CK(cudaMemset(b->d_pcm, 0, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
+    CK(cudaMalloc(&b->d_msmem, sizeof(int) * n));
+    CK(cudaMalloc(&b->d_psy, sizeof_psy_state() * n * 2));
     CK(cudaMalloc(&b->d_sw, sizeof(SwitchState) * n));
     CK(cudaMalloc(&b->d_sw_init, sizeof(SwitchState) * n));
     {
@@ -245,6 +254,9 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMalloc(&cb.xr, sizeof(float) * n * NG * 2 * 576));
         CK(cudaMalloc(&cb.raw, sizeof(PsyRaw) * n * NG * 2));
         CK(cudaMalloc(&cb.ms_raw, sizeof(int) * n * NG));
+        CK(cudaMalloc(&cb.ms, n * NG));
+        CK(cudaMalloc(&cb.sm, sizeof(float) * 2 * 72 * n * NG));
+        CK(cudaMalloc(&cb.prep, sizeof_prep_granule() * n * NG));
         if (!analysis_only) {
             CK(cudaMalloc(&cb.pack, sizeof_pack_gc() * n * NG * 2));
             CK(cudaMalloc(&cb.fr0, sizeof(int) * n));
@@ -272,6 +284,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
 }
 
 int plan_reset_state(hmp3_batch *b) {
+    launch_prepare_init(b->d_msmem, b->d_psy, b->n, b->stream);
     CK(cudaMemcpyAsync(b->d_sw, b->d_sw_init, sizeof(SwitchState) * b->n, cudaMemcpyDeviceToDevice, b->stream));
     return HMP3_OK;
 }
@@ -291,7 +304,7 @@ void mark(hmp3_batch *b, int phase, cudaStream_t st) {
 }
 
 // Phase A for the chunk starting at encode granule K0, into chunk buffer set `k`, on stream `st`.
-int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st) {
+int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_prepare = true) {
     const int n = b->n;
     const ChunkBufs &cb = b->cb2[k];
     mark(b, PH_POLY, st);
@@ -309,6 +322,12 @@ int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st) {
     mark(b, PH_PSY, st);
     launch_psy_stage1(b->d_tabs, b->d_st, cb, K0, n, st);
     mark(b, -1, st);
+    if (with_prepare) {
+        mark(b, PH_PREP, st);
+        launch_prepare(b->d_tabs, b->d_st, b->d_msmem, b->d_psy, cb, K0, n, st);
+        mark(b, -1, st);
+        b->launches += 3;
+    }
     b->launches += 5;
     CK(cudaGetLastError());
     return HMP3_OK;
@@ -953,7 +972,7 @@ int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long ns
     std::vector<GranuleInfo> GI(NG);
     std::vector<PsyRaw> RW((size_t)NG * 2);
     for (int K0 = 0; K0 < ngran; K0 += NG) {
-        r = launch_analysis(&b, K0, 0, b.stream);
+        r = launch_analysis(&b, K0, 0, b.stream, false);  // the taps want xr before the in-place prologue
         if (r != HMP3_OK) return r;
         CK(cudaStreamSynchronize(b.stream));
         CK(cudaMemcpy(P.data(), b.cb.P, P.size() * 4, cudaMemcpyDeviceToHost));

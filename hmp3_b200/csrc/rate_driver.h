@@ -67,8 +67,6 @@ HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros
 struct RateState {
     LongRate L;
     ShortRate S;
-    float echo[2][64];        // psychoacoustic pre-echo memory (CMp3Enc::ecsave[ch][0])
-    SigMask sig_mask[2][36];
     int ix[2][576];           // quantised lines in transmission order (persist between granules)
     unsigned char signx[2][576];
     GrSide gr[2][2];          // [granule][channel]
@@ -90,10 +88,6 @@ HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {
     for (unsigned i = 0; i < sizeof(RateState); i++) p[i] = 0;
     long_rate_init(T, &R->L);
     short_rate_init(&R->S);
-    for (int c = 0; c < 2; c++) {
-        for (int i = 0; i < 64; i++) R->echo[c][i] = 1.0e20f;
-        for (int i = 0; i < 36; i++) R->sig_mask[c][i].sig = R->sig_mask[c][i].mask = 100.0f;
-    }
     R->padcount = T->cfg.pad_divisor;
 }
 
@@ -468,14 +462,13 @@ HMP3_FN int pack_frame(const EncTables *T, FrameRec *fr, const PackGc *gc, unsig
 
 // ------------------------------------------------------------------ the rate loop of one granule
 // CBitAllo3::BitAllo (bitallo3.cpp:484-678).  xr is this granule's spectrum [2][576], consumed in place.
-HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int igr, int nchan, int min_bits,
-                              int target_bits, int max_bits, int pool_bits, int ms) {
+HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, const SigMask *sm, PrepGranule *prep, int igr,
+                              int nchan, int min_bits, int target_bits, int max_bits, int pool_bits, int ms) {
     LongRate *L = &R->L;
     GrSide *gr = R->gr[igr];
     ScaleFac *sf_out = R->sf[igr];
     int *ix = &R->ix[0][0];
     unsigned char *sg = &R->signx[0][0];
-    const SigMask *sm = &R->sig_mask[0][0];
     const int bt = gr[0].block_type;
     const int init = T->cfg.initial_mnr;
     L->block_type = bt;
@@ -521,8 +514,8 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int i
     if (L->mnr < -200) L->min_target = imax_(L->min_target, (3 * L->target) >> 2);
     L->max_target = imax_(L->min_target, L->max_target);
     L->min_target = imin_(L->min_target, L->max_target - 100);
-    if (ms) long_startup_ms(T, L, xr, sm, sg);
-    else long_startup_lr(T, L, xr, sm, sg);
+    if (ms) long_startup_ms(T, L, sm, prep, sg);
+    else long_startup_lr(T, L, sm, prep, sg);
     if (L->active_lines <= 0) {  // digital silence
         for (int ch = 0; ch < nchan; ch++) {
             GrSide *g = gr + ch;
@@ -576,27 +569,10 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, int i
 struct GranuleIn {
     GranuleInfo info;
     float *xr;            // [2][576], consumed in place
-    const PsyRaw *raw;    // [2]
-    int ms_raw;
+    const SigMask *sm;    // [2][36] psychoacoustic sig/mask of this granule (stage 2 done by the parallel pass)
+    PrepGranule *prep;    // long blocks: prepared energies / |x|^(3/4) / step bounds
+    int ms;               // M/S decision of the granule's frame (hysteresis applied by the scan pass)
 };
-
-// M/S correlation with hysteresis (bitallo3.cpp:691-696, 745-753)
-HMP3_HD int ms_correlation(LongRate *L, const GranuleIn *g) {
-    if (g->info.block_type == 2) {
-        L->ms_memory = 0;
-        return g->ms_raw;
-    }
-    int cm = g->ms_raw + L->ms_memory;
-    L->ms_memory = (cm > 0) ? 5000 : -5000;
-    return cm;
-}
-
-HMP3_FN void psy_stage2(const EncTables *T, RateState *R, const GranuleIn *g) {  // mp3enc.cpp:2597-2617
-    for (int ch = 0; ch < T->cfg.nchan; ch++) {
-        if (g->info.block_type != 2) psy_long_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type, R->sig_mask[ch]);
-        else psy_short_stage2(T, g->raw + ch, R->echo[ch], g->info.block_type_prev, R->sig_mask[ch]);
-    }
-}
 
 HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const GranuleIn *g) {
     // mp3enc.cpp:1429-1438: both channels carry the same decision; the aux fields live in channel 0
@@ -675,16 +651,10 @@ HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
     set_block_info(T, R, 0, g0);
     set_block_info(T, R, 1, g1);
     const int short_frame = (g0->info.block_type == 2) | (g1->info.block_type == 2);
-    int ms = 0;
-    if (nch == 2 && C.ms_flag) {
-        int m1 = ms_correlation(&R->L, g0);
-        int m2 = ms_correlation(&R->L, g1);
-        if ((m1 + m2) >= 0) ms = 1;
-    }
+    const int ms = g0->ms;  // frame decision (both granules carry it)
     int total = 0;
     for (int igr = 0; igr < 2; igr++) {
-        psy_stage2(T, R, gs[igr]);
-        granule_allocate(T, R, gs[igr]->xr, igr, nch, ba_min, target, ba_max, bit_pool, ms);
+        granule_allocate(T, R, gs[igr]->xr, gs[igr]->sm, gs[igr]->prep, igr, nch, ba_min, target, ba_max, bit_pool, ms);
         for (int ch = 0; ch < nch; ch++) {
             GrSide *g = &R->gr[igr][ch];
             int sfb = 0;
@@ -732,13 +702,8 @@ HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, Granul
     ba_bit_max -= nch * C.sf_bit_max;
     ba_bit_min -= nch * C.sf_bit_max;
     set_block_info(T, R, igr, g0);
-    int ms = 0;
-    if (nch == 2 && C.ms_flag) {
-        int m1 = ms_correlation(&R->L, g0);
-        if (m1 >= 0) ms = 1;
-    }
-    psy_stage2(T, R, g0);
-    granule_allocate(T, R, g0->xr, igr, nch, ba_bit_min, nch * C.ave_target_bits, ba_bit_max, bit_pool,
+    const int ms = g0->ms;
+    granule_allocate(T, R, g0->xr, g0->sm, g0->prep, igr, nch, ba_bit_min, nch * C.ave_target_bits, ba_bit_max, bit_pool,
                      nch == 2 ? ms : C.ms_flag);
     int total = 0;
     for (int ch = 0; ch < nch; ch++) {
@@ -854,13 +819,13 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, FrameRec *frames
 namespace hmp3 {
 
 // Run the serial stage of one stream over the encode granules [K0, K0+NG) that Phase A has prepared.
-// gi/xr/raw/ms_raw/pack point at this stream's slice of the chunk buffers (index 0 == granule K0; pack holds
+// gi/xr/sm/prep/ms/pack point at this stream's slice of the chunk buffers (index 0 == granule K0; pack holds
 // two records per granule).  ngran_real = granules of real encode calls (2 per call); after them the stream
 // keeps consuming zero-PCM granules until every real frame's main-data slot is filled (the CLI's tail flush,
 // test/tomp3.cpp:1015-1036), checked at call boundaries.
 HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
-                            const GranuleInfo *gi, float *xr, const PsyRaw *raw, const int *ms_raw, PackGc *pack,
-                            FrameRec *frames) {
+                            const GranuleInfo *gi, float *xr, const SigMask *sm, PrepGranule *prep,
+                            const signed char *ms, PackGc *pack, FrameRec *frames) {
     const bool m1 = T->cfg.h_id == 1;
     const int frames_real = m1 ? ngran_real / 2 : ngran_real;
     for (int K = K0; K + 1 < K0 + NG && K + 1 < ngran; K += 2) {
@@ -871,8 +836,9 @@ HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, in
             const int o = K - K0 + q;
             g[q].info = gi[o];
             g[q].xr = xr + (long long)o * 2 * 576;
-            g[q].raw = raw + (long long)o * 2;
-            g[q].ms_raw = ms_raw[o];
+            g[q].sm = sm + (long long)o * 72;
+            g[q].prep = prep + o;
+            g[q].ms = ms[o];
         }
         PackGc *pk = pack + (long long)(K - K0) * 2;
         if (m1) encode_one_frame(T, R, frames, 0, &g[0], &g[1], pk, K);

@@ -6,10 +6,10 @@
 #pragma once
 #include "rate_common.h"
 #include "psy_core.h"
+#include "prepare.h"
 
 namespace hmp3 {
 
-constexpr int kGminOffset = 70;   // bitallos.h:61
 constexpr int kPart23Max = 4021;  // bitallo3.h:61
 
 struct LongRate {
@@ -28,7 +28,7 @@ struct LongRate {
     int gzero[2][22], gmin[2][22], gsf[2][22];
     int G[2], preemp[2], sf_scale[2];
     RegionPlan plan[2];
-    float x34[2][576];
+    float (*x34)[576];  // |x|^(3/4) of the granule in flight: points into its PrepGranule
     float dd[2][576];  // per-line squared errors of the step search in flight (device build)
 };
 
@@ -124,87 +124,45 @@ HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
     }
 }
 
-HMP3_FN void long_step_bounds(const EncTables *T, LongRate *L, int ch, int nbands) {
-    // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
+// Take over what the parallel prepare pass computed for this granule (prepare.h): band energies, step bounds,
+// the |x|^(3/4) array (by reference) and the signs (expanded into the persistent sign array for the lines that
+// were rewritten, so that lines beyond them keep their old value like the reference's signx buffer).
+HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P, unsigned char *signx, int n_energy,
+                                 const int *n_bounds /*[2]*/) {
+    L->x34 = P->x34;
 #if HMP3_COOP
     HMP3_SYNC();
-    for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {  // bands dealt over the lanes
-        const float *y = L->x34[ch] + T->startBand_l[i];
-        const int n = T->nBand_l[i];
-        float m = 0.0f;
-        for (int k = 0; k < n; k++)
-            if (y[k] > m) m = y[k];
-        L->x34max[ch][i] = m;
-        L->gzero[ch][i] = imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
-        L->gmin[ch][i] = imax_(0, L->gzero[ch][i] - kGminOffset);
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int ne = n_energy < 0 ? n_bounds[ch] : n_energy;
+        for (int i = HMP3_LANE; i < ne; i += HMP3_W) L->xsxx[ch][i] = P->xsxx[ch][i];
+        for (int i = HMP3_LANE; i < n_bounds[ch]; i += HMP3_W) {
+            L->x34max[ch][i] = P->x34max[ch][i];
+            L->gzero[ch][i] = P->gzero[ch][i];
+            L->gmin[ch][i] = P->gmin[ch][i];
+        }
+        const int nl = P->nlines[ch];
+        for (int k = HMP3_LANE; k < nl; k += HMP3_W) signx[576 * ch + k] = (unsigned char)((P->sign[ch][k >> 5] >> (k & 31)) & 1u);
     }
     HMP3_SYNC();
 #else
-    const float *y = L->x34[ch];
-    for (int i = 0; i < nbands; i++) {
-        const int n = T->nBand_l[i];
-        float m = 0.0f;
-        for (int k = 0; k < n; k++)
-            if (y[k] > m) m = y[k];
-        L->x34max[ch][i] = m;
-        L->gzero[ch][i] = imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
-        L->gmin[ch][i] = imax_(0, L->gzero[ch][i] - kGminOffset);
-        y += n;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int ne = n_energy < 0 ? n_bounds[ch] : n_energy;
+        for (int i = 0; i < ne; i++) L->xsxx[ch][i] = P->xsxx[ch][i];
+        for (int i = 0; i < n_bounds[ch]; i++) {
+            L->x34max[ch][i] = P->x34max[ch][i];
+            L->gzero[ch][i] = P->gzero[ch][i];
+            L->gmin[ch][i] = P->gmin[ch][i];
+        }
+        for (int k = 0; k < P->nlines[ch]; k++) signx[576 * ch + k] = (unsigned char)((P->sign[ch][k >> 5] >> (k & 31)) & 1u);
     }
 #endif
 }
 
-#if HMP3_COOP
-// sums of v[] over each of the first nbands bands, accumulated in line order: one band per lane
-HMP3_HD void long_band_sums(const EncTables *T, const float *v, int nbands, float *out) {
-    HMP3_SYNC();
-    for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {
-        const float *y = v + T->startBand_l[i];
-        const int n = T->nBand_l[i];
-        float e = 0.0f;
-        for (int k = 0; k < n; k++) e += y[k];
-        out[i] = e;
-    }
-    HMP3_SYNC();
-}
-#endif
-
-// left/right granule (bitallo3.cpp:816-898).  xr is modified in place (signs stripped).
-HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][576]*/, const SigMask *sm /*[2][36]*/,
+// left/right granule (bitallo3.cpp:816-898): noise targets from the prepared band energies.
+HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, const SigMask *sm /*[2][36]*/, PrepGranule *P,
                              unsigned char *signx /*[2][576]*/) {
     const int mnr = L->mnr + 100;
-#if HMP3_COOP
-    for (int ch = 0; ch < L->nchan; ch++) {
-        float *x = xr + 576 * ch;
-        unsigned char *s = signx + 576 * ch;
-        float *sq = L->x34[ch];  // scratch until the 3/4 powers are taken below
-        const int nl = T->startBand_l[T->cfg.nsf3[ch]];
-        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
-            float v = x[k];
-            if (v >= 0.0f) s[k] = 0;
-            else { s[k] = 1; v = -v; x[k] = v; }
-            sq[k] = v * v;
-        }
-        long_band_sums(T, sq, T->cfg.nsf3[ch], L->xsxx[ch]);
-    }
-#else
-    for (int ch = 0; ch < L->nchan; ch++) {
-        float *x = xr + 576 * ch;
-        unsigned char *s = signx + 576 * ch;
-        for (int i = 0; i < T->cfg.nsf3[ch]; i++) {
-            const int n = T->nBand_l[i];
-            float e = 0.0f;
-            for (int k = 0; k < n; k++) {
-                if (x[k] >= 0.0f) s[k] = 0;
-                else { s[k] = 1; x[k] = -x[k]; }
-                e += x[k] * x[k];
-            }
-            L->xsxx[ch][i] = e;
-            x += n;
-            s += n;
-        }
-    }
-#endif
+    long_adopt_prepared(T, L, P, signx, -1, T->cfg.nsf3);
     L->active_lines = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
         for (int i = 0; i < T->cfg.nsf[ch]; i++) {
@@ -221,84 +179,20 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, float *xr /*[2][57
         }
     }
     long_flatten_targets(T, L);
-    for (int ch = 0; ch < L->nchan; ch++) {
-        const float *x = xr + 576 * ch;
-#if HMP3_COOP
-        HMP3_SYNC();
-        for (int k = HMP3_LANE; k < T->cfg.nbmax3[ch]; k += HMP3_W) L->x34[ch][k] = pow34(T, x[k]);
-#else
-        for (int k = 0; k < T->cfg.nbmax3[ch]; k++) L->x34[ch][k] = pow34(T, x[k]);
-#endif
-        long_step_bounds(T, L, ch, T->cfg.nsf3[ch]);
-    }
 }
 
-// mid/side granule (bitallo3.cpp:902-1065): xr becomes |L+R|, |L-R| in place (no 1/sqrt2; the
-// global gain is lowered by 2 steps on output instead).
-HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const SigMask *sm, unsigned char *signx) {
+// mid/side granule (bitallo3.cpp:902-1065): noise targets from the prepared energies (the spectra were rotated to
+// |L+R|, |L-R| without 1/sqrt2 by the prepare pass; the global gain is lowered by 2 steps on output instead).
+HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm, PrepGranule *P, unsigned char *signx) {
     if (T->cfg.vbr_flag == 0 && L->calls > 10 && (L->target - L->min_target) < 100)
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
     L->active_lines = 0;
     const int nsf0 = T->cfg.nsf[0];
-#if HMP3_COOP
-    {
-        float *sq0 = L->x34[0], *sq1 = L->x34[1];  // scratch until the 3/4 powers are taken below
-        const int nl = T->startBand_l[nsf0];
-        const int nrot = nl + (T->cfg.hf_flag ? T->nBand_l[21] : 0);  // the pseudo band above sfb 21 is rotated too
-        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
-            sq0[k] = xr[k] * xr[k];
-            sq1[k] = xr[576 + k] * xr[576 + k];
-        }
-        long_band_sums(T, sq0, nsf0, L->xsxx[0]);
-        long_band_sums(T, sq1, nsf0, L->xsxx[1]);
-        for (int k = HMP3_LANE; k < nrot; k += HMP3_W) {
-            float m = (xr[k] + xr[576 + k]);
-            float d = (xr[k] - xr[576 + k]);
-            unsigned char sm_ = 0, sd_ = 0;
-            if (m < 0.0f) { sm_ = 1; m = -m; }
-            if (d < 0.0f) { sd_ = 1; d = -d; }
-            signx[k] = sm_;
-            signx[576 + k] = sd_;
-            xr[k] = m;
-            xr[576 + k] = d;
-            sq0[k] = m * m;
-            sq1[k] = d * d;
-        }
-        long_band_sums(T, sq0, nsf0, L->x34max[0]);  // mid / side energies, parked until the step bounds are set
-        long_band_sums(T, sq1, nsf0, L->x34max[1]);
-    }
+    long_adopt_prepared(T, L, P, signx, nsf0, T->cfg.nsf2);
     for (int i = 0; i < nsf0; i++) {
         const int n = T->nBand_l[i];
-        const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = L->x34max[0][i], ed = L->x34max[1][i];
-#else
-    float *x = xr;
-    unsigned char *s = signx;
-    int n = 0;
-    for (int i = 0; i < nsf0; i++) {
-        n = T->nBand_l[i];
-        float el = 0.0f, er = 0.0f;
-        for (int k = 0; k < n; k++) {
-            el += x[k] * x[k];
-            er += x[576 + k] * x[576 + k];
-        }
-        for (int k = 0; k < n; k++) {
-            float m = (x[k] + x[576 + k]);
-            float d = (x[k] - x[576 + k]);
-            s[k] = s[576 + k] = 0;
-            if (m < 0.0f) { s[k] = 1; m = -m; }
-            if (d < 0.0f) { s[576 + k] = 1; d = -d; }
-            x[k] = m;
-            x[576 + k] = d;
-        }
-        float em = 0.0f, ed = 0.0f;
-        for (int k = 0; k < n; k++) {
-            em += x[k] * x[k];
-            ed += x[576 + k] * x[576 + k];
-        }
-        L->xsxx[0][i] = el;
-        L->xsxx[1][i] = er;
-#endif
+        const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = P->e2[0][i], ed = P->e2[1][i];
         const int cbw = T->log_cbw_l[i];
         int ntl, ntr;
         int n0l = mb_log(T, el) - cbw;
@@ -319,25 +213,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         L->snr[1][i] = n0r - ntr;
         L->noise0[0][i] = mb_log(T, em) - cbw;
         L->noise0[1][i] = mb_log(T, ed) - cbw;
-#if !HMP3_COOP
-        x += n;
-        s += n;
-#endif
     }
-#if !HMP3_COOP
-    if (T->cfg.hf_flag) {  // the pseudo band above sfb 21 is rotated too
-        n = T->nBand_l[21];
-        for (int k = 0; k < n; k++) {
-            float m = (x[k] + x[576 + k]);
-            float d = (x[k] - x[576 + k]);
-            s[k] = s[576 + k] = 0;
-            if (m < 0.0f) { s[k] = 1; m = -m; }
-            if (d < 0.0f) { s[576 + k] = 1; d = -d; }
-            x[k] = m;
-            x[576 + k] = d;
-        }
-    }
-#endif
     long_flatten_targets(T, L);
     for (int i = 0; i < nsf0; i++) {
         const int nsum = L->noise0[0][i], ndiff = L->noise0[1][i];
@@ -351,14 +227,6 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, float *xr, const S
         L->snr[0][i] = nsum - L->nt[0][i];
         L->snr[1][i] = ndiff - L->nt[1][i];
     }
-    HMP3_SYNC();
-    for (int ch = 0; ch < 2; ch++)
-#if HMP3_COOP
-        for (int k = HMP3_LANE; k < T->cfg.nbmax2[ch]; k += HMP3_W) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
-#else
-        for (int k = 0; k < T->cfg.nbmax2[ch]; k++) L->x34[ch][k] = pow34(T, xr[576 * ch + k]);
-#endif
-    for (int ch = 0; ch < L->nchan; ch++) long_step_bounds(T, L, ch, T->cfg.nsf2[ch]);
 }
 
 // ------------------------------------------------------------------ per-band step search

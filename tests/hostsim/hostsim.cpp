@@ -181,6 +181,39 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
             msr[K] = gi[K].block_type != 2 ? ms_measure_long(T, x0, x0 + 576) : ms_measure_short(T, x0, x0 + 576);
         }
     }
+    // the scans and the prepare pass that follow stage 1 (on the device: k_ms_scan, k_psy_stage2, k_prepare)
+    std::vector<signed char> msf(ngran + 2, 0);
+    std::vector<SigMask> smk((size_t)(ngran + 2) * 72);
+    std::vector<PrepGranule> prep(ngran + 2);
+    {
+        const bool stereo_ms = (nch == 2 && T->cfg.ms_flag);
+        int mem = 0;
+        for (int K = 0; K + 1 < ngran; K += 2) {
+            int f0 = 0, f1 = 0;
+            if (stereo_ms) {
+                const int a = ms_scan_step(&mem, gi[K].block_type, msr[K]);
+                const int b2 = ms_scan_step(&mem, gi[K + 1].block_type, msr[K + 1]);
+                if (!mpeg2) f0 = f1 = ((a + b2) >= 0);
+                else { f0 = (a >= 0); f1 = (b2 >= 0); }
+            }
+            msf[K] = (signed char)f0;
+            msf[K + 1] = (signed char)f1;
+        }
+        PsyState ps[2];
+        psy_state_init(&ps[0]);
+        psy_state_init(&ps[1]);
+        for (int K = 0; K < ngran; K++) {
+            for (int c = 0; c < nch; c++) {
+                if (gi[K].block_type != 2) psy_long_stage2(T, &raw[(size_t)K * 2 + c], ps[c].echo, gi[K].block_type, ps[c].sm);
+                else psy_short_stage2(T, &raw[(size_t)K * 2 + c], ps[c].echo, gi[K].block_type_prev, ps[c].sm);
+                for (int i = 0; i < 36; i++) smk[((size_t)K * 2 + c) * 36 + i] = ps[c].sm[i];
+            }
+            if (gi[K].block_type != 2) {
+                const int ms = (mpeg2 && nch != 2) ? T->cfg.ms_flag : (int)msf[K];
+                long_prepare(T, ms, &xr[(size_t)K * 2 * 576], &prep[K]);
+            }
+        }
+    }
     RateState *R = new RateState;
     rate_state_init(T, R);
     std::vector<unsigned char> mainbuf((size_t)(ngran + 4) * 2100, 0);
@@ -191,8 +224,8 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
     int bad = 0;
     for (int K = 0; K + 1 < ngran && !R->finished; K += 2) {
         const int f0 = R->frames;
-        rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &raw[(size_t)K * 2], &msr[K],
-                       pack.data(), frames.data());
+        rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &smk[(size_t)K * 72], &prep[K],
+                       &msf[K], pack.data(), frames.data());
         for (int f = f0; f < R->frames; f++)
             bad |= pack_frame(T, &frames[f], pack.data() + (size_t)(frames[f].granule0 - K) * 2, mainbuf.data());
         if (trace)
