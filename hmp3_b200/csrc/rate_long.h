@@ -245,14 +245,15 @@ HMP3_FN void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.c
         }
 }
 
-// walk the step of one band toward the noise target, at most 20 steps (bitallo3.cpp:1164-1238)
+// walk the step of one band toward the noise target, at most 20 steps (bitallo3.cpp:1164-1238); plain
+// sequential code, safe to run one band per lane
 HMP3_FN int seek_finer(const EncTables *T, const float *y34, const float *y, int s0, int n, int logn, int target,
                        int dn, int *noise_io) {
     int s = s0 - 1;
     int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
     const int niter = imin_(s, 20);
     for (int i = 0; i < niter; i++) {
-        int tn = band_noise(T, y34, y, s, n, logn);
+        int tn = band_noise_seq(T, y34, y, s, n, logn);
         int a = iabs(tn - target);
         if (a < best_abs) { best_abs = a; best_noise = tn; best_s = s; }
         if (tn <= target) break;
@@ -267,7 +268,7 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
     int best_abs = iabs(dn), best_noise = *noise_io, best_s = s0;
     for (int i = 0; i < 20; i++) {
         s++;
-        int tn = band_noise(T, y34, y, s, n, logn);
+        int tn = band_noise_seq(T, y34, y, s, n, logn);
         int a = iabs(tn - target);
         if (a < best_abs) { best_abs = a; best_noise = tn; best_s = s; }
         if (tn >= target) break;

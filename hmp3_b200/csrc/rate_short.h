@@ -28,22 +28,30 @@ HMP3_FN void short_rate_init(ShortRate *S) {
     for (unsigned i = 0; i < sizeof(ShortRate); i++) p[i] = 0;
 }
 
+// The short-block loops run over (channel, window, band) items that are independent of each other and short
+// (4..30 lines).  On the device the items are dealt over the lanes of the stream's group and each lane runs the
+// plain sequential code for its items; the host build visits them in order.  it = (ch * 3 + w) * 16 + i.
+#if HMP3_COOP
+#define HMP3_SHORT_ITEMS(it) for (int it = HMP3_LANE; it < 96; it += HMP3_W)
+#else
+#define HMP3_SHORT_ITEMS(it) for (int it = 0; it < 96; it++)
+#endif
+
 HMP3_FN void short_step_bounds(const EncTables *T, ShortRate *S) {
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++) {
-            const float *y = S->x34[ch][w];
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                const int n = T->nBand_s[i];
-                float m = 0.0f;
-                for (int k = 0; k < n; k++)
-                    if (y[k] > m) m = y[k];
-                S->x34max[ch][w][i] = m;
-                S->gzero[ch][w][i] =
-                    imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
-                S->gmin[ch][w][i] = imax_(0, S->gzero[ch][w][i] - kGminOffset);
-                y += n;
-            }
-        }
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
+        if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
+        const float *y = S->x34[ch][w] + T->startBand_s[i];
+        const int n = T->nBand_s[i];
+        float m = 0.0f;
+        for (int k = 0; k < n; k++)
+            if (y[k] > m) m = y[k];
+        S->x34max[ch][w][i] = m;
+        S->gzero[ch][w][i] = imax_(0, round_away((0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f))));
+        S->gmin[ch][w][i] = imax_(0, S->gzero[ch][w][i] - kGminOffset);
+    }
+    HMP3_SYNC();
 }
 
 // pull targets of audible bands halfway to their mean when the mean is high (bitallos.cpp:700-745)
@@ -64,164 +72,179 @@ HMP3_FN void short_flatten_targets(const EncTables *T, ShortRate *S) {
 // xr: [2][3][192] (window-major within the channel); sm: [2][3][12]
 HMP3_FN void short_startup_lr(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:455-546
     const int mnr = S->mnr;
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++) {
-            float *x = xr + 576 * ch + 192 * w;
-            unsigned char *s = S->sign[ch][w];
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                const int n = T->nBand_s[i];
-                float e = 0.0f;
-                for (int k = 0; k < n; k++) {
-                    if (x[k] >= 0.0f) s[k] = 0;
-                    else { s[k] = 1; x[k] = -x[k]; }
-                    e += x[k] * x[k];
-                }
-                S->xsxx[ch][w][i] = e;
-                x += n;
-                s += n;
-            }
+    int lines = 0;
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
+        if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
+        float *x = xr + 576 * ch + 192 * w + T->startBand_s[i];
+        unsigned char *s = S->sign[ch][w] + T->startBand_s[i];
+        const int n = T->nBand_s[i];
+        float e = 0.0f;
+        for (int k = 0; k < n; k++) {
+            if (x[k] >= 0.0f) s[k] = 0;
+            else { s[k] = 1; x[k] = -x[k]; }
+            e += x[k] * x[k];
         }
-    S->active_lines = 0;
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++)
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                const int cbw = T->log_cbw_s[i];
-                S->noise0[ch][w][i] = mb_log(T, S->xsxx[ch][w][i]) - cbw;
-                if (S->noise0[ch][w][i] < -2000) {
-                    S->nt[ch][w][i] = S->noise0[ch][w][i] + 1000;
-                    S->snr[ch][w][i] = -1000;
-                } else {
-                    int mask = (mb_log(T, sm[36 * ch + 12 * w + i].mask) - cbw);
-                    S->nt[ch][w][i] = nt_dropout_guard(S->noise0[ch][w][i], mask - mnr);
-                    S->snr[ch][w][i] = S->noise0[ch][w][i] - S->nt[ch][w][i];
-                    S->active_lines += T->nBand_s[i];
-                }
-            }
+        S->xsxx[ch][w][i] = e;
+        const int cbw = T->log_cbw_s[i];
+        S->noise0[ch][w][i] = mb_log(T, e) - cbw;
+        if (S->noise0[ch][w][i] < -2000) {
+            S->nt[ch][w][i] = S->noise0[ch][w][i] + 1000;
+            S->snr[ch][w][i] = -1000;
+        } else {
+            int mask = (mb_log(T, sm[36 * ch + 12 * w + i].mask) - cbw);
+            S->nt[ch][w][i] = nt_dropout_guard(S->noise0[ch][w][i], mask - mnr);
+            S->snr[ch][w][i] = S->noise0[ch][w][i] - S->nt[ch][w][i];
+            lines += n;
+        }
+    }
+#if HMP3_COOP
+    lines = gsum(lines);
+#endif
+    S->active_lines = lines;
+    HMP3_SYNC();
     short_flatten_targets(T, S);
+    HMP3_SYNC();
     for (int ch = 0; ch < S->nchan; ch++)
         for (int w = 0; w < 3; w++)
-            for (int k = 0; k < T->cfg.nbmax_s[ch]; k++) S->x34[ch][w][k] = pow34(T, xr[576 * ch + 192 * w + k]);
+#if HMP3_COOP
+            for (int k = HMP3_LANE; k < T->cfg.nbmax_s[ch]; k += HMP3_W)
+#else
+            for (int k = 0; k < T->cfg.nbmax_s[ch]; k++)
+#endif
+                S->x34[ch][w][k] = pow34(T, xr[576 * ch + 192 * w + k]);
     short_step_bounds(T, S);
 }
 
 HMP3_FN void short_startup_ms(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm) {  // bitallos.cpp:549-697
-    S->active_lines = 0;
     const int nsf0 = T->cfg.nsf_s[0];
-    for (int w = 0; w < 3; w++) {
-        float *x = xr + 192 * w;
-        unsigned char *s = S->sign[0][w];
-        const int so = (int)(&S->sign[1][0][0] - &S->sign[0][0][0]);  // sign[1] follows sign[0]
-        for (int i = 0; i < nsf0; i++) {
-            const int n = T->nBand_s[i];
-            float el = 0.0f, er = 0.0f;
-            for (int k = 0; k < n; k++) {
-                el += x[k] * x[k];
-                er += x[576 + k] * x[576 + k];
-            }
-            for (int k = 0; k < n; k++) {
-                float m = (x[k] + x[576 + k]);
-                float d = (x[k] - x[576 + k]);
-                s[k] = s[so + k] = 0;
-                if (m < 0.0f) { s[k] = 1; m = -m; }
-                if (d < 0.0f) { s[so + k] = 1; d = -d; }
-                x[k] = m;
-                x[576 + k] = d;
-            }
-            float em = 0.0f, ed = 0.0f;
-            for (int k = 0; k < n; k++) {
-                em += x[k] * x[k];
-                ed += x[576 + k] * x[576 + k];
-            }
-            S->xsxx[0][w][i] = el;
-            S->xsxx[1][w][i] = er;
-            const int cbw = T->log_cbw_s[i];
-            int ntl, ntr;
-            int n0l = mb_log(T, el) - cbw;
-            if (n0l < -2000) ntl = 10000;
-            else {
-                ntl = nt_dropout_guard(n0l, (mb_log(T, sm[12 * w + i].mask) - cbw) - S->mnr);
-                S->active_lines += n;
-            }
-            int n0r = mb_log(T, er) - cbw;
-            if (n0r < -2000) ntr = 10000;
-            else {
-                ntr = nt_dropout_guard(n0r, (mb_log(T, sm[36 + 12 * w + i].mask) - cbw) - S->mnr);
-                S->active_lines += n;
-            }
-            const int nsum = mb_log(T, em) - cbw, ndiff = mb_log(T, ed) - cbw;
-            S->noise0[0][w][i] = nsum;
-            S->noise0[1][w][i] = ndiff;
-            const int xnt = imin_(ntr, ntl) + 300;
-            S->nt[1][w][i] = S->nt[0][w][i] = xnt;
-            if (ndiff < xnt) S->nt[0][w][i] = mb_logsub(T, xnt, ndiff) - 200;
-            if (nsum < xnt) S->nt[1][w][i] = mb_logsub(T, xnt, nsum) - 200;
-            S->snr[0][w][i] = S->noise0[0][w][i] - S->nt[0][w][i];
-            S->snr[1][w][i] = S->noise0[1][w][i] - S->nt[1][w][i];
-            x += n;
-            s += n;
+    const int so = (int)(&S->sign[1][0][0] - &S->sign[0][0][0]);  // sign[1] follows sign[0]
+    int lines = 0;
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int w = it >> 4, i = it & 15;  // items = (window, band); both channels are handled together
+        if (w >= 3 || i >= nsf0) continue;
+        float *x = xr + 192 * w + T->startBand_s[i];
+        unsigned char *s = S->sign[0][w] + T->startBand_s[i];
+        const int n = T->nBand_s[i];
+        float el = 0.0f, er = 0.0f;
+        for (int k = 0; k < n; k++) {
+            el += x[k] * x[k];
+            er += x[576 + k] * x[576 + k];
         }
+        for (int k = 0; k < n; k++) {
+            float m = (x[k] + x[576 + k]);
+            float d = (x[k] - x[576 + k]);
+            s[k] = s[so + k] = 0;
+            if (m < 0.0f) { s[k] = 1; m = -m; }
+            if (d < 0.0f) { s[so + k] = 1; d = -d; }
+            x[k] = m;
+            x[576 + k] = d;
+        }
+        float em = 0.0f, ed = 0.0f;
+        for (int k = 0; k < n; k++) {
+            em += x[k] * x[k];
+            ed += x[576 + k] * x[576 + k];
+        }
+        S->xsxx[0][w][i] = el;
+        S->xsxx[1][w][i] = er;
+        const int cbw = T->log_cbw_s[i];
+        int ntl, ntr;
+        int n0l = mb_log(T, el) - cbw;
+        if (n0l < -2000) ntl = 10000;
+        else {
+            ntl = nt_dropout_guard(n0l, (mb_log(T, sm[12 * w + i].mask) - cbw) - S->mnr);
+            lines += n;
+        }
+        int n0r = mb_log(T, er) - cbw;
+        if (n0r < -2000) ntr = 10000;
+        else {
+            ntr = nt_dropout_guard(n0r, (mb_log(T, sm[36 + 12 * w + i].mask) - cbw) - S->mnr);
+            lines += n;
+        }
+        const int nsum = mb_log(T, em) - cbw, ndiff = mb_log(T, ed) - cbw;
+        S->noise0[0][w][i] = nsum;
+        S->noise0[1][w][i] = ndiff;
+        const int xnt = imin_(ntr, ntl) + 300;
+        S->nt[1][w][i] = S->nt[0][w][i] = xnt;
+        if (ndiff < xnt) S->nt[0][w][i] = mb_logsub(T, xnt, ndiff) - 200;
+        if (nsum < xnt) S->nt[1][w][i] = mb_logsub(T, xnt, nsum) - 200;
+        S->snr[0][w][i] = S->noise0[0][w][i] - S->nt[0][w][i];
+        S->snr[1][w][i] = S->noise0[1][w][i] - S->nt[1][w][i];
     }
+#if HMP3_COOP
+    lines = gsum(lines);
+#endif
+    S->active_lines = lines;
+    HMP3_SYNC();
     short_flatten_targets(T, S);
+    HMP3_SYNC();
     for (int w = 0; w < 3; w++)
         for (int ch = 0; ch < 2; ch++)
-            for (int k = 0; k < T->cfg.nbmax_s[ch]; k++) S->x34[ch][w][k] = pow34(T, xr[576 * ch + 192 * w + k]);
+#if HMP3_COOP
+            for (int k = HMP3_LANE; k < T->cfg.nbmax_s[ch]; k += HMP3_W)
+#else
+            for (int k = 0; k < T->cfg.nbmax_s[ch]; k++)
+#endif
+                S->x34[ch][w][k] = pow34(T, xr[576 * ch + 192 * w + k]);
     short_step_bounds(T, S);
 }
 
 HMP3_FN void short_seek_initial(const EncTables *T, ShortRate *S) {  // bitallos.cpp:748-776
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++)
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                float g4 = 0.017716950f * mb_log(T, S->x34max[ch][w][i]) + (88.411238f - 100.0f + 8.0f);
-                float d = (1.00f / 110.5f) * (1800 - (2 * 8) * i - (S->noise0[ch][w][i] - S->nt[ch][w][i]));
-                float g = g4 + d;
-                int v = round_away(g);
-                v = imin_(v, S->gzero[ch][w][i]);
-                v = imax_(v, S->gmin[ch][w][i]);
-                S->gsf[ch][w][i] = v;
-            }
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
+        if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
+        float g4 = 0.017716950f * mb_log(T, S->x34max[ch][w][i]) + (88.411238f - 100.0f + 8.0f);
+        float d = (1.00f / 110.5f) * (1800 - (2 * 8) * i - (S->noise0[ch][w][i] - S->nt[ch][w][i]));
+        float g = g4 + d;
+        int v = round_away(g);
+        v = imin_(v, S->gzero[ch][w][i]);
+        v = imax_(v, S->gmin[ch][w][i]);
+        S->gsf[ch][w][i] = v;
+    }
+    HMP3_SYNC();
 }
 
 HMP3_FN void short_seek_actual(const EncTables *T, ShortRate *S, const float *xr) {  // bitallos.cpp:841-886
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++) {
-            const float *y34 = S->x34[ch][w];
-            const float *y = xr + 576 * ch + 192 * w;
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                const int target = S->nt[ch][w][i];
-                const int n = T->nBand_s[i];
-                int s = S->gsf[ch][w][i];
-                if (S->noise0[ch][w][i] > target) {
-                    const int logn = T->log_cbw_s[i];
-                    int noise = band_noise(T, y34, y, s, n, logn);
-                    int dn = noise - target;
-                    if (dn > 100) s = seek_finer(T, y34, y, s, n, logn, target, dn, &noise);
-                    else if (dn < -100) s = seek_coarser(T, y34, y, s, n, logn, target, dn, &noise);
-                    S->gsf[ch][w][i] = s;
-                    S->noise[ch][w][i] = noise;
-                } else {
-                    S->gsf[ch][w][i] = S->gzero[ch][w][i] + 5;
-                    S->noise[ch][w][i] = S->noise0[ch][w][i];
-                }
-                y34 += n;
-                y += n;
-            }
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
+        if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
+        const float *y34 = S->x34[ch][w] + T->startBand_s[i];
+        const float *y = xr + 576 * ch + 192 * w + T->startBand_s[i];
+        const int target = S->nt[ch][w][i];
+        const int n = T->nBand_s[i];
+        int s = S->gsf[ch][w][i];
+        if (S->noise0[ch][w][i] > target) {
+            const int logn = T->log_cbw_s[i];
+            int noise = band_noise_seq(T, y34, y, s, n, logn);
+            int dn = noise - target;
+            if (dn > 100) s = seek_finer(T, y34, y, s, n, logn, target, dn, &noise);
+            else if (dn < -100) s = seek_coarser(T, y34, y, s, n, logn, target, dn, &noise);
+            S->gsf[ch][w][i] = s;
+            S->noise[ch][w][i] = noise;
+        } else {
+            S->gsf[ch][w][i] = S->gzero[ch][w][i] + 5;
+            S->noise[ch][w][i] = S->noise0[ch][w][i];
         }
+    }
+    HMP3_SYNC();
 }
 
 HMP3_FN void short_quantise(const EncTables *T, ShortRate *S, bool tuned) {  // bitallos.cpp:889-936
-    for (int ch = 0; ch < S->nchan; ch++)
-        for (int w = 0; w < 3; w++) {
-            const float *x = S->x34[ch][w];
-            int *q = S->ix[ch][w];
-            for (int i = 0; i < T->cfg.nsf_s[ch]; i++) {
-                const int n = T->nBand_s[i];
-                S->ixmax[ch][w][i] = tuned ? quant_tuned(T, x, q, S->gsf[ch][w][i], n, true, -.30f)
-                                           : quant_plain(T, x, q, S->gsf[ch][w][i], n);
-                x += n;
-                q += n;
-            }
-        }
+    HMP3_SYNC();
+    HMP3_SHORT_ITEMS(it) {
+        const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
+        if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
+        const float *x = S->x34[ch][w] + T->startBand_s[i];
+        int *q = S->ix[ch][w] + T->startBand_s[i];
+        const int n = T->nBand_s[i];
+        S->ixmax[ch][w][i] = tuned ? quant_tuned(T, x, q, S->gsf[ch][w][i], n, true, -.30f)
+                                   : quant_plain(T, x, q, S->gsf[ch][w][i], n);
+    }
+    HMP3_SYNC();
 }
 
 // per-window gains, scale factors on the coded grid, steps recomputed (bitallos.cpp:1195-1317)
