@@ -32,11 +32,23 @@
 #define HMP3_GSHIFT (threadIdx.x & 31u & ~(unsigned)(HMP3_W - 1))
 #define HMP3_GMASK ((HMP3_W == 32) ? 0xffffffffu : (((1u << (HMP3_W & 31)) - 1u) << HMP3_GSHIFT))
 #define HMP3_SYNC() __syncwarp(HMP3_GMASK)
+// independent items i = 0..n-1 dealt over the lanes of the group (sequential on the host)
+#define HMP3_FOR_LANES(i, n) for (int i = HMP3_LANE; i < (n); i += HMP3_W)
 #else
 #define HMP3_COOP 0
 #define HMP3_W 1
 #define HMP3_LANE 0
 #define HMP3_SYNC()
+#define HMP3_FOR_LANES(i, n) for (int i = 0; i < (n); i++)
+#endif
+
+#if !HMP3_COOP
+namespace hmp3 {
+// reductions over the lanes of a group: the host build has one "lane"
+static inline int gsum(int v) { return v; }
+static inline int gmax(int v) { return v; }
+static inline int gor(int v) { return v; }
+}
 #endif
 
 // Small constant look-up tables live at namespace scope in device memory (a function-local array would be
@@ -133,6 +145,16 @@ __device__ __forceinline__ unsigned gsum(unsigned v) {
     return r;
 }
 __device__ __forceinline__ int gsum(int v) { return (int)gsum((unsigned)v); }
+__device__ __forceinline__ int gmax(int v) {
+    int r;
+    asm volatile("redux.sync.max.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(HMP3_GMASK));
+    return r;
+}
+__device__ __forceinline__ int gor(int v) {
+    int r;
+    asm volatile("redux.sync.or.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(HMP3_GMASK));
+    return r;
+}
 __device__ __forceinline__ unsigned gballot(int pred) {  // bit i = lane i of the group
     unsigned r;
     asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; vote.sync.ballot.b32 %0, p, %2; }" : "=r"(r) : "r"(pred), "r"(HMP3_GMASK));

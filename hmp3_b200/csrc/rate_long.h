@@ -99,10 +99,11 @@ HMP3_HD int nt_dropout_guard(int noise0, int nt) {
 HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
     const int f = T->cfg.nt_flatten;
     if (f == 0) return;
+    HMP3_SYNC();
     for (int ch = 0; ch < L->nchan; ch++) {
         const int nsf = T->cfg.nsf[ch];
-        int na = 1, nab = 1, ab = 0;
-        for (int i = 0; i < nsf; i++) {
+        int na = 0, nab = 0, ab = 0;  // integer sums: the order of the bands does not matter
+        HMP3_FOR_LANES(i, nsf) {
             int th = i < 14 ? 0 : (i < 17 ? 100 : (i == 17 ? 200 : 300));
             if (L->snr[ch][i] > th) {
                 na++;
@@ -110,9 +111,11 @@ HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
                 nab += T->nBand_l[i];
             }
         }
-        ab = ab / nab;
+        na = 1 + gsum(na);
+        nab = 1 + gsum(nab);
+        ab = gsum(ab) / nab;
         if (na < 5) continue;
-        for (int i = 0; i < nsf; i++) {
+        HMP3_FOR_LANES(i, nsf) {
             int th = i < 14 ? 0 : (i < 17 ? 100 : (i == 17 ? 200 : 300));
             if (L->snr[ch][i] > th) {
                 int dmax = imax_(L->snr[ch][i] - 400, 0);
@@ -122,6 +125,7 @@ HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
             }
         }
     }
+    HMP3_SYNC();
 }
 
 // Take over what the parallel prepare pass computed for this granule (prepare.h): band energies, step bounds,
@@ -163,21 +167,22 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, const SigMask *sm 
                              unsigned char *signx /*[2][576]*/) {
     const int mnr = L->mnr + 100;
     long_adopt_prepared(T, L, P, signx, -1, T->cfg.nsf3);
-    L->active_lines = 0;
+    int lines = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
-        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+        HMP3_FOR_LANES(i, T->cfg.nsf[ch]) {
             const int cbw = T->log_cbw_l[i];
             L->noise0[ch][i] = mb_log(T, L->xsxx[ch][i]) - cbw;
             if (L->noise0[ch][i] < -2000) {
                 L->nt[ch][i] = L->noise0[ch][i] + 1000;
             } else {
-                L->active_lines += T->nBand_l[i];
+                lines += T->nBand_l[i];
                 int mask = mb_log(T, sm[36 * ch + i].mask) - cbw;
                 L->nt[ch][i] = nt_dropout_guard(L->noise0[ch][i], mask - mnr + T->taperNT[i]);
             }
             L->snr[ch][i] = L->noise0[ch][i] - L->nt[ch][i];
         }
     }
+    L->active_lines = gsum(lines);
     long_flatten_targets(T, L);
 }
 
@@ -187,10 +192,10 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
     if (T->cfg.vbr_flag == 0 && L->calls > 10 && (L->target - L->min_target) < 100)
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
-    L->active_lines = 0;
     const int nsf0 = T->cfg.nsf[0];
     long_adopt_prepared(T, L, P, signx, nsf0, T->cfg.nsf2);
-    for (int i = 0; i < nsf0; i++) {
+    int lines = 0;
+    HMP3_FOR_LANES(i, nsf0) {
         const int n = T->nBand_l[i];
         const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = P->e2[0][i], ed = P->e2[1][i];
         const int cbw = T->log_cbw_l[i];
@@ -199,13 +204,13 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
         if (n0l < -2000) ntl = 10000;
         else {
             ntl = nt_dropout_guard(n0l, (mb_log(T, sm[i].mask) - cbw) - mnr + T->taperNT[i]);
-            L->active_lines += n;
+            lines += n;
         }
         int n0r = mb_log(T, er) - cbw;
         if (n0r < -2000) ntr = 10000;
         else {
             ntr = nt_dropout_guard(n0r, (mb_log(T, sm[36 + i].mask) - cbw) - mnr + T->taperNT[i]);
-            L->active_lines += n;
+            lines += n;
         }
         L->nt[0][i] = ntl;
         L->nt[1][i] = ntr;
@@ -214,8 +219,9 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
         L->noise0[0][i] = mb_log(T, em) - cbw;
         L->noise0[1][i] = mb_log(T, ed) - cbw;
     }
+    L->active_lines = gsum(lines);
     long_flatten_targets(T, L);
-    for (int i = 0; i < nsf0; i++) {
+    HMP3_FOR_LANES(i, nsf0) {
         const int nsum = L->noise0[0][i], ndiff = L->noise0[1][i];
         const int xnt = imin_(L->nt[0][i], L->nt[1][i]) + 300;
         L->nt[1][i] = L->nt[0][i] = xnt;
@@ -227,12 +233,14 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
         L->snr[0][i] = nsum - L->nt[0][i];
         L->snr[1][i] = ndiff - L->nt[1][i];
     }
+    HMP3_SYNC();
 }
 
 // ------------------------------------------------------------------ per-band step search
 HMP3_FN void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.cpp:1130-1160
+    HMP3_SYNC();
     for (int ch = 0; ch < L->nchan; ch++)
-        for (int i = 0; i < T->cfg.nsf[ch]; i++) {
+        HMP3_FOR_LANES(i, T->cfg.nsf[ch]) {
             L->nt_adjust[ch][i] = imax_(L->nt_adjust[ch][i], -400);
             L->nt_adjust[ch][i] = imin_(L->nt_adjust[ch][i], 400);
             float g4 = 0.017716950f * mb_log(T, L->x34max[ch][i]) + (88.411238f - 100.0f + 8.0f);
@@ -243,6 +251,7 @@ HMP3_FN void long_seek_initial(const EncTables *T, LongRate *L) {  // bitallo3.c
             v = imax_(v, L->gmin[ch][i]);
             L->gsf[ch][i] = v;
         }
+    HMP3_SYNC();
 }
 
 // walk the step of one band toward the noise target, at most 20 steps (bitallo3.cpp:1164-1238); plain
@@ -518,102 +527,111 @@ HMP3_FN void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bit
 
 // ------------------------------------------------------------------ scale factors
 // choose (scalefac_scale, preflag): first combination whose ranges hold every active band
-// (bitallo3.cpp:1793-1888)
+// (bitallo3.cpp:1793-1888).  Bands are dealt over the lanes; the per-band sign tests are OR-reduced.
 HMP3_FN void long_pick_sf_mode(const EncTables *T, LongRate *L, int ch) {
     const int nsf = T->cfg.nsf[ch];
     if (T->cfg.h_id) {
-        int sp[4] = {0, 0, 0, 0};
-        for (int i = 0; i < nsf; i++)
+        int sp0 = 0, sp1 = 0, sp2 = 0, sp3 = 0;
+        HMP3_FOR_LANES(i, nsf)
             if (L->active[ch][i]) {
                 const int s = L->sf[ch][i];
-                for (int m = 0; m < 4; m++) sp[m] |= (sf_select_limit(m, i) - s);
-                sp[1] |= (s - sf_lower(0, 1, i));
-                sp[3] |= (s - sf_lower(1, 1, i));
+                sp0 |= (sf_select_limit(0, i) - s);
+                sp1 |= (sf_select_limit(1, i) - s);
+                sp2 |= (sf_select_limit(2, i) - s);
+                sp3 |= (sf_select_limit(3, i) - s);
+                sp1 |= (s - sf_lower(0, 1, i));
+                sp3 |= (s - sf_lower(1, 1, i));
             }
+        // only the sign bits matter
+        const int neg = gor(((sp0 >> 31) & 1) | ((sp1 >> 31) & 2) | ((sp2 >> 31) & 4) | ((sp3 >> 31) & 8));
         int scale, pre;
-        if (sp[0] >= 0) { scale = 0; pre = 0; }
-        else if (sp[1] >= 0) { scale = 0; pre = 1; }
-        else if (sp[2] >= 0) { scale = 1; pre = 0; }
-        else if (sp[3] >= 0) { scale = 1; pre = 1; }
+        if (!(neg & 1)) { scale = 0; pre = 0; }
+        else if (!(neg & 2)) { scale = 0; pre = 1; }
+        else if (!(neg & 4)) { scale = 1; pre = 0; }
+        else if (!(neg & 8)) { scale = 1; pre = 1; }
         else { scale = 1; pre = 0; }
         L->preemp[ch] = pre;
         L->sf_scale[ch] = scale;
     } else {
         int sp0 = 0;
-        for (int i = 0; i < nsf; i++)
+        HMP3_FOR_LANES(i, nsf)
             if (L->active[ch][i]) sp0 |= (sf_select_limit(0, i) - L->sf[ch][i]);
+        const int neg = gor((sp0 >> 31) & 1);
         L->preemp[ch] = 0;
-        L->sf_scale[ch] = (sp0 >= 0) ? 0 : 1;
+        L->sf_scale[ch] = neg ? 1 : 0;
     }
 }
 
 // derive G and scale factors from the per-band steps, round them to the coded grid and recompute the
-// steps (bitallo3.cpp:1892-2169).  ms selects the mid/side flavour of the rounding rules.
+// steps (bitallo3.cpp:1892-2169).  ms selects the mid/side flavour of the rounding rules.  Every per-band step
+// is independent, so bands are dealt over the lanes; the band maximum is a group reduction.
 HMP3_FN int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
     int gmin_all = 999;
     int gtop = -1;
     if (ms && L->hf_quant) gtop = L->gsf_hf;
+    HMP3_SYNC();
     for (int ch = 0; ch < L->nchan; ch++) {
         const int nsf = T->cfg.nsf[ch];
         if (!ms) gtop = L->gsf_hf_ch[ch];
-        for (int i = 0; i < nsf; i++) {
-            L->gsf[ch][i] = imax_(L->gsf[ch][i], L->gmin[ch][i]);
-            L->active[ch][i] = 0;
-            if (L->gsf[ch][i] < L->gzero[ch][i]) {
-                L->active[ch][i] = -1;
-                gtop = imax_(gtop, L->gsf[ch][i]);
+        {
+            int top = -1;
+            HMP3_FOR_LANES(i, nsf) {
+                L->gsf[ch][i] = imax_(L->gsf[ch][i], L->gmin[ch][i]);
+                L->active[ch][i] = 0;
+                if (L->gsf[ch][i] < L->gzero[ch][i]) {
+                    L->active[ch][i] = -1;
+                    top = imax_(top, L->gsf[ch][i]);
+                }
             }
+            gtop = imax_(gtop, gmax(top));
         }
         if (gtop < 0) {  // nothing to code in this channel
-            for (int i = 0; i < nsf; i++) {
+            int top = -1;
+            HMP3_FOR_LANES(i, nsf) {
                 L->sf[ch][i] = 0;
                 L->gsf[ch][i] = L->gzero[ch][i];
-                gtop = imax_(gtop, L->gsf[ch][i]);
+                top = imax_(top, L->gsf[ch][i]);
             }
+            gtop = imax_(gtop, gmax(top));
             L->preemp[ch] = 0;
             L->sf_scale[ch] = 0;
             L->G[ch] = gtop;
             gmin_all = imin_(gmin_all, 100);
+            HMP3_SYNC();
             continue;  // note: the mid/side flavour carries gtop into the next channel here (bitallo3.cpp:2059-2074)
         }
-        for (int i = 0; i < nsf; i++) L->sf[ch][i] = (gtop - L->gsf[ch][i]) & L->active[ch][i];
+        HMP3_FOR_LANES(i, nsf) L->sf[ch][i] = (gtop - L->gsf[ch][i]) & L->active[ch][i];
+        HMP3_SYNC();
         long_pick_sf_mode(T, L, ch);
-        int dsf;
-        if (L->sf_scale[ch] == 0) {
-            dsf = 2;
-            for (int i = 0; i < nsf; i++) {
+        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
+        const int dsf = scale == 0 ? 2 : 4;
+        HMP3_FOR_LANES(i, nsf) {
+            int sfv = L->sf[ch][i];
+            if (scale == 0) {
                 if (ms) {
                     if (L->active[ch][i]) {
-                        if ((L->gzero[ch][i] - L->gsf[ch][i]) < 5) L->sf[ch][i]++;
-                        else if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) L->sf[ch][i]++;
-                        L->sf[ch][i] &= (~1);
+                        if ((L->gzero[ch][i] - L->gsf[ch][i]) < 5) sfv++;
+                        else if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) sfv++;
+                        sfv &= (~1);
                     }
                 } else {
-                    if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) L->sf[ch][i]++;
-                    L->sf[ch][i] &= (~1);
+                    if ((i < 11) && (L->noise[ch][i] > L->nt[ch][i])) sfv++;
+                    sfv &= (~1);
                 }
-            }
-        } else {
-            dsf = 4;
-            for (int i = 0; i < nsf; i++) {
-                if (ms && !L->active[ch][i]) continue;
-                int s = L->sf[ch][i] & (~3);
-                int d = L->sf[ch][i] - s;
+            } else if (!(ms && !L->active[ch][i])) {
+                int s = sfv & (~3);
+                int d = sfv - s;
                 int dN = L->noise[ch][i] - L->nt[ch][i] + 150 * d;
                 if (dN > noise_gap_limit(i)) s = s + 4;
                 else if (ms && (L->gzero[ch][i] - L->gsf[ch][i] - d) < 5) s = s + 4;
-                L->sf[ch][i] = ms ? s : (s & L->active[ch][i]);
+                sfv = ms ? s : (s & L->active[ch][i]);
             }
-        }
-        const int scale = L->sf_scale[ch], pre = L->preemp[ch];
-        for (int i = 0; i < nsf; i++) {
             const int hi = sf_upper(scale, pre, i), lo = sf_lower(scale, pre, i);
-            if (L->sf[ch][i] > hi) L->sf[ch][i] = hi;
-            else if (L->sf[ch][i] < lo) L->sf[ch][i] = lo;
-        }
-        for (int i = 0; i < nsf; i++)
+            if (sfv > hi) sfv = hi;
+            else if (sfv < lo) sfv = lo;
+            L->sf[ch][i] = sfv;
             if (L->active[ch][i]) {
-                L->gsf[ch][i] = gtop - L->sf[ch][i];
+                L->gsf[ch][i] = gtop - sfv;
                 if (L->gsf[ch][i] < 0) {
                     L->gsf[ch][i] += dsf;
                     L->sf[ch][i] -= dsf;
@@ -623,9 +641,11 @@ HMP3_FN int long_scale_factors(const EncTables *T, LongRate *L, bool ms) {
                     L->sf[ch][i] = sf_lower(scale, pre, i);
                 }
             }
+        }
         L->G[ch] = gtop;
         gmin_all = imin_(gmin_all, gtop);
         if (ms) gtop = -1;
+        HMP3_SYNC();
     }
     return gmin_all;
 }
