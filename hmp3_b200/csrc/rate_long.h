@@ -29,7 +29,6 @@ struct LongRate {
     int G[2], preemp[2], sf_scale[2];
     RegionPlan plan[2];
     float (*x34)[576];  // |x|^(3/4) of the granule in flight: points into its PrepGranule
-    float dd[2][576];  // per-line squared errors of the step search in flight (device build)
 };
 
 HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
@@ -313,6 +312,9 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
             }
         }
     }
+    // per-line squared errors of one channel at a time, in shared memory (one 576-float row per stream of the block)
+    __shared__ float s_dd[kRateWarpsPerBlock * (32 / HMP3_W)][576];
+    float *dd = s_dd[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
     for (;;) {
         unsigned am[2] = {0u, 0u};  // bit b = band b of the channel is still searching
         for (int it = 0; it < NI; it++) am[it / NS] |= gballot(mode[it] != 0) << (HMP3_W * (it % NS));
@@ -322,7 +324,6 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
             const int nl = T->startBand_l[T->cfg.nsf[c]];
             const float *y34 = L->x34[c];
             const float *y = xr + 576 * c;
-            float *dd = L->dd[c];
             for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
                 const int k = k0 + lane;
                 const int b = (k < nl) ? (int)T->line_band_l[k] : 0;
@@ -344,57 +345,58 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
                     dd[k] = d * d;
                 }
             }
-        }
-        HMP3_SYNC();
-        for (int it = 0; it < NI; it++) {
-            if (mode[it] == 0) continue;
-            const int c = it / NS, bnd = lane + HMP3_W * (it % NS);
-            const float *v = L->dd[c] + T->startBand_l[bnd];
-            const int n = T->nBand_l[bnd];
-            float acc = 0.0f;
-            for (int k = 0; k < n; k++) acc += v[k];
-            const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];
-            bool done = false;
-            if (mode[it] == 1) {
-                const int dn = tn - target[it];
-                L->nt_adjust[c][bnd] = L->nt_adjust[c][bnd] + (dn >> 3);
-                best_abs[it] = iabs(dn);
-                best_noise[it] = tn;
-                best_s[it] = s_try[it];
-                iter[it] = 0;
-                if (dn > 100) {
-                    niter[it] = imin_(s_try[it] - 1, 20);
-                    s_try[it] = s_try[it] - 1;
-                    mode[it] = 2;
-                    done = niter[it] <= 0;
-                } else if (dn < -100) {
-                    niter[it] = 20;
-                    s_try[it] = s_try[it] + 1;
-                    mode[it] = 3;
-                } else done = true;
-            } else {
-                const int a = iabs(tn - target[it]);
-                if (a < best_abs[it]) {
-                    best_abs[it] = a;
+            HMP3_SYNC();
+            for (int j = 0; j < NS; j++) {
+                const int it = c * NS + j;
+                if (mode[it] == 0) continue;
+                const int bnd = lane + HMP3_W * j;
+                const float *v = dd + T->startBand_l[bnd];
+                const int n = T->nBand_l[bnd];
+                float acc = 0.0f;
+                for (int k = 0; k < n; k++) acc += v[k];
+                const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];
+                bool done = false;
+                if (mode[it] == 1) {
+                    const int dn = tn - target[it];
+                    L->nt_adjust[c][bnd] = L->nt_adjust[c][bnd] + (dn >> 3);
+                    best_abs[it] = iabs(dn);
                     best_noise[it] = tn;
                     best_s[it] = s_try[it];
-                }
-                iter[it]++;
-                if (mode[it] == 2) {
-                    if (tn <= target[it] || iter[it] >= niter[it]) done = true;
-                    else s_try[it]--;
+                    iter[it] = 0;
+                    if (dn > 100) {
+                        niter[it] = imin_(s_try[it] - 1, 20);
+                        s_try[it] = s_try[it] - 1;
+                        mode[it] = 2;
+                        done = niter[it] <= 0;
+                    } else if (dn < -100) {
+                        niter[it] = 20;
+                        s_try[it] = s_try[it] + 1;
+                        mode[it] = 3;
+                    } else done = true;
                 } else {
-                    if (tn >= target[it] || iter[it] >= niter[it]) done = true;
-                    else s_try[it]++;
+                    const int a = iabs(tn - target[it]);
+                    if (a < best_abs[it]) {
+                        best_abs[it] = a;
+                        best_noise[it] = tn;
+                        best_s[it] = s_try[it];
+                    }
+                    iter[it]++;
+                    if (mode[it] == 2) {
+                        if (tn <= target[it] || iter[it] >= niter[it]) done = true;
+                        else s_try[it]--;
+                    } else {
+                        if (tn >= target[it] || iter[it] >= niter[it]) done = true;
+                        else s_try[it]++;
+                    }
+                }
+                if (done) {
+                    L->gsf[c][bnd] = best_s[it];
+                    L->noise[c][bnd] = best_noise[it];
+                    mode[it] = 0;
                 }
             }
-            if (done) {
-                L->gsf[c][bnd] = best_s[it];
-                L->noise[c][bnd] = best_noise[it];
-                mode[it] = 0;
-            }
+            HMP3_SYNC();
         }
-        HMP3_SYNC();
     }
     HMP3_SYNC();
 }
