@@ -60,8 +60,6 @@ struct StreamResult {
 };
 
 // ---- launchers (all asynchronous on `stream`)
-void launch_stage_pcm(const StreamDev *st, const int16_t *const *src, int16_t *pcm, long long lo, long long hi, int n,
-                      cudaStream_t stream);
 void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
                       cudaStream_t stream);
 void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);

@@ -5,15 +5,6 @@
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-void launch_stage_pcm(const StreamDev *st, const int16_t *const *src, int16_t *pcm, long long lo, long long hi, int n,
-                      cudaStream_t stream) {
-    if (hi <= lo) return;
-    const long long per_stream = (hi - lo);  // samples per channel; 2 per thread-iteration when 4-byte copies apply
-    unsigned bx = (unsigned)((per_stream + 2047) / 2048);
-    if (bx < 1) bx = 1;
-    if (bx > 64) bx = 64;
-    k_stage_pcm<<<dim3(bx, (unsigned)n), 256, 0, stream>>>(st, src, pcm, lo, hi, n);
-}
 void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
                       cudaStream_t stream) {
     const long long G = cb.NG + 3;

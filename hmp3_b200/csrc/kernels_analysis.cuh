@@ -8,32 +8,6 @@
 
 namespace hmp3 {
 
-// ---- K0: PCM staging.  When the caller's PCM lives in pinned (device-mappable) host memory the device pulls
-// each chunk's new samples over PCIe itself, one launch per chunk, instead of the host queueing one copy per
-// stream up front; the transfer then overlaps the serial stage of the previous chunk.
-// src[s] = device-visible address of stream s's interleaved PCM; samples [lo, hi) per channel are copied.
-__global__ void __launch_bounds__(256) k_stage_pcm(const StreamDev *st, const int16_t *const *src, int16_t *pcm,
-                                                   long long lo_sample, long long hi_sample, int nstreams) {
-    const int s = blockIdx.y;
-    if (s >= nstreams) return;
-    const StreamDev sd = st[s];
-    long long lo = lo_sample < sd.nsamples ? lo_sample : sd.nsamples;
-    long long hi = hi_sample < sd.nsamples ? hi_sample : sd.nsamples;
-    lo *= sd.nch;
-    hi *= sd.nch;  // int16 element range
-    if (hi <= lo) return;
-    const int16_t *from = src[s];
-    int16_t *to = pcm + sd.pcm_off;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
-    if ((((unsigned long long)from | (unsigned long long)to) & 3ull) == 0 && ((lo | hi) & 1) == 0) {
-        const unsigned *f4 = (const unsigned *)from;
-        unsigned *t4 = (unsigned *)to;
-        for (long long k = (lo >> 1) + tid; k < (hi >> 1); k += nthr) t4[k] = f4[k];
-    } else {
-        for (long long k = lo + tid; k < hi; k += nthr) to[k] = from[k];
-    }
-}
-
 // ---- K1: polyphase analysis, one thread per (stream, polyphase granule, channel, time slot)
 __global__ void __launch_bounds__(128) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,
                                                    ChunkBufs cb, int K0, int nstreams) {

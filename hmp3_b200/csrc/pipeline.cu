@@ -76,8 +76,10 @@ struct hmp3_batch {
     cudaStream_t stream_p = nullptr;    // packing pass
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr},
                 ev_start = nullptr;
-    const int16_t **d_src = nullptr;    // [n] device-visible addresses of the callers' pinned PCM (staged runs)
-    bool staged = false;                // this run pulls PCM chunk by chunk with k_stage_pcm
+    const int16_t *const *h_src = nullptr;  // callers' pinned PCM pointers of a staged run
+    bool staged = false;                // this run copies PCM chunk by chunk (copy engine) ahead of each chunk's Phase A
+    cudaStream_t stream_c = nullptr;    // H2D staging copies
+    cudaEvent_t ev_c[2] = {nullptr, nullptr};
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
@@ -134,7 +136,9 @@ struct hmp3_batch {
         cudaFree(d_flags);
         cudaFree(d_msmem);
         cudaFree(d_psy);
-        cudaFree(d_src);
+        if (stream_c) cudaStreamDestroy(stream_c);
+        for (int k = 0; k < 2; k++)
+            if (ev_c[k]) cudaEventDestroy(ev_c[k]);
         if (stream_a) cudaStreamDestroy(stream_a);
         if (stream_p) cudaStreamDestroy(stream_p);
         for (auto e : ev) cudaEventDestroy(e);
@@ -359,10 +363,27 @@ int run_plan(hmp3_batch *b) {
     for (int K0 = 0; K0 < b->max_gran; K0 += b->NG, c++) {
         const int k = c & 1;
         if (c >= 2) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
-        if (b->staged) {  // samples first needed by this chunk's polyphase: up to the end of granule K0+NG-1
+        if (b->staged) {
+            // the samples this chunk's polyphase needs first (up to the end of granule K0+NG-1), one DMA copy per
+            // stream on the copy stream: the copy engine needs no SM resources, so the transfer overlaps the
+            // serial stage of the previous chunk whatever its occupancy
+            if (!b->stream_c) {
+                CK(cudaStreamCreate(&b->stream_c));
+                CK(cudaEventCreateWithFlags(&b->ev_c[0], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&b->ev_c[1], cudaEventDisableTiming));
+            }
+            if (c == 0) CK(cudaStreamWaitEvent(b->stream_c, b->ev_start, 0));
             const long long lo = c == 0 ? 0 : 576LL * K0, hi = 576LL * (K0 + b->NG);
-            launch_stage_pcm(b->d_st, b->d_src, b->d_pcm, lo, hi, n, b->stream_a);
-            b->launches++;
+            for (int i = 0; i < n; i++) {
+                const StreamDev &sd = b->st_h[i];
+                if (b->status[i] != HMP3_OK) continue;
+                const long long a = std::min<long long>(lo, sd.nsamples), e = std::min<long long>(hi, sd.nsamples);
+                if (e <= a) continue;
+                CK(cudaMemcpyAsync(b->d_pcm + sd.pcm_off + a * sd.nch, b->h_src[i] + a * sd.nch,
+                                   sizeof(int16_t) * (e - a) * sd.nch, cudaMemcpyHostToDevice, b->stream_c));
+            }
+            CK(cudaEventRecord(b->ev_c[k], b->stream_c));
+            CK(cudaStreamWaitEvent(b->stream_a, b->ev_c[k], 0));
         }
         r = launch_analysis(b, K0, k, b->stream_a);
         if (r != HMP3_OK) return r;
@@ -631,31 +652,13 @@ bool is_pinned(const void *p) {
 int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
     CK(cudaSetDevice(b->device));
-    // Pinned input: the device pulls each chunk's samples itself while the previous chunk is in the serial stage
-    // (k_stage_pcm).  Pageable input: one queued copy per stream before the first kernel.
+    // Pinned input: each chunk's samples are copied (DMA) right before that chunk's Phase A, overlapping the serial
+    // stage of the previous chunk.  Pageable input: one queued copy per stream before the first kernel.
     bool pinned_in = true, pinned_out = true;
     for (int i = 0; i < b->n && (pinned_in || pinned_out); i++) {
         if (b->status[i] != HMP3_OK) continue;
         if (pinned_in && b->st_h[i].nsamples > 0 && !is_pinned(pcm[i])) pinned_in = false;
         if (pinned_out && !is_pinned(out[i])) pinned_out = false;
-    }
-    if (pinned_in) {
-        std::vector<const int16_t *> src(b->n, nullptr);
-        for (int i = 0; i < b->n; i++) {
-            if (b->status[i] != HMP3_OK || b->st_h[i].nsamples == 0) continue;
-            void *dp = nullptr;
-            if (cudaHostGetDevicePointer(&dp, (void *)pcm[i], 0) != cudaSuccess) {
-                cudaGetLastError();
-                pinned_in = false;
-                break;
-            }
-            src[i] = (const int16_t *)dp;
-        }
-        if (pinned_in) {
-            if (!b->d_src) CK(cudaMalloc(&b->d_src, sizeof(int16_t *) * b->n));
-            CK(cudaMemcpyAsync(b->d_src, src.data(), sizeof(int16_t *) * b->n, cudaMemcpyHostToDevice, b->stream));
-            CK(cudaStreamSynchronize(b->stream));  // src is a local
-        }
     }
     if (!pinned_in) {
         for (int i = 0; i < b->n; i++) {
@@ -665,8 +668,10 @@ int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *co
         }
     }
     b->staged = pinned_in;
+    b->h_src = pcm;
     int r = run_plan(b);
     b->staged = false;
+    b->h_src = nullptr;
     if (r != HMP3_OK) return r;
     r = sync_plan(b);
     if (r != HMP3_OK) return r;

@@ -116,7 +116,7 @@ def test_encoder_handle_float_entry_and_rejections():
 
 
 def test_pinned_host_buffers_take_the_staged_path():
-    """Pinned PCM is pulled chunk by chunk by the device (k_stage_pcm) and pinned outputs are written directly:
+    """Pinned PCM is copied chunk by chunk ahead of each chunk's Phase A and pinned outputs are written directly:
     same bytes as the pageable path, for aligned and odd-aligned sources, stereo and mono."""
     import torch
     specs = [(44100, 2, dict(bitrate=64), 7.3, 0), (44100, 2, dict(bitrate=64), 3.1, 1), (22050, 1, dict(bitrate=32), 6.2, 1),
