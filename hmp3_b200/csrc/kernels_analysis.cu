@@ -7,8 +7,8 @@ static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((
 
 void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
                       cudaStream_t stream) {
-    const long long G = cb.NG + 3;
-    k_polyphase<<<blocks_for((long long)n * G * 2 * 18, 128), 128, 0, stream>>>(tabs, st, pcm, cb, K0, n);
+    const int G = cb.NG + 3;
+    k_polyphase<<<dim3((unsigned)((G + kPolyRun - 1) / kPolyRun), (unsigned)n), 256, 0, stream>>>(tabs, st, pcm, cb, K0, n);
 }
 void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
     const long long G = cb.NG + 3;

@@ -8,26 +8,68 @@
 
 namespace hmp3 {
 
-// ---- K1: polyphase analysis, one thread per (stream, polyphase granule, channel, time slot)
-__global__ void __launch_bounds__(128) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,
+// ---- K1: polyphase analysis.  One block = kPolyRun consecutive polyphase granules of one stream, both channels:
+// the PCM span they need (576 * run + 480 samples per channel) is staged once in shared memory as float
+// (coalesced 32-bit reads of the interleaved int16 input, zero outside the clip), then one thread per
+// (channel, time slot) folds its 512-sample window and runs the 32-point fast DCT in the reference's operation
+// order.  Shared-memory rows are padded (index + index / 32) so that the slots of a warp, whose windows start
+// 32 samples apart, hit 32 different banks.
+constexpr int kPolyRun = 7;                                 // granules per block: 126 slots per channel
+constexpr int kPolySpan = 576 * kPolyRun + 480;             // samples per channel staged
+constexpr int kPolyRow = kPolySpan + (kPolySpan >> 5) + 1;  // padded row length
+__global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,
                                                    ChunkBufs cb, int K0, int nstreams) {
+    __shared__ float s_pcm[2][kPolyRow];
     const int G = cb.NG + 3;
-    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)nstreams * G * 2 * 18;
-    if (id >= total) return;
-    int t = (int)(id % 18);
-    long long r = id / 18;
-    int ch = (int)(r & 1);
-    r >>= 1;
-    int jj = (int)(r % G);
-    int s = (int)(r / G);
+    const int s = blockIdx.y;
+    if (s >= nstreams) return;
     const StreamDev sd = st[s];
-    if (ch >= sd.nch) return;
-    long long j = (long long)K0 - 3 + jj;
-    if (j >= sd.ngran) return;
+    const int jj0 = blockIdx.x * kPolyRun;          // first polyphase granule of this block within the chunk
+    const long long j0 = (long long)K0 - 3 + jj0;   // ... and its absolute index (may be negative: zero history)
+    if (jj0 >= G || j0 >= sd.ngran) return;
     const EncTables *T = tabs + sd.cfg;
+    const int nch = sd.nch;
+    // stage samples n0 .. n0 + kPolySpan - 1 of every channel
+    const long long n0 = 576 * j0 - 480;
+    const int16_t *src = pcm + sd.pcm_off;
+    if (nch == 2) {
+        const unsigned *src2 = (const unsigned *)src;  // pcm_off is even-aligned: one 32-bit word = (left, right)
+        for (int p = threadIdx.x; p < kPolySpan; p += 256) {
+            const long long n = n0 + p;
+            float l = 0.0f, r = 0.0f;
+            if (n >= 0 && n < sd.nsamples) {
+                const unsigned w = src2[n];
+                l = (float)(short)(w & 0xffffu);
+                r = (float)(short)(w >> 16);
+            }
+            const int q = p + (p >> 5);
+            s_pcm[0][q] = l;
+            s_pcm[1][q] = r;
+        }
+    } else {
+        for (int p = threadIdx.x; p < kPolySpan; p += 256) {
+            const long long n = n0 + p;
+            s_pcm[0][p + (p >> 5)] = (n >= 0 && n < sd.nsamples) ? (float)src[n] : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int ch = threadIdx.x >> 7, slot = threadIdx.x & 127;  // slot = 18 * (granule within the run) + t
+    if (ch >= nch || slot >= 18 * kPolyRun) return;
+    const int jr = slot / 18, t = slot - 18 * jr;
+    const int jj = jj0 + jr;
+    if (jj >= G || j0 + jr >= sd.ngran) return;
+    const float *row = s_pcm[ch];
+    const int newest = 32 * slot + 31 + 480;  // position of this slot's newest sample in the staged span
+    auto fetch = [&](int i) -> float {
+        const int p = newest - i;
+        return row[p + (p >> 5)];
+    };
+    float col[32];
+    polyphase_slot(T, fetch, col, 1);
     float *out = cb.P + (((long long)s * G + jj) * 2 + ch) * 576;
-    polyphase_item(T, pcm + sd.pcm_off, (long)sd.nsamples, sd.nch, ch, (long)j, t, out);
+    const int nsb = T->cfg.nsb_hybrid;
+#pragma unroll
+    for (int sb = 0; sb < 32; sb++) out[18 * sb + t] = freq_inverted(sb, t, nsb) ? -col[sb] : col[sb];
 }
 
 // ---- K2: attack energies, one thread per (stream, polyphase granule, channel, slot pair)
