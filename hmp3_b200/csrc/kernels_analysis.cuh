@@ -113,9 +113,13 @@ __global__ void k_switch_scan(const EncTables *tabs, const StreamDev *st, Switch
     sw[s] = state;
 }
 
-// ---- K4: hybrid window + MDCT + alias reduction, one warp per (stream, granule, channel), lane = sub-band
+// ---- K4: hybrid window + MDCT + alias reduction, one warp per (stream, granule, channel), lane = sub-band.
+// The two polyphase granules are brought into shared memory with coalesced loads, the transform and the alias
+// butterflies run there, and the 576 lines go back with coalesced stores (the per-lane access pattern -- 18
+// consecutive values per sub-band -- would otherwise touch 32 different cache lines per instruction).
 __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
                                                 int nstreams) {
+    __shared__ float s_buf[4][3][576];
     const int G = cb.NG + 3;
     long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -132,9 +136,17 @@ __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const Str
     const float *prev = cb.P + (((long long)s * G + q) * 2 + ch) * 576;      // P[K-3]
     const float *cur = cb.P + (((long long)s * G + q + 1) * 2 + ch) * 576;   // P[K-2]
     float *xr = cb.xr + (((long long)s * cb.NG + q) * 2 + ch) * 576;
-    hybrid_item(T, prev, cur, bt, lane, xr);
+    float(*sb)[576] = s_buf[threadIdx.x >> 5];
+    for (int k = lane; k < 576; k += 32) {
+        sb[0][k] = prev[k];
+        sb[1][k] = cur[k];
+    }
     __syncwarp();
-    if (bt != 2) alias_item(T, lane, xr);
+    hybrid_item(T, sb[0], sb[1], bt, lane, sb[2]);
+    __syncwarp();
+    if (bt != 2) alias_item(T, lane, sb[2]);
+    __syncwarp();
+    for (int k = lane; k < 576; k += 32) xr[k] = sb[2][k];
 }
 
 // ---- K5: psychoacoustic stage 1 (one thread per granule-channel) and M/S measure (one per granule)
