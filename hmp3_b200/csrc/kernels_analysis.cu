@@ -22,7 +22,7 @@ void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int
     k_hybrid<<<blocks_for((long long)n * cb.NG * 2 * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
 }
 void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
-    k_psy_stage1<<<blocks_for((long long)n * cb.NG * 3, 64), 64, 0, stream>>>(tabs, st, cb, K0, n);
+    k_psy_stage1<<<blocks_for((long long)n * cb.NG * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
 }
 void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
                     cudaStream_t stream) {

@@ -149,31 +149,144 @@ __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const Str
     for (int k = lane; k < 576; k += 32) xr[k] = sb[2][k];
 }
 
-// ---- K5: psychoacoustic stage 1 (one thread per granule-channel) and M/S measure (one per granule)
-__global__ void __launch_bounds__(64) k_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
-                                                   int nstreams) {
-    long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)nstreams * cb.NG * 3;
-    if (id >= total) return;
-    int job = (int)(id % 3);
-    long long r = id / 3;
-    int q = (int)(r % cb.NG);
-    int s = (int)(r / cb.NG);
+// ---- K5: psychoacoustic stage 1 and the M/S measure, one warp per (stream, granule).  The granule's spectra are
+// staged in shared memory; long blocks run one partition (or scale-factor band) per lane -- each lane does the
+// reference's sequential sums for its partition, the integer statistics are warp reductions -- and the rare
+// short blocks run the plain sequential routine on one lane.
+__device__ __forceinline__ void psy_long_stage1_warp(const EncTables *T, const float *xr, PsyRaw *R, float *xtab,
+                                                     int *mbetab, int *snrv, int lane) {
+    const int nmap = T->psy_emap_n_l;
+    const int npart = T->psy_npart_l;
+    const int npart2 = (npart + 1) & ~1;
+    const float *w = T->w_spd_l;
+    for (int j = lane; j < 44; j += 32) {  // partition energies (emap.c:96-121)
+        float s = 0.0f;
+        if (j < nmap) {
+            const int n = T->psy_nsum_l[j];
+            const float *x = xr + T->psy_start_l[j];
+            for (int q = 0; q < n; q++) s += x[q] * x[q];
+        }
+        float e = 0.0f, xt = 0.0f;
+        int mbe = 0;
+        if (j < npart2) {
+            e = w[j] + s;
+            mbe = mb_log(T, e);
+            xt = mb_exp(T, (int)(0.30f * mbe));
+        }
+        R->e[j] = e;
+        mbetab[j] = mbe;
+        xtab[j] = xt;
+    }
+    __syncwarp();
+    int nsnr = 0, totsnr = 0;
+    float stab[2] = {0.0f, 0.0f};
+    for (int r = 0; r < 2; r++) {  // spreading (spdsmr.c:188-277)
+        const int i = lane + 32 * r;
+        if (i < npart) {
+            const int p = T->spd_off_l[i], n = T->spd_cnt_l[i], k = T->spd_w0_l[i];
+            float sp = 0.1f;
+            for (int j = 0; j < n; j++) sp += w[k + j] * xtab[p + j];
+            sp = (0.03f * 0.1f * 0.35f) * mb_exp(T, (int)((1.0f / 0.30f) * mb_log(T, sp))) + w[i];
+            stab[r] = sp;
+            const int snr = mbetab[i] - mb_log(T, w[i] + sp);
+            if (snr > 0) nsnr++;
+            totsnr += (snr > -200 ? snr : -200);
+            snrv[i] = snr;
+        }
+    }
+    __syncwarp();
+    int snrvar = 0;
+    for (int r = 0; r < 2; r++) {
+        const int i = lane + 32 * r;
+        if (i < npart) snrvar += iabs(snrv[i] - (i > 0 ? snrv[i - 1] : 0));
+    }
+    nsnr = __reduce_add_sync(0xffffffffu, nsnr);
+    totsnr = __reduce_add_sync(0xffffffffu, totsnr);
+    snrvar = __reduce_add_sync(0xffffffffu, snrvar);
+    int d = 0;
+    if (nsnr > 0) {
+        int d0 = round_away(1.3f * (totsnr / npart) - 850);
+        int itmp = snrvar / npart;
+        int dv = (500 - itmp) < 0 ? (500 - itmp) : 0;
+        d = d0 + dv;
+        d = d > -2000 ? d : -2000;
+        d = d < 600 ? d : 600;
+    }
+    d += 300;
+    const int dm0 = (300 - d) >> 4;
+    for (int r = 0; r < 2; r++) {
+        const int i = lane + 32 * r;
+        if (i < npart2) {
+            const int m = i >> 1;
+            const int t13 = (m - 13) > 0 ? (m - 13) : 0;
+            const int dm = dm0 * t13 > 0 ? dm0 * t13 : 0;
+            const float a = mb_exp(T, d + dm);
+            R->thr[i] = a * stab[r];
+        }
+    }
+}
+
+__device__ __forceinline__ int ms_measure_long_warp(const EncTables *T, const float *x0, const float *x1, int lane) {
+    int cm = 0;
+    const int nsf = T->cfg.nsf[0];
+    if (lane < nsf) {  // one scale-factor band per lane (bitallo3.cpp:698-744)
+        const int i = lane, n = T->nBand_l[i], k0 = T->startBand_l[i];
+        float el = 100.0f, er = 100.0f, t = 0.0f;
+        for (int k = k0; k < k0 + n; k++) {
+            float a = x0[k] * x0[k];
+            float b = x1[k] * x1[k];
+            float c = x0[k] * x1[k];
+            el += a;
+            er += b;
+            t += c;
+        }
+        float es = el + er, ed = es;
+        t = t + t;
+        es = es + t;
+        ed = ed - t;
+        int mblr = mb_log(T, el + er) - mb_log(T, el > er ? el : er);
+        int mbsd = mb_log(T, es + ed) - mb_log(T, es > ed ? es : ed);
+        int q = 75 - iabs(mblr - 120);
+        int psd = q > 0 ? q : 0;
+        int h = (mbsd >> 1) + 120;
+        mbsd = mbsd < h ? mbsd : h;
+        mbsd += psd;
+        cm = n * (mblr - mbsd);
+    }
+    return __reduce_add_sync(0xffffffffu, cm);
+}
+
+__global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
+                                                    int nstreams) {
+    __shared__ float s_x[4][2][576];
+    __shared__ float s_xtab[4][44];
+    __shared__ int s_mbe[4][44], s_snr[4][44];
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int q = (int)(wid % cb.NG), s = (int)(wid / cb.NG);
+    if (s >= nstreams) return;
     const StreamDev sd = st[s];
     if (K0 + q >= sd.ngran) return;
     const EncTables *T = tabs + sd.cfg;
-    const int bt = cb.gi[(long long)s * cb.NG + q].block_type;
-    const float *x0 = cb.xr + (((long long)s * cb.NG + q) * 2) * 576;
-    if (job < 2) {
-        if (job >= sd.nch) return;
-        PsyRaw *R = cb.raw + ((long long)s * cb.NG + q) * 2 + job;
-        if (bt != 2) psy_long_stage1(T, x0 + 576 * job, R);
-        else psy_short_stage1(T, x0 + 576 * job, R);
-    } else {
-        int m = 0;
-        if (sd.nch == 2) m = (bt != 2) ? ms_measure_long(T, x0, x0 + 576) : ms_measure_short(T, x0, x0 + 576);
-        cb.ms_raw[(long long)s * cb.NG + q] = m;
+    const long long o = (long long)s * cb.NG + q;
+    const int bt = cb.gi[o].block_type;
+    const float *x0 = cb.xr + o * 2 * 576;
+    for (int c = 0; c < sd.nch; c++)
+        for (int k = lane; k < 576; k += 32) s_x[wl][c][k] = x0[576 * c + k];
+    __syncwarp();
+    for (int c = 0; c < sd.nch; c++) {
+        PsyRaw *R = cb.raw + o * 2 + c;
+        if (bt != 2) psy_long_stage1_warp(T, s_x[wl][c], R, s_xtab[wl], s_mbe[wl], s_snr[wl], lane);
+        else if (lane == 0) psy_short_stage1(T, s_x[wl][c], R);
+        __syncwarp();
     }
+    int m = 0;
+    if (sd.nch == 2) {
+        if (bt != 2) m = ms_measure_long_warp(T, s_x[wl][0], s_x[wl][1], lane);
+        else if (lane == 0) m = ms_measure_short(T, s_x[wl][0], s_x[wl][1]);
+        if (bt == 2) m = __shfl_sync(0xffffffffu, m, 0);
+    }
+    if (lane == 0) cb.ms_raw[o] = m;
 }
 
 // ---- K5b: M/S decision scan (hysteresis memory), one thread per stream, sequential over the chunk.
