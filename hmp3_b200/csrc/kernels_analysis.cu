@@ -27,7 +27,7 @@ void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb,
 void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
                     cudaStream_t stream) {
     k_ms_scan<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, msmem, cb, K0, n);
-    k_psy_stage2<<<blocks_for(2LL * n, 64), 64, 0, stream>>>(tabs, st, psy, cb, K0, n);
+    k_psy_stage2<<<blocks_for(2LL * n * 32, 128), 128, 0, stream>>>(tabs, st, psy, cb, K0, n);
     k_prepare<<<blocks_for((long long)n * cb.NG * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
 }
 void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream) {

@@ -321,24 +321,104 @@ __global__ void k_ms_scan(const EncTables *tabs, const StreamDev *st, int *msmem
     msmem[s] = mem;
 }
 
-// ---- K5c: psychoacoustic stage 2 (pre-echo memory), one thread per (stream, channel), sequential over the chunk
-__global__ void k_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy, ChunkBufs cb, int K0,
-                             int nstreams) {
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- K5c: psychoacoustic stage 2 (pre-echo memory), one warp per (stream, channel), sequential over the chunk,
+// one partition pair (long) / one partition (short) per lane; the carried state lives in shared memory while the
+// chunk is scanned.  Same per-index operations as psy_long_stage2 / psy_short_stage2 (psy_core.h).
+__global__ void __launch_bounds__(128) k_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy, ChunkBufs cb,
+                                                    int K0, int nstreams) {
+    __shared__ float s_echo[4][64];
+    __shared__ SigMask s_sm[4][36];
+    const int id = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int s = id >> 1, ch = id & 1;
     if (s >= nstreams) return;
     const StreamDev sd = st[s];
     if (ch >= sd.nch) return;
     const EncTables *T = tabs + sd.cfg;
     PsyState *P = psy + (long long)s * 2 + ch;
+    float *echo = s_echo[wl];
+    SigMask *sm = s_sm[wl];
+    for (int i = lane; i < 64; i += 32) echo[i] = P->echo[i];
+    for (int i = lane; i < 36; i += 32) sm[i] = P->sm[i];
+    __syncwarp();
+    const int npl = T->psy_npart_l, mps = (T->psy_npart_s + 1) >> 1;
     for (int q = 0; q < cb.NG && K0 + q < sd.ngran; q++) {
         const GranuleInfo g = cb.gi[(long long)s * cb.NG + q];
         const PsyRaw *R = cb.raw + ((long long)s * cb.NG + q) * 2 + ch;
-        if (g.block_type != 2) psy_long_stage2(T, R, P->echo, g.block_type, P->sm);
-        else psy_short_stage2(T, R, P->echo, g.block_type_prev, P->sm);
-        SigMask *o = cb.sm + (((long long)s * cb.NG + q) * 2 + ch) * 36;
-        for (int i = 0; i < 36; i++) o[i] = P->sm[i];
+        if (g.block_type != 2) {
+            const int i = 2 * lane;
+            if (i < npl) {  // spdsmr.c:279-316
+                float s1 = R->thr[i];
+                float t = echo[i];
+                echo[i] = (float)(2.0 * s1);
+                if (g.block_type != 3) {
+                    if (s1 > t) {
+                        float x = 0.1f * s1;
+                        s1 = t;
+                        if (s1 < x) s1 = x;
+                    }
+                }
+                float s2 = R->thr[i + 1];
+                t = echo[i + 1];
+                echo[i + 1] = 2.0f * s2;
+                if (g.block_type != 3) {
+                    if (s2 > t) {
+                        float x = 0.1f * s2;
+                        s2 = t;
+                        if (s2 < x) s2 = x;
+                    }
+                }
+                float e0 = R->e[i], e1 = R->e[i + 1];
+                float emax = e0;
+                if (emax < e1) emax = e1;
+                sm[lane].sig = e0 + e1;
+                sm[lane].mask = (e0 * s1 + e1 * s2) / emax;
+            }
+        } else {
+            const int i = lane;
+            if (i < mps) {  // spdsmr.c:110-181
+                float k0 = R->thr[i], k1 = R->thr[16 + i], k2 = R->thr[32 + i];
+                float m0 = echo[i];
+                float m1 = (float)(2.0 * k0);
+                float m2 = (float)(2.0 * k1);
+                echo[i] = (float)(2.0 * k2);
+                if (g.block_type_prev == 2) {
+                    float t = k0;
+                    if (t > m0) {
+                        float tmp = 0.1f * t;
+                        k0 = (m0 > tmp) ? m0 : tmp;
+                    }
+                }
+                {
+                    float t = k1;
+                    if (t > m1) {
+                        float tmp = 0.1f * t;
+                        k1 = (m1 > tmp) ? m1 : tmp;
+                    }
+                }
+                {
+                    float t = k2;
+                    if (t > m2) {
+                        float tmp = 0.1f * t;
+                        k2 = (m2 > tmp) ? m2 : tmp;
+                    }
+                }
+                sm[i].mask = k0;
+                sm[12 + i].mask = k1 + 0.1f * k0;
+                sm[24 + i].mask = k2 + 0.1f * k1;
+                sm[i].sig = 0.0f;
+                sm[12 + i].sig = 0.0f;
+                sm[24 + i].sig = 0.0f;
+            }
+        }
+        __syncwarp();
+        float *o = (float *)(cb.sm + (((long long)s * cb.NG + q) * 2 + ch) * 36);
+        const float *src = (const float *)sm;
+        for (int k = lane; k < 72; k += 32) o[k] = src[k];
+        __syncwarp();
     }
+    for (int i = lane; i < 64; i += 32) P->echo[i] = echo[i];
+    for (int i = lane; i < 36; i += 32) P->sm[i] = sm[i];
 }
 
 // ---- K5d: prepare pass, one warp per (stream, granule): state-free part of the rate-loop prologue (long blocks)
