@@ -39,13 +39,14 @@ SHIFT = 563                        # samples between windows (not a multiple of 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "hmp3")
 METRIC = "encoded audio sec/sec (x realtime), 44.1k stereo CBR128"
 
-# algorithmic bytes of the serial stage per granule-channel (DESIGN.md "K6"): MDCT lines in (2304 B) +
-# psychoacoustic record in (368 B) + packed main data out (CBR128: 381 B / 4 granule-channels = 95 B)
-K6_BYTES_PER_GC = 2304 + 368 + 95
+# algorithmic bytes of the serial stage per granule-channel (DESIGN.md "K6"): MDCT magnitudes in (2304 B) +
+# prepared |x|^(3/4), signs, band energies and step bounds in (2816 B) + sig/mask in (288 B) + the record for the
+# packing pass out (1396 B)
+K6_BYTES_PER_GC = 2304 + 2816 + 288 + 1396
 # DRAM traffic of the same kernel per granule-channel, from the committed `ncu --set full` capture
-# (profiles/r1_rate_ncu_details.txt: dram read 2.202 GB + write 5.145 GB for a launch of 2368 streams x 128
+# (profiles/r1f_rate_ncu_details.txt: dram read 11.871 GB + write 12.052 GB for a launch of 4736 streams x 128
 # granules x 2 channels); per-launch traffic = this x the granule-channels one launch processes
-K6_NCU_DRAM_BYTES_PER_GC = (2.202276e9 + 5.144660e9) / (2368 * 128 * 2)
+K6_NCU_DRAM_BYTES_PER_GC = (11.870863e9 + 12.052254e9) / (4736 * 128 * 2)
 
 
 def base_clips():
@@ -293,11 +294,11 @@ def run_gpu(args, rank, local_rank, world):
                 "frac": achieved / hbm_peak,
                 "traffic": args.rate_traffic if args.rate_traffic is not None
                 else K6_NCU_DRAM_BYTES_PER_GC * B * gran_per_launch * NCH,
-                "traffic_source": "ncu --set full capture in profiles/r1_rate_ncu_details.txt, scaled per granule-channel",
+                "traffic_source": "ncu --set full capture in profiles/r1f_rate_ncu_details.txt, scaled per granule-channel",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": rate_ms / timed_run_ms,
                 "share_note": "wall share of the step during which this kernel is running (Phase A and the packing "
-                              "pass run concurrently on other streams; serialised share in profiles/: ~87 %)",
+                              "pass run concurrently on other streams; serialised share in profiles/r1f_launch_summary.txt: 86 %)",
                 "note": "latency/instruction-fetch bound serial code, not a bandwidth kernel: see DESIGN.md"}
         line = {
             "metric": METRIC, "value": audio_s_per_step * args.steps / t_res, "unit": "x realtime",

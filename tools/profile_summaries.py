@@ -63,5 +63,5 @@ def details(name, cmdline):
 
 launches()
 details("rate", "ncu --set full --clock-control none --import-source on -k regex:k_rate$ -s 2 -c 1 python tools/quick_bench.py 4736 6   (4736 streams x 6 s, 128 granules per launch)")
-details("pack", "ncu --set full --clock-control none --import-source on -k regex:k_pack -s 2 -c 1 python tools/quick_bench.py 4736 6")
+details("others", "ncu --set full --clock-control none --import-source on -k regex:'k_pack|k_polyphase|k_hybrid|k_psy_stage1|k_prepare$|k_psy_stage2' -s 6 -c 6 python tools/quick_bench.py 4736 6   (one launch of each Phase A / packing kernel)")
 print(open(os.path.join(P, tag + "_launch_summary.txt")).read())
