@@ -269,3 +269,33 @@ class Encoder:
         a = np.zeros(len(EC_FIELDS), np.int32)
         lib().hmp3_L3_audio_encode_info_ec(self.h, vp(a))
         return dict(zip(EC_FIELDS, a.tolist()))
+
+
+class MpegHead(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ["sync", "id", "option", "prot", "br_index", "sr_index", "pad", "private_bit", "mode",
+                                       "mode_ext", "cr", "original", "emphasis"]]
+
+
+def effective_control(ec):
+    """(effective control image, MpegHead) as CMp3Enc::L3_audio_encode_info_ec / _info_head report them."""
+    out = np.zeros(len(EC_FIELDS), np.int32)
+    h = MpegHead()
+    r = lib().hmp3_effective_control(vp(ec), vp(out), C.byref(h))
+    if r != 0:
+        raise Hmp3Error("control rejected (%d)" % r)
+    return out, h
+
+
+def info_frame(ec, channels, nsamples, audio, frames, frames_after_call, bytes_after_call, xing_flag=67, source_rate=None):
+    """The Xing/Info frame the reference CLI puts in front of `audio` (hmp3_info_frame)."""
+    eff, head = effective_control(ec)
+    buf = np.zeros(2048, np.uint8)
+    fa = np.ascontiguousarray(frames_after_call, dtype=np.int32)
+    ba = np.ascontiguousarray(bytes_after_call, dtype=np.int64)
+    a = np.ascontiguousarray(audio, dtype=np.uint8)
+    f = lib().hmp3_info_frame
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    n = f(vp(eff), head.mode, xing_flag, int(source_rate or eff[EC_FIELDS.index("samprate")]), channels, nsamples, vp(a),
+          a.size, frames, vp(fa), vp(ba), fa.size, vp(buf), buf.size)
+    return buf[:n].copy()

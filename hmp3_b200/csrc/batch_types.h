@@ -55,8 +55,10 @@ struct StreamOut {
 
 struct StreamResult {
     long long out_bytes;
-    int frames;
+    int frames;           // complete frames (what was written to the output)
     int finished;
+    int frames_recorded;  // frames the serial stage recorded (>= frames)
+    int pad_;
 };
 
 // ---- launchers (all asynchronous on `stream`)

@@ -1,0 +1,232 @@
+// hmp3b200 -- command-line front end with the reference CLI's calling convention
+//     hmp3b200 <input.wav> <output.mp3> [options]          (hmp3/src/test/tomp3.cpp:317-566)
+// over the B200 path: options are parsed with hmp3_control_apply_option (same letters, same meaning: -B<n> CBR
+// per-channel kbit/s, -V<n> VBR, -HF<n>, -F<hz>, -M<mode>, -X<flag> ...), the WAV is encoded through the C ABI and
+// the output file is the Xing/Info frame followed by the audio frames -- byte-identical to what `hmp3` writes.
+// Extension: `-@ <list>` encodes many files in ONE batch on the GPU (each line of <list>: input<TAB or space>output).
+// Only 16-bit PCM WAV at a native MPEG rate is in scope (SURVEY.md section 8f-2/4 list the rest as "next").
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hmp3_b200.h"
+
+namespace {
+
+struct Wav {
+    int channels = 0, rate = 0, bits = 0, type = 0;
+    std::vector<int16_t> pcm;  // interleaved
+};
+
+bool read_wav(const char *path, Wav *w, std::string *err) {
+    FILE *f = fopen(path, "rb");
+    if (!f) {
+        *err = "CANNOT_OPEN_INPUT_FILE";
+        return false;
+    }
+    unsigned char h[12];
+    if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) || memcmp(h + 8, "WAVE", 4)) {
+        fclose(f);
+        *err = "UNSUPPORTED PCM FILE TYPE";
+        return false;
+    }
+    bool have_fmt = false;
+    for (;;) {
+        unsigned char c[8];
+        if (fread(c, 1, 8, f) != 8) break;
+        const uint32_t n = c[4] | (c[5] << 8) | (c[6] << 16) | ((uint32_t)c[7] << 24);
+        if (!memcmp(c, "fmt ", 4)) {
+            std::vector<unsigned char> b(n);
+            if (fread(b.data(), 1, n, f) != n || n < 16) break;
+            w->type = b[0] | (b[1] << 8);
+            w->channels = b[2] | (b[3] << 8);
+            w->rate = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+            w->bits = b[14] | (b[15] << 8);
+            if (w->type == 0xFFFE && n >= 26) w->type = b[24] | (b[25] << 8);  // WAVE_FORMAT_EXTENSIBLE sub-format
+            have_fmt = true;
+            if (n & 1) fgetc(f);
+        } else if (!memcmp(c, "data", 4)) {
+            if (!have_fmt) break;
+            if (w->type != 1 || w->bits != 16 || w->channels < 1 || w->channels > 2) {
+                fclose(f);
+                *err = "UNSUPPORTED PCM FILE TYPE (this build takes 16-bit linear PCM, mono or stereo)";
+                return false;
+            }
+            std::vector<unsigned char> raw;
+            raw.resize(n == 0xFFFFFFFFu ? 0 : n);
+            size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
+            const size_t frame = 2 * (size_t)w->channels;
+            got -= got % frame;
+            w->pcm.resize(got / 2);
+            for (size_t i = 0; i < got / 2; i++) w->pcm[i] = (int16_t)(raw[2 * i] | (raw[2 * i + 1] << 8));
+            fclose(f);
+            return true;
+        } else {
+            if (fseek(f, (long)(n + (n & 1)), SEEK_CUR)) break;
+        }
+    }
+    fclose(f);
+    *err = "UNSUPPORTED PCM FILE TYPE";
+    return false;
+}
+
+struct Job {
+    std::string in, out;
+    Wav wav;
+    hmp3_control ec;
+    bool ok = false;
+};
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    hmp3_control base;
+    hmp3_control_defaults(&base);
+    int xing = 3 | 64;  // the reference default: Xing header + TOC + info tag (tomp3.cpp:387)
+    int device = 0;
+    std::vector<std::string> names;
+    const char *list = nullptr;
+    for (int i = 1; i < argc; i++) {
+        const char *a = argv[i];
+        if (a[0] != '-' || a[1] == 0) {
+            names.push_back(a);
+            continue;
+        }
+        if (a[1] == '@') {
+            list = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : nullptr);
+            continue;
+        }
+        if ((a[1] == 'g' || a[1] == 'G') && (a[2] == 'p' || a[2] == 'P')) {  // -GPU<n>: device index (extension)
+            device = atoi(a + 4);
+            continue;
+        }
+        if (a[1] == 'x' || a[1] == 'X') {
+            xing = atoi(a + 2);
+            if (xing == 2) xing = 3;
+        }
+        if (hmp3_control_apply_option(&base, a) != 0) {
+            fprintf(stderr, "\n Usage:  hmp3b200 <input> <output> [options]   (options as hmp3; -@ <list> for a batch)\n");
+            return 0;
+        }
+    }
+    std::vector<Job> jobs;
+    if (list) {
+        FILE *f = fopen(list, "r");
+        if (!f) {
+            fprintf(stderr, "\n CANNOT_OPEN_INPUT_FILE %s\n", list);
+            return 1;
+        }
+        char in[4096], out[4096];
+        while (fscanf(f, "%4095s %4095s", in, out) == 2) {
+            Job j;
+            j.in = in;
+            j.out = out;
+            jobs.push_back(j);
+        }
+        fclose(f);
+    } else if (names.size() >= 2) {
+        Job j;
+        j.in = names[0];
+        j.out = names[1];
+        jobs.push_back(j);
+    } else {
+        fprintf(stderr, "\n Usage:  hmp3b200 <input> <output> [options]\n");
+        return 0;
+    }
+    if (hmp3_device_count() <= device) {
+        fprintf(stderr, "\n NO CUDA DEVICE (this encoder has no CPU path)\n");
+        return 1;
+    }
+    // ---- read inputs, derive each file's control the way ff_encode does (tomp3.cpp:809-815)
+    std::vector<hmp3_control> ctl;
+    std::vector<int64_t> ns;
+    std::vector<int> idx;
+    for (size_t k = 0; k < jobs.size(); k++) {
+        Job &j = jobs[k];
+        std::string err;
+        fprintf(stderr, "\n  PCM input file: %s\nMPEG output file: %s", j.in.c_str(), j.out.c_str());
+        if (!read_wav(j.in.c_str(), &j.wav, &err)) {
+            fprintf(stderr, "\n %s\n", err.c_str());
+            continue;
+        }
+        j.ec = base;
+        if (j.ec.mode < 0) j.ec.mode = 0;
+        if (j.wav.channels == 1) j.ec.mode = 3;
+        if (j.wav.channels == 2 && j.ec.mode == 3) j.ec.mode = 1;
+        j.ec.samprate = j.wav.rate;
+        hmp3_control eff;
+        if (hmp3_effective_control(&j.ec, &eff, nullptr) != HMP3_OK) {
+            fprintf(stderr, "\n ENCODER INIT FAIL\n");
+            continue;
+        }
+        j.ok = true;
+        ctl.push_back(j.ec);
+        ns.push_back((int64_t)(j.wav.pcm.size() / j.wav.channels));
+        idx.push_back((int)k);
+    }
+    if (ctl.empty()) return 1;
+    // ---- one batch on the GPU
+    hmp3_batch *b = hmp3_batch_create(ctl.data(), ns.data(), (int)ctl.size(), device);
+    if (!b) {
+        fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
+        return 1;
+    }
+    const int n = (int)ctl.size();
+    std::vector<const int16_t *> pcm(n);
+    std::vector<std::vector<uint8_t>> out(n);
+    std::vector<uint8_t *> outp(n);
+    std::vector<int64_t> cap(n), nb(n);
+    std::vector<int32_t> nf(n), st(n);
+    for (int i = 0; i < n; i++) {
+        pcm[i] = jobs[idx[i]].wav.pcm.data();
+        cap[i] = hmp3_batch_out_bound(&ctl[i], ns[i]);
+        out[i].resize((size_t)cap[i]);
+        outp[i] = out[i].data();
+    }
+    if (hmp3_batch_encode_host(b, pcm.data(), outp.data(), cap.data(), nb.data(), nf.data(), st.data()) != HMP3_OK) {
+        fprintf(stderr, "\n ENCODE FAILED: %s\n", hmp3_get_last_error());
+        return 1;
+    }
+    int rc = 0;
+    for (int i = 0; i < n; i++) {
+        Job &j = jobs[idx[i]];
+        if (st[i] != HMP3_OK) {
+            fprintf(stderr, "\n ENCODE FAILED (%d) for %s\n", st[i], j.in.c_str());
+            rc = 1;
+            continue;
+        }
+        hmp3_control eff;
+        hmp3_mpeg_head head;
+        hmp3_effective_control(&ctl[i], &eff, &head);
+        uint8_t tag[2048];
+        int tag_bytes = 0;
+        if (xing) {
+            const int ncalls_main = (int)((ns[i] + 4 * 1152) / 1152);
+            std::vector<int32_t> fa(ncalls_main + 64);
+            std::vector<int64_t> ba(ncalls_main + 64);
+            int nc = hmp3_batch_call_log(b, i, fa.data(), ba.data(), (int)fa.size());
+            if (nc > ncalls_main) nc = ncalls_main;
+            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, ns[i], out[i].data(), nb[i],
+                                        (uint32_t)nf[i], fa.data(), ba.data(), nc, tag, (int)sizeof(tag));
+        }
+        FILE *f = fopen(j.out.c_str(), "wb");
+        if (!f) {
+            fprintf(stderr, "\n CANNOT CREATE OUTPUT FILE %s\n", j.out.c_str());
+            rc = 1;
+            continue;
+        }
+        if (tag_bytes) fwrite(tag, 1, (size_t)tag_bytes, f);
+        fwrite(out[i].data(), 1, (size_t)nb[i], f);
+        fclose(f);
+        const double secs = (double)ns[i] / j.wav.rate;
+        fprintf(stderr, "\n %s: %d frames, %lld bytes, %.2f kbps", j.out.c_str(), nf[i], (long long)(nb[i] + tag_bytes),
+                secs > 0 ? 8e-3 * (double)nb[i] / secs : 0.0);
+    }
+    fprintf(stderr, "\n");
+    hmp3_batch_destroy(b);
+    return rc;
+}

@@ -63,6 +63,7 @@ __global__ void k_results(const EncTables *tabs, const StreamDev *st, const Stre
     const RateState *R = rs + s;
     StreamResult r;
     r.frames = R->frames_done;
+    r.frames_recorded = R->frames;
     r.finished = R->finished;
     r.out_bytes = 0;
     if (r.frames > 0) {

@@ -16,6 +16,7 @@
 #include "enc_init.h"
 #include "analysis.h"
 #include "batch_types.h"
+#include "rate_driver.h"
 
 using namespace hmp3;
 
@@ -621,6 +622,32 @@ int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *t
     CK(cudaMemcpyAsync(out, b->d_out, nb, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     return HMP3_OK;
+}
+
+// Per-call output log of one stream, rebuilt from its frame records (one D2H copy of the records).
+int hmp3_batch_call_log(hmp3_batch *b, int i, int32_t *frames_after_call, int64_t *bytes_after_call, int cap) {
+    if (!b->results_valid || i < 0 || i >= b->n || b->status[i] != HMP3_OK) {
+        set_err("call_log: no completed run or bad index");
+        return HMP3_ERR_ARG;
+    }
+    const int nrec = b->res_h[i].frames_recorded;
+    if (nrec <= 0) return 0;
+    std::vector<unsigned char> raw((size_t)nrec * sizeof_frame_rec());
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemcpy(raw.data(), (const unsigned char *)b->d_frames + b->so_h[i].frames_off * sizeof_frame_rec(), raw.size(),
+                  cudaMemcpyDeviceToHost));
+    const FrameRec *fr = (const FrameRec *)raw.data();
+    const EncConfig &C = b->tabs_h[b->st_h[i].cfg].cfg;
+    const int per_call = (C.h_id == 1) ? 1 : 2;  // frames recorded per encode call
+    std::vector<long long> end_off(nrec + 1, 0);
+    for (int f = 0; f < nrec; f++) end_off[f + 1] = (long long)fr[f].out_off + 4 + C.side_bytes + fr[f].mf_bytes;
+    const int ncalls = nrec / per_call;
+    for (int c = 0; c < ncalls && c < cap; c++) {
+        const int done = fr[(c + 1) * per_call - 1].done_after;
+        if (frames_after_call) frames_after_call[c] = done;
+        if (bytes_after_call) bytes_after_call[c] = end_off[done];
+    }
+    return ncalls;
 }
 
 int hmp3_batch_last_launches(const hmp3_batch *b) { return b->launches; }

@@ -25,6 +25,7 @@ struct FrameRec {
     short ngr, igr0;      // granules in the frame (2 MPEG-1, 1 MPEG-2) and granule parity of the first
     short main_data_begin, short_frame;
     short scfsi[2];
+    int done_after;       // frames complete (emitted) after the encode call that recorded this frame
     unsigned char head[4];
     unsigned char side[32];
 };
@@ -812,6 +813,7 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, FrameRec *frames
         if ((long long)R->main_tot - (long long)f->main_start < f->mf_bytes) break;
         R->frames_done++;
     }
+    fr->done_after = R->frames_done;
 }
 
 }  // namespace hmp3

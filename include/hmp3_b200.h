@@ -177,6 +177,31 @@ int hmp3_L3_audio_encode_get_bitrate(hmp3_encoder *e);
 float hmp3_L3_audio_encode_get_bitrate_float(hmp3_encoder *e);
 
 /* ---------------------------------------------------------------------------------------------
+ * (3) Host post-pass of the CLI: the Xing/Info frame the reference writes in front of
+ * the audio frames.  Pure host code.  Replaces XingHeader / XingHeaderTOC / XingHeaderUpdateInfo
+ * (hmp3/src/xhead.c:255-709) as driven by ff_encode (hmp3/src/test/tomp3.cpp:871-896, 962-984, 1055-1072).
+ * --------------------------------------------------------------------------------------------- */
+/* The effective control block (CMp3Enc::L3_audio_encode_info_ec, mp3enc.cpp:3490) and header of a control. */
+int hmp3_effective_control(const hmp3_control *ec, hmp3_control *effective, hmp3_mpeg_head *head);
+/* Size of the Xing/Info frame for this configuration (0 = the CLI writes none / it does not fit). */
+int hmp3_info_frame_size(const hmp3_control *effective, int head_mode, int xing_flag, int channels);
+/* Builds the final Xing/Info frame.  effective/head_mode: from hmp3_effective_control; xing_flag: the CLI's -X
+ * value (default 67 = 3 | INFOTAG); source_rate/channels/nsamples: the input PCM (samples per channel);
+ * audio/audio_bytes/frames: every audio frame that follows (MusicCRC, counts); frames_after_call /
+ * bytes_after_call [ncalls]: the encoder's cumulative output after each encode call of the CLI's main loop
+ * (seek table; see hmp3_batch_call_log).  audio == NULL builds the placeholder the CLI writes first.
+ * Returns the frame size, 0 on failure. */
+int hmp3_info_frame(const hmp3_control *effective, int head_mode, int xing_flag, int source_rate, int channels,
+                    int64_t nsamples, const uint8_t *audio, int64_t audio_bytes, uint32_t frames,
+                    const int32_t *frames_after_call, const int64_t *bytes_after_call, int ncalls, uint8_t *buf,
+                    int cap);
+/* Per encode call of stream i in the last completed run: frames and bytes emitted so far (what
+ * CMp3Enc::L3_audio_encode_get_frames_bytes returns after that call).  Fills up to `cap` entries, returns the
+ * number of calls the stream made including the tail flush (the CLI's main loop is the first
+ * (num_samples + 4 * 1152) / 1152 of them). */
+int hmp3_batch_call_log(hmp3_batch *b, int i, int32_t *frames_after_call, int64_t *bytes_after_call, int cap);
+
+/* ---------------------------------------------------------------------------------------------
  * Resolved configuration, for boundary tests (what L3_audio_encode_init computes,
  * hmp3/src/mp3enc.cpp:289-870).  Pure host logic, needs no device.
  * --------------------------------------------------------------------------------------------- */

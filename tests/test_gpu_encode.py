@@ -139,3 +139,38 @@ def test_pinned_host_buffers_take_the_staged_path():
     for i in range(len(specs)):
         assert nb[i] == want[i].size and np.array_equal(outs[i].numpy()[:nb[i]], want[i]), i
     b.close()
+
+
+def test_cli_writes_the_same_file_as_the_reference_cli(tmp_path):
+    """hmp3b200 in.wav out.mp3 [opts] against oracle/_ref/hmp3 with the same arguments: identical files, Xing/Info
+    frame included; plus the batch extension (-@ list)."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "hmp3_b200", "_lib", "hmp3b200")
+    ref = os.path.join(root, "oracle", "_ref", "hmp3")
+    assert os.path.exists(cli) and os.path.exists(ref)
+    cases = [("c1", 1234, 44100, 2, ["-B64"], 7.0), ("c2", 1234, 44100, 2, [], 33.0), ("c3", 1235, 48000, 2, ["-V100", "-HF2", "-F19000"], 5.0),
+             ("c4a", 1236, 22050, 1, ["-B32"], 6.0), ("c4b", 1237, 32000, 2, [], 4.0), ("x0", 1, 44100, 2, ["-B96", "-X0"], 3.0)]
+    wavs = []
+    for name, seed, sr, nch, opts, secs in cases:
+        pcm = synth_pcm(seed + 11, secs, sr, nch)
+        data = np.ascontiguousarray(pcm, dtype="<i2").tobytes()
+        wav = str(tmp_path / (name + ".wav"))
+        with open(wav, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " +
+                    struct.pack("<IHHIIHH", 16, 1, nch, sr, sr * nch * 2, nch * 2, 16) + b"data" + struct.pack("<I", len(data)))
+            f.write(data)
+        wavs.append(wav)
+        a, b = str(tmp_path / (name + "_ref.mp3")), str(tmp_path / (name + "_gpu.mp3"))
+        subprocess.run([ref, wav, a] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        subprocess.run([cli, wav, b] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        x, y = np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)
+        assert x.size == y.size and np.array_equal(x, y), name
+    # batch extension: the two 44.1 kHz files with the same options in one GPU batch
+    lst = str(tmp_path / "list.txt")
+    with open(lst, "w") as f:
+        f.write("%s %s\n%s %s\n" % (wavs[0], tmp_path / "b0.mp3", wavs[1], tmp_path / "b1.mp3"))
+    subprocess.run([cli, "-@", lst, "-B64"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    assert np.array_equal(np.fromfile(str(tmp_path / "b0.mp3"), dtype=np.uint8), np.fromfile(str(tmp_path / "c1_ref.mp3"), dtype=np.uint8))
