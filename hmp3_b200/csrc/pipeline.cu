@@ -526,7 +526,17 @@ hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_s
     }
     hmp3_batch *b = new hmp3_batch;
     std::vector<long long> ns(num_samples, num_samples + n);
-    int ng = getenv("HMP3_CHUNK_GRANULES") ? atoi(getenv("HMP3_CHUNK_GRANULES")) : 128;
+    // chunk length: the longer the chunk, the less the serial-stage kernel idles at its tail (it ends when the
+    // slowest stream of the chunk does); bounded by the memory the two chunk buffer sets may take
+    int ng = 256;
+    if (getenv("HMP3_CHUNK_GRANULES")) ng = atoi(getenv("HMP3_CHUNK_GRANULES"));
+    else {
+        size_t free_b = 0, total_b = 0;
+        if (cudaSetDevice(device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const double per_granule = 2.0 * 19500.0 * n;  // bytes of both buffer sets per granule of every stream
+            while (ng > 32 && per_granule * ng > 0.35 * (double)free_b) ng >>= 1;
+        }
+    }
     if (ng < 2) ng = 2;
     ng &= ~1;
     int r = plan_create(b, controls, ns.data(), n, device, ng, false);

@@ -590,7 +590,11 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
 #if HMP3_COOP
     const int lane = HMP3_LANE;
     HMP3_SYNC();
-    for (int w = 0; w < 18; w++) {
+    // only the coded extent is ever read by the packing pass: the big-value pairs and the count1 quads
+    const GrSide *g = &R->gr[igr][ch];
+    const int extent = g->aux_not_null ? 2 * (g->aux_nreg[0] + g->aux_nreg[1] + g->aux_nreg[2]) + 4 * g->aux_nquads : 0;
+    const int nwords = imin_(18, (extent + 31) >> 5);
+    for (int w = 0; w < nwords; w++) {
         unsigned bits = 0;
         for (int h = 0; h < 32 / HMP3_W; h++) {
             const int k = 32 * w + HMP3_W * h + lane;
