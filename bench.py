@@ -285,15 +285,17 @@ def run_gpu(args, rank, local_rank, world):
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        gran_per_launch = plan.chunk_granules()                  # granules per stream per k_rate launch
-        bytes_per_launch = K6_BYTES_PER_GC * B * gran_per_launch * NCH
+        # granule-channels one launch of the serial stage processes, averaged over the step's launches (the first
+        # chunk is shorter than the others): 2 granules per frame, NCH channels
+        gc_per_launch = 2.0 * float(nf.sum()) * NCH / max(rate_launches, 1)
+        bytes_per_launch = K6_BYTES_PER_GC * gc_per_launch
         avg_launch_s = rate_ms / max(rate_launches, 1) / 1e3
         achieved = bytes_per_launch / avg_launch_s / 1e9
-        roof = {"kernel": "k_rate (serial stage: rate loop + Huffman packing, one warp per stream)",
+        roof = {"kernel": "k_rate (serial stage of the rate loop, one warp per stream)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak,
                 "traffic": args.rate_traffic if args.rate_traffic is not None
-                else K6_NCU_DRAM_BYTES_PER_GC * B * gran_per_launch * NCH,
+                else K6_NCU_DRAM_BYTES_PER_GC * gc_per_launch,
                 "traffic_source": "ncu --set full capture in profiles/r1f_rate_ncu_details.txt, scaled per granule-channel",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": rate_ms / timed_run_ms,

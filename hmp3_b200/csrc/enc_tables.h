@@ -176,7 +176,10 @@ __device__ __forceinline__ float gsum_ordered(float acc, float v, int m) {
 #endif
 
 // warps per thread block of the serial-stage kernel (each warp carries 32 / HMP3_W streams)
-constexpr int kRateWarpsPerBlock = 4;
+#ifndef HMP3_RATE_WARPS
+#define HMP3_RATE_WARPS 4
+#endif
+constexpr int kRateWarpsPerBlock = HMP3_RATE_WARPS;
 // warps (= frames) per thread block of the packing kernel
 constexpr int kPackWarpsPerBlock = 8;
 

@@ -7,7 +7,7 @@
 #include "rate_driver.h"
 
 #ifndef HMP3_RATE_MIN_BLOCKS
-#define HMP3_RATE_MIN_BLOCKS 8
+#define HMP3_RATE_MIN_BLOCKS (32 / HMP3_RATE_WARPS)  // 32 warps (1024 threads) per SM => 64 registers per thread
 #endif
 
 namespace hmp3 {

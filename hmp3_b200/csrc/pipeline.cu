@@ -309,9 +309,10 @@ void mark(hmp3_batch *b, int phase, cudaStream_t st) {
 }
 
 // Phase A for the chunk starting at encode granule K0, into chunk buffer set `k`, on stream `st`.
-int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_prepare = true) {
+int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_prepare = true, int ng = 0) {
     const int n = b->n;
-    const ChunkBufs &cb = b->cb2[k];
+    ChunkBufs cb = b->cb2[k];
+    if (ng > 0) cb.NG = ng;
     mark(b, PH_POLY, st);
     launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, cb, K0, n, st);
     mark(b, -1, st);
@@ -360,9 +361,16 @@ int run_plan(hmp3_batch *b) {
     CK(cudaEventRecord(b->ev_start, b->stream));
     CK(cudaStreamWaitEvent(b->stream_a, b->ev_start, 0));
     CK(cudaStreamWaitEvent(b->stream_p, b->ev_start, 0));
+    // the first chunk is short so that the serial stage starts early (its Phase A cannot overlap anything); a short
+    // chunk is just a narrower view of the same buffers (every kernel indexes with the view's NG)
     int c = 0;
-    for (int K0 = 0; K0 < b->max_gran; K0 += b->NG, c++) {
+    for (int K0 = 0; K0 < b->max_gran; c++) {
         const int k = c & 1;
+        const int ng_c = (c == 0 && b->NG > 32) ? 32 : b->NG;
+        ChunkBufs view = b->cb2[k];
+        view.NG = ng_c;
+        const int K0_this = K0;
+        K0 += ng_c;
         if (c >= 2) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
         if (b->staged) {
             // the samples this chunk's polyphase needs first (up to the end of granule K0+NG-1), one DMA copy per
@@ -374,7 +382,7 @@ int run_plan(hmp3_batch *b) {
                 CK(cudaEventCreateWithFlags(&b->ev_c[1], cudaEventDisableTiming));
             }
             if (c == 0) CK(cudaStreamWaitEvent(b->stream_c, b->ev_start, 0));
-            const long long lo = c == 0 ? 0 : 576LL * K0, hi = 576LL * (K0 + b->NG);
+            const long long lo = c == 0 ? 0 : 576LL * K0_this, hi = 576LL * (K0_this + ng_c);
             for (int i = 0; i < n; i++) {
                 const StreamDev &sd = b->st_h[i];
                 if (b->status[i] != HMP3_OK) continue;
@@ -386,18 +394,18 @@ int run_plan(hmp3_batch *b) {
             CK(cudaEventRecord(b->ev_c[k], b->stream_c));
             CK(cudaStreamWaitEvent(b->stream_a, b->ev_c[k], 0));
         }
-        r = launch_analysis(b, K0, k, b->stream_a);
+        r = launch_analysis(b, K0_this, k, b->stream_a, true, ng_c);
         if (r != HMP3_OK) return r;
         CK(cudaEventRecord(b->ev_a[k], b->stream_a));
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
-        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[k], b->d_main, b->d_frames, K0, n, b->stream);
+        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream);
         mark(b, -1, b->stream);
         CK(cudaEventRecord(b->ev_r[k], b->stream));
         CK(cudaStreamWaitEvent(b->stream_p, b->ev_r[k], 0));
         mark(b, PH_PACK, b->stream_p);
-        launch_pack(b->d_tabs, b->d_st, b->d_so, b->cb2[k], b->d_main, b->d_frames, b->d_flags, K0, n, b->stream_p);
+        launch_pack(b->d_tabs, b->d_st, b->d_so, view, b->d_main, b->d_frames, b->d_flags, K0_this, n, b->stream_p);
         mark(b, -1, b->stream_p);
         CK(cudaEventRecord(b->ev_p[k], b->stream_p));
         b->launches += 2;
