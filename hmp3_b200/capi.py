@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libhmp3_b200.so")
+LIB_PATH = os.environ.get("HMP3_B200_LIB", os.path.join(HERE, "_lib", "libhmp3_b200.so"))
 
 EC_FIELDS = ["mode", "bitrate", "samprate", "nsbstereo", "filter_select", "freq_limit", "nsb_limit", "layer",
              "cr_bit", "original", "hf_flag", "vbr_flag", "vbr_mnr", "vbr_br_limit", "vbr_delta_mnr",
