@@ -47,6 +47,21 @@ HMP3_HD void polyphase_item(const EncTables *T, const int16_t *pcm, long num_sam
     for (int sb = 0; sb < 32; sb++) out[18 * sb + t] = freq_inverted(sb, t, nsb) ? -col[sb] : col[sb];
 }
 
+// Same for a stream whose input went through the DC-blocking filter (float samples, `len` per channel).
+HMP3_HD void polyphase_item_f(const EncTables *T, const float *pcmf, long len, int nch, int ch, long j, int t, float *out) {
+    const long newest = 576 * j + 32 * t + 31;
+    auto fetch = [&](int i) -> float {
+        long n = newest - i;
+        if (n < 0 || n >= len) return 0.0f;
+        return pcmf[n * nch + ch];
+    };
+    float col[32];
+    polyphase_slot(T, fetch, col, 1);
+    const int nsb = T->cfg.nsb_hybrid;
+#pragma unroll
+    for (int sb = 0; sb < 32; sb++) out[18 * sb + t] = freq_inverted(sb, t, nsb) ? -col[sb] : col[sb];
+}
+
 // Block-type scan step for encode granule K (channels share the decision).  e_new[ch][9] are the
 // attack energies of P[K-1].
 HMP3_HD GranuleInfo switch_step(const EncTables *T, SwitchState *s, const int *e_new0, const int *e_new1) {

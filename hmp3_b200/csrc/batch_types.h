@@ -28,6 +28,8 @@ struct StreamDev {
     int ngran_real;      // granules that belong to real encode calls (2 * calls)
     long long out_off;   // byte offset of this stream's output region
     long long out_cap;
+    long long pcmf_off;  // DC-filtered float PCM of this stream (float elements), -1 = none (filter off)
+    long long pcmf_len;  // samples per channel held there (covers the zero tail the encoder is flushed with)
 };
 
 // Chunk work buffers (device).  G = NG + 3 polyphase granules are kept per chunk: P[K0-3 .. K0+NG-1].
@@ -62,8 +64,11 @@ struct StreamResult {
 };
 
 // ---- launchers (all asynchronous on `stream`)
-void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
-                      cudaStream_t stream);
+void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, const float *pcmf, ChunkBufs cb,
+                      int K0, int n, cudaStream_t stream);
+// DC-blocking input filter (-S1): samples [lo, hi) of every stream that has it on; dc = carried state [n][2]
+void launch_dc_filter(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, float *pcmf, float *dc,
+                      long long lo, long long hi, int n, cudaStream_t stream);
 void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
 void launch_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState *sw, ChunkBufs cb, int K0, int n,
                         cudaStream_t stream);

@@ -5,10 +5,15 @@
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, ChunkBufs cb, int K0, int n,
-                      cudaStream_t stream) {
+void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, const float *pcmf, ChunkBufs cb,
+                      int K0, int n, cudaStream_t stream) {
     const int G = cb.NG + 3;
-    k_polyphase<<<dim3((unsigned)((G + kPolyRun - 1) / kPolyRun), (unsigned)n), 256, 0, stream>>>(tabs, st, pcm, cb, K0, n);
+    k_polyphase<<<dim3((unsigned)((G + kPolyRun - 1) / kPolyRun), (unsigned)n), 256, 0, stream>>>(tabs, st, pcm, pcmf, cb,
+                                                                                                 K0, n);
+}
+void launch_dc_filter(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, float *pcmf, float *dc,
+                      long long lo, long long hi, int n, cudaStream_t stream) {
+    k_dc_filter<<<blocks_for(2LL * n, 64), 64, 0, stream>>>(tabs, st, pcm, pcmf, dc, lo, hi, n);
 }
 void launch_attack(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
     const long long G = cb.NG + 3;

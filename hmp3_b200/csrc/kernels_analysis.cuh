@@ -17,8 +17,31 @@ namespace hmp3 {
 constexpr int kPolyRun = 7;                                 // granules per block: 126 slots per channel
 constexpr int kPolySpan = 576 * kPolyRun + 480;             // samples per channel staged
 constexpr int kPolyRow = kPolySpan + (kPolySpan >> 5) + 1;  // padded row length
+// ---- K0: optional DC-blocking input filter (filter2.c:112-147, -S1): t = x - d; d += alpha * t over the whole
+// stream including the zero tail; one thread per (stream, channel), sequential (a 1-pole recursion), carried state d.
+__global__ void k_dc_filter(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, float *pcmf, float *dc,
+                            long long lo, long long hi, int nstreams) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = id >> 1, ch = id & 1;
+    if (s >= nstreams) return;
+    const StreamDev sd = st[s];
+    if (ch >= sd.nch || sd.pcmf_off < 0) return;
+    const float alpha = tabs[sd.cfg].cfg.dc_alpha;
+    const int16_t *src = pcm + sd.pcm_off;
+    float *dst = pcmf + sd.pcmf_off;
+    float d = dc[2 * s + ch];
+    const long long e = hi < sd.pcmf_len ? hi : sd.pcmf_len;
+    for (long long n = lo; n < e; n++) {
+        const float x = n < sd.nsamples ? (float)src[n * sd.nch + ch] : 0.0f;
+        const float t = (x - d);
+        d = d + alpha * t;
+        dst[n * sd.nch + ch] = t;
+    }
+    dc[2 * s + ch] = d;
+}
+
 __global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm,
-                                                   ChunkBufs cb, int K0, int nstreams) {
+                                                   const float *pcmf, ChunkBufs cb, int K0, int nstreams) {
     __shared__ float s_pcm[2][kPolyRow];
     const int G = cb.NG + 3;
     const int s = blockIdx.y;
@@ -32,7 +55,16 @@ __global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const 
     // stage samples n0 .. n0 + kPolySpan - 1 of every channel
     const long long n0 = 576 * j0 - 480;
     const int16_t *src = pcm + sd.pcm_off;
-    if (nch == 2) {
+    if (sd.pcmf_off >= 0) {  // filtered float input
+        const float *fsrc = pcmf + sd.pcmf_off;
+        for (int p = threadIdx.x; p < kPolySpan; p += 256) {
+            const long long n = n0 + p;
+            const bool in = (n >= 0 && n < sd.pcmf_len);
+            const int q = p + (p >> 5);
+            s_pcm[0][q] = in ? fsrc[n * nch] : 0.0f;
+            if (nch == 2) s_pcm[1][q] = in ? fsrc[n * nch + 1] : 0.0f;
+        }
+    } else if (nch == 2) {
         const unsigned *src2 = (const unsigned *)src;  // pcm_off is even-aligned: one 32-bit word = (left, right)
         for (int p = threadIdx.x; p < kPolySpan; p += 256) {
             const long long n = n0 + p;

@@ -81,6 +81,9 @@ struct hmp3_batch {
     bool staged = false;                // this run copies PCM chunk by chunk (copy engine) ahead of each chunk's Phase A
     cudaStream_t stream_c = nullptr;    // H2D staging copies
     cudaEvent_t ev_c[2] = {nullptr, nullptr};
+    float *d_pcmf = nullptr;            // DC-filtered float PCM of the streams that have -S1 on
+    float *d_dc = nullptr;              // [n][2] filter state
+    bool any_filter = false;
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
@@ -136,6 +139,8 @@ struct hmp3_batch {
         if (ev_start) cudaEventDestroy(ev_start);
         cudaFree(d_flags);
         cudaFree(d_msmem);
+        cudaFree(d_pcmf);
+        cudaFree(d_dc);
         cudaFree(d_psy);
         if (stream_c) cudaStreamDestroy(stream_c);
         for (int k = 0; k < 2; k++)
@@ -174,7 +179,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     b->status.assign(n, HMP3_OK);
     b->st_h.resize(n);
     b->so_h.resize(n);
-    long long pcm_off = 0, main_off = 0, frames_off = 0, out_cap = 0;
+    long long pcm_off = 0, pcmf_off = 0, main_off = 0, frames_off = 0, out_cap = 0;
     int max_gran = 0, max_frames = 0;
     for (int i = 0; i < n; i++) {
         int cfg = -1;
@@ -205,6 +210,14 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         if (streaming) sd.ngran_real = sd.ngran;  // a handle never decides by itself that the stream has ended
         pcm_off += nsamples[i] * (sd.nch ? sd.nch : 1);
         pcm_off = (pcm_off + 7) & ~7LL;
+        sd.pcmf_off = -1;
+        sd.pcmf_len = 0;
+        if (cfg >= 0 && b->tabs_h[cfg].cfg.filter_select) {
+            sd.pcmf_off = pcmf_off;
+            sd.pcmf_len = 576LL * sd.ngran;
+            pcmf_off += sd.pcmf_len * sd.nch;
+            b->any_filter = true;
+        }
         max_gran = std::max(max_gran, sd.ngran);
         StreamOut &so = b->so_h[i];
         so.main_off = main_off;
@@ -236,6 +249,10 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     CK(cudaMemcpy(b->d_st, b->st_h.data(), sizeof(StreamDev) * n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b->d_pcm, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
     CK(cudaMemset(b->d_pcm, 0, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
+    if (b->any_filter) {
+        CK(cudaMalloc(&b->d_pcmf, sizeof(float) * std::max<long long>(pcmf_off, 1)));
+        CK(cudaMalloc(&b->d_dc, sizeof(float) * 2 * n));
+    }
     CK(cudaMalloc(&b->d_msmem, sizeof(int) * n));
     CK(cudaMalloc(&b->d_psy, sizeof_psy_state() * n * 2));
     CK(cudaMalloc(&b->d_sw, sizeof(SwitchState) * n));
@@ -290,6 +307,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
 
 int plan_reset_state(hmp3_batch *b) {
     launch_prepare_init(b->d_msmem, b->d_psy, b->n, b->stream);
+    if (b->any_filter) CK(cudaMemsetAsync(b->d_dc, 0, sizeof(float) * 2 * b->n, b->stream));
     CK(cudaMemcpyAsync(b->d_sw, b->d_sw_init, sizeof(SwitchState) * b->n, cudaMemcpyDeviceToDevice, b->stream));
     return HMP3_OK;
 }
@@ -313,8 +331,10 @@ int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_pre
     const int n = b->n;
     ChunkBufs cb = b->cb2[k];
     if (ng > 0) cb.NG = ng;
+    if (b->any_filter)
+        launch_dc_filter(b->d_tabs, b->d_st, b->d_pcm, b->d_pcmf, b->d_dc, 576LL * K0, 576LL * (K0 + cb.NG), n, st);
     mark(b, PH_POLY, st);
-    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, cb, K0, n, st);
+    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, b->d_pcmf, cb, K0, n, st);
     mark(b, -1, st);
     mark(b, PH_ATTACK, st);
     launch_attack(b->d_tabs, b->d_st, cb, K0, n, st);

@@ -386,47 +386,77 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
 #endif
 
 // ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
+// Bit writer of the side information: the reference's 32-bit accumulator with lazy byte flush and NO masking of
+// the value (l3pack.c:98-153).  The masking matters: part2_3_length is written in 12 bits but can exceed 4095 at
+// the highest bitrates, and the reference then ORs the excess bit into the last bit of the previous field when
+// that bit is still in the accumulator.  Reproduced as is so that the bytes stay identical.
+struct SideBits {
+    unsigned char *buf;
+    unsigned bitbuf;
+    int room;
+};
+HMP3_HD void side_put(SideBits *w, unsigned x, int nbits) {
+    if (w->room < nbits) {
+        while (w->room < 24) {
+            *w->buf++ = (unsigned char)(w->bitbuf >> (24 - w->room));
+            w->room += 8;
+        }
+    }
+    w->bitbuf = (w->bitbuf << nbits) | x;
+    w->room -= nbits;
+}
+HMP3_HD void side_flush(SideBits *w) {
+    while (w->room < 24) {
+        *w->buf++ = (unsigned char)(w->bitbuf >> (24 - w->room));
+        w->room += 8;
+    }
+    if (w->room < 32) *w->buf++ = (unsigned char)(w->bitbuf << (w->room - 24));
+    w->room = 32;
+}
+
 // gc = the frame's granule-channel records in (granule, channel) order
 HMP3_FN void pack_side(const EncTables *T, const FrameRec *fr, const PackGc *gc, unsigned char *out) {
-    BitSink b;
-    sink_open(&b, out);
+    SideBits b;
+    b.buf = out;
+    b.bitbuf = 0;
+    b.room = 32;
     const int nch = T->cfg.nchan;
     const bool m1 = T->cfg.h_id == 1;
     if (m1) {
-        sink_put(&b, (unsigned)fr->main_data_begin, 9);
-        sink_put(&b, 0, T->cfg.h_mode == 3 ? 5 : 3);
-        for (int ch = 0; ch < nch; ch++) sink_put(&b, (unsigned)fr->scfsi[ch], 4);
+        side_put(&b, (unsigned)fr->main_data_begin, 9);
+        side_put(&b, 0, T->cfg.h_mode == 3 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) side_put(&b, (unsigned)fr->scfsi[ch], 4);
     } else {
-        sink_put(&b, (unsigned)fr->main_data_begin, 8);
-        sink_put(&b, 0, T->cfg.h_mode == 3 ? 1 : 2);
+        side_put(&b, (unsigned)fr->main_data_begin, 8);
+        side_put(&b, 0, T->cfg.h_mode == 3 ? 1 : 2);
     }
     for (int k = 0; k < fr->ngr * nch; k++) {
         const GrSide *g = &gc[k].gr;
-        sink_put(&b, (unsigned)g->part2_3_length, 12);
-        sink_put(&b, (unsigned)g->big_values, 9);
-        sink_put(&b, (unsigned)g->global_gain, 8);
-        sink_put(&b, (unsigned)g->scalefac_compress, m1 ? 4 : 9);
-        sink_put(&b, (unsigned)g->window_switching_flag, 1);
+        side_put(&b, (unsigned)g->part2_3_length, 12);
+        side_put(&b, (unsigned)g->big_values, 9);
+        side_put(&b, (unsigned)g->global_gain, 8);
+        side_put(&b, (unsigned)g->scalefac_compress, m1 ? 4 : 9);
+        side_put(&b, (unsigned)g->window_switching_flag, 1);
         if (g->window_switching_flag) {
-            sink_put(&b, (unsigned)g->block_type, 2);
-            sink_put(&b, (unsigned)g->mixed_block_flag, 1);
-            sink_put(&b, (unsigned)g->table_select[0], 5);
-            sink_put(&b, (unsigned)g->table_select[1], 5);
-            sink_put(&b, (unsigned)g->subblock_gain[0], 3);
-            sink_put(&b, (unsigned)g->subblock_gain[1], 3);
-            sink_put(&b, (unsigned)g->subblock_gain[2], 3);
+            side_put(&b, (unsigned)g->block_type, 2);
+            side_put(&b, (unsigned)g->mixed_block_flag, 1);
+            side_put(&b, (unsigned)g->table_select[0], 5);
+            side_put(&b, (unsigned)g->table_select[1], 5);
+            side_put(&b, (unsigned)g->subblock_gain[0], 3);
+            side_put(&b, (unsigned)g->subblock_gain[1], 3);
+            side_put(&b, (unsigned)g->subblock_gain[2], 3);
         } else {
-            sink_put(&b, (unsigned)g->table_select[0], 5);
-            sink_put(&b, (unsigned)g->table_select[1], 5);
-            sink_put(&b, (unsigned)g->table_select[2], 5);
-            sink_put(&b, (unsigned)g->region0_count, 4);
-            sink_put(&b, (unsigned)g->region1_count, 3);
+            side_put(&b, (unsigned)g->table_select[0], 5);
+            side_put(&b, (unsigned)g->table_select[1], 5);
+            side_put(&b, (unsigned)g->table_select[2], 5);
+            side_put(&b, (unsigned)g->region0_count, 4);
+            side_put(&b, (unsigned)g->region1_count, 3);
         }
-        if (m1) sink_put(&b, (unsigned)g->preflag, 1);
-        sink_put(&b, (unsigned)g->scalefac_scale, 1);
-        sink_put(&b, (unsigned)g->count1table_select, 1);
+        if (m1) side_put(&b, (unsigned)g->preflag, 1);
+        side_put(&b, (unsigned)g->scalefac_scale, 1);
+        side_put(&b, (unsigned)g->count1table_select, 1);
     }
-    sink_close(&b);
+    side_flush(&b);
 }
 
 // The packing pass for one frame (one warp on the device): scale factors + Huffman data of every granule-

@@ -10,6 +10,30 @@
 
 using namespace hmp3;
 
+// DC-blocking input filter (filter2.c:112-147) over the whole stream incl. the zero tail, when -S1 is on
+static std::vector<float> dc_filtered(const EncTables *T, const int16_t *pcm, long nsamples, int nch, long len) {
+    std::vector<float> f;
+    if (!T->cfg.filter_select) return f;
+    f.assign((size_t)len * nch, 0.0f);
+    for (int c = 0; c < nch; c++) {
+        float d = 0.0f;
+        for (long n = 0; n < len; n++) {
+            const float x = n < nsamples ? (float)pcm[n * nch + c] : 0.0f;
+            const float t = (x - d);
+            d = d + T->cfg.dc_alpha * t;
+            f[(size_t)n * nch + c] = t;
+        }
+    }
+    return f;
+}
+static void poly_granule(const EncTables *T, const int16_t *pcm, long nsamples, const std::vector<float> &pf, long len,
+                         int nch, int c, long j, float *o) {
+    for (int t = 0; t < 18; t++) {
+        if (pf.empty()) polyphase_item(T, pcm, nsamples, nch, c, j, t, o);
+        else polyphase_item_f(T, pf.data(), len, nch, c, j, t, o);
+    }
+}
+
 extern "C" {
 
 int sim_resolve(const hmp3_control *ec, int *out /*40*/) {
@@ -76,10 +100,11 @@ int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int 
     // P[j] for j = -3 .. ngran-1 (index j+3)
     std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
     std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
+    const std::vector<float> pf = dc_filtered(T, pcm, nsamples, nch, 576L * ngran);
     for (long j = -3; j < ngran; j++)
         for (int c = 0; c < nch; c++) {
             float *o = &P[((j + 3) * nch + c) * 576];
-            for (int t = 0; t < 18; t++) polyphase_item(T, pcm, nsamples, nch, c, j, t, o);
+            poly_granule(T, pcm, nsamples, pf, 576L * ngran, nch, c, j, o);
             for (int k = 0; k < 9; k++) E[((j + 3) * nch + c) * 9 + k] = attack_energy(T, o, k, mpeg2);
         }
     SwitchState sw;
@@ -150,10 +175,11 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
     int ngran = ngran_real + 2 * 12;
     std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
     std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
+    const std::vector<float> pf = dc_filtered(T, pcm, nsamples, nch, 576L * ngran);
     for (long j = -3; j < ngran; j++)
         for (int c = 0; c < nch; c++) {
             float *o = &P[((j + 3) * nch + c) * 576];
-            for (int t = 0; t < 18; t++) polyphase_item(T, pcm, nsamples, nch, c, j, t, o);
+            poly_granule(T, pcm, nsamples, pf, 576L * ngran, nch, c, j, o);
             for (int k = 0; k < 9; k++) E[((j + 3) * nch + c) * 9 + k] = attack_energy(T, o, k, mpeg2);
         }
     SwitchState sw;

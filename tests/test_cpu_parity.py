@@ -126,3 +126,27 @@ def test_ragged_and_empty_inputs_match_oracle():
     ref, _ = refmod.ref_encode_clip(refmod.make_ec(), z)
     got, _, _ = simmod.encode_clip(capi.control(), z)
     assert np.array_equal(ref, got)
+
+
+@need_sim
+@need_ref
+def test_control_sweep_host_build_matches_oracle():
+    """240 controls (tests/sweep_cases.py): init accepts/rejects like the reference, and every accepted one encodes
+    a 2 s clip to the same bytes (covers MPEG-2 stereo, mode 0, -HF, -S1, the 12-bit part2_3_length overflow ...)."""
+    from sweep_cases import sweep_cases
+    n_ok = 0
+    for k, sr, nch, kw in sweep_cases():
+        ecr = refmod.make_ec(samprate=sr, nch=nch, **kw)
+        ec = capi.control(samprate=sr, nch=nch, **kw)
+        info = refmod.ref_info(ecr)
+        r = simmod.resolve(ec)
+        if info is None:
+            assert r["bytes_in"] == 0, (sr, nch, kw)
+            continue
+        assert r["bytes_in"] == info["bytes_in"] and not r["unsupported"], (sr, nch, kw)
+        pcm = synth_pcm(4000 + k, 2.0, sr, nch)
+        ref, _ = refmod.ref_encode_clip(ecr, pcm)
+        got, _, _ = simmod.encode_clip(ec, pcm)
+        assert ref.size == got.size and np.array_equal(ref, got), (sr, nch, kw)
+        n_ok += 1
+    assert n_ok >= 220

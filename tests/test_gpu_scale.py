@@ -60,3 +60,22 @@ def test_c5_style_batch_properties_and_spot_parity():
     for i in (0, 7, 95, 191):
         ref, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=SR, nch=NCH, bitrate=64), pcms[i])
         assert outs[i].size == ref.size and np.array_equal(outs[i], ref), i
+
+
+def test_control_sweep_in_one_mixed_batch():
+    """Every accepted control of the sweep as ONE batch of 228 streams with 228 different tables: each stream's bytes
+    equal the reference's."""
+    from sweep_cases import sweep_cases
+    ctl, pcms, refs = [], [], []
+    for k, sr, nch, kw in sweep_cases():
+        ecr = refmod.make_ec(samprate=sr, nch=nch, **kw)
+        if refmod.ref_info(ecr) is None:
+            continue
+        pcm = synth_pcm(4000 + k, 2.0, sr, nch)
+        ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+        pcms.append(pcm)
+        refs.append(refmod.ref_encode_clip(ecr, pcm)[0])
+    assert len(ctl) >= 220
+    outs = capi.encode_batch(ctl, pcms)
+    bad = [i for i, (o, r) in enumerate(zip(outs, refs)) if o.size != r.size or not np.array_equal(o, r)]
+    assert not bad, bad
