@@ -73,17 +73,22 @@ def debug_analysis(ec, pcm_i16, ngran, nch, device=0):
     return out
 
 
+PCM_S16, PCM_F32 = 0, 1        # hmp3_stream_desc.pcm_format / hmp3_batch_create_ex formats
+
+
 class Batch:
     """Reusable batch plan (hmp3_batch_*): n streams of fixed control + length on one device."""
 
-    def __init__(self, controls, num_samples, device=0):
+    def __init__(self, controls, num_samples, device=0, formats=None):
+        """formats: per stream PCM_S16 (default) or PCM_F32 (float PCM on the +-32768 scale)."""
         L = lib()
         self.n = len(controls)
         self.ctl = np.ascontiguousarray(np.stack(controls).astype(np.int32))
         self.ns = np.ascontiguousarray(np.asarray(num_samples, dtype=np.int64))
-        L.hmp3_batch_create.restype = C.c_void_p
-        L.hmp3_batch_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        self.h = L.hmp3_batch_create(vp(self.ctl), vp(self.ns), self.n, device)
+        self.fmt = np.ascontiguousarray(np.zeros(self.n, np.int32) if formats is None else np.asarray(formats, np.int32))
+        L.hmp3_batch_create_ex.restype = C.c_void_p
+        L.hmp3_batch_create_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        self.h = L.hmp3_batch_create_ex(vp(self.ctl), vp(self.ns), vp(self.fmt), self.n, device)
         if not self.h:
             raise Hmp3Error("hmp3_batch_create failed: " + last_error())
         L.hmp3_batch_out_bound.restype = C.c_int64
@@ -98,6 +103,7 @@ class Batch:
         L.hmp3_batch_last_run_ms.argtypes = [C.c_void_p]
         L.hmp3_batch_last_run_ms.restype = C.c_float
         L.hmp3_batch_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.hmp3_batch_upload_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         L.hmp3_batch_results.argtypes = [C.c_void_p] * 5
         L.hmp3_batch_download_all.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.hmp3_batch_encode_host.argtypes = [C.c_void_p] * 7
@@ -117,9 +123,13 @@ class Batch:
         if r != 0:
             raise Hmp3Error("%s failed (%d): %s" % (what, r, last_error()))
 
-    def upload(self, i, pcm_i16):
-        a = np.ascontiguousarray(pcm_i16, dtype=np.int16)
-        self._ck(lib().hmp3_batch_upload(self.h, i, vp(a), a.shape[0]), "upload")
+    def upload(self, i, pcm):
+        if self.fmt[i] == PCM_F32:
+            a = np.ascontiguousarray(pcm, dtype=np.float32)
+            self._ck(lib().hmp3_batch_upload_f32(self.h, i, vp(a), a.shape[0]), "upload_f32")
+        else:
+            a = np.ascontiguousarray(pcm, dtype=np.int16)
+            self._ck(lib().hmp3_batch_upload(self.h, i, vp(a), a.shape[0]), "upload")
 
     def upload_ptr(self, i, ptr, nsamples):
         self._ck(lib().hmp3_batch_upload(self.h, i, C.c_void_p(ptr), nsamples), "upload")
@@ -177,7 +187,8 @@ class Batch:
         return nb, nf, st
 
     def encode_host(self, pcms):
-        pcms = [np.ascontiguousarray(p, dtype=np.int16) for p in pcms]
+        pcms = [np.ascontiguousarray(p, dtype=np.float32 if self.fmt[i] == PCM_F32 else np.int16)
+                for i, p in enumerate(pcms)]
         outs = [np.zeros(int(b), np.uint8) for b in self.bound]
         pp = np.array([p.ctypes.data for p in pcms], dtype=np.uint64)
         op = np.array([o.ctypes.data for o in outs], dtype=np.uint64)
@@ -189,8 +200,10 @@ class Batch:
 
 
 def encode_batch(controls, pcms, device=0):
-    """Encode a list of int16 PCM arrays (nsamples, nch) -> list of MP3 byte arrays (no Xing/Info frame)."""
-    b = Batch(controls, [p.shape[0] for p in pcms], device)
+    """Encode a list of PCM arrays (nsamples, nch), int16 or float32 (+-32768 scale) -> list of MP3 byte arrays
+    (no Xing/Info frame)."""
+    fmts = [PCM_F32 if np.asarray(p).dtype == np.float32 else PCM_S16 for p in pcms]
+    b = Batch(controls, [p.shape[0] for p in pcms], device, formats=fmts)
     try:
         outs, _ = b.encode_host(pcms)
     finally:
@@ -244,8 +257,9 @@ class Encoder:
     def _io(v):
         return int(v & 0xFFFFFFFF), int(v >> 32)
 
-    def encode_mp3(self, pcm_i16):
-        a = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+    def encode_mp3(self, pcm, raw=False):
+        """pcm: int16 samples, or (raw=True) the caller's bytes in the source format given to init_mp3."""
+        a = np.ascontiguousarray(pcm) if raw else np.ascontiguousarray(pcm, dtype=np.int16)
         i, o = self._io(lib().hmp3_MP3_audio_encode(self.h, vp(a), vp(self.out)))
         return i, self.out[:o].copy()
 

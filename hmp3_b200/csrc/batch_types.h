@@ -30,6 +30,8 @@ struct StreamDev {
     long long out_cap;
     long long pcmf_off;  // DC-filtered float PCM of this stream (float elements), -1 = none (filter off)
     long long pcmf_len;  // samples per channel held there (covers the zero tail the encoder is flushed with)
+    long long rawf_off;  // float input PCM of this stream (float elements, scaled to +-32768), -1 = the input is int16
+    float tail;          // value of the samples past nsamples (0 unless the caller's flush bytes decode otherwise: 8-bit WAV)
 };
 
 // Chunk work buffers (device).  G = NG + 3 polyphase granules are kept per chunk: P[K0-3 .. K0+NG-1].

@@ -4,7 +4,8 @@
 // per-channel kbit/s, -V<n> VBR, -HF<n>, -F<hz>, -M<mode>, -X<flag> ...), the WAV is encoded through the C ABI and
 // the output file is the Xing/Info frame followed by the audio frames -- byte-identical to what `hmp3` writes.
 // Extension: `-@ <list>` encodes many files in ONE batch on the GPU (each line of <list>: input<TAB or space>output).
-// Only 16-bit PCM WAV at a native MPEG rate is in scope (SURVEY.md section 8f-2/4 list the rest as "next").
+// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate (no sample-rate conversion, no
+// stdin/stdout pipes: SURVEY.md section 8f).
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -19,7 +20,9 @@ namespace {
 
 struct Wav {
     int channels = 0, rate = 0, bits = 0, type = 0;
-    std::vector<int16_t> pcm;  // interleaved
+    std::vector<int16_t> pcm;  // interleaved, 16-bit input
+    std::vector<float> pcmf;   // interleaved, every other input type converted the way Csrc::sr_convert does
+    size_t total() const { return bits == 16 && type == 1 ? pcm.size() : pcmf.size(); }
 };
 
 bool read_wav(const char *path, Wav *w, std::string *err) {
@@ -51,18 +54,42 @@ bool read_wav(const char *path, Wav *w, std::string *err) {
             if (n & 1) fgetc(f);
         } else if (!memcmp(c, "data", 4)) {
             if (!have_fmt) break;
-            if (w->type != 1 || w->bits != 16 || w->channels < 1 || w->channels > 2) {
+            const bool ok_type = (w->type == 1 && (w->bits == 8 || w->bits == 16 || w->bits == 24 || w->bits == 32)) ||
+                                 (w->type == 3 && w->bits == 32);
+            if (!ok_type || w->channels < 1 || w->channels > 2) {
                 fclose(f);
-                *err = "UNSUPPORTED PCM FILE TYPE (this build takes 16-bit linear PCM, mono or stereo)";
+                *err = "UNSUPPORTED PCM FILE TYPE\n Only 8, 16, 24 and 32 bit linear PCM or 32-bit floating point supported.";
                 return false;
             }
             std::vector<unsigned char> raw;
             raw.resize(n == 0xFFFFFFFFu ? 0 : n);
             size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
-            const size_t frame = 2 * (size_t)w->channels;
+            const size_t bps = (size_t)w->bits / 8, frame = bps * (size_t)w->channels;
             got -= got % frame;
-            w->pcm.resize(got / 2);
-            for (size_t i = 0; i < got / 2; i++) w->pcm[i] = (int16_t)(raw[2 * i] | (raw[2 * i + 1] << 8));
+            const size_t ns = got / bps;
+            const unsigned char *p = raw.data();
+            if (w->type == 1 && w->bits == 16) {
+                w->pcm.resize(ns);
+                for (size_t i = 0; i < ns; i++) w->pcm[i] = (int16_t)(p[2 * i] | (p[2 * i + 1] << 8));
+            } else {  // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834)
+                w->pcmf.resize(ns);
+                for (size_t i = 0; i < ns; i++) {
+                    if (w->type == 3) {
+                        float v;
+                        memcpy(&v, p + 4 * i, 4);
+                        w->pcmf[i] = (float)(v) * 32768.0f;
+                    } else if (w->bits == 32) {
+                        int v;
+                        memcpy(&v, p + 4 * i, 4);
+                        w->pcmf[i] = (float)(v / 65536.0f);
+                    } else if (w->bits == 24) {
+                        const int v = (int)(((unsigned)p[3 * i + 2] << 24) | ((unsigned)p[3 * i + 1] << 16) | ((unsigned)p[3 * i] << 8)) >> 8;
+                        w->pcmf[i] = (float)((float)v / 256.0f);
+                    } else {
+                        w->pcmf[i] = (((float)p[i]) - 128.0f) * (256.0f);
+                    }
+                }
+            }
             fclose(f);
             return true;
         } else {
@@ -144,6 +171,7 @@ int main(int argc, char **argv) {
     // ---- read inputs, derive each file's control the way ff_encode does (tomp3.cpp:809-815)
     std::vector<hmp3_control> ctl;
     std::vector<int64_t> ns;
+    std::vector<int32_t> fmts;
     std::vector<int> idx;
     for (size_t k = 0; k < jobs.size(); k++) {
         Job &j = jobs[k];
@@ -165,24 +193,27 @@ int main(int argc, char **argv) {
         }
         j.ok = true;
         ctl.push_back(j.ec);
-        ns.push_back((int64_t)(j.wav.pcm.size() / j.wav.channels));
+        ns.push_back((int64_t)(j.wav.total() / j.wav.channels));
+        fmts.push_back((j.wav.type == 1 && j.wav.bits == 16) ? HMP3_PCM_S16 : HMP3_PCM_F32);
         idx.push_back((int)k);
     }
     if (ctl.empty()) return 1;
     // ---- one batch on the GPU
-    hmp3_batch *b = hmp3_batch_create(ctl.data(), ns.data(), (int)ctl.size(), device);
+    hmp3_batch *b = hmp3_batch_create_ex(ctl.data(), ns.data(), fmts.data(), (int)ctl.size(), device);
     if (!b) {
         fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
         return 1;
     }
     const int n = (int)ctl.size();
-    std::vector<const int16_t *> pcm(n);
+    for (int i = 0; i < n; i++)  // the reference flushes with zero BYTES, which 8-bit samples decode to -32768
+        if (jobs[idx[i]].wav.bits == 8) hmp3_batch_set_tail(b, i, -32768.0f);
+    std::vector<const void *> pcm(n);
     std::vector<std::vector<uint8_t>> out(n);
     std::vector<uint8_t *> outp(n);
     std::vector<int64_t> cap(n), nb(n);
     std::vector<int32_t> nf(n), st(n);
     for (int i = 0; i < n; i++) {
-        pcm[i] = jobs[idx[i]].wav.pcm.data();
+        pcm[i] = fmts[i] == HMP3_PCM_F32 ? (const void *)jobs[idx[i]].wav.pcmf.data() : (const void *)jobs[idx[i]].wav.pcm.data();
         cap[i] = hmp3_batch_out_bound(&ctl[i], ns[i]);
         out[i].resize((size_t)cap[i]);
         outp[i] = out[i].data();

@@ -28,11 +28,13 @@ __global__ void k_dc_filter(const EncTables *tabs, const StreamDev *st, const in
     if (ch >= sd.nch || sd.pcmf_off < 0) return;
     const float alpha = tabs[sd.cfg].cfg.dc_alpha;
     const int16_t *src = pcm + sd.pcm_off;
+    const float *fsrc = pcmf + (sd.rawf_off >= 0 ? sd.rawf_off : 0);
+    const bool fin = sd.rawf_off >= 0;
     float *dst = pcmf + sd.pcmf_off;
     float d = dc[2 * s + ch];
     const long long e = hi < sd.pcmf_len ? hi : sd.pcmf_len;
     for (long long n = lo; n < e; n++) {
-        const float x = n < sd.nsamples ? (float)src[n * sd.nch + ch] : 0.0f;
+        const float x = n < sd.nsamples ? (fin ? fsrc[n * sd.nch + ch] : (float)src[n * sd.nch + ch]) : sd.tail;
         const float t = (x - d);
         d = d + alpha * t;
         dst[n * sd.nch + ch] = t;
@@ -55,14 +57,16 @@ __global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const 
     // stage samples n0 .. n0 + kPolySpan - 1 of every channel
     const long long n0 = 576 * j0 - 480;
     const int16_t *src = pcm + sd.pcm_off;
-    if (sd.pcmf_off >= 0) {  // filtered float input
-        const float *fsrc = pcmf + sd.pcmf_off;
+    if (sd.pcmf_off >= 0 || sd.rawf_off >= 0) {  // float samples: the DC-filtered copy, or float input as is
+        const float *fsrc = pcmf + (sd.pcmf_off >= 0 ? sd.pcmf_off : sd.rawf_off);
+        const long long flen = sd.pcmf_off >= 0 ? sd.pcmf_len : sd.nsamples;
         for (int p = threadIdx.x; p < kPolySpan; p += 256) {
             const long long n = n0 + p;
-            const bool in = (n >= 0 && n < sd.pcmf_len);
+            const bool in = (n >= 0 && n < flen);
+            const float out = n < 0 ? 0.0f : sd.tail;  // before the stream: silence; after it: the flush value
             const int q = p + (p >> 5);
-            s_pcm[0][q] = in ? fsrc[n * nch] : 0.0f;
-            if (nch == 2) s_pcm[1][q] = in ? fsrc[n * nch + 1] : 0.0f;
+            s_pcm[0][q] = in ? fsrc[n * nch] : out;
+            if (nch == 2) s_pcm[1][q] = in ? fsrc[n * nch + 1] : out;
         }
     } else if (nch == 2) {
         const unsigned *src2 = (const unsigned *)src;  // pcm_off is even-aligned: one 32-bit word = (left, right)

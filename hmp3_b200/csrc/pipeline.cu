@@ -77,11 +77,12 @@ struct hmp3_batch {
     cudaStream_t stream_p = nullptr;    // packing pass
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr},
                 ev_start = nullptr;
-    const int16_t *const *h_src = nullptr;  // callers' pinned PCM pointers of a staged run
+    const void *const *h_src = nullptr;  // callers' pinned PCM pointers of a staged run
     bool staged = false;                // this run copies PCM chunk by chunk (copy engine) ahead of each chunk's Phase A
     cudaStream_t stream_c = nullptr;    // H2D staging copies
     cudaEvent_t ev_c[2] = {nullptr, nullptr};
-    float *d_pcmf = nullptr;            // DC-filtered float PCM of the streams that have -S1 on
+    float *d_pcmf = nullptr;            // float PCM: float inputs and the DC-filtered copies of the streams with -S1
+    std::vector<int> fmt;               // per stream: 0 = int16 input, 1 = float32 input (scaled to +-32768)
     float *d_dc = nullptr;              // [n][2] filter state
     bool any_filter = false;
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
@@ -167,7 +168,7 @@ int max_main_frame_bytes(const EncConfig &C) {
 }
 
 int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *nsamples, int n, int device,
-                int chunk_granules, bool analysis_only, bool streaming = false) {
+                int chunk_granules, bool analysis_only, bool streaming = false, const int *formats = nullptr) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
         set_err("no usable CUDA device (this library has no CPU path)");
@@ -177,6 +178,10 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     b->device = device;
     b->n = n;
     b->status.assign(n, HMP3_OK);
+    b->fmt.assign(n, 0);
+    if (formats)
+        for (int i = 0; i < n; i++) b->fmt[i] = formats[i] ? 1 : 0;
+    bool any_float = false;
     b->st_h.resize(n);
     b->so_h.resize(n);
     long long pcm_off = 0, pcmf_off = 0, main_off = 0, frames_off = 0, out_cap = 0;
@@ -212,6 +217,12 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         pcm_off = (pcm_off + 7) & ~7LL;
         sd.pcmf_off = -1;
         sd.pcmf_len = 0;
+        sd.rawf_off = -1;
+        if (cfg >= 0 && b->fmt[i]) {
+            sd.rawf_off = pcmf_off;
+            pcmf_off += ((nsamples[i] * sd.nch + 3) & ~3LL);
+            any_float = true;
+        }
         if (cfg >= 0 && b->tabs_h[cfg].cfg.filter_select) {
             sd.pcmf_off = pcmf_off;
             sd.pcmf_len = 576LL * sd.ngran;
@@ -249,8 +260,9 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     CK(cudaMemcpy(b->d_st, b->st_h.data(), sizeof(StreamDev) * n, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b->d_pcm, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
     CK(cudaMemset(b->d_pcm, 0, sizeof(int16_t) * std::max<long long>(b->pcm_elems, 8)));
-    if (b->any_filter) {
+    if (b->any_filter || any_float) {
         CK(cudaMalloc(&b->d_pcmf, sizeof(float) * std::max<long long>(pcmf_off, 1)));
+        CK(cudaMemset(b->d_pcmf, 0, sizeof(float) * std::max<long long>(pcmf_off, 1)));
         CK(cudaMalloc(&b->d_dc, sizeof(float) * 2 * n));
     }
     CK(cudaMalloc(&b->d_msmem, sizeof(int) * n));
@@ -305,6 +317,16 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
     return HMP3_OK;
 }
 
+// device address / element size of stream i's input PCM
+char *pcm_dev_ptr(hmp3_batch *b, int i, long long sample, size_t *elem) {
+    const StreamDev &sd = b->st_h[i];
+    if (b->fmt[i]) {
+        *elem = sizeof(float);
+        return (char *)(b->d_pcmf + sd.rawf_off + sample * sd.nch);
+    }
+    *elem = sizeof(int16_t);
+    return (char *)(b->d_pcm + sd.pcm_off + sample * sd.nch);
+}
 int plan_reset_state(hmp3_batch *b) {
     launch_prepare_init(b->d_msmem, b->d_psy, b->n, b->stream);
     if (b->any_filter) CK(cudaMemsetAsync(b->d_dc, 0, sizeof(float) * 2 * b->n, b->stream));
@@ -408,8 +430,10 @@ int run_plan(hmp3_batch *b) {
                 if (b->status[i] != HMP3_OK) continue;
                 const long long a = std::min<long long>(lo, sd.nsamples), e = std::min<long long>(hi, sd.nsamples);
                 if (e <= a) continue;
-                CK(cudaMemcpyAsync(b->d_pcm + sd.pcm_off + a * sd.nch, b->h_src[i] + a * sd.nch,
-                                   sizeof(int16_t) * (e - a) * sd.nch, cudaMemcpyHostToDevice, b->stream_c));
+                size_t el;
+                char *dst = pcm_dev_ptr(b, i, a, &el);
+                CK(cudaMemcpyAsync(dst, (const char *)b->h_src[i] + el * a * sd.nch, el * (e - a) * sd.nch,
+                                   cudaMemcpyHostToDevice, b->stream_c));
             }
             CK(cudaEventRecord(b->ev_c[k], b->stream_c));
             CK(cudaStreamWaitEvent(b->stream_a, b->ev_c[k], 0));
@@ -548,6 +572,11 @@ int64_t hmp3_batch_out_bound(const hmp3_control *control, int64_t num_samples) {
 }
 
 hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_samples, int n, int device) {
+    return hmp3_batch_create_ex(controls, num_samples, nullptr, n, device);
+}
+
+hmp3_batch *hmp3_batch_create_ex(const hmp3_control *controls, const int64_t *num_samples, const int32_t *pcm_formats,
+                                 int n, int device) {
     if (n <= 0 || !controls || !num_samples) {
         set_err("bad arguments");
         return nullptr;
@@ -567,7 +596,7 @@ hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_s
     }
     if (ng < 2) ng = 2;
     ng &= ~1;
-    int r = plan_create(b, controls, ns.data(), n, device, ng, false);
+    int r = plan_create(b, controls, ns.data(), n, device, ng, false, false, pcm_formats);
     if (r != HMP3_OK) {
         delete b;
         return nullptr;
@@ -579,18 +608,39 @@ void hmp3_batch_destroy(hmp3_batch *b) { delete b; }
 
 int16_t *hmp3_batch_device_pcm(hmp3_batch *b) { return b->d_pcm; }
 int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i) { return b->st_h[i].pcm_off; }
-uint8_t *hmp3_batch_device_out(hmp3_batch *b) { return b->d_out; }
-int64_t hmp3_batch_out_capacity(const hmp3_batch *b) { return b->out_cap; }
 
-int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples) {
-    if (i < 0 || i >= b->n || num_samples != b->st_h[i].nsamples) {
-        set_err("upload: stream index or length does not match the plan");
+int hmp3_batch_set_tail(hmp3_batch *b, int i, float value) {
+    if (!b || i < 0 || i >= b->n || b->fmt[i] != HMP3_PCM_F32) {
+        set_err("hmp3_batch_set_tail: bad stream index or not a float stream");
         return HMP3_ERR_ARG;
     }
     CK(cudaSetDevice(b->device));
-    CK(cudaMemcpyAsync(b->d_pcm + b->st_h[i].pcm_off, pcm, sizeof(int16_t) * num_samples * b->st_h[i].nch,
-                       cudaMemcpyHostToDevice, b->stream));
+    b->st_h[i].tail = value;
+    CK(cudaMemcpy(b->d_st + i, &b->st_h[i], sizeof(StreamDev), cudaMemcpyHostToDevice));
     return HMP3_OK;
+}
+uint8_t *hmp3_batch_device_out(hmp3_batch *b) { return b->d_out; }
+int64_t hmp3_batch_out_capacity(const hmp3_batch *b) { return b->out_cap; }
+
+namespace {
+int upload_any(hmp3_batch *b, int i, const void *pcm, int64_t num_samples, int want_fmt) {
+    if (i < 0 || i >= b->n || num_samples != b->st_h[i].nsamples || b->fmt[i] != want_fmt) {
+        set_err("upload: stream index, length or sample format does not match the plan");
+        return HMP3_ERR_ARG;
+    }
+    CK(cudaSetDevice(b->device));
+    size_t el;
+    char *dst = pcm_dev_ptr(b, i, 0, &el);
+    CK(cudaMemcpyAsync(dst, pcm, el * num_samples * b->st_h[i].nch, cudaMemcpyHostToDevice, b->stream));
+    return HMP3_OK;
+}
+}  // namespace
+
+int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples) {
+    return upload_any(b, i, pcm, num_samples, 0);
+}
+int hmp3_batch_upload_f32(hmp3_batch *b, int i, const float *pcm, int64_t num_samples) {
+    return upload_any(b, i, pcm, num_samples, 1);
 }
 
 int hmp3_batch_wait_uploads(hmp3_batch *b) {
@@ -714,7 +764,7 @@ bool is_pinned(const void *p) {
 }
 }  // namespace
 
-int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
     CK(cudaSetDevice(b->device));
     // Pinned input: each chunk's samples are copied (DMA) right before that chunk's Phase A, overlapping the serial
@@ -728,7 +778,7 @@ int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *co
     if (!pinned_in) {
         for (int i = 0; i < b->n; i++) {
             if (b->status[i] != HMP3_OK) continue;
-            int r = hmp3_batch_upload(b, i, pcm[i], b->st_h[i].nsamples);
+            int r = upload_any(b, i, pcm[i], b->st_h[i].nsamples, b->fmt[i]);
             if (r != HMP3_OK) return r;
         }
     }
@@ -781,7 +831,8 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
     }
     std::vector<hmp3_control> ctl(n);
     std::vector<int64_t> ns(n), cap(n), nb(n);
-    std::vector<const int16_t *> pcm(n);
+    std::vector<const void *> pcm(n);
+    std::vector<int32_t> fmts(n);
     std::vector<uint8_t *> out(n);
     std::vector<int32_t> nf(n), st(n);
     for (int i = 0; i < n; i++) {
@@ -792,10 +843,11 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
         ctl[i] = *streams[i].control;
         ns[i] = streams[i].num_samples;
         pcm[i] = streams[i].pcm;
+        fmts[i] = streams[i].pcm_format;
         out[i] = streams[i].out;
         cap[i] = streams[i].out_capacity;
     }
-    hmp3_batch *b = hmp3_batch_create(ctl.data(), ns.data(), n, device);
+    hmp3_batch *b = hmp3_batch_create_ex(ctl.data(), ns.data(), fmts.data(), n, device);
     if (!b) {
         int ndev = hmp3_device_count();
         return ndev <= device ? HMP3_ERR_NO_DEVICE : HMP3_ERR_BAD_CONTROL;
@@ -824,9 +876,10 @@ struct hmp3_encoder {
     int frames_out = 0;
     long long bytes_out = 0;
     double ave_bytes = 0;
-    bool float_in = false;
+    bool float_in = false;      // the plan takes float PCM (every input format except 16-bit integer)
+    int src_bits = 16, src_float = 0;
     int capacity_seconds = 1200;
-    std::vector<int16_t> stage;
+    std::vector<float> stage;
     ~hmp3_encoder() { delete b; }
 };
 
@@ -850,7 +903,8 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     e->b = new hmp3_batch;
     long long ns = (long long)e->capacity_seconds * samprate;
     ns -= ns % 1152;
-    if (plan_create(e->b, ec, &ns, 1, e->device, 2, false, true) != HMP3_OK) {
+    const int fmt = float_in ? 1 : 0;
+    if (plan_create(e->b, ec, &ns, 1, e->device, 2, false, true, &fmt) != HMP3_OK) {
         delete e->b;
         e->b = nullptr;
         return 0;
@@ -858,7 +912,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     hmp3_batch *b = e->b;
     e->nch = b->st_h[0].nch;
     e->max_calls = b->st_h[0].ngran / 2;
-    e->stage.assign((size_t)1152 * e->nch, 0);
+    e->stage.assign((size_t)1152 * e->nch, 0.0f);
     cudaSetDevice(e->device);
     if (plan_reset_state(b) != HMP3_OK) return 0;
     cudaMemsetAsync(b->d_flags, 0, sizeof(int), b->stream);
@@ -871,7 +925,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
 }
 
 // one encode call: 1152 samples per channel in, whatever frames became complete out
-hmp3_in_out encoder_step(hmp3_encoder *e, const int16_t *pcm, unsigned char *bs_out) {
+hmp3_in_out encoder_step(hmp3_encoder *e, const void *pcm, unsigned char *bs_out) {
     hmp3_in_out io = {0, 0};
     hmp3_batch *b = e->b;
     if (!b) {
@@ -884,9 +938,10 @@ hmp3_in_out encoder_step(hmp3_encoder *e, const int16_t *pcm, unsigned char *bs_
     }
     cudaSetDevice(e->device);
     const int K0 = 2 * e->calls;
-    const size_t nb_in = sizeof(int16_t) * 1152 * e->nch;
-    if (cudaMemcpyAsync(b->d_pcm + (size_t)e->calls * 1152 * e->nch, pcm, nb_in, cudaMemcpyHostToDevice, b->stream) !=
-        cudaSuccess) {
+    size_t el;
+    char *dst = pcm_dev_ptr(b, 0, (long long)e->calls * 1152, &el);
+    const size_t nb_in = el * 1152 * e->nch;
+    if (cudaMemcpyAsync(dst, pcm, nb_in, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) {
         set_err("H2D copy failed");
         return io;
     }
@@ -934,47 +989,64 @@ int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds) {
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert) {
     if (!e || !ec) return 0;
-    // only what the hot path covers: 16-bit integer PCM at a native MPEG rate, no down-mix, no resampling
+    // in scope: 8/16/24/32-bit integer or 32-bit float PCM at a native MPEG rate; no down-mix, no resampling
     const int rates[6] = {16000, 22050, 24000, 32000, 44100, 48000};
     bool native = false;
     for (int r : rates) native |= (ec->samprate == r);
-    if (source_bits != 16 || source_is_float || !native || (mono_convert && ec->mode != 3) ||
-        (mpeg_select > 2 && mpeg_select != ec->samprate) || (mpeg_select == 1 && ec->samprate < 32000) ||
-        (mpeg_select == 2 && ec->samprate > 24000)) {
-        set_err("MP3_audio_encode_init: only 16-bit PCM at a native MPEG rate without conversion is in scope");
+    const bool fmt_ok = source_is_float ? (source_bits == 32)
+                                        : (source_bits == 8 || source_bits == 16 || source_bits == 24 || source_bits == 32);
+    if (!fmt_ok || !native || (mono_convert && ec->mode != 3) || (mpeg_select > 2 && mpeg_select != ec->samprate) ||
+        (mpeg_select == 1 && ec->samprate < 32000) || (mpeg_select == 2 && ec->samprate > 24000)) {
+        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate without rate or channel conversion is in scope");
         return 0;
     }
-    const int bytes_in = encoder_init(e, ec, false);
-    return bytes_in ? bytes_in / 2 : 0;  // 2 bytes per sample instead of 4
+    e->src_bits = source_bits;
+    e->src_float = source_is_float;
+    const int bytes_in = encoder_init(e, ec, !(source_bits == 16 && !source_is_float));
+    return bytes_in ? (bytes_in / 4) * (source_bits / 8) : 0;  // bytes the caller supplies per call
 }
 hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
-    return encoder_step(e, (const int16_t *)pcm, bs_out);
-}
-int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec) {
-    if (!e || !ec) return 0;
-    return encoder_init(e, ec, true);
-}
-hmp3_in_out hmp3_L3_audio_encode(hmp3_encoder *e, const float *pcm, unsigned char *bs_out) {
     hmp3_in_out io = {0, 0};
     if (!e || !e->b) {
         set_err("encoder not initialised");
         return io;
     }
-    // the kernels take 16-bit PCM: the float entry accepts exactly the values the reference's own front end
-    // produces from 16-bit input (integers in [-32768, 32767], srcc.cpp:804-834)
+    if (!e->float_in) return encoder_step(e, pcm, bs_out);
+    // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale
     const int n = 1152 * e->nch;
-    for (int i = 0; i < n; i++) {
-        const float v = pcm[i];
-        const int q = (int)v;
-        if ((float)q != v || q < -32768 || q > 32767) {
-            set_err("L3_audio_encode: sample is not a 16-bit integer value");
-            return io;
+    float *d = e->stage.data();
+    if (e->src_float) {
+        const float *s = (const float *)pcm;
+        for (int i = 0; i < n; i++) d[i] = (float)(s[i]) * 32768.0f;
+    } else if (e->src_bits == 32) {
+        const int *s = (const int *)pcm;
+        for (int i = 0; i < n; i++) d[i] = (float)(s[i] / 65536.0f);
+    } else if (e->src_bits == 24) {
+        const unsigned char *s = pcm;
+        for (int i = 0; i < n; i++, s += 3) {
+            const int v = (int)(((unsigned)s[2] << 24) | ((unsigned)s[1] << 16) | ((unsigned)s[0] << 8)) >> 8;
+            d[i] = (float)((float)v / 256.0f);
         }
-        e->stage[i] = (int16_t)q;
+    } else {  // 8-bit unsigned
+        for (int i = 0; i < n; i++) d[i] = (((float)pcm[i]) - 128.0f) * (256.0f);
     }
-    io = encoder_step(e, e->stage.data(), bs_out);
-    if (io.in_bytes) io.in_bytes = n * 4;
+    io = encoder_step(e, d, bs_out);
+    if (io.in_bytes) io.in_bytes = n * (e->src_bits / 8);
     return io;
+}
+int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec) {
+    if (!e || !ec) return 0;
+    e->src_bits = 32;
+    e->src_float = 1;
+    return encoder_init(e, ec, true);
+}
+hmp3_in_out hmp3_L3_audio_encode(hmp3_encoder *e, const float *pcm, unsigned char *bs_out) {
+    hmp3_in_out io = {0, 0};
+    if (!e || !e->b || !e->float_in) {
+        set_err("encoder not initialised for float input");
+        return io;
+    }
+    return encoder_step(e, pcm, bs_out);  // PCM already on the +-32768 scale (hmp3/src/pub/mp3enc.h:88-98)
 }
 void hmp3_L3_audio_encode_info_ec(hmp3_encoder *e, hmp3_control *ec) {
     if (e && e->b && ec) memcpy(ec, e->b->tabs_h[0].cfg.info_ec, sizeof(*ec));

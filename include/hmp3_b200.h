@@ -73,6 +73,11 @@ enum {
     HMP3_ERR_INTERNAL = -7     /* the packing pass disagreed with the bit accounting (a bug)      */
 };
 
+/* Sample formats of the batch entries.  Float PCM is on the +-32768 scale CMp3Enc::L3_audio_encode takes
+ * (hmp3/src/pub/mp3enc.h:88-98); other WAV sample types are converted to it the way Csrc::sr_convert does
+ * (hmp3/src/srcc.cpp:804-834: int8 -> (x-128)*256, int24 -> x/256, int32 -> x/65536, float -> x*32768). */
+enum { HMP3_PCM_S16 = 0, HMP3_PCM_F32 = 1 };
+
 /* Fill `ec` with the CLI defaults (hmp3/src/test/tomp3.cpp:357-387). */
 void hmp3_control_defaults(hmp3_control *ec);
 
@@ -95,13 +100,15 @@ int hmp3_device_count(void);
  * --------------------------------------------------------------------------------------------- */
 typedef struct hmp3_stream_desc {
     const hmp3_control *control; /* per-stream control (streams with equal controls share tables) */
-    const int16_t *pcm;          /* interleaved int16 PCM, HOST memory (pinned is faster)         */
+    const void *pcm;             /* interleaved PCM in HOST memory (pinned is faster): int16, or float */
+                                 /* on the +-32768 scale when pcm_format == HMP3_PCM_F32               */
     int64_t num_samples;         /* samples per channel                                           */
     uint8_t *out;                /* HOST buffer for the MP3 frames                                */
     int64_t out_capacity;        /* bytes available at `out` (see hmp3_batch_out_bound)           */
     int64_t out_bytes;           /* [out] bytes written                                           */
     int32_t out_frames;          /* [out] frames written                                          */
     int32_t status;              /* [out] HMP3_OK or an error for this stream                     */
+    int32_t pcm_format;          /* HMP3_PCM_S16 (0, default) or HMP3_PCM_F32                     */
 } hmp3_stream_desc;
 
 /* Upper bound of the output size for a stream. */
@@ -115,10 +122,13 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device);
  * any number of encodes of that shape.  hmp3_encode_batch is create + encode_host + destroy. */
 typedef struct hmp3_batch hmp3_batch; /* opaque */
 hmp3_batch *hmp3_batch_create(const hmp3_control *controls, const int64_t *num_samples, int n, int device);
+/* ... with a sample format per stream (NULL = all int16) */
+hmp3_batch *hmp3_batch_create_ex(const hmp3_control *controls, const int64_t *num_samples, const int32_t *pcm_formats,
+                                 int n, int device);
 void hmp3_batch_destroy(hmp3_batch *b);
 /* Host buffers in, host buffers out through a plan: uploads every stream's PCM (H2D), runs all kernels,
  * copies the frames back (D2H) into out[i].  Arrays have n entries; out_bytes/out_frames/status may be NULL. */
-int hmp3_batch_encode_host(hmp3_batch *b, const int16_t *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status);
 /* Device-resident legs (the benchmark's kernel-only measurement and custom feeders): */
 int16_t *hmp3_batch_device_pcm(hmp3_batch *b);          /* all streams' interleaved int16 PCM           */
@@ -126,6 +136,11 @@ int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i); /* int16 element offs
 uint8_t *hmp3_batch_device_out(hmp3_batch *b);          /* compact output: stream i at out_offsets[i]   */
 int64_t hmp3_batch_out_capacity(const hmp3_batch *b);
 int hmp3_batch_upload(hmp3_batch *b, int i, const int16_t *pcm, int64_t num_samples); /* async H2D      */
+int hmp3_batch_upload_f32(hmp3_batch *b, int i, const float *pcm, int64_t num_samples);
+/* Value of the samples after the end of float stream `i` (default 0).  The reference CLI flushes the encoder with
+ * zero BYTES (hmp3/src/test/tomp3.cpp:925-930, 1017), which an 8-bit source decodes to (0-128)*256 = -32768: a
+ * caller that wants the reference's file for 8-bit WAV input sets -32768 here.  Call before the run. */
+int hmp3_batch_set_tail(hmp3_batch *b, int i, float value);
 int hmp3_batch_wait_uploads(hmp3_batch *b);             /* block until queued uploads have landed       */
 /* run all kernels on the plan's stream over whatever PCM is resident.  Synchronous unless `async` != 0
  * (then hmp3_batch_sync must be called before reading results). */
@@ -158,8 +173,8 @@ void hmp3_encoder_delete(hmp3_encoder *e);
 int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds);
 
 /* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns the bytes the caller must
- * supply per call, 0 = failure.  Only 16-bit integer PCM at a native MPEG rate is in scope
- * (source_bits = 16, source_is_float = 0; no sample-rate conversion -- SURVEY.md section 8f). */
+ * supply per call, 0 = failure.  8/16/24/32-bit integer and 32-bit float PCM at a native MPEG rate are in
+ * scope (no sample-rate or channel conversion -- SURVEY.md section 8f). */
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert);
 /* CMp3Enc::MP3_audio_encode (hmp3/src/mp3enc.cpp:2812-2828). */

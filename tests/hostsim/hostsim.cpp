@@ -11,14 +11,23 @@
 using namespace hmp3;
 
 // DC-blocking input filter (filter2.c:112-147) over the whole stream incl. the zero tail, when -S1 is on
-static std::vector<float> dc_filtered(const EncTables *T, const int16_t *pcm, long nsamples, int nch, long len) {
+// (also the plain copy of float input when the filter is off: `pcmf` != null means the source is float PCM)
+static std::vector<float> dc_filtered(const EncTables *T, const int16_t *pcm, const float *pcmf, long nsamples, int nch,
+                                      long len, float tail = 0.0f) {
     std::vector<float> f;
-    if (!T->cfg.filter_select) return f;
+    if (!T->cfg.filter_select) {
+        if (pcmf) {
+            f.assign((size_t)len * nch, tail);
+            for (long n = 0; n < nsamples && n < len; n++)
+                for (int c = 0; c < nch; c++) f[(size_t)n * nch + c] = pcmf[n * nch + c];
+        }
+        return f;
+    }
     f.assign((size_t)len * nch, 0.0f);
     for (int c = 0; c < nch; c++) {
         float d = 0.0f;
         for (long n = 0; n < len; n++) {
-            const float x = n < nsamples ? (float)pcm[n * nch + c] : 0.0f;
+            const float x = n < nsamples ? (pcmf ? pcmf[n * nch + c] : (float)pcm[n * nch + c]) : tail;
             const float t = (x - d);
             d = d + T->cfg.dc_alpha * t;
             f[(size_t)n * nch + c] = t;
@@ -91,8 +100,10 @@ int sim_table(const hmp3_control *ec, const char *name, void *dst, int nbytes) {
 //   ms_raw [ngran]             M/S measure without hysteresis (long) / short measure
 //   att    [ngran][nch][9]     attack energies of P[K]
 //   raw    [ngran][nch][92]    psychoacoustic stage-1 record
-int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int ngran, float *sbt_out, int *ginfo,
+int sim_analysis(const hmp3_control *ec, const int16_t *pcm_any, long nsamples, int ngran, float *sbt_out, int *ginfo,
                  float *xr_out, float *sigmask, int *ms_raw, int *att, float *raw_out) {
+    const int is_float = 0;
+    const float tail = 0.0f;
     EncTables *T = new EncTables;
     if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
     const int nch = T->cfg.nchan;
@@ -100,7 +111,8 @@ int sim_analysis(const hmp3_control *ec, const int16_t *pcm, long nsamples, int 
     // P[j] for j = -3 .. ngran-1 (index j+3)
     std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
     std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
-    const std::vector<float> pf = dc_filtered(T, pcm, nsamples, nch, 576L * ngran);
+    const std::vector<float> pf = dc_filtered(T, is_float ? nullptr : (const int16_t *)pcm_any, is_float ? (const float *)pcm_any : nullptr, nsamples, nch, 576L * ngran, tail);
+    const int16_t *pcm = is_float ? nullptr : (const int16_t *)pcm_any;
     for (long j = -3; j < ngran; j++)
         for (int c = 0; c < nch; c++) {
             float *o = &P[((j + 3) * nch + c) * 576];
@@ -164,8 +176,14 @@ extern "C" {
 // Whole-clip encode on the host build of the kernel bodies (Phase A sequential + Phase B), CLI
 // semantics.  Returns bytes written to `out`, or <0.  `trace` (optional) receives per granule:
 // 27 GR ints x2 ch, sf_l 23 x2, sf_s 39 x2, ix 576 x2, ms flag, = 1333 ints per granule? (see tests/simmod.py)
+long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_float, float tail, long nsamples,
+                         unsigned char *out, long out_cap, int *trace, int max_trace_granules, int *nframes_out);
 long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, unsigned char *out, long out_cap,
                      int *trace, int max_trace_granules, int *nframes_out) {
+    return sim_encode_clip_any(ec, pcm, 0, 0.0f, nsamples, out, out_cap, trace, max_trace_granules, nframes_out);
+}
+long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_float, float tail, long nsamples,
+                         unsigned char *out, long out_cap, int *trace, int max_trace_granules, int *nframes_out) {
     EncTables *T = new EncTables;
     if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
     const int nch = T->cfg.nchan;
@@ -175,7 +193,8 @@ long sim_encode_clip(const hmp3_control *ec, const int16_t *pcm, long nsamples, 
     int ngran = ngran_real + 2 * 12;
     std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);
     std::vector<int> E((size_t)(ngran + 3) * nch * 9, 0);
-    const std::vector<float> pf = dc_filtered(T, pcm, nsamples, nch, 576L * ngran);
+    const std::vector<float> pf = dc_filtered(T, is_float ? nullptr : (const int16_t *)pcm_any, is_float ? (const float *)pcm_any : nullptr, nsamples, nch, 576L * ngran, tail);
+    const int16_t *pcm = is_float ? nullptr : (const int16_t *)pcm_any;
     for (long j = -3; j < ngran; j++)
         for (int c = 0; c < nch; c++) {
             float *o = &P[((j + 3) * nch + c) * 576];

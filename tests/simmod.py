@@ -60,18 +60,19 @@ def analysis(ec, pcm_i16, ngran, nch):
     return out
 
 
-def encode_clip(ec, pcm_i16, max_trace_granules=0):
+def encode_clip(ec, pcm_i16, max_trace_granules=0, tail=0.0):
     """Whole-clip encode through the host build of the kernel bodies. Returns (mp3 bytes, nframes, trace)."""
-    pcm = np.ascontiguousarray(pcm_i16, dtype=np.int16)
+    is_float = np.asarray(pcm_i16).dtype == np.float32      # float PCM on the +-32768 scale
+    pcm = np.ascontiguousarray(pcm_i16, dtype=np.float32 if is_float else np.int16)
     n = pcm.shape[0]
     cap = 4096 + int(n / 1152 + 80) * 2100
     out = np.zeros(cap, np.uint8)
     tr = np.zeros((max_trace_granules, 1400), np.int32) if max_trace_granules else None
     nf = C.c_int(0)
-    f = lib().sim_encode_clip
+    f = lib().sim_encode_clip_any
     f.restype = C.c_long
-    f.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
-    r = f(vp(ec), vp(pcm), n, vp(out), cap, vp(tr), max_trace_granules, C.byref(nf))
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_void_p]
+    r = f(vp(ec), vp(pcm), 1 if is_float else 0, float(tail), n, vp(out), cap, vp(tr), max_trace_granules, C.byref(nf))
     if r < 0:
         raise RuntimeError("sim_encode_clip failed %d" % r)
     return out[:r].copy(), nf.value, tr

@@ -96,10 +96,12 @@ def test_encoder_handle_matches_reference_call_by_call(name, seed, sr, nch, kw):
 
 def test_encoder_handle_float_entry_and_rejections():
     enc = capi.Encoder(capacity_seconds=10)
-    assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=64), source_bits=24) == 0   # out of scope
+    assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=64), source_bits=12) == 0   # no such source type
+    assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=64), source_bits=16, source_is_float=1) == 0
     assert enc.init_mp3(capi.control(samprate=44100, nch=2, bitrate=16)) == 0                    # reference rejects
     assert enc.init_l3(capi.control(samprate=44100, nch=2, bitrate=64)) == 2 * 4 * 1152
-    pcm = synth_pcm(3, 1.0, 44100, 2)
+    pcm = synth_pcm(3, 1.0, 44100, 2).astype(np.float32)
+    pcm += np.random.default_rng(2).uniform(-0.5, 0.5, size=pcm.shape).astype(np.float32)      # not 16-bit values
     ref_bytes, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=44100, nch=2, bitrate=64), pcm[:20 * 1152])
     out = []
     for c in range(20 + 4 + 6):
@@ -109,8 +111,6 @@ def test_encoder_handle_float_entry_and_rejections():
         out.append(b)
     got = np.concatenate(out)
     assert np.array_equal(got[:ref_bytes.size], ref_bytes)
-    used, _ = enc.encode_l3(np.full((1152, 2), 0.5, np.float32))                                # not 16-bit PCM
-    assert used == 0
     assert enc.info_ec()["bitrate"] == 64
     enc.close()
 

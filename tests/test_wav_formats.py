@@ -1,0 +1,133 @@
+"""8/24/32-bit integer and 32-bit float WAV input.  The reference CLI feeds every sample type through
+Csrc::sr_convert (hmp3/src/srcc.cpp:804-834) to the float entry of the encoder.  CPU: the conversion restated in
+tests/wavutil.py + the float path of the kernel bodies (host simulator) reproduce the audio frames of files written by
+the reference CLI.  GPU: `hmp3b200` writes the same file as `hmp3` for each sample type, the float batch entry and the
+handle's non-16-bit entry equal the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refmod
+import simmod
+import wavutil
+from hmp3_b200 import capi
+from hmp3_b200.synth import synth_pcm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "hmp3")
+CLI = os.path.join(ROOT, "hmp3_b200", "_lib", "hmp3b200")
+needs_ref = pytest.mark.skipif(not (os.path.exists(REF_BIN) and refmod.available()), reason="oracle/_ref not built")
+
+CASES = [(44100, 2, ["-B64"], dict(bitrate=64)), (22050, 1, ["-B32"], dict(bitrate=32)),
+         (48000, 2, ["-V100", "-HF2", "-F19000", "-S1"], dict(vbr_mnr=100, hf=2, freq_limit=19000, filter_select=1))]
+
+
+def ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name="a"):
+    wav, mp3 = str(tmp_path / (name + ".wav")), str(tmp_path / (name + "_ref.mp3"))
+    wavutil.write_wav(wav, samples, kind, sr, nch)
+    subprocess.run([REF_BIN, wav, mp3] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    return wav, np.fromfile(mp3, dtype=np.uint8)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", wavutil.KINDS)
+@pytest.mark.parametrize("sr,nch,opts,kw", CASES)
+def test_host_float_path_reproduces_reference_cli_audio(tmp_path, kind, sr, nch, opts, kw):
+    samples = wavutil.make_samples(synth_pcm(31, 2.6, sr, nch), kind, seed=5)
+    _, whole = ref_cli_file(tmp_path, samples, kind, sr, nch, opts)
+    src = samples if kind == "s16" else wavutil.to_encoder_float(samples, kind)
+    got, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=nch, **kw), src, tail=wavutil.tail_value(kind))
+    head = whole.size - got.size
+    assert head > 0 and np.array_equal(whole[head:], got)
+    # ... and the oracle library, fed the converted floats, agrees wherever the flush is silence
+    if kind != "u8":
+        ref, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), src)
+        assert np.array_equal(ref, got)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_identity_for_every_wav_sample_type(tmp_path):
+    assert os.path.exists(CLI)
+    for kind in wavutil.KINDS:
+        for k, (sr, nch, opts, kw) in enumerate(CASES):
+            samples = wavutil.make_samples(synth_pcm(41 + k, 3.3, sr, nch), kind, seed=6)
+            name = "%s_%d" % (kind, k)
+            wav, want = ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name)
+            out = str(tmp_path / (name + "_gpu.mp3"))
+            subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+            got = np.fromfile(out, dtype=np.uint8)
+            assert got.size == want.size and np.array_equal(got, want), name
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_float_and_int16_streams_in_one_batch():
+    """Float streams (fractional sample values, with and without the DC filter) next to int16 streams, ragged."""
+    rng = np.random.default_rng(7)
+    ctl, pcms, refs = [], [], []
+    specs = [(44100, 2, dict(bitrate=64), 3.1, True), (44100, 2, dict(bitrate=64), 2.0, False),
+             (48000, 2, dict(vbr_mnr=100, hf=2, freq_limit=19000, filter_select=1), 2.4, True),
+             (22050, 1, dict(bitrate=32), 4.2, True), (32000, 2, dict(vbr_mnr=50), 1.3, True),
+             (44100, 2, dict(vbr_mnr=50, filter_select=1), 1.9, False), (44100, 1, dict(bitrate=48), 0.0, True)]
+    for k, (sr, nch, kw, secs, is_float) in enumerate(specs):
+        pcm = synth_pcm(500 + k, max(secs, 0.01), sr, nch)
+        if secs == 0.0:
+            pcm = pcm[:0]
+        if is_float:
+            pcm = (pcm.astype(np.float32) + rng.uniform(-0.5, 0.5, size=pcm.shape).astype(np.float32)).astype(np.float32)
+        ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+        pcms.append(pcm)
+        refs.append(refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm)[0])
+    outs = capi.encode_batch(ctl, pcms)
+    for k, (o, r) in enumerate(zip(outs, refs)):
+        assert o.size == r.size and np.array_equal(o, r), "stream %d differs" % k
+    # device-resident leg with float uploads
+    b = capi.Batch(ctl, [p.shape[0] for p in pcms],
+                   formats=[capi.PCM_F32 if p.dtype == np.float32 else capi.PCM_S16 for p in pcms])
+    for i, p in enumerate(pcms):
+        b.upload(i, p)
+    b.run()
+    flat, off, nb, nf, st = b.download_all()
+    assert (st == 0).all()
+    for i, r in enumerate(refs):
+        assert np.array_equal(flat[off[i]:off[i] + nb[i]], r), i
+    b.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("kind", ["u8", "s24", "s32", "f32"])
+def test_handle_mp3_entry_takes_every_sample_type(kind):
+    """hmp3_MP3_audio_encode with source bits/is_float as CMp3Enc::MP3_audio_encode_init takes them
+    (mp3enc.cpp:2655-2810): raw bytes of the source type per call, converted like Csrc::sr_convert."""
+    sr, nch, kw = 44100, 2, dict(bitrate=64)
+    samples = wavutil.make_samples(synth_pcm(77, 1.0, sr, nch)[:24 * 1152], kind, seed=8)
+    f = wavutil.to_encoder_float(samples, kind)
+    bits = {"u8": 8, "s24": 24, "s32": 32, "f32": 32}[kind]
+    bps = bits // 8
+    enc = capi.Encoder(capacity_seconds=10)
+    assert enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw), source_bits=bits,
+                        source_is_float=1 if kind == "f32" else 0) == 1152 * nch * bps
+    raw = np.frombuffer(wavutil.raw_bytes(samples, kind), dtype=np.uint8)
+    zero = np.zeros(1152 * nch * bps, np.uint8)
+    out = []
+    for c in range(24 + 4 + 6):
+        blk = raw[c * 1152 * nch * bps:(c + 1) * 1152 * nch * bps] if c < 24 else zero
+        used, b = enc.encode_mp3(blk, raw=True)
+        assert used == 1152 * nch * bps
+        out.append(b)
+    got = np.concatenate(out)
+    enc.close()
+    # reference: the same floats through the oracle; the zero-byte flush is the tail (u8: -32768)
+    if kind == "u8":
+        want, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=nch, **kw), f, tail=-32768.0) \
+            if simmod.available() else (None, 0, 0)
+        if want is None:
+            pytest.skip("host simulator not built")
+    else:
+        want, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), f)
+    m = min(got.size, want.size)
+    assert m > 0.9 * want.size and np.array_equal(got[:m], want[:m])
