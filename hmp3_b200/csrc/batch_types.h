@@ -84,7 +84,8 @@ size_t sizeof_prep_granule();
 size_t sizeof_psy_state();
 void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream);
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
-                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);
+                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream,
+                 long long *cycles = nullptr);
 // packing pass of the frames the serial stage recorded in this chunk; `flags[s]` is set if a frame's written
 // bits ever differ from the accounted ones
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,

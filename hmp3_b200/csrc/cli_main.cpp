@@ -4,8 +4,10 @@
 // per-channel kbit/s, -V<n> VBR, -HF<n>, -F<hz>, -M<mode>, -X<flag> ...), the WAV is encoded through the C ABI and
 // the output file is the Xing/Info frame followed by the audio frames -- byte-identical to what `hmp3` writes.
 // Extension: `-@ <list>` encodes many files in ONE batch on the GPU (each line of <list>: input<TAB or space>output).
-// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate (no sample-rate conversion, no
-// stdin/stdout pipes: SURVEY.md section 8f).
+// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate (no sample-rate conversion).  "-" as
+// input reads the WAV from stdin and, like -IL, ignores the header's data length (tomp3.cpp:721-745); "-" as output
+// writes to stdout, where -- as with the reference, which cannot re-read its own stdout -- the Xing/Info frame stays
+// the placeholder written before encoding (tomp3.cpp:1055-1072).
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,18 +24,25 @@ struct Wav {
     int channels = 0, rate = 0, bits = 0, type = 0;
     std::vector<int16_t> pcm;  // interleaved, 16-bit input
     std::vector<float> pcmf;   // interleaved, every other input type converted the way Csrc::sr_convert does
+    size_t audio_bytes = 0;    // bytes of the data chunk actually read (the Info tag counts whole sample frames of it)
     size_t total() const { return bits == 16 && type == 1 ? pcm.size() : pcmf.size(); }
 };
 
-bool read_wav(const char *path, Wav *w, std::string *err) {
-    FILE *f = fopen(path, "rb");
+bool read_wav(const char *path, Wav *w, std::string *err, bool ignore_length) {
+    const bool from_pipe = !strcmp(path, "-");
+    if (from_pipe) ignore_length = true;
+    FILE *f = from_pipe ? stdin : fopen(path, "rb");
     if (!f) {
         *err = "CANNOT_OPEN_INPUT_FILE";
         return false;
     }
+    struct Closer {
+        FILE *f;
+        bool keep;
+        ~Closer() { if (!keep) fclose(f); }
+    } closer{f, from_pipe};
     unsigned char h[12];
     if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) || memcmp(h + 8, "WAVE", 4)) {
-        fclose(f);
         *err = "UNSUPPORTED PCM FILE TYPE";
         return false;
     }
@@ -57,15 +66,35 @@ bool read_wav(const char *path, Wav *w, std::string *err) {
             const bool ok_type = (w->type == 1 && (w->bits == 8 || w->bits == 16 || w->bits == 24 || w->bits == 32)) ||
                                  (w->type == 3 && w->bits == 32);
             if (!ok_type || w->channels < 1 || w->channels > 2) {
-                fclose(f);
-                *err = "UNSUPPORTED PCM FILE TYPE\n Only 8, 16, 24 and 32 bit linear PCM or 32-bit floating point supported.";
+                        *err = "UNSUPPORTED PCM FILE TYPE\n Only 8, 16, 24 and 32 bit linear PCM or 32-bit floating point supported.";
                 return false;
             }
             std::vector<unsigned char> raw;
-            raw.resize(n == 0xFFFFFFFFu ? 0 : n);
-            size_t got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
+            size_t got = 0;
+            if (ignore_length) {  // everything up to end of file is audio
+                for (;;) {
+                    raw.resize(got + (1u << 20));
+                    const size_t r = fread(raw.data() + got, 1, 1u << 20, f);
+                    got += r;
+                    if (r < (1u << 20)) break;
+                }
+            } else {
+                raw.resize(n == 0xFFFFFFFFu ? 0 : n);
+                got = raw.empty() ? 0 : fread(raw.data(), 1, raw.size(), f);
+            }
             const size_t bps = (size_t)w->bits / 8, frame = bps * (size_t)w->channels;
-            got -= got % frame;
+            w->audio_bytes = got;
+            // The reference feeds BYTES: a trailing partial sample frame (possible with -IL / stdin) is followed by its
+            // zero padding and encoded as one more sample per channel.  Keep it unless that would add an encode call
+            // the reference does not make (its call count comes from the byte count, rounded down).
+            if (got % frame) {
+                const size_t whole = got / frame;
+                if ((whole + 1) % 1152 != 0) {
+                    raw.resize((whole + 1) * frame + frame);
+                    memset(raw.data() + got, 0, (whole + 1) * frame - got);
+                    got = (whole + 1) * frame;
+                } else got = whole * frame;
+            }
             const size_t ns = got / bps;
             const unsigned char *p = raw.data();
             if (w->type == 1 && w->bits == 16) {
@@ -90,13 +119,18 @@ bool read_wav(const char *path, Wav *w, std::string *err) {
                     }
                 }
             }
-            fclose(f);
-            return true;
+                return true;
         } else {
-            if (fseek(f, (long)(n + (n & 1)), SEEK_CUR)) break;
+            bool ok = true;  // skip the chunk (by reading: stdin cannot seek)
+            for (uint32_t left = n + (n & 1); left && ok;) {
+                unsigned char skip[4096];
+                const size_t want = left < sizeof(skip) ? left : sizeof(skip);
+                ok = fread(skip, 1, want, f) == want;
+                left -= (uint32_t)want;
+            }
+            if (!ok) break;
         }
     }
-    fclose(f);
     *err = "UNSUPPORTED PCM FILE TYPE";
     return false;
 }
@@ -115,14 +149,16 @@ int main(int argc, char **argv) {
     hmp3_control_defaults(&base);
     int xing = 3 | 64;  // the reference default: Xing header + TOC + info tag (tomp3.cpp:387)
     int device = 0;
+    bool ignore_length = false;
     std::vector<std::string> names;
     const char *list = nullptr;
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i];
-        if (a[0] != '-' || a[1] == 0) {
+        if (a[0] != '-' || a[1] == 0) {  // a file name, or "-" = stdin/stdout
             names.push_back(a);
             continue;
         }
+        if ((a[1] == 'i' || a[1] == 'I') && (a[2] == 'l' || a[2] == 'L')) ignore_length = true;  // tomp3.cpp:521-524
         if (a[1] == '@') {
             list = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : nullptr);
             continue;
@@ -177,7 +213,7 @@ int main(int argc, char **argv) {
         Job &j = jobs[k];
         std::string err;
         fprintf(stderr, "\n  PCM input file: %s\nMPEG output file: %s", j.in.c_str(), j.out.c_str());
-        if (!read_wav(j.in.c_str(), &j.wav, &err)) {
+        if (!read_wav(j.in.c_str(), &j.wav, &err, ignore_length)) {
             fprintf(stderr, "\n %s\n", err.c_str());
             continue;
         }
@@ -235,16 +271,21 @@ int main(int argc, char **argv) {
         hmp3_effective_control(&ctl[i], &eff, &head);
         uint8_t tag[2048];
         int tag_bytes = 0;
-        if (xing) {
+        const bool to_pipe = (j.out == "-");
+        if (xing && to_pipe) {
+            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, ns[i], nullptr, 0, 0, nullptr,
+                                        nullptr, 0, tag, (int)sizeof(tag));
+        } else if (xing) {
             const int ncalls_main = (int)((ns[i] + 4 * 1152) / 1152);
             std::vector<int32_t> fa(ncalls_main + 64);
             std::vector<int64_t> ba(ncalls_main + 64);
             int nc = hmp3_batch_call_log(b, i, fa.data(), ba.data(), (int)fa.size());
             if (nc > ncalls_main) nc = ncalls_main;
-            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, ns[i], out[i].data(), nb[i],
+            const int64_t samples_audio = (int64_t)(j.wav.audio_bytes / ((size_t)j.wav.channels * (j.wav.bits / 8)));
+            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, samples_audio, out[i].data(), nb[i],
                                         (uint32_t)nf[i], fa.data(), ba.data(), nc, tag, (int)sizeof(tag));
         }
-        FILE *f = fopen(j.out.c_str(), "wb");
+        FILE *f = to_pipe ? stdout : fopen(j.out.c_str(), "wb");
         if (!f) {
             fprintf(stderr, "\n CANNOT CREATE OUTPUT FILE %s\n", j.out.c_str());
             rc = 1;
@@ -252,7 +293,8 @@ int main(int argc, char **argv) {
         }
         if (tag_bytes) fwrite(tag, 1, (size_t)tag_bytes, f);
         fwrite(out[i].data(), 1, (size_t)nb[i], f);
-        fclose(f);
+        if (to_pipe) fflush(f);
+        else fclose(f);
         const double secs = (double)ns[i] / j.wav.rate;
         fprintf(stderr, "\n %s: %d frames, %lld bytes, %.2f kbps", j.out.c_str(), nf[i], (long long)(nb[i] + tag_bytes),
                 secs > 0 ? 8e-3 * (double)nb[i] / secs : 0.0);

@@ -177,7 +177,14 @@ int hmp3_info_frame(const hmp3_control *eff, int head_mode, int xing_flag, int s
     p += 4;
     put_be32(p, (uint32_t)head_flags);
     p += 4;
-    if (!audio) return frame_bytes;  // placeholder frame only (what the CLI writes before encoding)
+    if (!audio) {  // the frame XingHeader() itself writes before encoding (xhead.c:396-462): counts and seek table
+                   // zero, quality field set; it stays in the file when the output cannot be updated (stdout)
+        if (head_flags & FRAMES_FLAG) p += 4;
+        if (head_flags & BYTES_FLAG) p += 4;
+        if (head_flags & TOC_FLAG) p += 100;
+        if (head_flags & VBR_SCALE_FLAG) put_be32(p, (uint32_t)vbr_scale);
+        return frame_bytes;
+    }
 
     // ---- the seek table as the CLI's main loop fills it (tomp3.cpp:976-984)
     SeekTable *toc = new SeekTable;

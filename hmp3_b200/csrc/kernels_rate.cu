@@ -41,9 +41,9 @@ void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs,
     k_rate_init<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, rs, n);
 }
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
-                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream) {
+                 unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream, long long *cycles) {
     k_rate<<<blocks_for((long long)n * HMP3_W_HOST, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
-        tabs, st, so, rs, cb, main_buf, frames, K0, n);
+        tabs, st, so, rs, cb, main_buf, frames, K0, n, cycles);
 }
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
                  FrameRec *frames, int *flags, int K0, int n, cudaStream_t stream) {

@@ -24,9 +24,10 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
 // per-band loops are split across them (HMP3_COOP sections of rate_*.h).
 __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
-           unsigned char *main_buf, FrameRec *frames, int K0, int nstreams) {
+           unsigned char *main_buf, FrameRec *frames, int K0, int nstreams, long long *cycles) {
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) / HMP3_W);
     if (s >= nstreams) return;
+    const long long t0 = clock64();
     const StreamDev sd = st[s];
     if (HMP3_LANE == 0) cb.fr0[s] = cb.fr1[s] = rs[s].frames;  // nothing recorded in this chunk unless the loop below runs
     HMP3_SYNC();
@@ -36,7 +37,10 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     rate_run_chunk(tabs + sd.cfg, rs + s, K0, cb.NG, sd.ngran, sd.ngran_real, cb.gi + q0, cb.xr + q0 * 2 * 576,
                    cb.sm + q0 * 72, cb.prep + q0, cb.ms + q0, cb.pack + q0 * 2, frames + o.frames_off);
     HMP3_SYNC();
-    if (HMP3_LANE == 0) cb.fr1[s] = rs[s].frames;
+    if (HMP3_LANE == 0) {
+        cb.fr1[s] = rs[s].frames;
+        if (cycles) cycles[s] = clock64() - t0;  // load-balance diagnostics (hmp3_debug_rate_cycles)
+    }
 }
 
 // ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)

@@ -44,6 +44,8 @@ const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybr
 
 }  // namespace
 
+constexpr int kCycleLaunches = 64;
+
 struct hmp3_batch {
     int device = 0;
     int n = 0;
@@ -88,6 +90,8 @@ struct hmp3_batch {
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
+    long long *d_cycles = nullptr;      // [kCycleLaunches][n] serial-stage clocks per launch (diagnostics, on request)
+    int cycle_launches = 0;
     std::vector<int> flags_h;
     int nbuf = 2;
     int launches = 0;
@@ -139,6 +143,7 @@ struct hmp3_batch {
         }
         if (ev_start) cudaEventDestroy(ev_start);
         cudaFree(d_flags);
+        cudaFree(d_cycles);
         cudaFree(d_msmem);
         cudaFree(d_pcmf);
         cudaFree(d_dc);
@@ -444,7 +449,9 @@ int run_plan(hmp3_batch *b) {
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
         if (c >= 2) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
-        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream);
+        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
+                    (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
+        if (b->d_cycles && c < kCycleLaunches) b->cycle_launches = c + 1;
         mark(b, -1, b->stream);
         CK(cudaEventRecord(b->ev_r[k], b->stream));
         CK(cudaStreamWaitEvent(b->stream_p, b->ev_r[k], 0));
@@ -1096,6 +1103,21 @@ int hmp3_control_apply_option(hmp3_control *ec, const char *opt) { return contro
 
 // Debug / parity entry: Phase A of ONE stream on the device, stage outputs copied back to the host.
 // Same argument meaning as the host simulator's sim_analysis (tests/hostsim/hostsim.cpp).
+int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches) {
+    // first call (cycles == NULL or nothing recorded yet): switch recording on for the following runs
+    if (!b) return HMP3_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    if (!b->d_cycles) {
+        CK(cudaMalloc(&b->d_cycles, sizeof(long long) * kCycleLaunches * b->n));
+        CK(cudaMemset(b->d_cycles, 0, sizeof(long long) * kCycleLaunches * b->n));
+        return 0;
+    }
+    const int m = std::min(max_launches, b->cycle_launches);
+    if (cycles && m > 0)
+        CK(cudaMemcpy(cycles, b->d_cycles, sizeof(long long) * m * b->n, cudaMemcpyDeviceToHost));
+    return m;
+}
+
 int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long nsamples, int ngran, int device,
                         float *sbt_out, int *ginfo, float *xr_out, float *raw_out, int *ms_raw, int *att) {
     hmp3_batch b;

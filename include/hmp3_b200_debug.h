@@ -17,6 +17,10 @@ extern "C" {
  * antialias (hwin.c:147-319), emap* (emap.c:61-121), spd_smr* (spdsmr.c:64-319). */
 int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long nsamples, int ngran, int device,
                         float *sbt, int *ginfo, float *xr, float *raw, int *ms_raw, int *att);
+/* Load-balance diagnostics of the serial stage: the first call switches recording on; after a run, a call with a
+ * buffer copies cycles[launch][stream] (SM clocks each stream's warp spent in that k_rate launch, up to 64 launches)
+ * and returns the number of launches recorded. */
+int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches);
 #ifdef __cplusplus
 }
 #endif

@@ -131,3 +131,49 @@ def test_handle_mp3_entry_takes_every_sample_type(kind):
         want, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), f)
     m = min(got.size, want.size)
     assert m > 0.9 * want.size and np.array_equal(got[:m], want[:m])
+
+
+@needs_ref
+@pytest.mark.parametrize("sr,nch,opts,kw", CASES)
+def test_stdout_keeps_the_placeholder_info_frame(tmp_path, sr, nch, opts, kw):
+    """`hmp3 in.wav -` cannot re-read stdout, so its first frame is what XingHeader() wrote before encoding
+    (xhead.c:255-462); hmp3_info_frame(audio=NULL) builds that frame."""
+    import ctypes as C
+    pcm = synth_pcm(13, 1.5, sr, nch)
+    wav = str(tmp_path / "a.wav")
+    wavutil.write_wav(wav, pcm, "s16", sr, nch)
+    so = np.frombuffer(subprocess.run([REF_BIN, wav, "-"] + opts, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                      check=True).stdout, dtype=np.uint8)
+    eff, head = capi.effective_control(capi.control(samprate=sr, nch=nch, **kw))
+    buf = np.zeros(2048, np.uint8)
+    f = capi.lib().hmp3_info_frame
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    n = f(eff.ctypes.data_as(C.c_void_p), head.mode, 67, sr, nch, pcm.shape[0], None, 0, 0, None, None, 0,
+          buf.ctypes.data_as(C.c_void_p), buf.size)
+    assert n > 0 and np.array_equal(so[:n], buf[:n])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_pipes_and_ignore_length(tmp_path):
+    """`-` as input (stdin, data length ignored), `-` as output (stdout, placeholder Info frame) and -IL, each
+    against the reference CLI run the same way."""
+    sr, nch, opts = 44100, 2, ["-B64"]
+    samples = wavutil.make_samples(synth_pcm(91, 2.2, sr, nch), "s24", seed=9)
+    wav = str(tmp_path / "p.wav")
+    wavutil.write_wav(wav, samples, "s24", sr, nch)
+    with open(wav, "ab") as f:                        # trailing bytes after the data chunk: audio only under -IL / stdin
+        f.write(b"LIST" + (20).to_bytes(4, "little") + bytes(range(20)))
+
+    def run(binary, src, dst, extra=()):
+        with open(wav, "rb") as fin:
+            r = subprocess.run([binary, src, dst] + opts + list(extra), stdin=fin if src == "-" else None,
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+        return np.frombuffer(r.stdout, dtype=np.uint8) if dst == "-" else np.fromfile(dst, dtype=np.uint8)
+
+    for src, dst, extra in [("-", "out", ()), (wav, "-", ()), ("-", "-", ()), (wav, "out", ("-IL",)), (wav, "out", ())]:
+        a = run(REF_BIN, src, str(tmp_path / "ref.mp3") if dst == "out" else "-", extra)
+        b = run(CLI, src, str(tmp_path / "gpu.mp3") if dst == "out" else "-", extra)
+        diff = np.nonzero(a[:min(a.size, b.size)] != b[:min(a.size, b.size)])[0]
+        assert a.size > 1000 and a.size == b.size and diff.size == 0, (src, dst, extra, a.size, b.size, diff[:8])

@@ -1,0 +1,22 @@
+"""Build a variant of the product library with extra flags for the rate TU: tools/build_variant.py <name> <flags...>
+-> hmp3_b200/_lib/var_<name>.so (select it with HMP3_B200_LIB).  Experiments only."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+name, flags = sys.argv[1], sys.argv[2:]
+objdir = os.path.join(ROOT, "hmp3_b200", "_build")
+obj = os.path.join(objdir, "kernels_rate_%s.o" % name)
+extra = [f for f in g.TUS["kernels_rate.cu"]]
+cmd = ["timeout", "1500", "/usr/local/cuda/bin/nvcc"] + g.NVCC_COMMON + extra + flags + ["-c", "-o", obj, os.path.join(g.CSRC, "kernels_rate.cu")]
+r = subprocess.run(cmd, capture_output=True, text=True)
+if r.returncode:
+    print(r.stderr[-3000:]); sys.exit(1)
+for line in r.stderr.splitlines():
+    if "k_rateE" in line or ("registers" in line and "k_rate" in prev):
+        print(line[:200])
+    prev = line
+objs = [os.path.join(objdir, t.rsplit(".", 1)[0] + ".o") for t in g.TUS if t != "kernels_rate.cu"] + [obj]
+out = os.path.join(g.LIBDIR, "var_%s.so" % name)
+subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-shared", "-o", out] + objs + ["-lcudart"])
+print("built", out)
