@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "../../include/hmp3_b200.h"
@@ -45,6 +46,7 @@ const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybr
 }  // namespace
 
 constexpr int kCycleLaunches = 64;
+constexpr int kMaxSets = 3;
 
 struct hmp3_batch {
     int device = 0;
@@ -72,17 +74,19 @@ struct hmp3_batch {
     long long *d_out_off = nullptr;
     unsigned char *d_out = nullptr;
     long long out_cap = 0;
-    ChunkBufs cb2[2]{};                 // double-buffered chunk work areas: Phase A of chunk c+1 overlaps the serial stage of c
+    ChunkBufs cb2[kMaxSets]{};          // rotating chunk work areas: Phase A runs up to nbuf-1 chunks ahead of the serial stage
     ChunkBufs &cb = cb2[0];
     cudaStream_t stream = nullptr;      // serial stage, finish, copies
+    bool one_stream = false;
     cudaStream_t stream_a = nullptr;    // Phase A
     cudaStream_t stream_p = nullptr;    // packing pass
-    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_r[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr},
+    cudaEvent_t ev_a[kMaxSets] = {nullptr, nullptr, nullptr}, ev_r[kMaxSets] = {nullptr, nullptr, nullptr},
+                ev_p[kMaxSets] = {nullptr, nullptr, nullptr},
                 ev_start = nullptr;
     const void *const *h_src = nullptr;  // callers' pinned PCM pointers of a staged run
     bool staged = false;                // this run copies PCM chunk by chunk (copy engine) ahead of each chunk's Phase A
     cudaStream_t stream_c = nullptr;    // H2D staging copies
-    cudaEvent_t ev_c[2] = {nullptr, nullptr};
+    cudaEvent_t ev_c[kMaxSets] = {nullptr, nullptr, nullptr};
     float *d_pcmf = nullptr;            // float PCM: float inputs and the DC-filtered copies of the streams with -S1
     std::vector<int> fmt;               // per stream: 0 = int16 input, 1 = float32 input (scaled to +-32768)
     float *d_dc = nullptr;              // [n][2] filter state
@@ -90,6 +94,7 @@ struct hmp3_batch {
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
+    std::vector<std::array<float, 3>> timeline;
     long long *d_cycles = nullptr;      // [kCycleLaunches][n] serial-stage clocks per launch (diagnostics, on request)
     int cycle_launches = 0;
     std::vector<int> flags_h;
@@ -124,7 +129,7 @@ struct hmp3_batch {
         cudaFree(d_res);
         cudaFree(d_out_off);
         cudaFree(d_out);
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kMaxSets; k++) {
             cudaFree(cb2[k].P);
             cudaFree(cb2[k].E);
             cudaFree(cb2[k].gi);
@@ -149,10 +154,10 @@ struct hmp3_batch {
         cudaFree(d_dc);
         cudaFree(d_psy);
         if (stream_c) cudaStreamDestroy(stream_c);
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < kMaxSets; k++)
             if (ev_c[k]) cudaEventDestroy(ev_c[k]);
-        if (stream_a) cudaStreamDestroy(stream_a);
-        if (stream_p) cudaStreamDestroy(stream_p);
+        if (stream_a && !one_stream) cudaStreamDestroy(stream_a);
+        if (stream_p && !one_stream) cudaStreamDestroy(stream_p);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_run0) cudaEventDestroy(ev_run0);
         if (ev_run1) cudaEventDestroy(ev_run1);
@@ -170,6 +175,15 @@ const int kFlushCalls = 12;  // upper bound of the tail-flush calls we provision
 
 int max_main_frame_bytes(const EncConfig &C) {
     return C.vbr_flag ? C.vbr_main_framebytes[C.ivbr_max] : C.main_framebytes + 1;
+}
+
+// Number of chunk buffer sets of a batch plan.  Two: Phase A of chunk c+1 overlaps the serial stage of c.  Three
+// (HMP3_CHUNK_SETS=3) lets Phase A run a chunk further ahead; measured no faster (Phase A only gets SM slots in
+// the tail of a serial-stage launch either way), so it is not the default.
+int chunk_sets() {
+    const char *e = getenv("HMP3_CHUNK_SETS");
+    const int s = e ? atoi(e) : 2;
+    return s < 2 ? 2 : (s > kMaxSets ? kMaxSets : s);
 }
 
 int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *nsamples, int n, int device,
@@ -280,9 +294,17 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMemcpy(b->d_sw_init, sw.data(), sizeof(SwitchState) * n, cudaMemcpyHostToDevice));
     }
     const long long NG = b->NG, G = NG + 3;
-    b->nbuf = analysis_only ? 1 : 2;
-    CK(cudaStreamCreate(&b->stream_a));
-    CK(cudaStreamCreate(&b->stream_p));
+    b->nbuf = analysis_only ? 1 : (streaming ? 1 : chunk_sets());
+    if (getenv("HMP3_SERIALIZE")) {  // diagnostics: every kernel on one stream, so per-kernel times are uncontended
+        b->stream_a = b->stream_p = b->stream;
+        b->one_stream = true;
+    } else {  // Phase A and the packing pass get the free SM slots before the serial stage's next launch does
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const bool prio = !(getenv("HMP3_NO_STREAM_PRIO"));
+        CK(cudaStreamCreateWithPriority(&b->stream_a, cudaStreamDefault, prio ? hi : lo));
+        CK(cudaStreamCreateWithPriority(&b->stream_p, cudaStreamDefault, (prio && !getenv("HMP3_PACK_LOW")) ? hi : lo));
+    }
     CK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
     for (int k = 0; k < b->nbuf; k++) {
         ChunkBufs &cb = b->cb2[k];
@@ -403,7 +425,8 @@ int run_plan(hmp3_batch *b) {
     b->launches++;
     // Phase A runs on its own stream one chunk ahead of the serial stage, the packing pass on a third stream
     // one chunk behind it (two chunk buffer sets):
-    //   analysis(c) -> ev_a -> serial(c) -> ev_r -> pack(c) -> ev_p ;  analysis(c+2) waits ev_r(c), serial(c+2) waits ev_p(c)
+    //   analysis(c) -> ev_a -> serial(c) -> ev_r -> pack(c) -> ev_p ;  with S buffer sets analysis(c+S) waits ev_r(c) and
+    //   serial(c+S) waits ev_p(c): S = 3 lets Phase A finish a whole chunk ahead, so the serial stage never waits for it
     CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * n, b->stream));
     CK(cudaEventRecord(b->ev_start, b->stream));
     CK(cudaStreamWaitEvent(b->stream_a, b->ev_start, 0));
@@ -412,21 +435,21 @@ int run_plan(hmp3_batch *b) {
     // chunk is just a narrower view of the same buffers (every kernel indexes with the view's NG)
     int c = 0;
     for (int K0 = 0; K0 < b->max_gran; c++) {
-        const int k = c & 1;
+        const int nb = b->nbuf;
+        const int k = c % nb;
         const int ng_c = (c == 0 && b->NG > 32) ? 32 : b->NG;
         ChunkBufs view = b->cb2[k];
         view.NG = ng_c;
         const int K0_this = K0;
         K0 += ng_c;
-        if (c >= 2) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
+        if (c >= nb) CK(cudaStreamWaitEvent(b->stream_a, b->ev_r[k], 0));
         if (b->staged) {
             // the samples this chunk's polyphase needs first (up to the end of granule K0+NG-1), one DMA copy per
             // stream on the copy stream: the copy engine needs no SM resources, so the transfer overlaps the
             // serial stage of the previous chunk whatever its occupancy
             if (!b->stream_c) {
                 CK(cudaStreamCreate(&b->stream_c));
-                CK(cudaEventCreateWithFlags(&b->ev_c[0], cudaEventDisableTiming));
-                CK(cudaEventCreateWithFlags(&b->ev_c[1], cudaEventDisableTiming));
+                for (int q = 0; q < kMaxSets; q++) CK(cudaEventCreateWithFlags(&b->ev_c[q], cudaEventDisableTiming));
             }
             if (c == 0) CK(cudaStreamWaitEvent(b->stream_c, b->ev_start, 0));
             const long long lo = c == 0 ? 0 : 576LL * K0_this, hi = 576LL * (K0_this + ng_c);
@@ -447,7 +470,7 @@ int run_plan(hmp3_batch *b) {
         if (r != HMP3_OK) return r;
         CK(cudaEventRecord(b->ev_a[k], b->stream_a));
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
-        if (c >= 2) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
+        if (c >= nb) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
         launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
                     (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
@@ -461,7 +484,7 @@ int run_plan(hmp3_batch *b) {
         CK(cudaEventRecord(b->ev_p[k], b->stream_p));
         b->launches += 2;
     }
-    for (int k = 0; k < 2 && k < c; k++) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
+    for (int k = 0; k < b->nbuf && k < c; k++) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
     cudaEvent_t ev_asm = nullptr;
     if (b->timing) {
         mark(b, PH_ASSEMBLE, b->stream);  // re-recorded by launch_finish right before the assembly kernel
@@ -497,6 +520,14 @@ int sync_plan(hmp3_batch *b) {
             cudaEventElapsedTime(&ms, b->ev[i], b->ev[i + 1]);
             b->phase_ms[p] += ms;
             b->phase_launches[p]++;
+        }
+        b->timeline.clear();  // (phase, begin, end) in ms since the run began
+        for (size_t i = 0; i + 1 < b->ev_used; i += 2) {
+            if (b->ev_phase[i] < 0) continue;
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, b->ev_run0, b->ev[i]);
+            cudaEventElapsedTime(&t1, b->ev_run0, b->ev[i + 1]);
+            b->timeline.push_back({(float)b->ev_phase[i], t0, t1});
         }
     }
     return HMP3_OK;
@@ -597,8 +628,8 @@ hmp3_batch *hmp3_batch_create_ex(const hmp3_control *controls, const int64_t *nu
     else {
         size_t free_b = 0, total_b = 0;
         if (cudaSetDevice(device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            const double per_granule = 2.0 * 19500.0 * n;  // bytes of both buffer sets per granule of every stream
-            while (ng > 32 && per_granule * ng > 0.35 * (double)free_b) ng >>= 1;
+            const double per_granule = chunk_sets() * 19500.0 * n;  // bytes of all buffer sets per granule of every stream
+            while (ng > 32 && per_granule * ng > 0.45 * (double)free_b) ng >>= 1;
         }
     }
     if (ng < 2) ng = 2;
@@ -1103,6 +1134,13 @@ int hmp3_control_apply_option(hmp3_control *ec, const char *opt) { return contro
 
 // Debug / parity entry: Phase A of ONE stream on the device, stage outputs copied back to the host.
 // Same argument meaning as the host simulator's sim_analysis (tests/hostsim/hostsim.cpp).
+int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap) {
+    int k = 0;
+    for (; k < (int)b->timeline.size() && k < cap; k++)
+        for (int j = 0; j < 3; j++) rows[3 * k + j] = b->timeline[k][j];
+    return k;
+}
+
 int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches) {
     // first call (cycles == NULL or nothing recorded yet): switch recording on for the following runs
     if (!b) return HMP3_ERR_ARG;

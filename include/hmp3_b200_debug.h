@@ -21,6 +21,9 @@ int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long ns
  * buffer copies cycles[launch][stream] (SM clocks each stream's warp spent in that k_rate launch, up to 64 launches)
  * and returns the number of launches recorded. */
 int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches);
+/* Kernel timeline of the last run with timing on (hmp3_batch_set_timing): rows of (phase index as in
+ * hmp3_batch_phase_ms, begin ms, end ms) since the run began; returns the number of rows. */
+int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap);
 #ifdef __cplusplus
 }
 #endif
