@@ -300,7 +300,7 @@ def run_gpu(args, rank, local_rank, world):
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": rate_ms / timed_run_ms,
                 "share_note": "wall share of the step during which this kernel is running (Phase A and the packing "
-                              "pass run concurrently on other streams; serialised share in profiles/r1f_launch_summary.txt: 86 %)",
+                              "pass run concurrently on other streams; serialised share in profiles/r1g_launch_summary.txt: 77 %)",
                 "note": "latency/instruction-fetch bound serial code, not a bandwidth kernel: see DESIGN.md"}
         line = {
             "metric": METRIC, "value": audio_s_per_step * args.steps / t_res, "unit": "x realtime",

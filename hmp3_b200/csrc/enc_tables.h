@@ -283,6 +283,20 @@ HMP3_HD float mb_exp(const EncTables *T, int x) {
     return t;
 }
 // round half away from zero (l3math.c:360-364)
+// The serial-stage translation unit is built without loop unrolling (code size), so the few hot sequential loops
+// are unrolled by hand: the loads of four elements are issued together, the arithmetic keeps its order.
+HMP3_HD float sum_seq(const float *v, int n, float acc) {  // acc + v[0] + v[1] + ... in that order
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        const float a0 = v[k], a1 = v[k + 1], a2 = v[k + 2], a3 = v[k + 3];
+        acc += a0;
+        acc += a1;
+        acc += a2;
+        acc += a3;
+    }
+    for (; k < n; k++) acc += v[k];
+    return acc;
+}
 HMP3_HD int round_away(float x) { return (int)(x + ((f2u(x) >> 31) ? -0.5f : 0.5f)); }
 // 2*antilog(a) - antilog(b) in millibels (l3math.c:367-382)
 HMP3_HD int mb_logsub(const EncTables *T, int a, int b) {

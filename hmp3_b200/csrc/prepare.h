@@ -50,11 +50,7 @@ HMP3_HD int ms_scan_step(int *memory, int block_type, int ms_raw) {
 HMP3_HD void long_band_sums(const EncTables *T, const float *v, int nbands, float *out) {
     HMP3_SYNC();
     for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {
-        const float *y = v + T->startBand_l[i];
-        const int n = T->nBand_l[i];
-        float e = 0.0f;
-        for (int k = 0; k < n; k++) e += y[k];
-        out[i] = e;
+        out[i] = sum_seq(v + T->startBand_l[i], T->nBand_l[i], 0.0f);
     }
     HMP3_SYNC();
 }

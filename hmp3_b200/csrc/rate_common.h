@@ -31,6 +31,13 @@ struct RegionPlan {
 HMP3_HD int imin_(int a, int b) { return a < b ? a : b; }
 HMP3_HD int imax_(int a, int b) { return a > b ? a : b; }
 
+// (hot sequential loops are unrolled by hand: see sum_seq in enc_tables.h)
+HMP3_HD int max_seq(const int *v, int n) {  // max(0, v[0], ..., v[n-1])
+    int m = 0, k = 0;
+    for (; k < n; k++) m = imax_(m, v[k]);
+    return m;
+}
+
 // ------------------------------------------------------------------ quantiser passes (l3math.c)
 // plain rounding quantiser (l3math.c:655-671)
 HMP3_FN int quant_plain(const EncTables *T, const float *x34, int *ix, int g, int n) {
@@ -82,27 +89,33 @@ HMP3_HD float dequant43(const EncTables *T, int q) {
 
 // quantisation noise of one band at step g, in millibels relative to the band width (l3math.c:511-544)
 // the plain sequential loop (host build; on the device also used one band per lane where bands are short)
+HMP3_HD float noise_line(const EncTables *T, float ig, float gn, float x34, float x) {  // squared error of one line
+    float t = (ig * x34 + (0.0f - 0.0946f));
+    int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
+    float xh;
+    if (q >= 0 && q < 256) xh = gn * T->ix43[q];
+    else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
+    float d = x - xh;
+    return d * d;
+}
 HMP3_HD int band_noise_seq(const EncTables *T, const float *x34, const float *x, int g, int n, int logn) {
     const float ig = T->igain34[g], gn = T->gain[g];
     float acc = 0.0f;
-    for (int i = 0; i < n; i++) {
-        float t = (ig * x34[i] + (0.0f - 0.0946f));
-        int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
-        float xh;
-        if (q >= 0 && q < 256) xh = gn * T->ix43[q];
-        else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
-        float d = x[i] - xh;
-        acc += d * d;
-    }
+    int i = 0;
+    for (; i < n; i++) acc += noise_line(T, ig, gn, x34[i], x[i]);
     return mb_log(T, 1.0e-12f + acc) - logn;
+}
+HMP3_HD float dequant43_sq(const EncTables *T, int q) {  // (q^(4/3))^2 as band_refit_gain takes it
+    float v;
+    if (q < 256) v = T->ix43[q];
+    else v = (float)(pow((double)q, (4.0 / 3.0)));
+    return v * v;
 }
 HMP3_HD int band_refit_gain_seq(const EncTables *T, const int *q, const float *x, int n) {
     float sqq = 0, sxx = 0;
-    for (int i = 0; i < n; i++) {
-        float v;
-        if (q[i] < 256) v = T->ix43[q[i]];
-        else v = (float)(pow((double)q[i], (4.0 / 3.0)));
-        sqq += v * v;
+    int i = 0;
+    for (; i < n; i++) {
+        sqq += dequant43_sq(T, q[i]);
         sxx += x[i] * x[i];
     }
     return 54 * mb_log(T, sxx / sqq) + (8 << 13);

@@ -324,27 +324,31 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
             const int nl = T->startBand_l[T->cfg.nsf[c]];
             const float *y34 = L->x34[c];
             const float *y = xr + 576 * c;
+            // two blocks of HMP3_W lines per iteration: the spectrum loads of both are in flight before either is used
+#define HMP3_EVAL_LOAD(kk, bb, aa, v34, vx)                          \
+    const int bb = ((kk) < nl) ? (int)T->line_band_l[kk] : 0;        \
+    const bool aa = ((kk) < nl) && ((am[c] >> bb) & 1u);             \
+    float v34 = 0.0f, vx = 0.0f;                                     \
+    if (aa) {                                                        \
+        v34 = y34[kk];                                               \
+        vx = y[kk];                                                  \
+    }
+#define HMP3_EVAL_LINE(kk, bb, aa, v34, vx)                                                   \
+    if (gballot(aa) != 0) {                                                                   \
+        int st = gshfl(s_try[c * NS], bb & (HMP3_W - 1));                                     \
+        if (NS > 1) {                                                                         \
+            const int st1 = gshfl(s_try[c * NS + NS - 1], bb & (HMP3_W - 1));                 \
+            if (bb >= HMP3_W) st = st1;                                                       \
+        }                                                                                     \
+        if (aa) dd[kk] = noise_line(T, T->igain34[st], T->gain[st], v34, vx);                 \
+    }
             for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
-                const int k = k0 + lane;
-                const int b = (k < nl) ? (int)T->line_band_l[k] : 0;
-                const bool act = (k < nl) && ((am[c] >> b) & 1u);
-                if (gballot(act) == 0) continue;
-                int st = gshfl(s_try[c * NS], b & (HMP3_W - 1));
-                if (NS > 1) {
-                    const int st1 = gshfl(s_try[c * NS + NS - 1], b & (HMP3_W - 1));
-                    if (b >= HMP3_W) st = st1;
-                }
-                if (act) {
-                    const float ig = T->igain34[st], gn = T->gain[st];
-                    float t = (ig * y34[k] + (0.0f - 0.0946f));
-                    int q = (int)(t + ((f2u(t) >> 31) ? -0.5f : 0.5f));
-                    float xh;
-                    if (q >= 0 && q < 256) xh = gn * T->ix43[q];
-                    else xh = (float)((double)gn * pow((double)q, (4.0 / 3.0)));
-                    float d = y[k] - xh;
-                    dd[k] = d * d;
-                }
+                const int ka = k0 + lane;
+                HMP3_EVAL_LOAD(ka, b0, act0, p0, x0)
+                HMP3_EVAL_LINE(ka, b0, act0, p0, x0)
             }
+#undef HMP3_EVAL_LOAD
+#undef HMP3_EVAL_LINE
             HMP3_SYNC();
             for (int j = 0; j < NS; j++) {
                 const int it = c * NS + j;
@@ -352,8 +356,7 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
                 const int bnd = lane + HMP3_W * j;
                 const float *v = dd + T->startBand_l[bnd];
                 const int n = T->nBand_l[bnd];
-                float acc = 0.0f;
-                for (int k = 0; k < n; k++) acc += v[k];
+                const float acc = sum_seq(v, n, 0.0f);
                 const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];
                 bool done = false;
                 if (mode[it] == 1) {
@@ -786,14 +789,7 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
             q[k] = v;
         }
         HMP3_SYNC();
-        for (int i = HMP3_LANE; i < nb; i += HMP3_W) {
-            const int *qb = q + T->startBand_l[i];
-            const int n = T->nBand_l[i];
-            int m = 0;
-            for (int k = 0; k < n; k++)
-                if (qb[k] > m) m = qb[k];
-            L->ixmax[ch][i] = m;
-        }
+        for (int i = HMP3_LANE; i < nb; i += HMP3_W) L->ixmax[ch][i] = max_seq(q + T->startBand_l[i], T->nBand_l[i]);
     }
     HMP3_SYNC();
 #else

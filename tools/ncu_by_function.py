@@ -1,12 +1,15 @@
 #!/usr/bin/env python3
 """Aggregate an ncu source-page capture of a kernel per (noinline) device function.
 
-usage: ncu_by_function.py <report.ncu-rep> <library.so> <kernel-substring>
+usage: ncu_by_function.py <report.ncu-rep> <library.so> <kernel-substring> [units]
+(units = granules x streams of the captured launch: adds per-function code footprint columns -- static instructions,
+instructions executed at least once per two units ("hot"), dynamic instructions per unit)
 Joins `ncu --page source --print-source sass` (per-instruction samples / executed counts) with the
 function symbol table of the cubin extracted from the library."""
 import csv, subprocess, sys, os, re, tempfile, collections
 
 rep, so, kern = sys.argv[1], sys.argv[2], sys.argv[3]
+units = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 syms = []
@@ -27,7 +30,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(src.splitlines()))
 hdr = None
 base = None
-agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0])
+agg = collections.defaultdict(lambda: [0, 0, 0, 0, 0, 0, 0, 0])
 for r in rows:
     if r and r[0] == "Address":
         hdr = r
@@ -50,6 +53,9 @@ for r in rows:
     agg[fn][3] += int(d.get("stall_no_inst") or 0)
     agg[fn][4] += int(d.get("stall_long_sb") or 0)
     agg[fn][5] += int(d.get("stall_wait") or 0)
+    agg[fn][6] += 1
+    if units and int(d["Instructions Executed"] or 0) >= 0.5 * units:
+        agg[fn][7] += 1
 ts = sum(v[0] for v in agg.values()) or 1
 ti = sum(v[1] for v in agg.values()) or 1
 print("%-28s %8s %8s %14s %8s %8s %8s %8s" % ("function", "samples%", "instr%", "warp-instr", "thr/inst", "no_inst%", "long_sb%", "wait%"))
@@ -57,3 +63,9 @@ for fn, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print("%-28s %7.2f%% %7.2f%% %14d %8.1f %7.2f%% %7.2f%% %7.2f%%" % (fn, 100 * v[0] / ts, 100 * v[1] / ti, v[1], v[2] / max(v[1], 1),
                                                             100 * v[3] / ts, 100 * v[4] / ts, 100 * v[5] / ts))
 print("total warp instructions", ti, "samples", ts)
+if units:
+    print()
+    print("%-28s %8s %8s %8s %10s %8s" % ("function", "static", "hot", "hot KB", "dyn/unit", "samples%"))
+    for fn, v in sorted(agg.items(), key=lambda kv: -kv[1][7]):
+        print("%-28s %8d %8d %8.1f %10.0f %7.2f%%" % (fn, v[6], v[7], v[7] * 16 / 1024, v[1] / units, 100 * v[0] / ts))
+    print("hot footprint: %.1f KB of %.1f KB" % (sum(v[7] for v in agg.values()) * 16 / 1024, sum(v[6] for v in agg.values()) * 16 / 1024))

@@ -30,7 +30,7 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, tag + "_launch_summary.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 1 --warmup 1 "
-                "--clips-per-gpu 1184 --no-cpu-baseline\n(first 400 launches; serialised and cold-cache under the "
+                "--no-cpu-baseline\n(first 400 launches; serialised and cold-cache under the "
                 "profiler: compare SHARES, not absolutes)\n\n")
         f.write("%-22s %6s %12s %7s\n" % ("kernel", "count", "total ms", "share"))
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
