@@ -8,6 +8,10 @@ name, flags = sys.argv[1], sys.argv[2:]
 objdir = os.path.join(ROOT, "hmp3_b200", "_build")
 obj = os.path.join(objdir, "kernels_rate_%s.o" % name)
 extra = [f for f in g.TUS["kernels_rate.cu"]]
+for tool in ("-Xcicc", "-Xptxas"):          # a variant's own optimisation level replaces the default one
+    if tool in flags and tool in extra:
+        i = extra.index(tool)
+        del extra[i:i + 2]
 cmd = ["timeout", "1500", "/usr/local/cuda/bin/nvcc"] + g.NVCC_COMMON + extra + flags + ["-c", "-o", obj, os.path.join(g.CSRC, "kernels_rate.cu")]
 r = subprocess.run(cmd, capture_output=True, text=True)
 if r.returncode:
