@@ -24,8 +24,10 @@ struct Wav {
     int channels = 0, rate = 0, bits = 0, type = 0;
     std::vector<int16_t> pcm;  // interleaved, 16-bit input
     std::vector<float> pcmf;   // interleaved, every other input type converted the way Csrc::sr_convert does
+    int enc_channels = 0;      // channels handed to the encoder (1 after a -M3 down-mix of a stereo file)
+    bool use_float = false;
     size_t audio_bytes = 0;    // bytes of the data chunk actually read (the Info tag counts whole sample frames of it)
-    size_t total() const { return bits == 16 && type == 1 ? pcm.size() : pcmf.size(); }
+    size_t total() const { return use_float ? pcmf.size() : pcm.size(); }
 };
 
 bool read_wav(const char *path, Wav *w, std::string *err, bool ignore_length) {
@@ -218,9 +220,25 @@ int main(int argc, char **argv) {
             continue;
         }
         j.ec = base;
+        const bool mono_convert = (base.mode == 3);  // -M3 on a stereo file: down-mix (tomp3.cpp:560-561, 813-815)
         if (j.ec.mode < 0) j.ec.mode = 0;
         if (j.wav.channels == 1) j.ec.mode = 3;
-        if (j.wav.channels == 2 && j.ec.mode == 3) j.ec.mode = 1;
+        j.wav.use_float = !(j.wav.type == 1 && j.wav.bits == 16);
+        j.wav.enc_channels = j.wav.channels;
+        if (j.wav.channels == 2 && mono_convert) {  // Csrc::src_filter_to_mono_case0 (srccf.cpp:458-468)
+            const size_t nfr = j.wav.total() / 2;
+            std::vector<float> m(nfr);
+            for (size_t i = 0; i < nfr; i++) {
+                const float l = j.wav.use_float ? j.wav.pcmf[2 * i] : (float)j.wav.pcm[2 * i];
+                const float r = j.wav.use_float ? j.wav.pcmf[2 * i + 1] : (float)j.wav.pcm[2 * i + 1];
+                m[i] = (float)((l + r) * 0.5);
+            }
+            j.wav.pcmf.swap(m);
+            j.wav.pcm.clear();
+            j.wav.use_float = true;
+            j.wav.enc_channels = 1;
+            j.ec.mode = 3;
+        }
         j.ec.samprate = j.wav.rate;
         hmp3_control eff;
         if (hmp3_effective_control(&j.ec, &eff, nullptr) != HMP3_OK) {
@@ -229,8 +247,8 @@ int main(int argc, char **argv) {
         }
         j.ok = true;
         ctl.push_back(j.ec);
-        ns.push_back((int64_t)(j.wav.total() / j.wav.channels));
-        fmts.push_back((j.wav.type == 1 && j.wav.bits == 16) ? HMP3_PCM_S16 : HMP3_PCM_F32);
+        ns.push_back((int64_t)(j.wav.total() / j.wav.enc_channels));
+        fmts.push_back(j.wav.use_float ? HMP3_PCM_F32 : HMP3_PCM_S16);
         idx.push_back((int)k);
     }
     if (ctl.empty()) return 1;

@@ -916,6 +916,7 @@ struct hmp3_encoder {
     double ave_bytes = 0;
     bool float_in = false;      // the plan takes float PCM (every input format except 16-bit integer)
     int src_bits = 16, src_float = 0;
+    int src_chan = 0;           // channels of the caller's PCM (2 with nch == 1: down-mix to mono, Csrc kfilter 2)
     int capacity_seconds = 1200;
     std::vector<float> stage;
     ~hmp3_encoder() { delete b; }
@@ -1033,15 +1034,21 @@ int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int sour
     for (int r : rates) native |= (ec->samprate == r);
     const bool fmt_ok = source_is_float ? (source_bits == 32)
                                         : (source_bits == 8 || source_bits == 16 || source_bits == 24 || source_bits == 32);
-    if (!fmt_ok || !native || (mono_convert && ec->mode != 3) || (mpeg_select > 2 && mpeg_select != ec->samprate) ||
+    if (!fmt_ok || !native || (mpeg_select > 2 && mpeg_select != ec->samprate) ||
         (mpeg_select == 1 && ec->samprate < 32000) || (mpeg_select == 2 && ec->samprate > 24000)) {
-        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate without rate or channel conversion is in scope");
+        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate without rate conversion is in scope");
         return 0;
     }
+    // channels as CMp3Enc::MP3_audio_encode_init derives them (mp3enc.cpp:2689-2696): the source has two unless the
+    // mode is mono; mono_convert encodes a two-channel source as mono (Csrc kfilter 2: (L + R) * 0.5)
+    hmp3_control ec2 = *ec;
+    e->src_chan = ec->mode == 3 ? 1 : 2;
+    const bool downmix = mono_convert && e->src_chan == 2;
+    if (downmix) ec2.mode = 3;
     e->src_bits = source_bits;
     e->src_float = source_is_float;
-    const int bytes_in = encoder_init(e, ec, !(source_bits == 16 && !source_is_float));
-    return bytes_in ? (bytes_in / 4) * (source_bits / 8) : 0;  // bytes the caller supplies per call
+    const int bytes_in = encoder_init(e, &ec2, downmix || !(source_bits == 16 && !source_is_float));
+    return bytes_in ? (bytes_in / 4 / e->nch) * e->src_chan * (source_bits / 8) : 0;  // bytes the caller supplies per call
 }
 hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
     hmp3_in_out io = {0, 0};
@@ -1051,7 +1058,9 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
     }
     if (!e->float_in) return encoder_step(e, pcm, bs_out);
     // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale
-    const int n = 1152 * e->nch;
+    const int n = 1152 * e->src_chan;
+    const bool downmix = e->src_chan == 2 && e->nch == 1;
+    if ((int)e->stage.size() < n) e->stage.resize(n);
     float *d = e->stage.data();
     if (e->src_float) {
         const float *s = (const float *)pcm;
@@ -1065,9 +1074,14 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
             const int v = (int)(((unsigned)s[2] << 24) | ((unsigned)s[1] << 16) | ((unsigned)s[0] << 8)) >> 8;
             d[i] = (float)((float)v / 256.0f);
         }
+    } else if (e->src_bits == 16) {
+        const short *s = (const short *)pcm;
+        for (int i = 0; i < n; i++) d[i] = (float)s[i];
     } else {  // 8-bit unsigned
         for (int i = 0; i < n; i++) d[i] = (((float)pcm[i]) - 128.0f) * (256.0f);
     }
+    if (downmix)  // src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468)
+        for (int i = 0; i < 1152; i++) d[i] = (float)((d[2 * i] + d[2 * i + 1]) * 0.5);
     io = encoder_step(e, d, bs_out);
     if (io.in_bytes) io.in_bytes = n * (e->src_bits / 8);
     return io;

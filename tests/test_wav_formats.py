@@ -177,3 +177,45 @@ def test_cli_pipes_and_ignore_length(tmp_path):
         b = run(CLI, src, str(tmp_path / "gpu.mp3") if dst == "out" else "-", extra)
         diff = np.nonzero(a[:min(a.size, b.size)] != b[:min(a.size, b.size)])[0]
         assert a.size > 1000 and a.size == b.size and diff.size == 0, (src, dst, extra, a.size, b.size, diff[:8])
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["s16", "s24", "u8"])
+@pytest.mark.parametrize("sr,opts,kw", [(44100, ["-B64", "-M3"], dict(bitrate=64)), (22050, ["-M3"], dict())])
+def test_mono_downmix_reproduces_reference_cli_audio(tmp_path, kind, sr, opts, kw):
+    """-M3 on a stereo file: the reference down-mixes (L + R) * 0.5 and encodes mono (tomp3.cpp:560-561, 813-820;
+    srccf.cpp:458-468)."""
+    samples = wavutil.make_samples(synth_pcm(51, 2.4, sr, 2), kind, seed=4)
+    _, whole = ref_cli_file(tmp_path, samples, kind, sr, 2, opts)
+    mono = wavutil.downmix(wavutil.to_encoder_float(samples, kind))
+    got, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=1, **kw), mono, tail=wavutil.tail_value(kind))
+    head = whole.size - got.size
+    assert head > 0 and np.array_equal(whole[head:], got)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_and_handle_mono_downmix(tmp_path):
+    sr = 44100
+    for kind, opts in [("s16", ["-B64", "-M3"]), ("s24", ["-M3", "-V80"]), ("f32", ["-B48", "-M3"])]:
+        samples = wavutil.make_samples(synth_pcm(61, 3.0, sr, 2), kind, seed=2)
+        wav, want = ref_cli_file(tmp_path, samples, kind, sr, 2, opts, "dm_" + kind)
+        out = str(tmp_path / ("dm_%s_gpu.mp3" % kind))
+        subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        got = np.fromfile(out, dtype=np.uint8)
+        assert got.size == want.size and np.array_equal(got, want), kind
+    # the handle: MP3_audio_encode_init(..., mono_convert = 1) with a two-channel 16-bit source
+    samples = wavutil.make_samples(synth_pcm(62, 1.0, sr, 2)[:24 * 1152], "s16")
+    enc = capi.Encoder(capacity_seconds=10)
+    assert enc.init_mp3(capi.control(samprate=sr, nch=2, bitrate=64), mono_convert=1) == 1152 * 2 * 2
+    zero = np.zeros((1152, 2), np.int16)
+    out = []
+    for c in range(24 + 4 + 6):
+        used, b = enc.encode_mp3(samples[c * 1152:(c + 1) * 1152] if c < 24 else zero)
+        assert used == 1152 * 2 * 2
+        out.append(b)
+    got = np.concatenate(out)
+    enc.close()
+    want, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=1, bitrate=64), wavutil.downmix(samples.astype(np.float32)))
+    m = min(got.size, want.size)
+    assert m > 0.9 * want.size and np.array_equal(got[:m], want[:m])

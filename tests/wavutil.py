@@ -62,3 +62,8 @@ def write_wav(path, samples, kind, sr, nch):
                 struct.pack("<IHHIIHH", 16, tag, nch, sr, sr * nch * bits // 8, nch * bits // 8, bits) +
                 b"data" + struct.pack("<I", len(data)))
         f.write(data)
+
+
+def downmix(f):
+    """Csrc::src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468): (float)((L + R) * 0.5), the sum taken in float."""
+    return ((f[:, 0] + f[:, 1]).astype(np.float32).astype(np.float64) * 0.5).astype(np.float32).reshape(-1, 1)
