@@ -20,6 +20,9 @@
 
 namespace {
 
+// encode calls of the reference CLI's main loop for n sample frames (see calls_for in pipeline.cu)
+long long calls_main(long long n) { return (n + 3 * 1153 + 1152) / 1152; }
+
 struct Wav {
     int channels = 0, rate = 0, bits = 0, type = 0;
     std::vector<int16_t> pcm;  // interleaved, 16-bit input
@@ -91,7 +94,7 @@ bool read_wav(const char *path, Wav *w, std::string *err, bool ignore_length) {
             // the reference does not make (its call count comes from the byte count, rounded down).
             if (got % frame) {
                 const size_t whole = got / frame;
-                if ((whole + 1) % 1152 != 0) {
+                if (calls_main((long long)whole + 1) == calls_main((long long)whole)) {
                     raw.resize((whole + 1) * frame + frame);
                     memset(raw.data() + got, 0, (whole + 1) * frame - got);
                     got = (whole + 1) * frame;
@@ -294,7 +297,7 @@ int main(int argc, char **argv) {
             tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, ns[i], nullptr, 0, 0, nullptr,
                                         nullptr, 0, tag, (int)sizeof(tag));
         } else if (xing) {
-            const int ncalls_main = (int)((ns[i] + 4 * 1152) / 1152);
+            const int ncalls_main = (int)calls_main(ns[i]);
             std::vector<int32_t> fa(ncalls_main + 64);
             std::vector<int64_t> ba(ncalls_main + 64);
             int nc = hmp3_batch_call_log(b, i, fa.data(), ba.data(), (int)fa.size());

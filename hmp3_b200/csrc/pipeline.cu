@@ -170,7 +170,11 @@ namespace {
 
 // number of encode calls the CLI makes for a clip (tomp3.cpp:923-931: four zero frames appended at EOF,
 // whole frames only)
-long long calls_for(long long nsamples) { return (nsamples + 4 * 1152) / 1152; }
+// Encode calls of the CLI's main loop for a stream of `nsamples` (test/tomp3.cpp:908-942): at end of file it appends
+// 4 x bytes_in_init zero bytes and keeps calling while bytes_in_init bytes are buffered; bytes_in_init is what
+// Csrc::sr_convert_init returns, 1152 * source/target + ntaps (= 1 without down-sampling) sample frames
+// (srcc.cpp:185-187, 769-773) = 1153, and every call consumes 1152: floor((n + 3 * 1153) / 1152) + 1 calls.
+long long calls_for(long long nsamples) { return (nsamples + 3 * 1153 + 1152) / 1152; }
 const int kFlushCalls = 12;  // upper bound of the tail-flush calls we provision analysis data for
 
 int max_main_frame_bytes(const EncConfig &C) {

@@ -96,7 +96,8 @@ int hmp3_device_count(void);
  * (1) Batch entry: the GPU path.  Replaces one `hmp3 in.wav out.mp3 [opts]` process per clip
  * (ff_encode, hmp3/src/test/tomp3.cpp:640-1090, minus WAV parsing and the Xing/Info frame):
  * for every stream the output is the exact frame sequence CMp3Enc::MP3_audio_encode emits for
- * that PCM with four zero frames appended at EOF and the tail flush (tomp3.cpp:923-931, 1015-1036).
+ * that PCM with its end-of-file protocol -- 4 x 1153 zero sample frames appended, one encode call while 1153 frames
+ * are buffered, then the tail flush (tomp3.cpp:908-942, 1015-1036).
  * --------------------------------------------------------------------------------------------- */
 typedef struct hmp3_stream_desc {
     const hmp3_control *control; /* per-stream control (streams with equal controls share tables) */
@@ -213,7 +214,7 @@ int hmp3_info_frame(const hmp3_control *effective, int head_mode, int xing_flag,
 /* Per encode call of stream i in the last completed run: frames and bytes emitted so far (what
  * CMp3Enc::L3_audio_encode_get_frames_bytes returns after that call).  Fills up to `cap` entries, returns the
  * number of calls the stream made including the tail flush (the CLI's main loop is the first
- * (num_samples + 4 * 1152) / 1152 of them). */
+ * (num_samples + 3 * 1153 + 1152) / 1152 of them: the CLI keeps calling while 1153 sample frames are buffered). */
 int hmp3_batch_call_log(hmp3_batch *b, int i, int32_t *frames_after_call, int64_t *bytes_after_call, int cap);
 
 /* ---------------------------------------------------------------------------------------------

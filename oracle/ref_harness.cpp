@@ -258,9 +258,10 @@ long ref_encode_clip(const int *ec_words, const float *pcm, long nsamples_per_ch
     if (!bytes_in) return -1;
     int nch = g_enc->nchan;
     long per_call = 1152;
-    // CLI semantics (test/tomp3.cpp:923-931): four frames of zeros are appended once at EOF and only
-    // whole frames are encoded.
-    long ncalls = (nsamples_per_ch + 4 * per_call) / per_call;
+    // CLI semantics (test/tomp3.cpp:908-942): 4 x bytes_in_init zero bytes are appended once at EOF and a call is
+    // made while bytes_in_init bytes are buffered; bytes_in_init = 1153 sample frames (what Csrc::sr_convert_init
+    // returns without rate conversion, srcc.cpp:185-187), each call consumes 1152.
+    long ncalls = (nsamples_per_ch + 3 * 1153 + per_call) / per_call;
     int calls_per_frame_mult = (g_enc->h_id == 0) ? 2 : 1;
     float *buf = (float *)calloc((size_t)nch * 1152, sizeof(float));
     unsigned char tmp[16384];

@@ -188,7 +188,7 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
     if (!build_tables(ec, T, nullptr)) { delete T; return -1; }
     const int nch = T->cfg.nchan;
     const int mpeg2 = T->cfg.h_id == 0;
-    long calls = (nsamples + 4 * 1152) / 1152;
+    long calls = (nsamples + 3 * 1153 + 1152) / 1152;  // the CLI's main loop (pipeline.cu: calls_for)
     int ngran_real = (int)(2 * calls);
     int ngran = ngran_real + 2 * 12;
     std::vector<float> P((size_t)(ngran + 3) * nch * 576, 0.0f);

@@ -90,7 +90,7 @@ def ref_info(ec):
 
 
 def ref_encode_clip(ec, pcm_i16, max_trace_calls=0):
-    """Encode int16 PCM (nsamples, nch) the way the CLI does (int16 -> float cast, 4 zero frames at EOF,
+    """Encode int16 PCM (nsamples, nch) the way the CLI does (int16 -> float cast, the CLI's zero padding at EOF,
     tail flush) and return (mp3_bytes, traces or None).  No Xing/Info frame."""
     L = lib()
     pcm = np.ascontiguousarray(pcm_i16.astype(np.float32))

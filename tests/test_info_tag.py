@@ -49,7 +49,7 @@ def test_info_frame_matches_reference_cli(name, seed, sr, nch, kw, secs):
     audio, tr = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, max_trace_calls=100000)
     head_bytes = whole.size - audio.size
     assert head_bytes > 0 and np.array_equal(whole[head_bytes:], audio)       # the CLI's audio frames = the harness'
-    ncalls = (pcm.shape[0] + 4 * 1152) // 1152                                # the CLI's main loop
+    ncalls = (pcm.shape[0] + 3 * 1153 + 1152) // 1152                         # the CLI's main loop
     bytes_after = np.cumsum(tr["out_bytes"][:ncalls].astype(np.int64))
     # frames are emitted whole: count the frames that end at or before each cumulative byte count
     ends, p = [], 0

@@ -219,3 +219,40 @@ def test_cli_and_handle_mono_downmix(tmp_path):
     want, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=1, bitrate=64), wavutil.downmix(samples.astype(np.float32)))
     m = min(got.size, want.size)
     assert m > 0.9 * want.size and np.array_equal(got[:m], want[:m])
+
+
+EDGE_LENGTHS = [5, 1149, 1152 * 40 + 1148, 1152 * 40 + 1149, 1152 * 40 + 1150, 1152 * 40 + 1151, 1152 * 41, 1152 * 41 + 1]
+
+
+@needs_ref
+@pytest.mark.parametrize("sr,nch,opts,kw", CASES[:2])
+def test_end_of_file_call_count_matches_reference_cli(tmp_path, sr, nch, opts, kw):
+    """The CLI keeps calling the encoder while bytes_in_init = 1153 sample frames are buffered (what
+    Csrc::sr_convert_init returns, srcc.cpp:185-187, 769-773) after appending 4 x 1153 frames of zero bytes: stream
+    lengths with n % 1152 in {1149, 1150, 1151} get one more frame than "n plus four frames" would give."""
+    base = synth_pcm(71, 1.2, sr, nch)
+    for n in EDGE_LENGTHS:
+        _, whole = ref_cli_file(tmp_path, base[:n], "s16", sr, nch, opts)
+        got, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=nch, **kw), base[:n])
+        ref, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), base[:n])
+        head = whole.size - got.size
+        assert head > 0 and np.array_equal(whole[head:], got), n
+        assert np.array_equal(ref, got), n
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_identity_at_end_of_file_edge_lengths(tmp_path):
+    sr, nch, opts = 44100, 2, ["-B64"]
+    base = synth_pcm(72, 1.2, sr, nch)
+    lst = str(tmp_path / "edge.txt")
+    wants = []
+    with open(lst, "w") as f:
+        for n in EDGE_LENGTHS:
+            wav, want = ref_cli_file(tmp_path, base[:n], "s16", sr, nch, opts, "e%d" % n)
+            wants.append(want)
+            f.write("%s %s\n" % (wav, tmp_path / ("e%d_gpu.mp3" % n)))
+    subprocess.run([CLI, "-@", lst] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    for n, want in zip(EDGE_LENGTHS, wants):
+        got = np.fromfile(str(tmp_path / ("e%d_gpu.mp3" % n)), dtype=np.uint8)
+        assert got.size == want.size and np.array_equal(got, want), n
