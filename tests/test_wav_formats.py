@@ -256,3 +256,29 @@ def test_cli_identity_at_end_of_file_edge_lengths(tmp_path):
     for n, want in zip(EDGE_LENGTHS, wants):
         got = np.fromfile(str(tmp_path / ("e%d_gpu.mp3" % n)), dtype=np.uint8)
         assert got.size == want.size and np.array_equal(got, want), n
+
+
+FUZZ_COMBOS = [(44100, 2, ["-B64"], dict(bitrate=64)), (44100, 2, [], dict()),
+               (48000, 2, ["-V100", "-HF2", "-F19000"], dict(vbr_mnr=100, hf=2, freq_limit=19000)),
+               (22050, 1, ["-B32"], dict(bitrate=32)), (32000, 2, [], dict()), (16000, 2, ["-B24"], dict(bitrate=24)),
+               (24000, 1, ["-V30"], dict(vbr_mnr=30)), (44100, 1, ["-B96"], dict(bitrate=96)),
+               (48000, 2, ["-B160"], dict(bitrate=160)), (32000, 2, ["-B160"], dict(bitrate=160)),
+               (44100, 2, ["-V150"], dict(vbr_mnr=150)), (44100, 2, ["-B64", "-M0"], dict(bitrate=64, mode=0)),
+               (44100, 2, ["-B64", "-S1"], dict(bitrate=64, filter_select=1))]
+
+
+@needs_ref
+def test_fuzz_against_the_reference_cli(tmp_path):
+    """Random stream lengths (tiny, ragged, around multiples of 1152), sample types and option sets: the audio frames
+    of the file the reference CLI writes equal the host build of the kernel bodies."""
+    rng = np.random.default_rng(2024)
+    for it in range(26):
+        sr, nch, opts, kw = FUZZ_COMBOS[it % len(FUZZ_COMBOS)]
+        n = int([rng.integers(1, 3000), rng.integers(3000, 60000), 1152 * rng.integers(1, 40) + rng.integers(-3, 4)][it % 3])
+        kind = wavutil.KINDS[it % len(wavutil.KINDS)]
+        samples = wavutil.make_samples(synth_pcm(300 + it, n / sr + 0.1, sr, nch)[:n], kind, seed=it)
+        _, whole = ref_cli_file(tmp_path, samples, kind, sr, nch, opts, "fz")
+        src = samples if kind == "s16" else wavutil.to_encoder_float(samples, kind)
+        got, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=nch, **kw), src, tail=wavutil.tail_value(kind))
+        head = whole.size - got.size
+        assert head > 0 and np.array_equal(whole[head:], got), (sr, nch, opts, n, kind)
