@@ -282,3 +282,26 @@ def test_fuzz_against_the_reference_cli(tmp_path):
         got, _, _ = simmod.encode_clip(capi.control(samprate=sr, nch=nch, **kw), src, tail=wavutil.tail_value(kind))
         head = whole.size - got.size
         assert head > 0 and np.array_equal(whole[head:], got), (sr, nch, opts, n, kind)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_gpu_cli_fuzz_against_the_reference_cli(tmp_path):
+    """Whole files (Info frame included) for random lengths and sample types, one GPU batch per option set."""
+    rng = np.random.default_rng(77)
+    for c, (sr, nch, opts, kw) in enumerate([FUZZ_COMBOS[0], FUZZ_COMBOS[2], FUZZ_COMBOS[3], FUZZ_COMBOS[4], FUZZ_COMBOS[12]]):
+        lst = str(tmp_path / ("fz%d.txt" % c))
+        wants = []
+        with open(lst, "w") as f:
+            for it in range(6):
+                n = int([rng.integers(1, 3000), rng.integers(3000, 120000), 1152 * rng.integers(1, 60) + rng.integers(-3, 4)][it % 3])
+                kind = wavutil.KINDS[(it + c) % len(wavutil.KINDS)]
+                samples = wavutil.make_samples(synth_pcm(500 + 10 * c + it, n / sr + 0.1, sr, nch)[:n], kind, seed=it)
+                name = "g%d_%d" % (c, it)
+                wav, want = ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name)
+                wants.append((name, want))
+                f.write("%s %s\n" % (wav, tmp_path / (name + "_gpu.mp3")))
+        subprocess.run([CLI, "-@", lst] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        for name, want in wants:
+            got = np.fromfile(str(tmp_path / (name + "_gpu.mp3")), dtype=np.uint8)
+            assert got.size == want.size and np.array_equal(got, want), (name, opts)
