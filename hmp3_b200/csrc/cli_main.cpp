@@ -4,7 +4,8 @@
 // per-channel kbit/s, -V<n> VBR, -HF<n>, -F<hz>, -M<mode>, -X<flag> ...), the WAV is encoded through the C ABI and
 // the output file is the Xing/Info frame followed by the audio frames -- byte-identical to what `hmp3` writes.
 // Extension: `-@ <list>` encodes many files in ONE batch on the GPU (each line of <list>: input<TAB or space>output).
-// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate (no sample-rate conversion).  "-" as
+// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate, or at 8 / 11.025 / 12 kHz (up-converted
+// 1:2 as the reference does; no general sample-rate conversion).  "-" as
 // input reads the WAV from stdin and, like -IL, ignores the header's data length (tomp3.cpp:721-745); "-" as output
 // writes to stdout, where -- as with the reference, which cannot re-read its own stdout -- the Xing/Info frame stays
 // the placeholder written before encoding (tomp3.cpp:1055-1072).
@@ -144,6 +145,7 @@ struct Job {
     std::string in, out;
     Wav wav;
     hmp3_control ec;
+    int enc_rate = 0;  // sample rate handed to the encoder (twice the file's for 8 / 11.025 / 12 kHz input)
     bool ok = false;
 };
 
@@ -228,21 +230,72 @@ int main(int argc, char **argv) {
         if (j.wav.channels == 1) j.ec.mode = 3;
         j.wav.use_float = !(j.wav.type == 1 && j.wav.bits == 16);
         j.wav.enc_channels = j.wav.channels;
-        if (j.wav.channels == 2 && mono_convert) {  // Csrc::src_filter_to_mono_case0 (srccf.cpp:458-468)
-            const size_t nfr = j.wav.total() / 2;
-            std::vector<float> m(nfr);
-            for (size_t i = 0; i < nfr; i++) {
-                const float l = j.wav.use_float ? j.wav.pcmf[2 * i] : (float)j.wav.pcm[2 * i];
-                const float r = j.wav.use_float ? j.wav.pcmf[2 * i + 1] : (float)j.wav.pcm[2 * i + 1];
-                m[i] = (float)((l + r) * 0.5);
+        // encode rate as CMp3Enc::MP3_audio_encode_init picks it (mp3enc.cpp:2700-2714, mpeg_select 0): a source below
+        // 16 kHz is doubled when that is an MPEG-2 rate (Csrc case 1); any other non-MPEG rate would need the general
+        // resampler, which is not built
+        j.enc_rate = j.wav.rate;
+        const bool native = j.wav.rate == 16000 || j.wav.rate == 22050 || j.wav.rate == 24000 || j.wav.rate == 32000 ||
+                            j.wav.rate == 44100 || j.wav.rate == 48000;
+        const bool up2 = !native && (j.wav.rate == 8000 || j.wav.rate == 11025 || j.wav.rate == 12000);
+        if (!native && !up2) {
+            fprintf(stderr, "\n ENCODER INIT FAIL (input rate %d needs the general sample-rate converter, which is not built)\n",
+                    j.wav.rate);
+            continue;
+        }
+        const bool downmix = j.wav.channels == 2 && mono_convert;
+        if (downmix || up2) {
+            const int ch = j.wav.channels;
+            const size_t nfr = j.wav.total() / ch;
+            const float pad = j.wav.bits == 8 ? -32768.0f : 0.0f;  // what the zero bytes after the end decode to
+            auto in = [&](size_t i, int c) -> float {
+                if (i >= nfr) return pad;
+                return j.wav.use_float ? j.wav.pcmf[ch * i + c] : (float)j.wav.pcm[ch * i + c];
+            };
+            std::vector<float> y;
+            if (!up2) {  // Csrc::src_filter_to_mono_case0 (srccf.cpp:458-468)
+                y.resize(nfr);
+                for (size_t i = 0; i < nfr; i++) y[i] = (float)((in(i, 0) + in(i, 1)) * 0.5);
+            } else if (ch == 1) {  // src_filter_mono_case1 (srccf.cpp:80-100): integer samples, truncated
+                y.resize(2 * nfr + 3, pad);
+                for (size_t i = 0; i < nfr; i++) {
+                    const int a = (int)in(i, 0), b = (int)in(i + 1, 0);
+                    y[2 * i] = (float)a;
+                    y[2 * i + 1] = (float)((a + b) >> 1);
+                }
+            } else if (downmix) {  // src_filter_to_mono_case1 (srccf.cpp:472-492)
+                y.resize(2 * nfr + 3, pad);
+                for (size_t i = 0; i < nfr; i++) {
+                    const float a = in(i, 0) + in(i, 1), b = in(i + 1, 0) + in(i + 1, 1);
+                    y[2 * i] = (float)(a * 0.5);
+                    y[2 * i + 1] = (float)((a + b) * 0.25);
+                }
+            } else {  // src_filter_dual_case1 (srccf.cpp:258-276)
+                y.resize(2 * (2 * nfr + 3), pad);
+                for (size_t i = 0; i < nfr; i++)
+                    for (int c = 0; c < 2; c++) {
+                        y[2 * (2 * i) + c] = in(i, c);
+                        y[2 * (2 * i + 1) + c] = (float)((in(i, c) + in(i + 1, c)) * 0.5);
+                    }
             }
-            j.wav.pcmf.swap(m);
+            // (2 n + 3 samples: the reference's main loop makes floor((n + 3 * 577) / 576) + 1 calls of 576 input
+            // samples = the calls of an encoder-rate stream of 2 n + 3 samples; the 3 extra ones are padding)
+            j.wav.pcmf.swap(y);
             j.wav.pcm.clear();
             j.wav.use_float = true;
-            j.wav.enc_channels = 1;
-            j.ec.mode = 3;
+            if (downmix) {
+                j.wav.enc_channels = 1;
+                j.ec.mode = 3;
+            }
+            if (up2) {  // band limit of the up-converted signal (mp3enc.cpp:2765-2787)
+                j.enc_rate = 2 * j.wav.rate;
+                const int cutoff = (int)(0.90f * j.wav.rate / 2);
+                int nsb = (64 * cutoff + j.enc_rate / 2) / j.enc_rate;
+                if (nsb > 30) nsb = 30;
+                if (j.ec.nsb_limit <= 0) j.ec.nsb_limit = 30;
+                if (j.ec.nsb_limit > nsb) j.ec.nsb_limit = nsb;
+            }
         }
-        j.ec.samprate = j.wav.rate;
+        j.ec.samprate = j.enc_rate;
         hmp3_control eff;
         if (hmp3_effective_control(&j.ec, &eff, nullptr) != HMP3_OK) {
             fprintf(stderr, "\n ENCODER INIT FAIL\n");
@@ -316,7 +369,7 @@ int main(int argc, char **argv) {
         fwrite(out[i].data(), 1, (size_t)nb[i], f);
         if (to_pipe) fflush(f);
         else fclose(f);
-        const double secs = (double)ns[i] / j.wav.rate;
+        const double secs = (double)ns[i] / j.enc_rate;
         fprintf(stderr, "\n %s: %d frames, %lld bytes, %.2f kbps", j.out.c_str(), nf[i], (long long)(nb[i] + tag_bytes),
                 secs > 0 ? 8e-3 * (double)nb[i] / secs : 0.0);
     }

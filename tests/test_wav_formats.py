@@ -305,3 +305,44 @@ def test_gpu_cli_fuzz_against_the_reference_cli(tmp_path):
         for name, want in wants:
             got = np.fromfile(str(tmp_path / (name + "_gpu.mp3")), dtype=np.uint8)
             assert got.size == want.size and np.array_equal(got, want), (name, opts)
+
+
+UP2_CASES = [(1, ["-B24"], dict(bitrate=24), False), (2, [], dict(), False), (2, ["-M3", "-B32"], dict(bitrate=32), True)]
+
+
+@needs_ref
+@pytest.mark.parametrize("sr", [8000, 11025, 12000])
+def test_up_conversion_1_to_2_reproduces_reference_cli_audio(tmp_path, sr):
+    """8 / 11.025 / 12 kHz input: the reference doubles the rate (Csrc case 1: linear interpolation, integer for mono
+    sources) and limits the coded sub-bands (mp3enc.cpp:2700-2714, 2765-2787; srccf.cpp:80-100, 258-276, 472-492)."""
+    for nch, opts, kw, to_mono in UP2_CASES:
+        for kind, n in [("s16", 20000), ("u8", 1152 * 9 + 575), ("s24", 1152 * 9 + 576), ("f32", 577)]:
+            samples = wavutil.make_samples(synth_pcm(81, 3.0, sr, nch)[:n], kind, seed=1)
+            _, whole = ref_cli_file(tmp_path, samples, kind, sr, nch, opts)
+            f = wavutil.to_encoder_float(samples, kind).reshape(-1, nch)
+            y = wavutil.upsample2(f, wavutil.tail_value(kind), to_mono=to_mono)
+            ec = capi.control(samprate=2 * sr, nch=y.shape[1], nsb_limit=wavutil.up2_nsb_limit(sr), **kw)
+            got, _, _ = simmod.encode_clip(ec, y, tail=wavutil.tail_value(kind))
+            head = whole.size - got.size
+            assert head > 0 and np.array_equal(whole[head:], got), (sr, nch, opts, kind, n)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_identity_for_up_converted_input(tmp_path):
+    for sr in (8000, 11025, 12000):
+        for c, (nch, opts, kw, to_mono) in enumerate(UP2_CASES):
+            for kind, n in [("s16", 30000), ("u8", 1152 * 9 + 575), ("s24", 1152 * 9 + 576)]:
+                samples = wavutil.make_samples(synth_pcm(82, 4.0, sr, nch)[:n], kind, seed=2)
+                name = "up_%d_%d_%s" % (sr, c, kind)
+                wav, want = ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name)
+                out = str(tmp_path / (name + "_gpu.mp3"))
+                subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+                got = np.fromfile(out, dtype=np.uint8)
+                assert got.size == want.size and np.array_equal(got, want), name
+    # a rate that would need the general resampler is refused, not mis-encoded
+    samples = wavutil.make_samples(synth_pcm(83, 0.5, 37800, 2), "s16")
+    wav = str(tmp_path / "odd.wav")
+    wavutil.write_wav(wav, samples, "s16", 37800, 2)
+    r = subprocess.run([CLI, wav, str(tmp_path / "odd.mp3")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and not os.path.exists(str(tmp_path / "odd.mp3"))

@@ -67,3 +67,33 @@ def write_wav(path, samples, kind, sr, nch):
 def downmix(f):
     """Csrc::src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468): (float)((L + R) * 0.5), the sum taken in float."""
     return ((f[:, 0] + f[:, 1]).astype(np.float32).astype(np.float64) * 0.5).astype(np.float32).reshape(-1, 1)
+
+
+def upsample2(f, pad, to_mono=False):
+    """Csrc 1:2 up-conversion (hmp3/src/srccf.cpp:80-100 mono, 258-276 stereo, 472-492 stereo -> mono) of float samples
+    f (n, ch); `pad` is the value of the samples after the end.  Returns (2 n + 3, ch') samples: the reference's main
+    loop makes as many calls as an encoder-rate stream of 2 n + 3 samples would (see calls_for in pipeline.cu)."""
+    n, ch = f.shape
+    x = np.concatenate([f, np.full((1, ch), pad, np.float32)]).astype(np.float32)
+    if ch == 1:
+        a = np.trunc(x[:, 0]).astype(np.int64)                   # int a = x[i]
+        y = np.full((2 * n + 3, 1), pad, np.float32)
+        y[0:2 * n:2, 0] = a[:n].astype(np.float32)
+        y[1:2 * n:2, 0] = ((a[:n] + a[1:]) >> 1).astype(np.float32)
+        return y
+    if to_mono:
+        s = (x[:, 0] + x[:, 1]).astype(np.float32)
+        y = np.full((2 * n + 3, 1), pad, np.float32)
+        y[0:2 * n:2, 0] = (s[:n].astype(np.float64) * 0.5).astype(np.float32)
+        y[1:2 * n:2, 0] = ((s[:n] + s[1:]).astype(np.float32).astype(np.float64) * 0.25).astype(np.float32)
+        return y
+    y = np.full((2 * n + 3, 2), pad, np.float32)
+    y[0:2 * n:2] = x[:n]
+    y[1:2 * n:2] = ((x[:n] + x[1:]).astype(np.float32).astype(np.float64) * 0.5).astype(np.float32)
+    return y
+
+
+def up2_nsb_limit(source_rate):
+    """Sub-band limit CMp3Enc::MP3_audio_encode_init sets for an up-converted source (mp3enc.cpp:2765-2787)."""
+    cutoff = int(np.float32(0.90) * np.float32(source_rate) / np.float32(2))
+    return min(30, (64 * cutoff + source_rate) // (2 * source_rate))
