@@ -47,6 +47,7 @@ struct ChunkBufs {
     PrepGranule *prep; // [n][NG]  state-free part of the rate-loop prologue (long blocks)
     PackGc *pack;    // [n][NG][2]  granule-channel records for the packing pass
     int *fr0, *fr1;  // [n] frames recorded by each stream before / after this chunk's serial stage
+    int *fd1;        // [n] frames complete (main-data slot filled) after this chunk's serial stage
     int NG;
 };
 
@@ -88,6 +89,11 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
                  long long *cycles = nullptr);
 // packing pass of the frames the serial stage recorded in this chunk; `flags[s]` is set if a frame's written
 // bits ever differ from the accounted ones
+// Incremental output (host entry with pinned buffers): after the packing pass of a chunk, the frames that became
+// complete in it are assembled into the stream's fixed output region and the byte count reached is published.
+void launch_assemble_inc(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, int *done_lo,
+                         const unsigned char *main_buf, const FrameRec *frames, unsigned char *out, long long *bytes_done,
+                         int n, cudaStream_t stream);
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
                  FrameRec *frames, int *flags, int K0, int n, cudaStream_t stream);
 // per-stream totals, compact output offsets (out_off[n] = total) and frame assembly

@@ -50,6 +50,13 @@ void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so
     k_pack<<<blocks_for((long long)n * cb.NG * 32, 32 * kPackWarpsPerBlock), 32 * kPackWarpsPerBlock, 0, stream>>>(
         tabs, st, so, cb, main_buf, frames, flags, K0, n);
 }
+void launch_assemble_inc(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, int *done_lo,
+                         const unsigned char *main_buf, const FrameRec *frames, unsigned char *out, long long *bytes_done,
+                         int n, cudaStream_t stream) {
+    k_assemble_inc<<<blocks_for((long long)n * kIncSlots * 32, 256), 256, 0, stream>>>(tabs, st, so, cb, done_lo, main_buf,
+                                                                                       frames, out, n);
+    k_advance_inc<<<blocks_for(n, 128), 128, 0, stream>>>(tabs, st, so, cb, done_lo, frames, bytes_done, n);
+}
 void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *so, const RateState *rs,
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
                    unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble,

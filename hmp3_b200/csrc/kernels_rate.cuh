@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     if (s >= nstreams) return;
     const long long t0 = clock64();
     const StreamDev sd = st[s];
-    if (HMP3_LANE == 0) cb.fr0[s] = cb.fr1[s] = rs[s].frames;  // nothing recorded in this chunk unless the loop below runs
+    if (HMP3_LANE == 0) {  // nothing recorded in this chunk unless the loop below runs
+        cb.fr0[s] = cb.fr1[s] = rs[s].frames;
+        cb.fd1[s] = rs[s].frames_done;
+    }
     HMP3_SYNC();
     if (K0 >= sd.ngran) return;
     const StreamOut o = so[s];
@@ -39,6 +42,7 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     HMP3_SYNC();
     if (HMP3_LANE == 0) {
         cb.fr1[s] = rs[s].frames;
+        cb.fd1[s] = rs[s].frames_done;
         if (cycles) cycles[s] = clock64() - t0;  // load-balance diagnostics (hmp3_debug_rate_cycles)
     }
 }
@@ -96,6 +100,44 @@ __global__ void __launch_bounds__(256) k_assemble(const EncTables *tabs, const S
     const unsigned char *src = main_buf + so[s].main_off + fr->main_start;
     dst += 4 + side;
     for (int k = lane; k < fr->mf_bytes; k += 32) dst[k] = src[k];
+}
+
+// ---- K7b: incremental assembly.  Frames [done_lo[s], fd1[s]) of every stream -> the stream's fixed output region
+// (StreamDev::out_off); one warp per (stream, slot), slots stride over the new frames.
+constexpr int kIncSlots = 64;
+__global__ void __launch_bounds__(256) k_assemble_inc(const EncTables *tabs, const StreamDev *st, const StreamOut *so,
+                                                      ChunkBufs cb, const int *done_lo, const unsigned char *main_buf,
+                                                      const FrameRec *frames, unsigned char *out, int nstreams) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int s = (int)(wid / kIncSlots), j = (int)(wid % kIncSlots);
+    if (s >= nstreams) return;
+    const int hi = cb.fd1[s];
+    const StreamDev sd = st[s];
+    const int side = tabs[sd.cfg].cfg.side_bytes;
+    for (int f = done_lo[s] + j; f < hi; f += kIncSlots) {
+        const FrameRec *fr = frames + so[s].frames_off + f;
+        if ((long long)fr->out_off + 4 + side + fr->mf_bytes > sd.out_cap) continue;  // never past the region
+        unsigned char *dst = out + sd.out_off + fr->out_off;
+        if (lane < 4) dst[lane] = fr->head[lane];
+        if (lane < side) dst[4 + lane] = fr->side[lane];
+        const unsigned char *src = main_buf + so[s].main_off + fr->main_start;
+        dst += 4 + side;
+        for (int k = lane; k < fr->mf_bytes; k += 32) dst[k] = src[k];
+    }
+}
+__global__ void k_advance_inc(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, int *done_lo,
+                              const FrameRec *frames, long long *bytes_done, int nstreams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams) return;
+    const int hi = cb.fd1[s];
+    long long nb = 0;
+    if (hi > 0) {
+        const FrameRec *f = frames + so[s].frames_off + (hi - 1);
+        nb = (long long)f->out_off + frame_bytes(tabs + st[s].cfg, f);
+    }
+    bytes_done[s] = nb;
+    done_lo[s] = hi;
 }
 
 }  // namespace hmp3

@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <array>
+#include <chrono>
 #include <vector>
 
 #include "../../include/hmp3_b200.h"
@@ -94,6 +95,20 @@ struct hmp3_batch {
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
     int *d_flags = nullptr;             // [n] packing/accounting mismatch flags (must stay 0)
+    // incremental output of the host entry (pinned out buffers): frames are assembled chunk by chunk into fixed
+    // per-stream regions and copied out (DMA) while later chunks are still being encoded
+    bool direct = false;
+    std::vector<void *> cp_dst, cp_src;  // staging copies of one chunk (batched submission)
+    std::vector<size_t> cp_len;
+    bool no_batch_copy = false;
+    unsigned char *d_out_inc = nullptr; // [out_cap] fixed regions: stream s at StreamDev::out_off
+    int *d_done_lo = nullptr;           // [n] frames assembled so far
+    long long *d_bytes_done = nullptr;  // [n] output bytes complete after the chunk
+    long long *h_prog = nullptr;        // pinned [chunks][n] copies of d_bytes_done
+    int h_prog_chunks = 0;
+    std::vector<cudaEvent_t> ev_o;      // per chunk: its h_prog row has landed
+    cudaStream_t stream_o = nullptr;    // D2H copies of finished output (copy engine)
+    int chunks_run = 0;
     std::vector<std::array<float, 3>> timeline;
     long long *d_cycles = nullptr;      // [kCycleLaunches][n] serial-stage clocks per launch (diagnostics, on request)
     int cycle_launches = 0;
@@ -142,12 +157,19 @@ struct hmp3_batch {
             cudaFree(cb2[k].pack);
             cudaFree(cb2[k].fr0);
             cudaFree(cb2[k].fr1);
+            cudaFree(cb2[k].fd1);
             if (ev_a[k]) cudaEventDestroy(ev_a[k]);
             if (ev_r[k]) cudaEventDestroy(ev_r[k]);
             if (ev_p[k]) cudaEventDestroy(ev_p[k]);
         }
         if (ev_start) cudaEventDestroy(ev_start);
         cudaFree(d_flags);
+        cudaFree(d_out_inc);
+        cudaFree(d_done_lo);
+        cudaFree(d_bytes_done);
+        if (h_prog) cudaFreeHost(h_prog);
+        for (auto e : ev_o) cudaEventDestroy(e);
+        if (stream_o) cudaStreamDestroy(stream_o);
         cudaFree(d_cycles);
         cudaFree(d_msmem);
         cudaFree(d_pcmf);
@@ -263,7 +285,9 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
             so.frames_cap = nfr;
             main_off += ((long long)nfr * max_main_frame_bytes(C) + 4096 + 15) & ~15LL;
             frames_off += nfr;
-            out_cap += (long long)nfr * (4 + C.side_bytes + max_main_frame_bytes(C));
+            sd.out_off = out_cap;
+            sd.out_cap = (long long)nfr * (4 + C.side_bytes + max_main_frame_bytes(C));
+            out_cap += (sd.out_cap + 15) & ~15LL;
             max_frames = std::max(max_frames, nfr);
         }
     }
@@ -326,6 +350,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
             CK(cudaMalloc(&cb.pack, sizeof_pack_gc() * n * NG * 2));
             CK(cudaMalloc(&cb.fr0, sizeof(int) * n));
             CK(cudaMalloc(&cb.fr1, sizeof(int) * n));
+            CK(cudaMalloc(&cb.fd1, sizeof(int) * n));
         }
         CK(cudaEventCreateWithFlags(&b->ev_a[k], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&b->ev_r[k], cudaEventDisableTiming));
@@ -432,13 +457,18 @@ int run_plan(hmp3_batch *b) {
     //   analysis(c) -> ev_a -> serial(c) -> ev_r -> pack(c) -> ev_p ;  with S buffer sets analysis(c+S) waits ev_r(c) and
     //   serial(c+S) waits ev_p(c): S = 3 lets Phase A finish a whole chunk ahead, so the serial stage never waits for it
     CK(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * n, b->stream));
+    if (b->direct) CK(cudaMemsetAsync(b->d_done_lo, 0, sizeof(int) * n, b->stream));
     CK(cudaEventRecord(b->ev_start, b->stream));
     CK(cudaStreamWaitEvent(b->stream_a, b->ev_start, 0));
     CK(cudaStreamWaitEvent(b->stream_p, b->ev_start, 0));
     // the first chunk is short so that the serial stage starts early (its Phase A cannot overlap anything); a short
     // chunk is just a narrower view of the same buffers (every kernel indexes with the view's NG)
     int c = 0;
+    const bool trace = getenv("HMP3_TRACE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     for (int K0 = 0; K0 < b->max_gran; c++) {
+        const double t_c0 = trace ? ms_now() : 0.0;
         const int nb = b->nbuf;
         const int k = c % nb;
         const int ng_c = (c == 0 && b->NG > 32) ? 32 : b->NG;
@@ -457,6 +487,11 @@ int run_plan(hmp3_batch *b) {
             }
             if (c == 0) CK(cudaStreamWaitEvent(b->stream_c, b->ev_start, 0));
             const long long lo = c == 0 ? 0 : 576LL * K0_this, hi = 576LL * (K0_this + ng_c);
+            // one batched submission for the whole chunk (cudaMemcpyBatchAsync, CUDA 12.8+): thousands of separate
+            // cudaMemcpyAsync calls cost ~15 us of host time each, which delays the first chunks
+            b->cp_dst.clear();
+            b->cp_src.clear();
+            b->cp_len.clear();
             for (int i = 0; i < n; i++) {
                 const StreamDev &sd = b->st_h[i];
                 if (b->status[i] != HMP3_OK) continue;
@@ -464,11 +499,31 @@ int run_plan(hmp3_batch *b) {
                 if (e <= a) continue;
                 size_t el;
                 char *dst = pcm_dev_ptr(b, i, a, &el);
-                CK(cudaMemcpyAsync(dst, (const char *)b->h_src[i] + el * a * sd.nch, el * (e - a) * sd.nch,
-                                   cudaMemcpyHostToDevice, b->stream_c));
+                b->cp_dst.push_back(dst);
+                b->cp_src.push_back((void *)((const char *)b->h_src[i] + el * a * sd.nch));
+                b->cp_len.push_back(el * (e - a) * sd.nch);
             }
+            bool batched = false;
+            if (!b->cp_len.empty() && !b->no_batch_copy) {
+                cudaMemcpyAttributes at;
+                memset(&at, 0, sizeof(at));
+                at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+                size_t idx0 = 0, fail = 0;
+                if (cudaMemcpyBatchAsync(b->cp_dst.data(), b->cp_src.data(), b->cp_len.data(), b->cp_len.size(), &at, &idx0,
+                                         1, &fail, b->stream_c) == cudaSuccess)
+                    batched = true;
+                else {
+                    cudaGetLastError();
+                    b->no_batch_copy = true;  // older driver: fall back for good
+                }
+            }
+            if (!batched)
+                for (size_t q = 0; q < b->cp_len.size(); q++)
+                    CK(cudaMemcpyAsync(b->cp_dst[q], b->cp_src[q], b->cp_len[q], cudaMemcpyHostToDevice, b->stream_c));
             CK(cudaEventRecord(b->ev_c[k], b->stream_c));
             CK(cudaStreamWaitEvent(b->stream_a, b->ev_c[k], 0));
+            if (trace) fprintf(stderr, "[run_plan] chunk %2d (%3d granules): copies enqueued %8.2f -> %8.2f ms\n", c, ng_c, t_c0, ms_now());
         }
         r = launch_analysis(b, K0_this, k, b->stream_a, true, ng_c);
         if (r != HMP3_OK) return r;
@@ -485,9 +540,18 @@ int run_plan(hmp3_batch *b) {
         mark(b, PH_PACK, b->stream_p);
         launch_pack(b->d_tabs, b->d_st, b->d_so, view, b->d_main, b->d_frames, b->d_flags, K0_this, n, b->stream_p);
         mark(b, -1, b->stream_p);
+        if (b->direct && c < b->h_prog_chunks) {
+            launch_assemble_inc(b->d_tabs, b->d_st, b->d_so, view, b->d_done_lo, b->d_main, b->d_frames, b->d_out_inc,
+                                b->d_bytes_done, n, b->stream_p);
+            CK(cudaMemcpyAsync(b->h_prog + (size_t)c * n, b->d_bytes_done, sizeof(long long) * n, cudaMemcpyDeviceToHost,
+                               b->stream_p));
+            CK(cudaEventRecord(b->ev_o[c], b->stream_p));
+            b->launches += 2;
+        }
         CK(cudaEventRecord(b->ev_p[k], b->stream_p));
         b->launches += 2;
     }
+    b->chunks_run = c;
     for (int k = 0; k < b->nbuf && k < c; k++) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
     cudaEvent_t ev_asm = nullptr;
     if (b->timing) {
@@ -809,6 +873,13 @@ bool is_pinned(const void *p) {
 int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
     CK(cudaSetDevice(b->device));
+    const bool trace = getenv("HMP3_TRACE_HOST") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[encode_host] %-28s %8.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     // Pinned input: each chunk's samples are copied (DMA) right before that chunk's Phase A, overlapping the serial
     // stage of the previous chunk.  Pageable input: one queued copy per stream before the first kernel.
     bool pinned_in = true, pinned_out = true;
@@ -824,14 +895,85 @@ int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const
             if (r != HMP3_OK) return r;
         }
     }
+    stamp("pinned checks / uploads");
+    // Pinned output with room for every stream's bound: finished frames leave the device chunk by chunk
+    bool direct = pinned_out && !getenv("HMP3_NO_INCREMENTAL_OUT");
+    for (int i = 0; i < b->n && direct; i++)
+        if (b->status[i] == HMP3_OK && out_cap[i] < b->st_h[i].out_cap) direct = false;
+    std::vector<long long> copied;
+    if (direct) {
+        const int chunks = (b->max_gran + 31) / 32 + 2;  // upper bound of the chunk count
+        if (!b->d_out_inc) {
+            CK(cudaMalloc(&b->d_out_inc, std::max<long long>(b->out_cap, 16)));
+            CK(cudaMalloc(&b->d_done_lo, sizeof(int) * b->n));
+            CK(cudaMalloc(&b->d_bytes_done, sizeof(long long) * b->n));
+            CK(cudaStreamCreate(&b->stream_o));
+        }
+        if (b->h_prog_chunks < chunks) {
+            if (b->h_prog) cudaFreeHost(b->h_prog);
+            b->h_prog = nullptr;
+            b->h_prog_chunks = 0;
+            CK(cudaMallocHost(&b->h_prog, sizeof(long long) * (size_t)chunks * b->n));
+            b->h_prog_chunks = chunks;
+            while ((int)b->ev_o.size() < chunks) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                b->ev_o.push_back(e);
+            }
+        }
+        copied.assign(b->n, 0);
+    }
+    stamp("output set-up");
+    b->direct = direct;
     b->staged = pinned_in;
     b->h_src = pcm;
     int r = run_plan(b);
+    stamp("run enqueued");
     b->staged = false;
     b->h_src = nullptr;
+    b->direct = false;
     if (r != HMP3_OK) return r;
+    if (direct) {  // follow the run: as each chunk's progress row lands, queue the copies of the bytes it completed
+        const int rows = std::min(b->chunks_run, b->h_prog_chunks);
+        for (int c = 0; c < rows; c++) {
+            CK(cudaEventSynchronize(b->ev_o[c]));
+            const long long *row = b->h_prog + (size_t)c * b->n;
+            b->cp_dst.clear();
+            b->cp_src.clear();
+            b->cp_len.clear();
+            for (int i = 0; i < b->n; i++) {
+                if (b->status[i] != HMP3_OK) continue;
+                const long long hi = std::min<long long>(row[i], out_cap[i]);
+                if (hi > copied[i]) {
+                    b->cp_dst.push_back(out[i] + copied[i]);
+                    b->cp_src.push_back(b->d_out_inc + b->st_h[i].out_off + copied[i]);
+                    b->cp_len.push_back((size_t)(hi - copied[i]));
+                    copied[i] = hi;
+                }
+            }
+            bool batched = false;
+            if (!b->cp_len.empty() && !b->no_batch_copy) {
+                cudaMemcpyAttributes at;
+                memset(&at, 0, sizeof(at));
+                at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+                at.flags = cudaMemcpyFlagPreferOverlapWithCompute;
+                size_t idx0 = 0, fail = 0;
+                if (cudaMemcpyBatchAsync(b->cp_dst.data(), b->cp_src.data(), b->cp_len.data(), b->cp_len.size(), &at, &idx0,
+                                         1, &fail, b->stream_o) == cudaSuccess)
+                    batched = true;
+                else {
+                    cudaGetLastError();
+                    b->no_batch_copy = true;
+                }
+            }
+            if (!batched)
+                for (size_t q = 0; q < b->cp_len.size(); q++)
+                    CK(cudaMemcpyAsync(b->cp_dst[q], b->cp_src[q], b->cp_len[q], cudaMemcpyDeviceToHost, b->stream_o));
+        }
+    }
     r = sync_plan(b);
     if (r != HMP3_OK) return r;
+    stamp("run finished");
     const long long total = b->out_off_h[b->n];
     if (!pinned_out) {  // one bulk D2H into pinned staging, then scatter to the callers' pageable buffers
         if (b->h_stage_bytes < total) {
@@ -854,8 +996,12 @@ int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const
             nb = 0;
         }
         if (nb) {
-            if (pinned_out)  // straight into the caller's pinned buffer
-                CK(cudaMemcpyAsync(out[i], b->d_out + b->out_off_h[i], nb, cudaMemcpyDeviceToHost, b->stream));
+            if (pinned_out) {  // straight into the caller's pinned buffer (whatever the incremental copies left)
+                const long long have = direct ? std::min(copied[i], nb) : 0;
+                if (nb > have)
+                    CK(cudaMemcpyAsync(out[i] + have, b->d_out + b->out_off_h[i] + have, nb - have, cudaMemcpyDeviceToHost,
+                                       b->stream));
+            }
             else memcpy(out[i], b->h_stage + b->out_off_h[i], nb);
         }
         if (out_bytes) out_bytes[i] = nb;
@@ -863,6 +1009,8 @@ int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const
         if (status) status[i] = st;
     }
     if (pinned_out) CK(cudaStreamSynchronize(b->stream));
+    if (direct) CK(cudaStreamSynchronize(b->stream_o));
+    stamp("results / residual copies");
     return HMP3_OK;
 }
 
