@@ -117,7 +117,10 @@ class Batch:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown: module globals may already be gone
+            pass
 
     def _ck(self, r, what):
         if r != 0:
@@ -245,7 +248,10 @@ class Encoder:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown
+            pass
 
     def init_mp3(self, ec, source_bits=16, source_is_float=0, mpeg_select=0, mono_convert=0):
         return lib().hmp3_MP3_audio_encode_init(self.h, vp(ec), source_bits, source_is_float, mpeg_select, mono_convert)
