@@ -194,8 +194,29 @@ def workload_config(args):
 # ------------------------------------------------------------------------------------------------
 # the GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Host feeder placement (one process per GPU): run on the cores next to the GPU so that the pinned PCM / output
+    buffers are allocated on its NUMA node and the staging copies do not cross sockets.  Returns the core count."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_gpu(args, rank, local_rank, world):
     import ctypes as C
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     import torch
     from hmp3_b200 import capi
 
