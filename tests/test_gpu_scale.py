@@ -79,3 +79,32 @@ def test_control_sweep_in_one_mixed_batch():
     outs = capi.encode_batch(ctl, pcms)
     bad = [i for i, (o, r) in enumerate(zip(outs, refs)) if o.size != r.size or not np.array_equal(o, r)]
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_long_streams_many_chunks():
+    """Five-minute streams (about 90 serial-stage launches) next to a short one: CBR and VBR, pageable and pinned
+    host buffers, against the oracle."""
+    import torch
+    specs = [(44100, 2, dict(bitrate=64), 300.0), (48000, 2, dict(vbr_mnr=100, hf=2, freq_limit=19000), 240.0),
+             (22050, 1, dict(bitrate=32), 300.0), (44100, 2, dict(), 1.0)]
+    ctl, pcms, refs = [], [], []
+    for k, (sr, nch, kw, secs) in enumerate(specs):
+        unit = synth_pcm(4000 + k, min(secs, 20.0), sr, nch)
+        reps = int(np.ceil(secs / 20.0))
+        pcm = np.concatenate([np.roll(unit, 911 * r, axis=0) for r in range(reps)])[:int(secs * sr)]
+        ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+        pcms.append(np.ascontiguousarray(pcm))
+        refs.append(refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm)[0])
+    outs = capi.encode_batch(ctl, pcms)
+    for k, (o, r) in enumerate(zip(outs, refs)):
+        assert o.size == r.size and np.array_equal(o, r), "stream %d differs (pageable)" % k
+    pins = [torch.from_numpy(p).pin_memory() for p in pcms]
+    b = capi.Batch(ctl, [p.shape[0] for p in pcms])
+    obuf = [torch.zeros(int(c), dtype=torch.uint8).pin_memory() for c in b.bound]
+    nb, nf, st = b.encode_host_ptrs(np.array([t.data_ptr() for t in pins], dtype=np.uint64),
+                                    np.array([o.data_ptr() for o in obuf], dtype=np.uint64), b.bound)
+    assert (st == 0).all()
+    for k, r in enumerate(refs):
+        assert nb[k] == r.size and np.array_equal(obuf[k].numpy()[:nb[k]], r), "stream %d differs (pinned)" % k
+    b.close()
