@@ -45,7 +45,8 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
     // the kernel needs 8 x 10 KB of shared memory per SM; left to itself the driver configures 135 KB, at the expense
     // of L1.  Ask for the smallest carve-out that still holds eight blocks (40 % -> the 100 KB configuration: step
     // 1.63 s -> 1.55 s; 20 % costs occupancy, >= 50 % is the driver's choice again; giving the Phase A kernels the same
-    // preference starves them of shared memory and is slower).
+    // preference starves them of shared memory and is slower; halving the step search's scratch to reach the 64 KB
+    // configuration gains nothing net: the two half passes cost what the extra L1 saves).
     static bool configured = false;
     if (!configured) {
         configured = true;
