@@ -44,9 +44,9 @@ METRIC = "encoded audio sec/sec (x realtime), 44.1k stereo CBR128"
 # packing pass out (1396 B)
 K6_BYTES_PER_GC = 2304 + 2816 + 288 + 1396
 # DRAM traffic of the same kernel per granule-channel, from the committed `ncu --set full` capture
-# (profiles/r1f_rate_ncu_details.txt: dram read 11.871 GB + write 12.052 GB for a launch of 4736 streams x 128
+# (profiles/r1h_rate_ncu_details.txt: dram read 24.749 GB + write 25.116 GB for a launch of 4736 streams x 256
 # granules x 2 channels); per-launch traffic = this x the granule-channels one launch processes
-K6_NCU_DRAM_BYTES_PER_GC = (11.870863e9 + 12.052254e9) / (4736 * 128 * 2)
+K6_NCU_DRAM_BYTES_PER_GC = (24.749032e9 + 25.115575e9) / (4736 * 256 * 2)
 
 
 def base_clips():
@@ -317,11 +317,11 @@ def run_gpu(args, rank, local_rank, world):
                 "frac": achieved / hbm_peak,
                 "traffic": args.rate_traffic if args.rate_traffic is not None
                 else K6_NCU_DRAM_BYTES_PER_GC * gc_per_launch,
-                "traffic_source": "ncu --set full capture in profiles/r1f_rate_ncu_details.txt, scaled per granule-channel",
+                "traffic_source": "ncu --set full capture in profiles/r1h_rate_ncu_details.txt, scaled per granule-channel",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "share_of_step": rate_ms / timed_run_ms,
                 "share_note": "wall share of the step during which this kernel is running (Phase A and the packing "
-                              "pass run concurrently on other streams; serialised share in profiles/r1g_launch_summary.txt: 77 %)",
+                              "pass run concurrently on other streams; serialised share in profiles/r1h_launch_summary.txt: 77 %)",
                 "note": "latency/instruction-fetch bound serial code, not a bandwidth kernel: see DESIGN.md"}
         line = {
             "metric": METRIC, "value": audio_s_per_step * args.steps / t_res, "unit": "x realtime",
