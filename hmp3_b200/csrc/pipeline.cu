@@ -1069,6 +1069,9 @@ struct hmp3_encoder {
     bool float_in = false;      // the plan takes float PCM (every input format except 16-bit integer)
     int src_bits = 16, src_float = 0;
     int src_chan = 0;           // channels of the caller's PCM (2 with nch == 1: down-mix to mono, Csrc kfilter 2)
+    bool up2 = false;           // 1:2 up-conversion (Csrc case 1)
+    int frames_in = 1152;       // sample frames of the caller's PCM consumed per call
+    std::vector<float> conv;    // the call's samples after sr_convert's type conversion
     int capacity_seconds = 1200;
     std::vector<float> stage;
     ~hmp3_encoder() { delete b; }
@@ -1180,27 +1183,44 @@ int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds) {
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert) {
     if (!e || !ec) return 0;
-    // in scope: 8/16/24/32-bit integer or 32-bit float PCM at a native MPEG rate; no down-mix, no resampling
+    // in scope: 8/16/24/32-bit integer or 32-bit float PCM at a native MPEG rate, or at half of an MPEG-2 rate (1:2
+    // up-conversion, Csrc case 1); the general resampler (cases 2-4) is not built
     const int rates[6] = {16000, 22050, 24000, 32000, 44100, 48000};
     bool native = false;
     for (int r : rates) native |= (ec->samprate == r);
+    const bool up2 = !native && (ec->samprate == 8000 || ec->samprate == 11025 || ec->samprate == 12000) &&
+                     (mpeg_select == 0 || mpeg_select == 2 || mpeg_select == 2 * ec->samprate);
     const bool fmt_ok = source_is_float ? (source_bits == 32)
                                         : (source_bits == 8 || source_bits == 16 || source_bits == 24 || source_bits == 32);
-    if (!fmt_ok || !native || (mpeg_select > 2 && mpeg_select != ec->samprate) ||
-        (mpeg_select == 1 && ec->samprate < 32000) || (mpeg_select == 2 && ec->samprate > 24000)) {
-        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate without rate conversion is in scope");
+    if (!fmt_ok || (!native && !up2) ||
+        (native && ((mpeg_select > 2 && mpeg_select != ec->samprate) || (mpeg_select == 1 && ec->samprate < 32000) ||
+                    (mpeg_select == 2 && ec->samprate > 24000)))) {
+        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate (or half of an MPEG-2 rate) is in scope");
         return 0;
     }
     // channels as CMp3Enc::MP3_audio_encode_init derives them (mp3enc.cpp:2689-2696): the source has two unless the
-    // mode is mono; mono_convert encodes a two-channel source as mono (Csrc kfilter 2: (L + R) * 0.5)
+    // mode is mono; mono_convert encodes a two-channel source as mono (Csrc kfilter 2)
     hmp3_control ec2 = *ec;
     e->src_chan = ec->mode == 3 ? 1 : 2;
     const bool downmix = mono_convert && e->src_chan == 2;
     if (downmix) ec2.mode = 3;
+    e->up2 = up2;
+    if (up2) {  // encode rate and band limit of the up-converted signal (mp3enc.cpp:2700-2714, 2765-2787)
+        ec2.samprate = 2 * ec->samprate;
+        const int cutoff = (int)(0.90f * ec->samprate / 2);
+        int nsb = (64 * cutoff + ec2.samprate / 2) / ec2.samprate;
+        if (nsb > 30) nsb = 30;
+        if (ec2.nsb_limit <= 0) ec2.nsb_limit = 30;
+        if (ec2.nsb_limit > nsb) ec2.nsb_limit = nsb;
+    }
     e->src_bits = source_bits;
     e->src_float = source_is_float;
-    const int bytes_in = encoder_init(e, &ec2, downmix || !(source_bits == 16 && !source_is_float));
-    return bytes_in ? (bytes_in / 4 / e->nch) * e->src_chan * (source_bits / 8) : 0;  // bytes the caller supplies per call
+    const int bytes_in = encoder_init(e, &ec2, up2 || downmix || !(source_bits == 16 && !source_is_float));
+    if (!bytes_in) return 0;
+    // what Csrc::sr_convert_init returns: the sample frames that must be buffered for a call (srcc.cpp:185-187, 769-773):
+    // the 1152 (576 when up-converting) it consumes plus one
+    e->frames_in = up2 ? 576 : 1152;
+    return (e->frames_in + 1) * e->src_chan * (source_bits / 8);
 }
 hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
     hmp3_in_out io = {0, 0};
@@ -1208,12 +1228,17 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
         set_err("encoder not initialised");
         return io;
     }
-    if (!e->float_in) return encoder_step(e, pcm, bs_out);
-    // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale
-    const int n = 1152 * e->src_chan;
+    if (!e->float_in) {
+        io = encoder_step(e, pcm, bs_out);
+        return io;
+    }
+    // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale.
+    // Up-conversion looks one sample frame past the 576 it consumes (the caller buffers frames_in + 1, see init).
+    const int nfr = e->frames_in + (e->up2 ? 1 : 0);
+    const int n = nfr * e->src_chan;
     const bool downmix = e->src_chan == 2 && e->nch == 1;
-    if ((int)e->stage.size() < n) e->stage.resize(n);
-    float *d = e->stage.data();
+    if ((int)e->conv.size() < n) e->conv.resize(n);
+    float *d = e->conv.data();
     if (e->src_float) {
         const float *s = (const float *)pcm;
         for (int i = 0; i < n; i++) d[i] = (float)(s[i]) * 32768.0f;
@@ -1232,10 +1257,34 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
     } else {  // 8-bit unsigned
         for (int i = 0; i < n; i++) d[i] = (((float)pcm[i]) - 128.0f) * (256.0f);
     }
-    if (downmix)  // src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468)
-        for (int i = 0; i < 1152; i++) d[i] = (float)((d[2 * i] + d[2 * i + 1]) * 0.5);
-    io = encoder_step(e, d, bs_out);
-    if (io.in_bytes) io.in_bytes = n * (e->src_bits / 8);
+    if ((int)e->stage.size() < 1152 * e->nch) e->stage.resize((size_t)1152 * e->nch);
+    float *y = e->stage.data();
+    if (!e->up2) {
+        if (downmix)  // src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468)
+            for (int i = 0; i < 1152; i++) y[i] = (float)((d[2 * i] + d[2 * i + 1]) * 0.5);
+        else
+            for (int i = 0; i < n; i++) y[i] = d[i];
+    } else if (e->src_chan == 1) {  // src_filter_mono_case1 (srccf.cpp:80-100): integer samples, truncated
+        for (int i = 0; i < 576; i++) {
+            const int a = (int)d[i], b2 = (int)d[i + 1];
+            y[2 * i] = (float)a;
+            y[2 * i + 1] = (float)((a + b2) >> 1);
+        }
+    } else if (downmix) {  // src_filter_to_mono_case1 (srccf.cpp:472-492)
+        for (int i = 0; i < 576; i++) {
+            const float a = d[2 * i] + d[2 * i + 1], b2 = d[2 * i + 2] + d[2 * i + 3];
+            y[2 * i] = (float)(a * 0.5);
+            y[2 * i + 1] = (float)((a + b2) * 0.25);
+        }
+    } else {  // src_filter_dual_case1 (srccf.cpp:258-276)
+        for (int i = 0; i < 576; i++)
+            for (int c = 0; c < 2; c++) {
+                y[2 * (2 * i) + c] = d[2 * i + c];
+                y[2 * (2 * i + 1) + c] = (float)((d[2 * i + c] + d[2 * i + 2 + c]) * 0.5);
+            }
+    }
+    io = encoder_step(e, y, bs_out);
+    if (io.in_bytes) io.in_bytes = e->frames_in * e->src_chan * (e->src_bits / 8);
     return io;
 }
 int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec) {

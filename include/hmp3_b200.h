@@ -173,9 +173,12 @@ void hmp3_encoder_delete(hmp3_encoder *e);
 /* A handle reserves device buffers for a bounded stream length at init (default 1200 s); call before init. */
 int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds);
 
-/* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns the bytes the caller must
- * supply per call, 0 = failure.  8/16/24/32-bit integer and 32-bit float PCM at a native MPEG rate are in
- * scope (no sample-rate or channel conversion -- SURVEY.md section 8f). */
+/* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns, like the reference, the bytes the
+ * caller must have buffered for a call (what Csrc::sr_convert_init returns: 1153 sample frames, 577 when the source
+ * is up-converted; a call consumes 1152 / 576 of them, reported in hmp3_in_out.in_bytes), 0 = failure.
+ * In scope: 8/16/24/32-bit integer and 32-bit float PCM at a native MPEG rate or at 8 / 11.025 / 12 kHz (1:2
+ * up-conversion, Csrc case 1); mono_convert down-mixes a two-channel source.  Other rates would need the general
+ * resampler (Csrc cases 2-4), which is not built: init fails. */
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert);
 /* CMp3Enc::MP3_audio_encode (hmp3/src/mp3enc.cpp:2812-2828). */

@@ -71,8 +71,10 @@ def test_encoder_handle_matches_reference_call_by_call(name, seed, sr, nch, kw):
     pcm = synth_pcm(seed + 7, 4.0, sr, nch)
     ref_bytes, tr = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, max_trace_calls=4000)
     enc = capi.Encoder(capacity_seconds=30)
-    per_call = enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw))
-    assert per_call == 2304 * nch
+    # init returns what Csrc::sr_convert_init does: the bytes that must be buffered for a call = 1153 sample frames;
+    # a call consumes 1152
+    assert enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw)) == 1153 * 2 * nch
+    per_call = 2304 * nch
     ncalls_real = (pcm.shape[0] + 3 * 1153 + 1152) // 1152
     padded = np.zeros(((ncalls_real + 40) * 1152, nch), np.int16)
     padded[:pcm.shape[0]] = pcm

@@ -110,7 +110,7 @@ def test_handle_mp3_entry_takes_every_sample_type(kind):
     bps = bits // 8
     enc = capi.Encoder(capacity_seconds=10)
     assert enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw), source_bits=bits,
-                        source_is_float=1 if kind == "f32" else 0) == 1152 * nch * bps
+                        source_is_float=1 if kind == "f32" else 0) == 1153 * nch * bps
     raw = np.frombuffer(wavutil.raw_bytes(samples, kind), dtype=np.uint8)
     zero = np.zeros(1152 * nch * bps, np.uint8)
     out = []
@@ -207,7 +207,7 @@ def test_cli_and_handle_mono_downmix(tmp_path):
     # the handle: MP3_audio_encode_init(..., mono_convert = 1) with a two-channel 16-bit source
     samples = wavutil.make_samples(synth_pcm(62, 1.0, sr, 2)[:24 * 1152], "s16")
     enc = capi.Encoder(capacity_seconds=10)
-    assert enc.init_mp3(capi.control(samprate=sr, nch=2, bitrate=64), mono_convert=1) == 1152 * 2 * 2
+    assert enc.init_mp3(capi.control(samprate=sr, nch=2, bitrate=64), mono_convert=1) == 1153 * 2 * 2
     zero = np.zeros((1152, 2), np.int16)
     out = []
     for c in range(24 + 4 + 6):
@@ -346,3 +346,29 @@ def test_cli_identity_for_up_converted_input(tmp_path):
     wavutil.write_wav(wav, samples, "s16", 37800, 2)
     r = subprocess.run([CLI, wav, str(tmp_path / "odd.mp3")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     assert r.returncode != 0 and not os.path.exists(str(tmp_path / "odd.mp3"))
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("nch,to_mono,kw", [(1, False, dict(bitrate=24)), (2, False, dict()), (2, True, dict(bitrate=32))])
+def test_handle_up_conversion(nch, to_mono, kw):
+    """MP3_audio_encode_init with an 11.025 kHz source: 577 sample frames buffered per call, 576 consumed, encoded at
+    22.05 kHz; the same bytes as the (CPU-validated) restatement of the reference's up-conversion gives."""
+    sr, ncalls = 11025, 30
+    samples = wavutil.make_samples(synth_pcm(91, 2.0, sr, nch)[:576 * ncalls], "s16")
+    enc = capi.Encoder(capacity_seconds=10)
+    ec = capi.control(samprate=sr, nch=nch, **kw)
+    assert enc.init_mp3(ec, mono_convert=1 if to_mono else 0) == 577 * nch * 2
+    padded = np.zeros((576 * (ncalls + 12) + 1, nch), np.int16)
+    padded[:samples.shape[0]] = samples
+    out = []
+    for c in range(ncalls + 10):
+        used, b = enc.encode_mp3(padded[576 * c:576 * c + 577])
+        assert used == 576 * nch * 2
+        out.append(b)
+    got = np.concatenate(out)
+    enc.close()
+    y = wavutil.upsample2(samples.astype(np.float32).reshape(-1, nch), 0.0, to_mono=to_mono)
+    want, _, _ = simmod.encode_clip(capi.control(samprate=2 * sr, nch=y.shape[1], nsb_limit=wavutil.up2_nsb_limit(sr), **kw), y)
+    m = min(got.size, want.size)
+    assert m > 0.85 * want.size and np.array_equal(got[:m], want[:m])
