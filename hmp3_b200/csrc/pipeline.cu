@@ -331,7 +331,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const bool prio = !(getenv("HMP3_NO_STREAM_PRIO"));
         CK(cudaStreamCreateWithPriority(&b->stream_a, cudaStreamDefault, prio ? hi : lo));
-        CK(cudaStreamCreateWithPriority(&b->stream_p, cudaStreamDefault, (prio && !getenv("HMP3_PACK_LOW")) ? hi : lo));
+        CK(cudaStreamCreateWithPriority(&b->stream_p, cudaStreamDefault, prio ? hi : lo));
     }
     CK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
     for (int k = 0; k < b->nbuf; k++) {
