@@ -16,12 +16,12 @@
 #define HMP3_FN static inline
 #endif
 
-// Device code of the serial stage runs one stream per GROUP of HMP3_W lanes (two streams share a warp by
-// default): scalar control flow is executed uniformly by the lanes of a group and the per-line / per-band loops
-// are split over them (HMP3_COOP sections).  Two streams per warp is an instruction-FETCH optimisation: the rate
-// loop is ~190 KB of code walked once per granule, its speed is set by instruction-cache misses, and two groups
-// running the same functions in near lock-step share those misses (divergence between the groups is handled by
-// the hardware; every warp-level primitive below names only the lanes of its own group).
+// Device code of the serial stage runs one stream per GROUP of HMP3_W lanes: scalar control flow is executed
+// uniformly by the lanes of a group and the per-line / per-band loops are split over them (HMP3_COOP sections).
+// The product is built with HMP3_W = 32 (a warp per stream).  HMP3_W = 16 puts two streams in a warp so that they can
+// share instruction fetches while they run the same code (the serial stage is instruction-fetch bound, DESIGN.md
+// 7.2); they diverge too often for that to pay below ~9500 streams per GPU, so it is a build option only
+// (HMP3_RATE_W=16).  Every warp-level primitive below names only the lanes of its own group.
 // The host build (test-only simulator) runs the plain sequential loops.
 #if defined(__CUDA_ARCH__)
 #define HMP3_COOP 1
