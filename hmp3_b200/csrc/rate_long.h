@@ -315,12 +315,14 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
     // per-line squared errors of one channel at a time, in shared memory (one 576-float row per stream of the block)
     __shared__ float s_dd[kRateWarpsPerBlock * (32 / HMP3_W)][576];
     float *dd = s_dd[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
-    for (;;) {
-        unsigned am[2] = {0u, 0u};  // bit b = band b of the channel is still searching
-        for (int it = 0; it < NI; it++) am[it / NS] |= gballot(mode[it] != 0) << (HMP3_W * (it % NS));
-        if ((am[0] | am[1]) == 0) break;
-        for (int c = 0; c < L->nchan; c++) {
-            if (am[c] == 0) continue;
+    // channel-major: one channel's bands are searched to the end before the other channel is touched, so that the
+    // rounds of a search work on one channel's spectra (4.6 KB) instead of both (the bands are independent: the order
+    // of the evaluations does not change any result)
+    for (int c = 0; c < L->nchan; c++) {
+        for (;;) {
+            unsigned am[2] = {0u, 0u};  // bit b = band b of the channel is still searching
+            for (int j = 0; j < NS; j++) am[c] |= gballot(mode[c * NS + j] != 0) << (HMP3_W * j);
+            if (am[c] == 0) break;
             const int nl = T->startBand_l[T->cfg.nsf[c]];
             const float *y34 = L->x34[c];
             const float *y = xr + 576 * c;
