@@ -293,113 +293,105 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
 // its little state machine exactly as seek_finer / seek_coarser do.  Rounds end when no band is searching.
 HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) {  // bitallo3.cpp:1242-1288
     constexpr int NS = (22 + HMP3_W - 1) / HMP3_W;  // band slots per lane: band = lane + HMP3_W * slot
-    constexpr int NI = 2 * NS;                      // items per lane: item = channel * NS + slot
     const int lane = HMP3_LANE;
-    int mode[NI], s_try[NI], target[NI], best_abs[NI], best_noise[NI], best_s[NI], iter[NI], niter[NI];
-    HMP3_SYNC();
-    for (int it = 0; it < NI; it++) {
-        const int c = it / NS, bnd = lane + HMP3_W * (it % NS);
-        mode[it] = 0;
-        s_try[it] = target[it] = best_abs[it] = best_noise[it] = best_s[it] = iter[it] = niter[it] = 0;
-        if (c < L->nchan && bnd < T->cfg.nsf[c]) {
-            target[it] = L->nt[c][bnd];
-            if (L->noise0[c][bnd] > target[it]) {
-                mode[it] = 1;
-                s_try[it] = L->gsf[c][bnd];
-            } else {
-                L->gsf[c][bnd] = L->gzero[c][bnd] + 5;
-                L->noise[c][bnd] = L->noise0[c][bnd];
-            }
-        }
-    }
     // per-line squared errors of one channel at a time, in shared memory (one 576-float row per stream of the block)
     __shared__ float s_dd[kRateWarpsPerBlock * (32 / HMP3_W)][576];
     float *dd = s_dd[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
+    HMP3_SYNC();
     // channel-major: one channel's bands are searched to the end before the other channel is touched, so that the
     // rounds of a search work on one channel's spectra (4.6 KB) instead of both (the bands are independent: the order
-    // of the evaluations does not change any result)
+    // of the evaluations does not change any result).  The per-band state machine of a lane lives in scalars
+    // (slot 0) plus, for groups narrower than 22 lanes, a second set (slot 1).
     for (int c = 0; c < L->nchan; c++) {
+        int mode0 = 0, try0 = 0, target0 = 0, babs0 = 0, bnoise0 = 0, bs0 = 0, iter0 = 0, niter0 = 0;
+        int mode1 = 0, try1 = 0, target1 = 0, babs1 = 0, bnoise1 = 0, bs1 = 0, iter1 = 0, niter1 = 0;
+#define HMP3_SEEK_INIT(bnd, mode, stry, target)                  \
+    if ((bnd) < T->cfg.nsf[c]) {                                 \
+        target = L->nt[c][bnd];                                  \
+        if (L->noise0[c][bnd] > target) {                        \
+            mode = 1;                                            \
+            stry = L->gsf[c][bnd];                               \
+        } else {                                                 \
+            L->gsf[c][bnd] = L->gzero[c][bnd] + 5;               \
+            L->noise[c][bnd] = L->noise0[c][bnd];                \
+        }                                                        \
+    }
+        HMP3_SEEK_INIT(lane, mode0, try0, target0)
+        if (NS > 1) { HMP3_SEEK_INIT(lane + HMP3_W, mode1, try1, target1) }
+#undef HMP3_SEEK_INIT
+        const int nl = T->startBand_l[T->cfg.nsf[c]];
+        const float *y34 = L->x34[c];
+        const float *y = xr + 576 * c;
         for (;;) {
-            unsigned am[2] = {0u, 0u};  // bit b = band b of the channel is still searching
-            for (int j = 0; j < NS; j++) am[c] |= gballot(mode[c * NS + j] != 0) << (HMP3_W * j);
-            if (am[c] == 0) break;
-            const int nl = T->startBand_l[T->cfg.nsf[c]];
-            const float *y34 = L->x34[c];
-            const float *y = xr + 576 * c;
-            // two blocks of HMP3_W lines per iteration: the spectrum loads of both are in flight before either is used
-#define HMP3_EVAL_LOAD(kk, bb, aa, v34, vx)                          \
-    const int bb = ((kk) < nl) ? (int)T->line_band_l[kk] : 0;        \
-    const bool aa = ((kk) < nl) && ((am[c] >> bb) & 1u);             \
-    float v34 = 0.0f, vx = 0.0f;                                     \
-    if (aa) {                                                        \
-        v34 = y34[kk];                                               \
-        vx = y[kk];                                                  \
-    }
-#define HMP3_EVAL_LINE(kk, bb, aa, v34, vx)                                                   \
-    if (gballot(aa) != 0) {                                                                   \
-        int st = gshfl(s_try[c * NS], bb & (HMP3_W - 1));                                     \
-        if (NS > 1) {                                                                         \
-            const int st1 = gshfl(s_try[c * NS + NS - 1], bb & (HMP3_W - 1));                 \
-            if (bb >= HMP3_W) st = st1;                                                       \
-        }                                                                                     \
-        if (aa) dd[kk] = noise_line(T, T->igain34[st], T->gain[st], v34, vx);                 \
-    }
+            unsigned am = gballot(mode0 != 0);  // bit b = band b of the channel is still searching
+            if (NS > 1) am |= gballot(mode1 != 0) << (HMP3_W & 31);
+            if (am == 0) break;
             for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
-                const int ka = k0 + lane;
-                HMP3_EVAL_LOAD(ka, b0, act0, p0, x0)
-                HMP3_EVAL_LINE(ka, b0, act0, p0, x0)
+                const int kk = k0 + lane;
+                const int bb = (kk < nl) ? (int)T->line_band_l[kk] : 0;
+                const bool aa = (kk < nl) && ((am >> bb) & 1u);
+                float v34 = 0.0f, vx = 0.0f;
+                if (aa) {
+                    v34 = y34[kk];
+                    vx = y[kk];
+                }
+                if (gballot(aa) != 0) {
+                    int st = gshfl(try0, bb & (HMP3_W - 1));
+                    if (NS > 1) {
+                        const int st1 = gshfl(try1, bb & (HMP3_W - 1));
+                        if (bb >= HMP3_W) st = st1;
+                    }
+                    if (aa) dd[kk] = noise_line(T, T->igain34[st], T->gain[st], v34, vx);
+                }
             }
-#undef HMP3_EVAL_LOAD
-#undef HMP3_EVAL_LINE
             HMP3_SYNC();
-            for (int j = 0; j < NS; j++) {
-                const int it = c * NS + j;
-                if (mode[it] == 0) continue;
-                const int bnd = lane + HMP3_W * j;
-                const float *v = dd + T->startBand_l[bnd];
-                const int n = T->nBand_l[bnd];
-                const float acc = sum_seq(v, n, 0.0f);
-                const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];
-                bool done = false;
-                if (mode[it] == 1) {
-                    const int dn = tn - target[it];
-                    L->nt_adjust[c][bnd] = L->nt_adjust[c][bnd] + (dn >> 3);
-                    best_abs[it] = iabs(dn);
-                    best_noise[it] = tn;
-                    best_s[it] = s_try[it];
-                    iter[it] = 0;
-                    if (dn > 100) {
-                        niter[it] = imin_(s_try[it] - 1, 20);
-                        s_try[it] = s_try[it] - 1;
-                        mode[it] = 2;
-                        done = niter[it] <= 0;
-                    } else if (dn < -100) {
-                        niter[it] = 20;
-                        s_try[it] = s_try[it] + 1;
-                        mode[it] = 3;
-                    } else done = true;
-                } else {
-                    const int a = iabs(tn - target[it]);
-                    if (a < best_abs[it]) {
-                        best_abs[it] = a;
-                        best_noise[it] = tn;
-                        best_s[it] = s_try[it];
-                    }
-                    iter[it]++;
-                    if (mode[it] == 2) {
-                        if (tn <= target[it] || iter[it] >= niter[it]) done = true;
-                        else s_try[it]--;
-                    } else {
-                        if (tn >= target[it] || iter[it] >= niter[it]) done = true;
-                        else s_try[it]++;
-                    }
-                }
-                if (done) {
-                    L->gsf[c][bnd] = best_s[it];
-                    L->noise[c][bnd] = best_noise[it];
-                    mode[it] = 0;
-                }
-            }
+#define HMP3_SEEK_STEP(bnd, mode, stry, target, babs, bnoise, bs, iter, niter)                \
+    if (mode != 0) {                                                                          \
+        const float acc = sum_seq(dd + T->startBand_l[bnd], T->nBand_l[bnd], 0.0f);           \
+        const int tn = mb_log(T, 1.0e-12f + acc) - T->log_cbw_l[bnd];                         \
+        bool done = false;                                                                    \
+        if (mode == 1) {                                                                      \
+            const int dn = tn - target;                                                       \
+            L->nt_adjust[c][bnd] = L->nt_adjust[c][bnd] + (dn >> 3);                          \
+            babs = iabs(dn);                                                                  \
+            bnoise = tn;                                                                      \
+            bs = stry;                                                                        \
+            iter = 0;                                                                         \
+            if (dn > 100) {                                                                   \
+                niter = imin_(stry - 1, 20);                                                  \
+                stry = stry - 1;                                                              \
+                mode = 2;                                                                     \
+                done = niter <= 0;                                                            \
+            } else if (dn < -100) {                                                           \
+                niter = 20;                                                                   \
+                stry = stry + 1;                                                              \
+                mode = 3;                                                                     \
+            } else done = true;                                                               \
+        } else {                                                                              \
+            const int a = iabs(tn - target);                                                  \
+            if (a < babs) {                                                                   \
+                babs = a;                                                                     \
+                bnoise = tn;                                                                  \
+                bs = stry;                                                                    \
+            }                                                                                 \
+            iter++;                                                                           \
+            if (mode == 2) {                                                                  \
+                if (tn <= target || iter >= niter) done = true;                               \
+                else stry--;                                                                  \
+            } else {                                                                          \
+                if (tn >= target || iter >= niter) done = true;                               \
+                else stry++;                                                                  \
+            }                                                                                 \
+        }                                                                                     \
+        if (done) {                                                                           \
+            L->gsf[c][bnd] = bs;                                                              \
+            L->noise[c][bnd] = bnoise;                                                        \
+            mode = 0;                                                                         \
+        }                                                                                     \
+    }
+            HMP3_SEEK_STEP(lane, mode0, try0, target0, babs0, bnoise0, bs0, iter0, niter0)
+            if (NS > 1) { HMP3_SEEK_STEP(lane + HMP3_W, mode1, try1, target1, babs1, bnoise1, bs1, iter1, niter1) }
+#undef HMP3_SEEK_STEP
             HMP3_SYNC();
         }
     }
