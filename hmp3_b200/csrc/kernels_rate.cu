@@ -47,9 +47,11 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
     // 1.63 s -> 1.55 s; 20 % costs occupancy, >= 50 % is the driver's choice again; giving the Phase A kernels the same
     // preference starves them of shared memory and is slower; halving the step search's scratch to reach the 64 KB
     // configuration gains nothing net: the two half passes cost what the extra L1 saves).
-    static bool configured = false;
-    if (!configured) {
-        configured = true;
+    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
+        configured |= 1ull << (dev & 63);
         const char *e = getenv("HMP3_RATE_CARVEOUT");
         const int pct = e ? atoi(e) : 40;
         if (pct >= 0) cudaFuncSetAttribute(k_rate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
