@@ -66,3 +66,32 @@ def test_info_frame_matches_reference_cli(name, seed, sr, nch, kw, secs):
                           bytes_after)
     assert got.size == head_bytes
     assert np.array_equal(got, whole[:head_bytes])
+
+
+def _frame_ends(audio, sr):
+    ends, p = [], 0
+    br = ([0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320] if sr >= 32000 else
+          [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160])
+    while p < audio.size:
+        h2 = int(audio[p + 2])
+        p += (144000 if sr >= 32000 else 72000) * br[h2 >> 4] // sr + ((h2 >> 1) & 1)
+        ends.append(p)
+    return np.array(ends)
+
+
+@pytest.mark.parametrize("xflag", [1, 2, 3, 65, 66, 67])
+def test_info_frame_for_every_x_option(xflag):
+    """-X<n>: 1 = frame/byte counts only, 2 / 3 = with seek table, +64 = with the info tag (tomp3.cpp:682-689)."""
+    for sr, nch, kw, opts in [(44100, 2, dict(bitrate=64), ["-B64"]), (44100, 2, dict(), []),
+                              (22050, 1, dict(bitrate=32), ["-B32"])]:
+        pcm = synth_pcm(5, 6.0, sr, nch)
+        whole = ref_cli_encode(pcm, sr, nch, opts + ["-X%d" % xflag])
+        audio, tr = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, max_trace_calls=100000)
+        head_bytes = whole.size - audio.size
+        ncalls = (pcm.shape[0] + 3 * 1153 + 1152) // 1152
+        bytes_after = np.cumsum(tr["out_bytes"][:ncalls].astype(np.int64))
+        ends = _frame_ends(audio, sr)
+        frames_after = np.searchsorted(ends, bytes_after, side="right")
+        got = capi.info_frame(capi.control(samprate=sr, nch=nch, **kw), nch, pcm.shape[0], audio, len(ends), frames_after,
+                              bytes_after, xing_flag=xflag)
+        assert got.size == head_bytes and np.array_equal(got, whole[:head_bytes]), (sr, nch, opts, xflag)
