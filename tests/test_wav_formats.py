@@ -372,3 +372,53 @@ def test_handle_up_conversion(nch, to_mono, kw):
     want, _, _ = simmod.encode_clip(capi.control(samprate=2 * sr, nch=y.shape[1], nsb_limit=wavutil.up2_nsb_limit(sr), **kw), y)
     m = min(got.size, want.size)
     assert m > 0.85 * want.size and np.array_equal(got[:m], want[:m])
+
+
+def control_from_options(opts, sr, nch):
+    """The control block the CLI builds: hmp3_control_defaults + hmp3_control_apply_option per argument, then the
+    channel / rate fix-ups of ff_encode (tomp3.cpp:357-566, 809-815)."""
+    import ctypes as C
+    L = capi.lib()
+    L.hmp3_control_apply_option.argtypes = [C.c_void_p, C.c_char_p]
+    ec = np.zeros(len(capi.EC_FIELDS), np.int32)
+    L.hmp3_control_defaults(capi.vp(ec))
+    for o in opts:
+        assert L.hmp3_control_apply_option(capi.vp(ec), o.encode()) == 0, o
+    f = capi.EC_FIELDS
+    if ec[f.index("mode")] < 0:
+        ec[f.index("mode")] = 0
+    if nch == 1:
+        ec[f.index("mode")] = 3
+    elif ec[f.index("mode")] == 3:
+        ec[f.index("mode")] = 1
+    ec[f.index("samprate")] = sr
+    return ec
+
+
+OPTION_SETS = [["-B64", "-C1", "-O0"], ["-V75", "-L96"], ["-F16000", "-B56"], ["-Q1"], ["-T1", "-B80"], ["-U2"], ["-V20"],
+               ["-V120", "-HF1"], ["-B112", "-M1"], ["-B64", "-M0"], ["-SBT20", "-B64"], ["-TX5"], ["-V60", "-F14000"],
+               ["-B128"], ["-B48", "-S1"], ["-B40"]]
+
+
+@needs_ref
+def test_option_strings_through_the_parser_against_the_reference_cli(tmp_path):
+    """Command-line arguments -> hmp3_control_apply_option -> encode (host build) == the reference CLI given the same
+    arguments; a control the reference refuses (e.g. -B40 at 44.1 kHz) is refused too."""
+    for it, opts in enumerate(OPTION_SETS):
+        for sr, nch in [(44100, 2), (32000, 1), (24000, 2)]:
+            pcm = synth_pcm(600 + it, 1.5, sr, nch)
+            wav, mp3 = str(tmp_path / "o.wav"), str(tmp_path / "o.mp3")
+            if os.path.exists(mp3):
+                os.remove(mp3)
+            wavutil.write_wav(wav, pcm, "s16", sr, nch)
+            subprocess.run([REF_BIN, wav, mp3] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ref_ok = os.path.exists(mp3) and os.path.getsize(mp3) > 0
+            try:
+                got, _, _ = simmod.encode_clip(control_from_options(opts, sr, nch), pcm)
+            except Exception:
+                got = None
+            assert (got is not None) == ref_ok, (opts, sr, nch)
+            if got is not None:
+                whole = np.fromfile(mp3, dtype=np.uint8)
+                head = whole.size - got.size
+                assert head >= 0 and np.array_equal(whole[head:], got), (opts, sr, nch)
