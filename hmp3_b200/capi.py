@@ -73,6 +73,15 @@ def debug_analysis(ec, pcm_i16, ngran, nch, device=0):
     return out
 
 
+def fp32_peak(device=0):
+    """FP32 issue-rate microbenchmark (hmp3_debug_fp32_peak): TFLOP/s of FFMA chains and of the non-fused mix."""
+    a, b = C.c_float(0), C.c_float(0)
+    r = lib().hmp3_debug_fp32_peak(device, C.byref(a), C.byref(b))
+    if r != 0:
+        return {"ffma_tflops": None, "nonfused_tflops": None}
+    return {"ffma_tflops": a.value, "nonfused_tflops": b.value}
+
+
 PCM_S16, PCM_F32 = 0, 1        # hmp3_stream_desc.pcm_format / hmp3_batch_create_ex formats
 
 
@@ -148,6 +157,11 @@ class Batch:
 
     def set_timing(self, on):
         lib().hmp3_batch_set_timing(self.h, 1 if on else 0)
+
+    def set_serialize(self, on):
+        f = lib().hmp3_batch_set_serialize
+        f.argtypes = [C.c_void_p, C.c_int]
+        f(self.h, 1 if on else 0)
 
     def launches(self):
         return lib().hmp3_batch_last_launches(self.h)
@@ -274,8 +288,31 @@ class Encoder:
         i, o = self._io(lib().hmp3_L3_audio_encode(self.h, vp(a), vp(self.out)))
         return i, self.out[:o].copy()
 
+    def encode_l3_packet(self, pcm_f32, want_bs=True):
+        """hmp3_L3_audio_encode_Packet: returns (in_bytes, bitstream bytes, [packet bytes, ...])."""
+        a = np.ascontiguousarray(pcm_f32, dtype=np.float32)
+        pk = np.zeros(1 << 14, np.uint8)
+        nb = (C.c_int * 2)(0, 0)
+        f = lib().hmp3_L3_audio_encode_Packet
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        f.restype = C.c_uint64
+        i, o = self._io(f(self.h, vp(a), vp(self.out) if want_bs else None, vp(pk), nb))
+        return i, self.out[:o].copy(), [pk[:nb[0]].copy(), pk[nb[0]:nb[0] + nb[1]].copy()]
+
     def frames(self):
         return int(lib().hmp3_L3_audio_encode_get_frames(self.h))
+
+    def frames_bytes(self):
+        f = lib().hmp3_L3_audio_encode_get_frames_bytes
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_uint64
+        return self._io(f(self.h))
+
+    def bitrate2(self):
+        f = lib().hmp3_L3_audio_encode_get_bitrate2_float
+        f.argtypes = [C.c_void_p]
+        f.restype = C.c_float
+        return float(f(self.h))
 
     def bitrate(self):
         return float(lib().hmp3_L3_audio_encode_get_bitrate_float(self.h))

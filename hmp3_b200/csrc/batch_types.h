@@ -78,8 +78,11 @@ void launch_switch_scan(const EncTables *tabs, const StreamDev *st, SwitchState 
 void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
 void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
 // scans and prepare pass that follow psy stage 1 (carry: msmem [n], psy [n][2])
-void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
-                    cudaStream_t stream);
+void launch_ms_scan(const EncTables *tabs, const StreamDev *st, int *msmem, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+void launch_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy, ChunkBufs cb, int K0, int n,
+                       cudaStream_t stream);
+void launch_prepare(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
+int fp32_peak(int device, float *ffma_tflops, float *nonfused_tflops);
 void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream);
 size_t sizeof_prep_granule();
 size_t sizeof_psy_state();
@@ -101,6 +104,10 @@ void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *
                    const FrameRec *frames, StreamResult *res, long long *out_off, const unsigned char *main_buf,
                    unsigned char *out, int max_frames, int n, cudaStream_t stream, cudaEvent_t before_assemble,
                    int frame_lo = 0, long long out_base = 0);
+// Handle streaming (one stream): shift the serial stage's positional state by dK granules, keeping the frames that
+// are not complete yet (moved to index 0) and their main data; res receives the state's counters afterwards.
+void launch_handle_rebase(RateState *rs, FrameRec *frames, unsigned char *main_buf, int dK, StreamResult *res,
+                          cudaStream_t stream);
 size_t sizeof_rate_state();
 size_t sizeof_frame_rec();
 size_t sizeof_pack_gc();

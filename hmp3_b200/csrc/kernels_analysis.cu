@@ -29,11 +29,68 @@ void launch_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int
 void launch_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
     k_psy_stage1<<<blocks_for((long long)n * cb.NG * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
 }
-void launch_prepare(const EncTables *tabs, const StreamDev *st, int *msmem, PsyState *psy, ChunkBufs cb, int K0, int n,
+void launch_ms_scan(const EncTables *tabs, const StreamDev *st, int *msmem, ChunkBufs cb, int K0, int n,
                     cudaStream_t stream) {
     k_ms_scan<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, msmem, cb, K0, n);
+}
+void launch_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy, ChunkBufs cb, int K0, int n,
+                       cudaStream_t stream) {
     k_psy_stage2<<<blocks_for(2LL * n * 32, 128), 128, 0, stream>>>(tabs, st, psy, cb, K0, n);
+}
+void launch_prepare(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream) {
     k_prepare<<<blocks_for((long long)n * cb.NG * 32, 128), 128, 0, stream>>>(tabs, st, cb, K0, n);
+}
+
+// FP32 issue-rate microbenchmark (SURVEY 8d / BASELINE.md 3): the ceilings the exact-order kernels are quoted against.
+// mode 0: dependent FFMA chains, 8 per thread (2 flop per lane per issue); mode 1: alternating FMUL / FADD chains, the
+// instruction mix of code compiled --fmad=false (1 flop per lane per issue).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = (float)(threadIdx.x + j) * 1.0e-3f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (MODE == 0) v[j] = __fmaf_rn(v[j], a, b);
+            else v[j] = __fadd_rn(__fmul_rn(v[j], a), b);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += v[j];
+    if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+int fp32_peak(int device, float *ffma_tflops, float *nonfused_tflops) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) return -1;
+    float *d = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 1 << 15, blocks = pr.multiProcessorCount * 8;
+    float best[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++)
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            if (mode == 0) k_fp32_peak<0><<<blocks, 256>>>(d, iters, 0.999f, 1.0e-3f);
+            else k_fp32_peak<1><<<blocks, 256>>>(d, iters, 0.999f, 1.0e-3f);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double flop = (double)blocks * 256 * iters * 8 * 2;  // mul + add per element either way
+            const float tf = (float)(flop / (ms * 1e-3) / 1e12);
+            if (rep > 0 && tf > best[mode]) best[mode] = tf;
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (ffma_tflops) *ffma_tflops = best[0];
+    if (nonfused_tflops) *nonfused_tflops = best[1];
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream) {
     k_prepare_init<<<blocks_for(2LL * n, 128), 128, 0, stream>>>(msmem, psy, n);

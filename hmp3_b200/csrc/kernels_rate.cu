@@ -82,6 +82,55 @@ void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *
                                                                                      frames, out, max_frames, n, frame_lo,
                                                                                      out_base);
 }
+// one warp, one stream (see encoder_rebase in pipeline.cu)
+__global__ void k_handle_rebase(RateState *R, FrameRec *fr, unsigned char *main_buf, int dK, StreamResult *res) {
+    const int lane = threadIdx.x;
+    const int f0 = R->frames_done, nf = R->frames - f0;
+    unsigned mbase = R->main_tot < R->mf_tot ? R->main_tot : R->mf_tot, obase = R->out_tot;
+    if (nf > 0) {  // offsets grow with the frame index: the first kept frame has the smallest
+        mbase = min(mbase, min(fr[f0].main_start, fr[f0].data_start));
+        obase = fr[f0].out_off;
+    }
+    const unsigned top = R->main_tot > R->mf_tot ? R->main_tot : R->mf_tot;
+    __syncwarp();
+    if (mbase > 0)
+        for (unsigned i = 0; i < top - mbase; i += 32) {  // forward copy; a round's reads complete before its writes
+            const unsigned k = i + lane;
+            unsigned char v = 0;
+            if (k < top - mbase) v = main_buf[mbase + k];
+            __syncwarp();
+            if (k < top - mbase) main_buf[k] = v;
+            __syncwarp();
+        }
+    if (lane == 0) {
+        for (int k = 0; k < nf; k++) {
+            FrameRec f = fr[f0 + k];
+            f.main_start -= mbase;
+            f.data_start -= mbase;
+            f.out_off -= obase;
+            f.granule0 -= dK;
+            f.done_after -= f0;
+            fr[k] = f;
+        }
+        R->frames = nf;
+        R->frames_done = 0;
+        R->main_tot -= mbase;
+        R->mf_tot -= mbase;
+        R->out_tot -= obase;
+        R->next_granule -= dK;
+        StreamResult r;
+        r.frames = 0;
+        r.frames_recorded = nf;
+        r.finished = R->finished;
+        r.out_bytes = 0;
+        r.pad_ = 0;
+        *res = r;
+    }
+}
+void launch_handle_rebase(RateState *rs, FrameRec *frames, unsigned char *main_buf, int dK, StreamResult *res,
+                          cudaStream_t stream) {
+    k_handle_rebase<<<1, 32, 0, stream>>>(rs, frames, main_buf, dK, res);
+}
 size_t sizeof_rate_state() { return sizeof(RateState); }
 size_t sizeof_frame_rec() { return sizeof(FrameRec); }
 size_t sizeof_pack_gc() { return sizeof(PackGc); }

@@ -40,9 +40,9 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
-const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "ms_psy2_prepare",
-                                     "rate_loop", "pack", "assemble"};
+enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_MS, PH_PSY2, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
+const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "ms_scan",
+                                     "psy_stage2", "prepare", "rate_loop", "pack", "assemble"};
 
 }  // namespace
 
@@ -81,6 +81,7 @@ struct hmp3_batch {
     bool one_stream = false;
     cudaStream_t stream_a = nullptr;    // Phase A
     cudaStream_t stream_p = nullptr;    // packing pass
+    cudaStream_t stream_a0 = nullptr, stream_p0 = nullptr;  // the plan's own Phase A / packing streams (see hmp3_batch_set_serialize)
     cudaEvent_t ev_a[kMaxSets] = {nullptr, nullptr, nullptr}, ev_r[kMaxSets] = {nullptr, nullptr, nullptr},
                 ev_p[kMaxSets] = {nullptr, nullptr, nullptr},
                 ev_start = nullptr;
@@ -178,8 +179,8 @@ struct hmp3_batch {
         if (stream_c) cudaStreamDestroy(stream_c);
         for (int k = 0; k < kMaxSets; k++)
             if (ev_c[k]) cudaEventDestroy(ev_c[k]);
-        if (stream_a && !one_stream) cudaStreamDestroy(stream_a);
-        if (stream_p && !one_stream) cudaStreamDestroy(stream_p);
+        if (stream_a0) cudaStreamDestroy(stream_a0);
+        if (stream_p0) cudaStreamDestroy(stream_p0);
         for (auto e : ev) cudaEventDestroy(e);
         if (ev_run0) cudaEventDestroy(ev_run0);
         if (ev_run1) cudaEventDestroy(ev_run1);
@@ -330,8 +331,10 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const bool prio = !(getenv("HMP3_NO_STREAM_PRIO"));
-        CK(cudaStreamCreateWithPriority(&b->stream_a, cudaStreamDefault, prio ? hi : lo));
-        CK(cudaStreamCreateWithPriority(&b->stream_p, cudaStreamDefault, prio ? hi : lo));
+        CK(cudaStreamCreateWithPriority(&b->stream_a0, cudaStreamDefault, prio ? hi : lo));
+        CK(cudaStreamCreateWithPriority(&b->stream_p0, cudaStreamDefault, prio ? hi : lo));
+        b->stream_a = b->stream_a0;
+        b->stream_p = b->stream_p0;
     }
     CK(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
     for (int k = 0; k < b->nbuf; k++) {
@@ -427,8 +430,14 @@ int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_pre
     launch_psy_stage1(b->d_tabs, b->d_st, cb, K0, n, st);
     mark(b, -1, st);
     if (with_prepare) {
+        mark(b, PH_MS, st);
+        launch_ms_scan(b->d_tabs, b->d_st, b->d_msmem, cb, K0, n, st);
+        mark(b, -1, st);
+        mark(b, PH_PSY2, st);
+        launch_psy_stage2(b->d_tabs, b->d_st, b->d_psy, cb, K0, n, st);
+        mark(b, -1, st);
         mark(b, PH_PREP, st);
-        launch_prepare(b->d_tabs, b->d_st, b->d_msmem, b->d_psy, cb, K0, n, st);
+        launch_prepare(b->d_tabs, b->d_st, cb, K0, n, st);
         mark(b, -1, st);
         b->launches += 3;
     }
@@ -760,6 +769,15 @@ int hmp3_batch_set_timing(hmp3_batch *b, int on) {
     return HMP3_OK;
 }
 
+int hmp3_batch_set_serialize(hmp3_batch *b, int on) {
+    if (!b) return HMP3_ERR_ARG;
+    if (!b->stream_a0) return HMP3_OK;  // created with HMP3_SERIALIZE: always on
+    b->one_stream = on != 0;
+    b->stream_a = on ? b->stream : b->stream_a0;
+    b->stream_p = on ? b->stream : b->stream_p0;
+    return HMP3_OK;
+}
+
 int hmp3_batch_run(hmp3_batch *b, int async) {
     int r = run_plan(b);
     if (r != HMP3_OK) return r;
@@ -1062,17 +1080,22 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
 struct hmp3_encoder {
     int device = 0;
     hmp3_batch *b = nullptr;
-    int nch = 0, calls = 0, max_calls = 0;
-    int frames_out = 0;
+    int nch = 0;
+    int calls = 0;              // encode calls made inside the current window of the device buffers
+    int window_calls = 0;       // calls the window holds; when it is full the handle rebases (encoder_rebase)
+    int frames_out = 0;         // CMp3Enc::tot_frames_out / tot_bytes_out: the whole stream
     long long bytes_out = 0;
-    double ave_bytes = 0;
+    int win_frames_out = 0;     // the same counters relative to the current window (what the device state counts)
+    long long win_bytes_out = 0;
+    int win_recorded = 0;       // frames the serial stage has recorded in the window
+    int ave_bytes = 0;          // CMp3Enc::ave_tot_bytes_out: running average of the bytes per call, x256
     bool float_in = false;      // the plan takes float PCM (every input format except 16-bit integer)
     int src_bits = 16, src_float = 0;
     int src_chan = 0;           // channels of the caller's PCM (2 with nch == 1: down-mix to mono, Csrc kfilter 2)
     bool up2 = false;           // 1:2 up-conversion (Csrc case 1)
     int frames_in = 1152;       // sample frames of the caller's PCM consumed per call
     std::vector<float> conv;    // the call's samples after sr_convert's type conversion
-    int capacity_seconds = 1200;
+    int capacity_seconds = 20;
     std::vector<float> stage;
     ~hmp3_encoder() { delete b; }
 };
@@ -1081,8 +1104,8 @@ namespace {
 int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     delete e->b;
     e->b = nullptr;
-    e->calls = e->frames_out = 0;
-    e->bytes_out = 0;
+    e->calls = e->frames_out = e->win_frames_out = e->win_recorded = 0;
+    e->bytes_out = e->win_bytes_out = 0;
     e->ave_bytes = 0;
     e->float_in = float_in;
     EncTables *T = new EncTables;
@@ -1097,6 +1120,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     e->b = new hmp3_batch;
     long long ns = (long long)e->capacity_seconds * samprate;
     ns -= ns % 1152;
+    if (ns < 16 * 1152) ns = 16 * 1152;
     const int fmt = float_in ? 1 : 0;
     if (plan_create(e->b, ec, &ns, 1, e->device, 2, false, true, &fmt) != HMP3_OK) {
         delete e->b;
@@ -1105,7 +1129,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     }
     hmp3_batch *b = e->b;
     e->nch = b->st_h[0].nch;
-    e->max_calls = b->st_h[0].ngran / 2;
+    e->window_calls = (int)(ns / 1152);
     e->stage.assign((size_t)1152 * e->nch, 0.0f);
     cudaSetDevice(e->device);
     if (plan_reset_state(b) != HMP3_OK) return 0;
@@ -1118,19 +1142,44 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     return bytes_in;
 }
 
-// one encode call: 1152 samples per channel in, whatever frames became complete out
-hmp3_in_out encoder_step(hmp3_encoder *e, const void *pcm, unsigned char *bs_out) {
+// The window of the handle's device buffers is full: keep what the next calls still need -- the last kKeepCalls
+// calls of PCM (polyphase history and the three-granule look-back of the hybrid transform), the frames whose
+// main-data slot is not complete yet and their main data -- move it to the start of the buffers and shift every
+// absolute index (granule, frame, main-data and output offsets) by the same amounts.  Nothing else of the state is
+// positional, so the stream continues exactly as if the buffers were unbounded.
+constexpr int kKeepCalls = 4;
+int encoder_rebase(hmp3_encoder *e) {
+    hmp3_batch *b = e->b;
+    const StreamDev &sd = b->st_h[0];
+    const long long s0 = (long long)(e->calls - kKeepCalls) * 1152, ns = (long long)kKeepCalls * 1152;
+    size_t el;
+    char *base = pcm_dev_ptr(b, 0, 0, &el);
+    CK(cudaMemcpyAsync(base, base + el * s0 * sd.nch, el * ns * sd.nch, cudaMemcpyDeviceToDevice, b->stream));
+    if (sd.pcmf_off >= 0)  // the DC-filtered copy (-S1) is indexed by sample as well
+        CK(cudaMemcpyAsync(b->d_pcmf + sd.pcmf_off, b->d_pcmf + sd.pcmf_off + s0 * sd.nch, sizeof(float) * ns * sd.nch,
+                           cudaMemcpyDeviceToDevice, b->stream));
+    launch_handle_rebase(b->d_rs, b->d_frames, b->d_main, 2 * (e->calls - kKeepCalls), b->d_res, b->stream);
+    CK(cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    e->calls = kKeepCalls;
+    e->win_frames_out = 0;
+    e->win_bytes_out = 0;
+    e->win_recorded = b->res_h[0].frames_recorded;
+    return HMP3_OK;
+}
+
+// one encode call: 1152 samples per channel in, whatever frames became complete out; with `packet` also the frame(s)
+// this call produced as self-contained packets (CMp3Enc::L3_audio_encode_*Packet, mp3enc.cpp:2868-3440)
+hmp3_in_out encoder_step(hmp3_encoder *e, const void *pcm, unsigned char *bs_out, bool want_bs = true,
+                         unsigned char *packet = nullptr, int *nbytes_out = nullptr) {
     hmp3_in_out io = {0, 0};
     hmp3_batch *b = e->b;
     if (!b) {
         set_err("encoder not initialised");
         return io;
     }
-    if (e->calls >= e->max_calls) {
-        set_err("stream longer than the handle's capacity (hmp3_encoder_set_capacity_seconds)");
-        return io;
-    }
     cudaSetDevice(e->device);
+    if (e->calls >= e->window_calls && encoder_rebase(e) != HMP3_OK) return io;
     const int K0 = 2 * e->calls;
     size_t el;
     char *dst = pcm_dev_ptr(b, 0, (long long)e->calls * 1152, &el);
@@ -1143,21 +1192,48 @@ hmp3_in_out encoder_step(hmp3_encoder *e, const void *pcm, unsigned char *bs_out
     launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
     launch_pack(b->d_tabs, b->d_st, b->d_so, b->cb2[0], b->d_main, b->d_frames, b->d_flags, K0, 1, b->stream);
     launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out, 48, 1,
-                  b->stream, nullptr, e->frames_out, e->bytes_out);
+                  b->stream, nullptr, e->win_frames_out, e->win_bytes_out);
     cudaMemcpyAsync(b->res_h.data(), b->d_res, sizeof(StreamResult), cudaMemcpyDeviceToHost, b->stream);
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
         set_err(std::string("device error: ") + cudaGetErrorString(cudaGetLastError()));
         return io;
     }
     const StreamResult &r = b->res_h[0];
-    const long long nb = r.out_bytes - e->bytes_out;
-    if (nb > 0) cudaMemcpy(bs_out, b->d_out, nb, cudaMemcpyDeviceToHost);
-    e->frames_out = r.frames;
-    e->bytes_out = r.out_bytes;
-    e->ave_bytes += ((256.0 * nb) - e->ave_bytes) / 64.0;  // tracks CMp3Enc::ave_tot_bytes_out (mp3enc.cpp:2315-2317)
+    const EncConfig &C = b->tabs_h[0].cfg;
+    const long long nb = r.out_bytes - e->win_bytes_out;
+    if (nb > 0 && want_bs) cudaMemcpy(bs_out, b->d_out, nb, cudaMemcpyDeviceToHost);
+    if (nbytes_out) nbytes_out[0] = nbytes_out[1] = 0;
+    if (packet && nbytes_out) {
+        // the frames recorded by this call: header (CBR form: L3_pack_head, also in VBR mode) | side information with
+        // main_data_begin still zero | the frame's own scale-factor and Huffman bytes
+        const int nf = r.frames_recorded - e->win_recorded;
+        std::vector<FrameRec> fr(nf > 0 ? nf : 0);
+        if (nf > 0)
+            cudaMemcpy(fr.data(), b->d_frames + (r.frames_recorded - nf), sizeof(FrameRec) * nf, cudaMemcpyDeviceToHost);
+        for (int k = 0; k < nf && k < 2; k++) {
+            unsigned char *p = packet;
+            memcpy(p, fr[k].head, 4);
+            if (C.vbr_flag) p[2] = C.head[2];
+            memcpy(p + 4, fr[k].side, C.side_bytes);
+            p[4] = 0;
+            if (C.h_id == 1) p[5] &= 0x7F;
+            const int bytes = (fr[k].data_bits + 7) >> 3;
+            if (bytes > 0) cudaMemcpy(p + 4 + C.side_bytes, b->d_main + fr[k].data_start, bytes, cudaMemcpyDeviceToHost);
+            nbytes_out[k] = 4 + C.side_bytes + bytes;
+            packet += nbytes_out[k];
+        }
+    }
+    const long long counted = want_bs ? nb : 0;  // with bs_out == NULL the reference counts frames but no bytes
+    e->frames_out += r.frames - e->win_frames_out;
+    e->bytes_out += counted;
+    e->win_frames_out = r.frames;
+    e->win_bytes_out = r.out_bytes;
+    e->win_recorded = r.frames_recorded;
+    // CMp3Enc::ave_tot_bytes_out (mp3enc.cpp:2209, 2316: >> 7 per MPEG-1 call; :2476, 2590: >> 6 per MPEG-2 call)
+    e->ave_bytes += (int)(((int)counted << 8) - e->ave_bytes) >> (C.h_id == 1 ? 7 : 6);
     e->calls++;
     io.in_bytes = (int)nb_in;
-    io.out_bytes = (int)nb;
+    io.out_bytes = (int)counted;
     return io;
 }
 }  // namespace
@@ -1222,14 +1298,17 @@ int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int sour
     e->frames_in = up2 ? 576 : 1152;
     return (e->frames_in + 1) * e->src_chan * (source_bits / 8);
 }
-hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
+}  // extern "C"
+namespace {
+hmp3_in_out mp3_encode_call(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out, bool want_bs,
+                            unsigned char *packet, int *nbytes_out) {
     hmp3_in_out io = {0, 0};
     if (!e || !e->b) {
         set_err("encoder not initialised");
         return io;
     }
     if (!e->float_in) {
-        io = encoder_step(e, pcm, bs_out);
+        io = encoder_step(e, pcm, bs_out, want_bs, packet, nbytes_out);
         return io;
     }
     // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale.
@@ -1283,9 +1362,27 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
                 y[2 * (2 * i + 1) + c] = (float)((d[2 * i + c] + d[2 * i + 2 + c]) * 0.5);
             }
     }
-    io = encoder_step(e, y, bs_out);
+    io = encoder_step(e, y, bs_out, want_bs, packet, nbytes_out);
     if (io.in_bytes) io.in_bytes = e->frames_in * e->src_chan * (e->src_bits / 8);
     return io;
+}
+}  // namespace
+extern "C" {
+hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out) {
+    return mp3_encode_call(e, pcm, bs_out, true, nullptr, nullptr);
+}
+hmp3_in_out hmp3_MP3_audio_encode_Packet(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out,
+                                         unsigned char *packet, int nbytes_out[2]) {
+    return mp3_encode_call(e, pcm, bs_out, bs_out != nullptr, packet, nbytes_out);
+}
+hmp3_in_out hmp3_L3_audio_encode_Packet(hmp3_encoder *e, const float *pcm, unsigned char *bs_out, unsigned char *packet,
+                                        int nbytes_out[2]) {
+    hmp3_in_out io = {0, 0};
+    if (!e || !e->b || !e->float_in) {
+        set_err("encoder not initialised for float input");
+        return io;
+    }
+    return encoder_step(e, pcm, bs_out, bs_out != nullptr, packet, nbytes_out);
 }
 int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec) {
     if (!e || !ec) return 0;
@@ -1344,11 +1441,29 @@ float hmp3_L3_audio_encode_get_bitrate_float(hmp3_encoder *e) {  // mp3enc.cpp:3
     const float samples = (C.h_id == 1) ? 1152.0f : 576.0f;
     return ((0.001f * 8.0f) * e->bytes_out * C.samprate / (samples * e->frames_out));
 }
+float hmp3_L3_audio_encode_get_bitrate2_float(hmp3_encoder *e) {  // mp3enc.cpp:3466-3480 (recent average)
+    if (!e || !e->b || e->frames_out <= 0) return 0.0f;
+    const EncConfig &C = e->b->tabs_h[0].cfg;
+    return (float)((0.001f * 8.0f / (1152.0 * 256.0)) * e->ave_bytes * C.samprate);
+}
+hmp3_int_pair hmp3_L3_audio_encode_get_frames_bytes(hmp3_encoder *e) {  // mp3enc.cpp:3513-3521
+    hmp3_int_pair x = {0, 0};
+    if (e) {
+        x.a = e->frames_out;
+        x.b = (int)e->bytes_out;
+    }
+    return x;
+}
 int hmp3_L3_audio_encode_get_bitrate(hmp3_encoder *e) { return (int)(hmp3_L3_audio_encode_get_bitrate_float(e) + 0.5f); }
 int hmp3_control_apply_option(hmp3_control *ec, const char *opt) { return control_apply_option(ec, opt); }
 
 // Debug / parity entry: Phase A of ONE stream on the device, stage outputs copied back to the host.
 // Same argument meaning as the host simulator's sim_analysis (tests/hostsim/hostsim.cpp).
+int hmp3_debug_fp32_peak(int device, float *ffma_tflops, float *nonfused_tflops) {
+    if (hmp3_device_count() <= device) return HMP3_ERR_NO_DEVICE;
+    return fp32_peak(device, ffma_tflops, nonfused_tflops) == 0 ? HMP3_OK : HMP3_ERR_CUDA;
+}
+
 int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap) {
     int k = 0;
     for (; k < (int)b->timeline.size() && k < cap; k++)

@@ -57,6 +57,12 @@ typedef struct hmp3_in_out {
     int out_bytes;
 } hmp3_in_out;
 
+/* Mirror of INT_PAIR (hmp3/src/pub/encapp.h:167-171). */
+typedef struct hmp3_int_pair {
+    int a;
+    int b;
+} hmp3_int_pair;
+
 /* Mirror of MPEG_HEAD (hmp3/src/pub/encapp.h:141-157). */
 typedef struct hmp3_mpeg_head {
     int sync, id, option, prot, br_index, sr_index, pad, private_bit, mode, mode_ext, cr, original, emphasis;
@@ -161,6 +167,10 @@ float hmp3_batch_last_run_ms(const hmp3_batch *b);
 /* per-kernel device time (CUDA events on the plan's stream) of the last synchronous run made after
  * hmp3_batch_set_timing(b, 1): fills up to `cap` entries, returns the count; names[i] are static. */
 int hmp3_batch_set_timing(hmp3_batch *b, int on);
+/* Diagnostics: on != 0 puts every kernel of the following runs on ONE stream (no overlap between Phase A, the serial
+ * stage and the packing pass), so that the per-kernel times of hmp3_batch_phase_ms are uncontended; 0 restores the
+ * three-stream pipeline.  The output is the same either way. */
+int hmp3_batch_set_serialize(hmp3_batch *b, int on);
 int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap);
 
 /* ---------------------------------------------------------------------------------------------
@@ -170,7 +180,9 @@ int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int 
 typedef struct hmp3_encoder hmp3_encoder;
 hmp3_encoder *hmp3_encoder_new(int device);
 void hmp3_encoder_delete(hmp3_encoder *e);
-/* A handle reserves device buffers for a bounded stream length at init (default 1200 s); call before init. */
+/* A handle encodes a stream of any length in bounded memory: its device buffers hold a window of `seconds` of audio
+ * (default 20 s, about 0.5 MB per second of window for 44.1 kHz stereo) and are recycled when the window is full.
+ * Call before init. */
 int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds);
 
 /* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns, like the reference, the bytes the
@@ -187,6 +199,16 @@ hmp3_in_out hmp3_MP3_audio_encode(hmp3_encoder *e, const unsigned char *pcm, uns
  * (hmp3/src/mp3enc.cpp:220-870, 2031-2047). */
 int hmp3_L3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec);
 hmp3_in_out hmp3_L3_audio_encode(hmp3_encoder *e, const float *pcm, unsigned char *bs_out);
+/* CMp3Enc::L3_audio_encode_Packet / MP3_audio_encode_Packet (hmp3/src/mp3enc.cpp:2831-3440; pub/mp3enc.h:100-125):
+ * the same encode call, which additionally returns the frame(s) produced by THIS call as self-contained
+ * "reformatted" packets for streaming: header | side info with main_data_begin = 0 | the frame's own main data (no
+ * bit reservoir).  MPEG-1 yields one packet per call, MPEG-2 two; nbytes_out[k] is the size of packet k (0 = none),
+ * packet k+1 follows packet k in `packet`.  bs_out may be NULL (no standard bitstream wanted: out_bytes is then 0,
+ * as in the reference), packet may be NULL (plain encode). */
+hmp3_in_out hmp3_L3_audio_encode_Packet(hmp3_encoder *e, const float *pcm, unsigned char *bs_out, unsigned char *packet,
+                                        int nbytes_out[2]);
+hmp3_in_out hmp3_MP3_audio_encode_Packet(hmp3_encoder *e, const unsigned char *pcm, unsigned char *bs_out,
+                                         unsigned char *packet, int nbytes_out[2]);
 /* Info getters (hmp3/src/mp3enc.cpp:3444-3527). */
 void hmp3_L3_audio_encode_info_ec(hmp3_encoder *e, hmp3_control *ec);
 void hmp3_L3_audio_encode_info_head(hmp3_encoder *e, hmp3_mpeg_head *head);
@@ -194,6 +216,12 @@ void hmp3_L3_audio_encode_info_string(hmp3_encoder *e, char *s);
 unsigned int hmp3_L3_audio_encode_get_frames(hmp3_encoder *e);
 int hmp3_L3_audio_encode_get_bitrate(hmp3_encoder *e);
 float hmp3_L3_audio_encode_get_bitrate_float(hmp3_encoder *e);
+/* CMp3Enc::L3_audio_encode_get_bitrate2_float (mp3enc.cpp:3466-3480; pub/mp3enc.h:132): bitrate of the recent
+ * calls, from the running average the encoder keeps (used by the CLI's progress line, test/tomp3.cpp:633). */
+float hmp3_L3_audio_encode_get_bitrate2_float(hmp3_encoder *e);
+/* CMp3Enc::L3_audio_encode_get_frames_bytes (mp3enc.cpp:3513-3521; pub/mp3enc.h:137): frames and bytes emitted
+ * so far (the CLI's seek table, test/tomp3.cpp:981). */
+hmp3_int_pair hmp3_L3_audio_encode_get_frames_bytes(hmp3_encoder *e);
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Host post-pass of the CLI: the Xing/Info frame the reference writes in front of

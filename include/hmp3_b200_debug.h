@@ -24,6 +24,9 @@ int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches);
 /* Kernel timeline of the last run with timing on (hmp3_batch_set_timing): rows of (phase index as in
  * hmp3_batch_phase_ms, begin ms, end ms) since the run began; returns the number of rows. */
 int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap);
+/* FP32 issue-rate microbenchmark on `device`: TFLOP/s of dependent FFMA chains and of the FMUL + FADD mix that code
+ * compiled without contraction issues (the ceiling the exact-order kernels are quoted against). */
+int hmp3_debug_fp32_peak(int device, float *ffma_tflops, float *nonfused_tflops);
 #ifdef __cplusplus
 }
 #endif

@@ -249,6 +249,22 @@ int ref_encode(const float *pcm, unsigned char *out, void *trace) {
 
 unsigned int ref_frames() { return g_enc ? g_enc->L3_audio_encode_get_frames() : 0; }
 
+// One call of CMp3Enc::L3_audio_encode_Packet (mp3enc.cpp:3445-3440): standard bitstream (out may be NULL) plus the
+// reformatted packet(s) of this call.  Returns out_bytes.
+int ref_encode_packet(const float *pcm, unsigned char *out, unsigned char *packet, int *nbytes_out) {
+    g_call = nullptr;
+    IN_OUT x = g_enc->L3_audio_encode_Packet(const_cast<float *>(pcm), out, packet, nbytes_out);
+    return x.out_bytes;
+}
+// The info getters after the calls made so far: frames, bytes, bitrate (float), recent bitrate (float).
+void ref_getters(int *frames_bytes, float *bitrates) {
+    INT_PAIR fb = g_enc->L3_audio_encode_get_frames_bytes();
+    frames_bytes[0] = fb.a;
+    frames_bytes[1] = fb.b;
+    bitrates[0] = g_enc->L3_audio_encode_get_bitrate_float();
+    bitrates[1] = g_enc->L3_audio_encode_get_bitrate2_float();
+}
+
 // Whole-clip convenience used by tests and by bench.py's CPU baseline: float PCM in, raw MP3 frames out
 // (no Xing/Info tag), following the CLI's flush protocol (test/tomp3.cpp:1015-1036): keep feeding zero
 // frames until every started frame has been emitted.  Returns bytes written.

@@ -1,0 +1,119 @@
+"""The rest of the CMp3Enc surface on the GPU: the two getters the reference CLI itself uses, the *_Packet calls, a
+stream longer than the handle's device window (rebasing), and the reference's UNMODIFIED command line compiled
+against the GPU library (oracle/_ref/tomp3_gpu, built by oracle/Makefile from test/tomp3.cpp +
+include/cmp3enc_gpu.h) writing the same file as the reference's own binary."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refmod
+from hmp3_b200 import capi
+from hmp3_b200.synth import synth_pcm
+from wavutil import write_wav
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _ref_calls(ec, pcm_f32, ncalls, packet):
+    """The reference call by call: per call (bitstream bytes, packets, (frames, bytes), (bitrate, bitrate2))."""
+    L = refmod.lib()
+    assert L.ref_init(ec.ctypes.data_as(C.c_void_p)) > 0
+    L.ref_encode_packet.argtypes = [C.c_void_p] * 4
+    L.ref_getters.argtypes = [C.c_void_p] * 2
+    nch = pcm_f32.shape[1]
+    out = []
+    for c in range(ncalls):
+        blk = np.zeros((1152, nch), np.float32)
+        seg = pcm_f32[c * 1152:(c + 1) * 1152]
+        blk[:seg.shape[0]] = seg
+        bs, pk = np.zeros(1 << 14, np.uint8), np.zeros(1 << 14, np.uint8)
+        nb = (C.c_int * 2)(0, 0)
+        if packet:
+            ob = L.ref_encode_packet(blk.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p),
+                                     pk.ctypes.data_as(C.c_void_p), nb)
+        else:
+            ob = L.ref_encode(blk.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p), None)
+        fb, br = (C.c_int * 2)(), (C.c_float * 2)()
+        L.ref_getters(fb, br)
+        out.append((bs[:ob].copy(), [pk[:nb[0]].copy(), pk[nb[0]:nb[0] + nb[1]].copy()], (fb[0], fb[1]),
+                    (br[0], br[1])))
+    return out
+
+
+@pytest.mark.parametrize("sr,nch,kw", [(44100, 2, dict(bitrate=64)), (44100, 2, dict()), (22050, 1, dict(bitrate=32)),
+                                        (24000, 2, dict(vbr_mnr=80))])
+def test_packet_calls_and_getters_match_the_reference_call_by_call(sr, nch, kw):
+    pcm = synth_pcm(4100 + sr // 1000, 2.5, sr, nch).astype(np.float32)
+    ncalls = pcm.shape[0] // 1152 + 8
+    ref = _ref_calls(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, ncalls, packet=True)
+    enc = capi.Encoder(capacity_seconds=10)
+    assert enc.init_l3(capi.control(samprate=sr, nch=nch, **kw)) == nch * 4 * 1152
+    for c in range(ncalls):
+        blk = np.zeros((1152, nch), np.float32)
+        seg = pcm[c * 1152:(c + 1) * 1152]
+        blk[:seg.shape[0]] = seg
+        used, bs, pk = enc.encode_l3_packet(blk)
+        rbs, rpk, rfb, rbr = ref[c]
+        assert used == nch * 4 * 1152
+        assert np.array_equal(bs, rbs), "call %d bitstream" % c
+        for k in range(2):
+            assert pk[k].size == rpk[k].size and np.array_equal(pk[k], rpk[k]), "call %d packet %d" % (c, k)
+        assert enc.frames_bytes() == rfb, "call %d" % c
+        assert abs(enc.bitrate() - rbr[0]) <= 1e-4 * max(1.0, rbr[0])
+        assert abs(enc.bitrate2() - rbr[1]) <= 1e-4 * max(1.0, rbr[1])
+    enc.close()
+
+
+def test_packet_call_without_a_bitstream_buffer():
+    """bs_out == NULL: frames are counted, bytes are not (mp3enc.cpp:2972-2993)."""
+    pcm = synth_pcm(77, 1.0, 44100, 2).astype(np.float32)
+    enc = capi.Encoder(capacity_seconds=10)
+    enc.init_l3(capi.control(samprate=44100, nch=2, bitrate=64))
+    for c in range(12):
+        used, bs, pk = enc.encode_l3_packet(pcm[c * 1152:(c + 1) * 1152], want_bs=False)
+        assert bs.size == 0 and pk[0].size > 36 and pk[1].size == 0
+    assert enc.frames_bytes()[0] > 0 and enc.frames_bytes()[1] == 0
+    enc.close()
+
+
+@pytest.mark.parametrize("sr,nch,kw", [(44100, 2, dict(bitrate=64)), (22050, 1, dict(bitrate=32)), (32000, 2, dict())])
+def test_stream_longer_than_the_device_window(sr, nch, kw):
+    """A handle whose window holds 16 calls encodes a 9 s stream (hundreds of calls, a rebase every 12 calls) with the
+    reference's output call by call: the handle is O(1) in memory for any stream length."""
+    pcm = synth_pcm(5200 + sr // 1000, 9.0, sr, nch)
+    ref_bytes, tr = refmod.ref_encode_clip(refmod.make_ec(samprate=sr, nch=nch, **kw), pcm, max_trace_calls=4096)
+    enc = capi.Encoder(capacity_seconds=1)       # rounded up to the smallest window: 16 calls
+    assert enc.init_mp3(capi.control(samprate=sr, nch=nch, **kw)) == 1153 * nch * 2
+    padded = np.concatenate([pcm, np.zeros((64 * 1152, nch), np.int16)])
+    out = []
+    for c in range(len(tr)):
+        used, b = enc.encode_mp3(padded[c * 1152:(c + 1) * 1152])
+        assert b.size == tr["out_bytes"][c], "call %d" % c
+        out.append(b)
+    got = np.concatenate(out)
+    assert got.size == ref_bytes.size and np.array_equal(got, ref_bytes)
+    enc.close()
+
+
+@pytest.mark.parametrize("opts,sr,nch", [(["-B64"], 44100, 2), ([], 44100, 2), (["-V100", "-HF2", "-F19000"], 48000, 2),
+                                          (["-B32"], 22050, 1), (["-B48", "-X0"], 32000, 2)])
+def test_reference_cli_source_over_the_gpu_library_writes_the_same_file(tmp_path, opts, sr, nch):
+    exe = os.path.join(REFDIR, "tomp3_gpu")
+    ref = os.path.join(REFDIR, "hmp3")
+    if not (os.path.exists(exe) and os.path.exists(ref)):
+        pytest.skip("oracle/_ref/tomp3_gpu not built")
+    wav = str(tmp_path / "in.wav")
+    write_wav(wav, synth_pcm(6100 + sr // 1000, 6.0, sr, nch), "s16", sr, nch)
+    a, b = str(tmp_path / "gpu.mp3"), str(tmp_path / "ref.mp3")
+    r1 = subprocess.run([exe, wav, a] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    r2 = subprocess.run([ref, wav, b] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r1.returncode == r2.returncode, r1.stdout[-400:]
+    assert open(a, "rb").read() == open(b, "rb").read()
+    # the progress lines (frames, bytes, current / average bitrate from the two getters) read the same too
+    tail = lambda t: [ln for ln in t.splitlines() if "Kbps" in ln or "Compress" in ln]
+    assert tail(r1.stdout) == tail(r2.stdout)

@@ -25,6 +25,16 @@ def test_clip_bytes_match_reference(name, seed, sr, nch, kw):
     assert np.array_equal(got, ref)
 
 
+def test_baseline_configs_at_their_stated_60_seconds():
+    """BASELINE.json configs 1-4 at the length they are stated for (60 s), all five in one batch."""
+    ctl = [capi.control(samprate=sr, nch=nch, **kw) for (_, _, sr, nch, kw) in CONFIGS]
+    pcms = [synth_pcm(seed, 60.0, sr, nch) for (_, seed, sr, nch, _) in CONFIGS]
+    outs = capi.encode_batch(ctl, pcms)
+    for (name, seed, sr, nch, kw), pcm, got in zip(CONFIGS, pcms, outs):
+        ref = ref_encode(sr, nch, kw, pcm)
+        assert got.size == ref.size and np.array_equal(got, ref), name
+
+
 def test_mixed_batch_matches_reference():
     """Streams with different controls, rates, channel counts and ragged lengths in one batch."""
     ctl, pcms, refs = [], [], []
