@@ -5,6 +5,7 @@
 #include "enc_init.h"
 
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 
@@ -713,6 +714,13 @@ int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
         for (i = 0; i < 576; i++) T.line_band_l[i] = 22;
         for (i = 0; i < 22; i++)
             for (int k = T.startBand_l[i]; k < T.startBand_l[i + 1] && k < 576; k++) T.line_band_l[k] = (unsigned char)i;
+        for (int k = 0; k < 576; k++) {
+            const int b = T.line_band_l[k], k0 = k & ~31;
+            const int s = b < 22 ? T.startBand_l[b] : T.startBand_l[22], e = b < 22 ? T.startBand_l[b + 1] : 576;
+            const int lo = std::max(s - k0, 0), hi = std::min(e - k0, 32);
+            T.line_seg_l[k] = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            T.line_segflag_l[k] = (unsigned char)(((k - k0) == lo ? 1 : 0) | (e <= k0 + 32 ? 2 : 0));
+        }
         kk = 0;
         for (i = 0; i < 13; i++) { T.startBand_s[i] = kk; kk += T.nBand_s[i]; }
         T.startBand_s[13] = kk;

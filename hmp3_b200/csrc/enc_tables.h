@@ -256,6 +256,10 @@ struct EncTables {
     int cnt_ncand[kCountClasses];      // 2 or 4 (0 for the null class)
     // ---- line -> scale-factor band (long blocks), 22 = above the last band
     unsigned char line_band_l[576];
+    // for the warp-wide quantiser pass (chunks of 32 lines, lane = line & 31): the lanes of a line's chunk that hold
+    // lines of the same band, and flags: 1 = first such lane of the chunk, 2 = the band ends inside this chunk
+    uint32_t line_seg_l[576];
+    unsigned char line_segflag_l[576];
 };
 
 // ------------------------------------------------------------------ scalar table functions

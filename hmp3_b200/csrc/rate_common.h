@@ -28,11 +28,15 @@ struct RegionPlan {
     int nbig, nquads, bits;
 };
 
+// A quantised spectral magnitude.  The step range (gmin = gzero - 70) bounds them by 8191, so 16 bits hold them:
+// half the state bytes, and a pair (the unit of the Huffman big-value tables) is one 32-bit word.
+typedef short QLine;
+
 HMP3_HD int imin_(int a, int b) { return a < b ? a : b; }
 HMP3_HD int imax_(int a, int b) { return a > b ? a : b; }
 
 // (hot sequential loops are unrolled by hand: see sum_seq in enc_tables.h)
-HMP3_HD int max_seq(const int *v, int n) {  // max(0, v[0], ..., v[n-1])
+HMP3_HD int max_seq(const QLine *v, int n) {  // max(0, v[0], ..., v[n-1])
     int m = 0, k = 0;
     for (; k < n; k++) m = imax_(m, v[k]);
     return m;
@@ -40,19 +44,19 @@ HMP3_HD int max_seq(const int *v, int n) {  // max(0, v[0], ..., v[n-1])
 
 // ------------------------------------------------------------------ quantiser passes (l3math.c)
 // plain rounding quantiser (l3math.c:655-671)
-HMP3_FN int quant_plain(const EncTables *T, const float *x34, int *ix, int g, int n) {
+HMP3_FN int quant_plain(const EncTables *T, const float *x34, QLine *ix, int g, int n) {
     const float ig = T->igain34[g];
     int m = 0;
     for (int i = 0; i < n; i++) {
         int q = (int)(ig * x34[i] + (0.5f - 0.0946f));
-        ix[i] = q;
+        ix[i] = (QLine)q;
         if (q > m) m = q;
     }
     return m;
 }
 // RD-tuned quantiser: magnitude-dependent rounding offset (l3math.c:674-694); `r0` replaces the offset of
 // magnitude class 0 (l3math.c:697-725 when given), clamp_lo mirrors the extra lower clamp of that variant.
-HMP3_FN int quant_tuned(const EncTables *T, const float *x34, int *ix, int g, int n, bool alt, float r0) {
+HMP3_FN int quant_tuned(const EncTables *T, const float *x34, QLine *ix, int g, int n, bool alt, float r0) {
     const float ig = T->igain34[g];
     int m = 0;
     for (int i = 0; i < n; i++) {
@@ -62,7 +66,7 @@ HMP3_FN int quant_tuned(const EncTables *T, const float *x34, int *ix, int g, in
         if (alt && c < 0) c = 0;
         float off = (alt && c == 0) ? r0 : T->quantB_round[c];
         int q = (int)(t - off);
-        ix[i] = q;
+        ix[i] = (QLine)q;
         if (q > m) m = q;
     }
     return m;
@@ -111,7 +115,7 @@ HMP3_HD float dequant43_sq(const EncTables *T, int q) {  // (q^(4/3))^2 as band_
     else v = (float)(pow((double)q, (4.0 / 3.0)));
     return v * v;
 }
-HMP3_HD int band_refit_gain_seq(const EncTables *T, const int *q, const float *x, int n) {
+HMP3_HD int band_refit_gain_seq(const EncTables *T, const QLine *q, const float *x, int n) {
     float sqq = 0, sxx = 0;
     int i = 0;
     for (; i < n; i++) {
@@ -156,7 +160,7 @@ HMP3_FN int band_noise(const EncTables *T, const float *x34, const float *x, int
 }
 
 // gain (scaled by 2^13) that best maps quantised values back onto the spectrum (l3math.c:1087-1114)
-HMP3_FN int band_refit_gain(const EncTables *T, const int *q, const float *x, int n) {
+HMP3_FN int band_refit_gain(const EncTables *T, const QLine *q, const float *x, int n) {
     float sqq = 0, sxx = 0;
 #if HMP3_COOP
     const int lane = HMP3_LANE;
@@ -204,7 +208,18 @@ HMP3_HD int count_class_of(const EncTables *T, int m) {
 
 // bits of n values (n/2 pairs) under the candidate tables of class c; ties go to the higher candidate
 // (cnt.c:96-292)
-HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n) {
+// (device: ix + even offsets are 4-byte aligned -- band edges and region ends are even -- so a pair is one load)
+HMP3_HD void load_pair(const QLine *p, int *a, int *b) {
+#if HMP3_COOP
+    const unsigned w = *(const unsigned *)p;
+    *a = (int)(short)(w & 0xffffu);
+    *b = (int)(short)(w >> 16);
+#else
+    *a = p[0];
+    *b = p[1];
+#endif
+}
+HMP3_FN CountResult count_pairs(const EncTables *T, int c, const QLine *ix, int n) {
     CountResult r;
     r.bits = r.index = 0;
     const int nc = T->cnt_ncand[c];
@@ -218,14 +233,23 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
 #endif
     if (c >= 7) {  // escape tables: values above 15 use the row/column of 15
         for (int i = i_first; i < n; i += i_step) {
-            int a = ix[i] > 15 ? 15 : ix[i], b = ix[i + 1] > 15 ? 15 : ix[i + 1];
+            int a, b;
+            load_pair(ix + i, &a, &b);
+            a = a > 15 ? 15 : a;
+            b = b > 15 ? 15 : b;
             s0 += lut[a * 16 + b][0];
         }
     } else if (nc == 2) {
-        for (int i = i_first; i < n; i += i_step) s0 += lut[(ix[i] & 15) * 16 + (ix[i + 1] & 15)][0];
+        for (int i = i_first; i < n; i += i_step) {
+            int a, b;
+            load_pair(ix + i, &a, &b);
+            s0 += lut[(a & 15) * 16 + (b & 15)][0];
+        }
     } else {
         for (int i = i_first; i < n; i += i_step) {
-            const uint32_t *e = lut[(ix[i] & 15) * 16 + (ix[i + 1] & 15)];
+            int a, b;
+            load_pair(ix + i, &a, &b);
+            const uint32_t *e = lut[(a & 15) * 16 + (b & 15)];
             s0 += e[0];
             s1 += e[1];
         }
@@ -247,7 +271,7 @@ HMP3_FN CountResult count_pairs(const EncTables *T, int c, const int *ix, int n)
 }
 
 // count1 region: table A (variable length) against table B (4 bits), sign bits included (cnt.c:295-326)
-HMP3_FN CountResult count_quads(const int *ix, int nquads) {
+HMP3_FN CountResult count_quads(const QLine *ix, int nquads) {
     CountResult r;
     r.bits = r.index = 0;
     if (nquads <= 0) return r;
@@ -258,7 +282,10 @@ HMP3_FN CountResult count_quads(const int *ix, int nquads) {
 #else
     for (int i = 0, k = 0; i < nquads; i++, k += 4) {
 #endif
-        int j = ((ix[k] << 3) + (ix[k + 1] << 2) + (ix[k + 2] << 1) + ix[k + 3]) & 15;
+        int q0, q1, q2, q3;
+        load_pair(ix + k, &q0, &q1);
+        load_pair(ix + k + 2, &q2, &q3);
+        int j = ((q0 << 3) + (q1 << 2) + (q2 << 1) + q3) & 15;
         int ones = (j & 1) + ((j >> 1) & 1) + ((j >> 2) & 1) + ((j >> 3) & 1);
         a += kQuadLenA[j] + ones;
         b += 4 + ones;
@@ -281,7 +308,7 @@ HMP3_HD void region_split_rule(int nbands, int *r0, int *r1) {
 // Region planning + bit count for a long-block granule channel (block types 0 / 1,3).
 // ixmax[] = per-band maxima, ix[] = the persistent quantised-line buffer (lines past the last coded band
 // keep whatever earlier granules left there, as in the reference).  bitalloc.cpp:470-754.
-HMP3_FN int plan_regions_long(const EncTables *T, int block_type, const int *ixmax, const int *ix, int ncb,
+HMP3_FN int plan_regions_long(const EncTables *T, int block_type, const int *ixmax, const QLine *ix, int ncb,
                               RegionPlan *P) {
     const int *start = T->startBand_l, *width = T->nBand_l;
     int i, j, n;

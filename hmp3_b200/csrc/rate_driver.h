@@ -68,7 +68,7 @@ HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros
 struct RateState {
     LongRate L;
     ShortRate S;
-    int ix[2][576];           // quantised lines in transmission order (persist between granules)
+    alignas(16) QLine ix[2][576];  // quantised lines in transmission order (persist between granules)
     unsigned char signx[2][576];
     GrSide gr[2][2];          // [granule][channel]
     ScaleFac sf[2][2];
@@ -498,7 +498,7 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, const
     LongRate *L = &R->L;
     GrSide *gr = R->gr[igr];
     ScaleFac *sf_out = R->sf[igr];
-    int *ix = &R->ix[0][0];
+    QLine *ix = &R->ix[0][0];
     unsigned char *sg = &R->signx[0][0];
     const int bt = gr[0].block_type;
     const int init = T->cfg.initial_mnr;
@@ -615,7 +615,7 @@ HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const Gra
 
 // Record what the packing pass needs of granule-channel (igr, ch): quantised lines, signs, scale factors, side info.
 HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
-    const int *ix = R->ix[ch];
+    const QLine *ix = R->ix[ch];
     const unsigned char *sg = R->signx[ch];
 #if HMP3_COOP
     const int lane = HMP3_LANE;
@@ -628,7 +628,7 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
         unsigned bits = 0;
         for (int h = 0; h < 32 / HMP3_W; h++) {
             const int k = 32 * w + HMP3_W * h + lane;
-            out->ix[k] = (short)ix[k];
+            out->ix[k] = ix[k];
             bits |= gballot(sg[k] & 1) << (HMP3_W * h);
         }
         if (lane == 0) out->sign[w] = bits;
@@ -641,7 +641,7 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
     for (int k = lane; k < (int)(sizeof(GrSide) / sizeof(int)); k += HMP3_W) gd[k] = gs[k];
     HMP3_SYNC();
 #else
-    for (int k = 0; k < 576; k++) out->ix[k] = (short)ix[k];
+    for (int k = 0; k < 576; k++) out->ix[k] = ix[k];
     for (int w = 0; w < 18; w++) {
         unsigned m = 0;
         for (int k = 0; k < 32; k++) m |= (unsigned)(sg[32 * w + k] & 1) << k;

@@ -29,6 +29,8 @@ struct LongRate {
     int G[2], preemp[2], sf_scale[2];
     RegionPlan plan[2];
     float (*x34)[576];  // |x|^(3/4) of the granule in flight: points into its PrepGranule
+    const float *exx[2];  // band energies of the spectra the loop works on (left/right, or mid/side), same place
+    int n_exx[2];         // bands they cover
 };
 
 HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
@@ -166,6 +168,10 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, const SigMask *sm 
                              unsigned char *signx /*[2][576]*/) {
     const int mnr = L->mnr + 100;
     long_adopt_prepared(T, L, P, signx, -1, T->cfg.nsf3);
+    for (int ch = 0; ch < 2; ch++) {
+        L->exx[ch] = P->xsxx[ch];
+        L->n_exx[ch] = T->cfg.nsf3[ch];
+    }
     int lines = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
         HMP3_FOR_LANES(i, T->cfg.nsf[ch]) {
@@ -193,6 +199,10 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
     const int mnr = L->mnr;
     const int nsf0 = T->cfg.nsf[0];
     long_adopt_prepared(T, L, P, signx, nsf0, T->cfg.nsf2);
+    for (int ch = 0; ch < 2; ch++) {
+        L->exx[ch] = P->e2[ch];
+        L->n_exx[ch] = nsf0;
+    }
     int lines = 0;
     HMP3_FOR_LANES(i, nsf0) {
         const int n = T->nBand_l[i];
@@ -286,6 +296,19 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
 }
 
 #if HMP3_COOP
+// One 576-float row of shared memory per stream of the block: per-line scratch of the line-parallel sections
+// (step search, sparse-band refit); nothing is kept in it between sections.
+__device__ __forceinline__ float *rate_scratch_row() {
+    __shared__ float s_row[kRateWarpsPerBlock * (32 / HMP3_W)][576];
+    return s_row[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
+}
+// max of v over the lanes named in `seg` (a lane mask inside the group, the caller's lane included); lanes with
+// different masks may execute this together
+__device__ __forceinline__ int gmax_seg(int v, unsigned seg) {
+    int r;
+    asm volatile("redux.sync.max.s32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(seg << HMP3_GSHIFT));
+    return r;
+}
 // Device form of the per-band step search: all bands of both channels walk together.  Lane b owns band b of
 // each channel (its search state lives in that lane's registers).  Every round (1) all lanes evaluate the
 // squared error of every line whose band is still searching, at that band's current trial step, into L->dd;
@@ -295,8 +318,7 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
     constexpr int NS = (22 + HMP3_W - 1) / HMP3_W;  // band slots per lane: band = lane + HMP3_W * slot
     const int lane = HMP3_LANE;
     // per-line squared errors of one channel at a time, in shared memory (one 576-float row per stream of the block)
-    __shared__ float s_dd[kRateWarpsPerBlock * (32 / HMP3_W)][576];
-    float *dd = s_dd[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
+    float *dd = rate_scratch_row();
     HMP3_SYNC();
     // channel-major: one channel's bands are searched to the end before the other channel is touched, so that the
     // rounds of a search work on one channel's spectra (4.6 KB) instead of both (the bands are independent: the order
@@ -518,7 +540,7 @@ HMP3_HD void long_hf_reset_lr(LongRate *L) {
     L->gsf_hf_ch[0] = L->gsf_hf_ch[1] = -1;
     L->ixmax[0][21] = L->ixmax[1][21] = 0;
 }
-HMP3_FN void long_clear_hf_lines(const EncTables *T, int *ix, int nch) {  // bitallo3.cpp:1629-1654
+HMP3_FN void long_clear_hf_lines(const EncTables *T, QLine *ix, int nch) {  // bitallo3.cpp:1629-1654
     const int b = T->startBand_l[21], n = T->nBand_l[21];
     for (int ch = 0; ch < nch; ch++)
         for (int k = 0; k < n; k++) ix[576 * ch + b + k] = 0;
@@ -720,30 +742,63 @@ HMP3_FN void long_coarsen_low_bands(const EncTables *T, LongRate *L, const float
 }
 
 // re-fit the scale factor of bands whose largest quantised value is 1 or 2 (bitallo3.cpp:1471-1536)
-HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const int *ix) {
+HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const float *xr, const QLine *ix) {
 #if HMP3_COOP
+    // Line-parallel: every lane squares the de-quantised value of every 32nd line of the bands to refit into the
+    // stream's scratch row, then the band's owner adds them up in line order.  The other sum of the fit, the energy
+    // of the band's spectrum in the same order, is the one the prepare pass already took (exx).
+    constexpr int NS = (22 + HMP3_W - 1) / HMP3_W;
+    const int lane = HMP3_LANE;
+    float *dd = rate_scratch_row();
     HMP3_SYNC();
-    for (int it = HMP3_LANE; it < 64; it += HMP3_W) {  // one (channel, band) per lane
-        const int ch = it >> 5, i = it & 31;
-        if (ch >= L->nchan || i >= T->cfg.nsf[ch]) continue;
-        if (!((L->ixmax[ch][i] == 1) || (L->ixmax[ch][i] == 2))) continue;
+    for (int ch = 0; ch < L->nchan; ch++) {
+        const int nb = T->cfg.nsf[ch];
+        unsigned fm = 0;  // bit b = band b of the channel is refitted
+        for (int sl = 0; sl < NS; sl++) {
+            const int i = lane + HMP3_W * sl;
+            const int m = i < nb ? L->ixmax[ch][i] : 0;
+            fm |= gballot((m == 1) || (m == 2)) << ((HMP3_W * sl) & 31);
+        }
+        if (fm == 0) continue;
+        const int nl = T->startBand_l[nb];
+        const QLine *q = ix + 576 * ch;
+        for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
+            const int k = k0 + lane;
+            if (k < nl && ((fm >> T->line_band_l[k]) & 1u)) {
+                const int v = q[k];
+                const float d = (v < 256) ? T->ix43[v] : (float)(pow((double)v, (4.0 / 3.0)));
+                dd[k] = d * d;
+            }
+        }
+        HMP3_SYNC();
         const int gscale = L->G[ch] << 13;
         const int scale = L->sf_scale[ch], pre = L->preemp[ch];
-        const int t = band_refit_gain_seq(T, ix + 576 * ch + T->startBand_l[i], xr + 576 * ch + T->startBand_l[i], T->nBand_l[i]);
-        int s;
-        if (scale == 0) s = ((gscale - t + (1 << 13)) & (~((1 << 14) - 1))) >> 13;
-        else s = ((gscale - t + (1 << 14)) & (~((1 << 15) - 1))) >> 13;
-        s = imin_(s, sf_upper(scale, pre, i));
-        s = imax_(s, sf_lower(scale, pre, i));
-        L->sf[ch][i] = s;
+        for (int i = lane; i < nb; i += HMP3_W) {
+            if (!((fm >> i) & 1u)) continue;
+            const int n = T->nBand_l[i], k0 = T->startBand_l[i];
+            const float sqq = sum_seq(dd + k0, n, 0.0f);
+            float sxx;
+            if (i < L->n_exx[ch]) sxx = L->exx[ch][i];
+            else {
+                sxx = 0.0f;
+                for (int k = 0; k < n; k++) sxx += xr[576 * ch + k0 + k] * xr[576 * ch + k0 + k];
+            }
+            const int t = 54 * mb_log(T, sxx / sqq) + (8 << 13);
+            int s;
+            if (scale == 0) s = ((gscale - t + (1 << 13)) & (~((1 << 14) - 1))) >> 13;
+            else s = ((gscale - t + (1 << 14)) & (~((1 << 15) - 1))) >> 13;
+            s = imin_(s, sf_upper(scale, pre, i));
+            s = imax_(s, sf_lower(scale, pre, i));
+            L->sf[ch][i] = s;
+        }
+        HMP3_SYNC();
     }
-    HMP3_SYNC();
 #else
     for (int ch = 0; ch < L->nchan; ch++) {
         const int gscale = L->G[ch] << 13;
         const int scale = L->sf_scale[ch], pre = L->preemp[ch];
         const float *y = xr + 576 * ch;
-        const int *q = ix + 576 * ch;
+        const QLine *q = ix + 576 * ch;
         for (int i = 0; i < T->cfg.nsf[ch]; i++) {
             const int n = T->nBand_l[i];
             if ((L->ixmax[ch][i] == 1) || (L->ixmax[ch][i] == 2)) {
@@ -763,33 +818,65 @@ HMP3_FN void long_refit_sparse_bands(const EncTables *T, LongRate *L, const floa
 }
 
 // ------------------------------------------------------------------ quantise + count
-HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned) {  // bitallo3.cpp:1540-1581
+HMP3_FN void long_quantise(const EncTables *T, LongRate *L, QLine *ix, bool tuned) {  // bitallo3.cpp:1540-1581
 #if HMP3_COOP
-    // every lane quantises every 32nd line with its band's step; band maxima are then gathered one band per lane
+    // Every lane quantises every 32nd line with its band's step.  The band maxima come out of the same pass: the
+    // lanes of a chunk that hold lines of one band reduce their values among themselves (enc_init's line_seg_l is
+    // that lane mask), a band that continues into the next chunk carries its running maximum along, and the first
+    // lane of the band's last piece stores the result.
     HMP3_SYNC();
+    const int lane = HMP3_LANE;
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *x = L->x34[ch];
-        int *q = ix + 576 * ch;
+        QLine *q = ix + 576 * ch;
         const int nb = T->cfg.nsf[ch], nl = T->startBand_l[nb];
-        for (int k = HMP3_LANE; k < nl; k += HMP3_W) {
-            const float ig = T->igain34[L->gsf[ch][T->line_band_l[k]]];
-            int v;
-            if (tuned) {
-                float t = ig * x[k] + (0.5f - 0.4375f);
-                int c = (int)t;
-                if (c > 31) c = 31;
-                v = (int)(t - T->quantB_round[c]);
-            } else v = (int)(ig * x[k] + (0.5f - 0.0946f));
-            q[k] = v;
+        float ig_own = 0.0f;  // W = 32: lane b holds the inverse step of band b
+        if (HMP3_W == 32 && lane < nb) ig_own = T->igain34[L->gsf[ch][lane]];
+        int carry_b = -1, carry_m = 0;
+        for (int k0 = 0; k0 < nl; k0 += HMP3_W) {
+            const int k = k0 + lane;
+            const bool in = k < nl;
+            const int b = in ? (int)T->line_band_l[k] : -2;
+            float ig;
+            if (HMP3_W == 32) ig = gshfl(ig_own, b & 31);
+            else ig = in ? T->igain34[L->gsf[ch][b]] : 0.0f;
+            int v = 0;
+            unsigned seg = 1u << lane;
+            bool first = false, last = false;
+            if (in) {
+                const float xv = x[k];
+                if (tuned) {
+                    float t = ig * xv + (0.5f - 0.4375f);
+                    int c = (int)t;
+                    if (c > 31) c = 31;
+                    v = (int)(t - T->quantB_round[c]);
+                } else v = (int)(ig * xv + (0.5f - 0.0946f));
+                q[k] = (QLine)v;
+                if (HMP3_W == 32) {
+                    seg = T->line_seg_l[k];
+                    const int f = T->line_segflag_l[k];
+                    first = f & 1;
+                    last = f & 2;
+                } else {
+                    const int s = T->startBand_l[b], e = s + T->nBand_l[b];
+                    const int lo = imax_(s - k0, 0), hi = imin_(e - k0, HMP3_W);
+                    seg = (((hi - lo) >= 32) ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << lo;
+                    first = lane == lo;
+                    last = e <= k0 + HMP3_W;
+                }
+            }
+            int m = gmax_seg(v, seg);
+            if (b == carry_b) m = imax_(m, carry_m);
+            if (first && last) L->ixmax[ch][b] = imax_(m, 0);
+            carry_b = gshfl(b, HMP3_W - 1);
+            carry_m = gshfl(m, HMP3_W - 1);
         }
-        HMP3_SYNC();
-        for (int i = HMP3_LANE; i < nb; i += HMP3_W) L->ixmax[ch][i] = max_seq(q + T->startBand_l[i], T->nBand_l[i]);
     }
     HMP3_SYNC();
 #else
     for (int ch = 0; ch < L->nchan; ch++) {
         const float *x = L->x34[ch];
-        int *q = ix + 576 * ch;
+        QLine *q = ix + 576 * ch;
         for (int i = 0; i < T->cfg.nsf[ch]; i++) {
             const int n = T->nBand_l[i];
             L->ixmax[ch][i] = tuned ? quant_tuned(T, x, q, L->gsf[ch][i], n, false, 0.0f)
@@ -801,7 +888,7 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, int *ix, bool tuned)
 #endif
 }
 // drop isolated single-valued quads from the top, at most level/16 of them (bitallo3.cpp:1657-1687)
-HMP3_FN void sparsify_quads(int *q, int n, int level) {
+HMP3_FN void sparsify_quads(QLine *q, int n, int level) {
     int c = 0;
     for (int i = 0; i < n; i++) c += q[i];
     c = (level * c) >> 4;
@@ -813,7 +900,7 @@ HMP3_FN void sparsify_quads(int *q, int n, int level) {
             if (++dropped >= c) break;
         }
 }
-HMP3_FN void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms) {  // bitallo3.cpp:1690-1736
+HMP3_FN void long_quantise_hf(const EncTables *T, LongRate *L, QLine *ix, bool ms) {  // bitallo3.cpp:1690-1736
     const int b = T->startBand_l[21], n = T->nBand_l[21];
     if (ms) {
         L->ixmax[0][21] = quant_tuned(T, L->x34[0] + b, ix + b, L->G[0], n, true, -.30f);
@@ -825,7 +912,7 @@ HMP3_FN void long_quantise_hf(const EncTables *T, LongRate *L, int *ix, bool ms)
             sparsify_quads(ix + 576 * ch + b, n, 4);
         }
 }
-HMP3_FN int long_count(const EncTables *T, LongRate *L, const int *ix, const int *ncb) {  // bitallo3.cpp:1740-1779
+HMP3_FN int long_count(const EncTables *T, LongRate *L, const QLine *ix, const int *ncb) {  // bitallo3.cpp:1740-1779
     int bits = 0;
     for (int ch = 0; ch < L->nchan; ch++) {
         L->huff_bits[ch] = plan_regions_long(T, L->block_type, L->ixmax[ch], ix + 576 * ch, ncb[ch], &L->plan[ch]);
@@ -835,7 +922,7 @@ HMP3_FN int long_count(const EncTables *T, LongRate *L, const int *ix, const int
 }
 
 // ------------------------------------------------------------------ bit-budget control loops
-HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, bool ms) {  // :2569-2721
+HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, QLine *ix, int bits0, bool ms) {  // :2569-2721
     const int thres = L->min_target - (L->min_target >> 4);
     if (bits0 > thres) return bits0;
     int g[2][21];
@@ -881,7 +968,7 @@ HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, int *ix, int bits0, 
     return bits;
 }
 
-HMP3_FN int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, int *ix, int bits0) {  // :2814-2852
+HMP3_FN int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, QLine *ix, int bits0) {  // :2814-2852
     const int f = (250 * 1024) / (L->active_lines + 10);
     int dN = imax_((f * (bits0 - L->max_target)) >> 10, 40);
     int bits = bits0;
@@ -899,7 +986,7 @@ HMP3_FN int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, in
     }
     return bits;
 }
-HMP3_FN int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_channel) {  // :2725-2772
+HMP3_FN int long_cap_bits(const EncTables *T, LongRate *L, QLine *ix, bool per_channel) {  // :2725-2772
     int bits = 0;
     for (int k = 0; k < 100; k++) {
         for (int ch = 0; ch < L->nchan; ch++)
@@ -917,7 +1004,7 @@ HMP3_FN int long_cap_bits(const EncTables *T, LongRate *L, int *ix, bool per_cha
 
 // the allocation of one long granule; returns the bit count before the budget loops (the CBR
 // feedback signal) (bitallo3.cpp:2948-3149)
-HMP3_FN int long_allocate(const EncTables *T, LongRate *L, float *xr, int *ix, bool ms) {
+HMP3_FN int long_allocate(const EncTables *T, LongRate *L, float *xr, QLine *ix, bool ms) {
     const int hf = T->cfg.hf_flag;
     if (hf) {
         if (ms) {

@@ -17,9 +17,9 @@ struct ShortRate {
     int subgain[2][3], G[2][3], GG[2], sf_scale[2];
     RegionPlan plan[2];
     float x34[2][3][192];
-    int ix[2][3][192];
+    alignas(16) QLine ix[2][3][192];
     unsigned char sign[2][3][192];
-    int quad_scratch[580];
+    alignas(16) QLine quad_scratch[580];
 };
 
 HMP3_FN void short_rate_init(ShortRate *S) {
@@ -239,7 +239,7 @@ HMP3_FN void short_quantise(const EncTables *T, ShortRate *S, bool tuned) {  // 
         const int ch = it / 48, w = (it >> 4) % 3, i = it & 15;
         if (ch >= S->nchan || i >= T->cfg.nsf_s[ch]) continue;
         const float *x = S->x34[ch][w] + T->startBand_s[i];
-        int *q = S->ix[ch][w] + T->startBand_s[i];
+        QLine *q = S->ix[ch][w] + T->startBand_s[i];
         const int n = T->nBand_s[i];
         S->ixmax[ch][w][i] = tuned ? quant_tuned(T, x, q, S->gsf[ch][w][i], n, true, -.30f)
                                    : quant_plain(T, x, q, S->gsf[ch][w][i], n);
@@ -373,7 +373,7 @@ HMP3_FN int short_plan_regions(const EncTables *T, ShortRate *S, int ch) {
                 const uint32_t(*lut)[2] = T->cnt_lut[c];
                 s0 = s1 = 0;
                 for (int w = 0; w < 3; w++) {
-                    const int *q = S->ix[ch][w];
+                    const QLine *q = S->ix[ch][w];
                     for (int k = a; k < b; k += 2) {
                         int u = q[k], v = q[k + 1];
                         if (c >= 7) { u = u > 15 ? 15 : u; v = v > 15 ? 15 : v; }
@@ -399,7 +399,7 @@ HMP3_FN int short_plan_regions(const EncTables *T, ShortRate *S, int ch) {
     }
     P->table[2] = 0;
     int k = 0;
-    int *qs = S->quad_scratch;
+    QLine *qs = S->quad_scratch;
     for (i = cb1; i < cb2; i++)
         for (int w = 0; w < 3; w++)
             for (int j = start[i]; j < start[i + 1]; j++) qs[k++] = S->ix[ch][w][j];
@@ -525,7 +525,7 @@ HMP3_FN void short_allocate(const EncTables *T, ShortRate *S, const float *xr) {
 // records of this granule; ix_out/sign_out receive the lines in transmission order
 // (bitallos.cpp:202-372).
 HMP3_FN int short_granule(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm, int nchan, int min_bits,
-                          int target_bits, int max_bits, int pool_bits, ScaleFac *sf_out, GrSide *gr, int *ix_out,
+                          int target_bits, int max_bits, int pool_bits, ScaleFac *sf_out, GrSide *gr, QLine *ix_out,
                           unsigned char *sign_out, int ms, int mnr) {
     S->mnr = mnr;
     if (T->cfg.h_id == 0) S->mnr = imin_(S->mnr, 850);
@@ -596,7 +596,7 @@ HMP3_FN int short_granule(const EncTables *T, ShortRate *S, float *xr, const Sig
     }
     // lines in transmission order: [band][window][line] (bitallos.cpp:329-366)
     for (int ch = 0; ch < nchan; ch++) {
-        int *dst = ix_out + 576 * ch;
+        QLine *dst = ix_out + 576 * ch;
         unsigned char *ds = sign_out + 576 * ch;
         for (int k = 0; k < 576; k++) dst[k] = 0;
         int k = 0;

@@ -285,7 +285,7 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
                     memcpy(t + 100 + 39 * c, R->sf[q][c].s, 39 * sizeof(int));
                 }
                 // ix is shared by both granules of the call: only meaningful for the last granule processed
-                memcpy(t + 200, R->ix, 2 * 576 * sizeof(int));
+                for (int k = 0; k < 2 * 576; k++) t[200 + k] = (&R->ix[0][0])[k];
                 t[1360] = R->L.mnr;
                 t[1361] = R->byte_pool;
                 t[1362] = frames[R->frames - 1].head[3];

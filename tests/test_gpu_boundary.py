@@ -76,7 +76,7 @@ def test_packet_call_without_a_bitstream_buffer():
     enc.init_l3(capi.control(samprate=44100, nch=2, bitrate=64))
     for c in range(12):
         used, bs, pk = enc.encode_l3_packet(pcm[c * 1152:(c + 1) * 1152], want_bs=False)
-        assert bs.size == 0 and pk[0].size > 36 and pk[1].size == 0
+        assert bs.size == 0 and pk[0].size >= 36 and pk[1].size == 0
     assert enc.frames_bytes()[0] > 0 and enc.frames_bytes()[1] == 0
     enc.close()
 
