@@ -8,6 +8,8 @@
 #define HMP3_W_HOST_VALUE 16
 #endif
 static constexpr int HMP3_W_HOST = HMP3_W_HOST_VALUE;
+// one 576-float scratch row per stream of a block (rate_scratch_row)
+static constexpr size_t kRateSmem = sizeof(float) * 576 * hmp3::kRateWarpsPerBlock * (32 / HMP3_W_HOST_VALUE);
 
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
@@ -55,8 +57,9 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
         const char *e = getenv("HMP3_RATE_CARVEOUT");
         const int pct = e ? atoi(e) : 40;
         if (pct >= 0) cudaFuncSetAttribute(k_rate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRateSmem);
     }
-    k_rate<<<blocks_for((long long)n * HMP3_W_HOST, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, 0, stream>>>(
+    k_rate<<<blocks_for((long long)n * HMP3_W_HOST, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, kRateSmem, stream>>>(
         tabs, st, so, rs, cb, main_buf, frames, K0, n, cycles);
 }
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,

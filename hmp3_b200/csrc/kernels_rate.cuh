@@ -26,7 +26,18 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
            unsigned char *main_buf, FrameRec *frames, int K0, int nstreams, long long *cycles) {
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) / HMP3_W);
+#ifdef HMP3_RATE_BARRIER
+    if (s >= nstreams || K0 >= st[s].ngran) {  // no stream / nothing left: still a member of the block's barriers
+        if (s < nstreams && HMP3_LANE == 0) {
+            cb.fr0[s] = cb.fr1[s] = rs[s].frames;
+            cb.fd1[s] = rs[s].frames_done;
+        }
+        rate_run_chunk(nullptr, nullptr, K0, cb.NG, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+        return;
+    }
+#else
     if (s >= nstreams) return;
+#endif
     const long long t0 = clock64();
     const StreamDev sd = st[s];
     if (HMP3_LANE == 0) {  // nothing recorded in this chunk unless the loop below runs

@@ -10,6 +10,19 @@
 
 namespace hmp3 {
 
+// HMP3_RATE_BARRIER (build option, experiments): the warps of a block start every frame together (block-wide
+// barrier), so that they walk the code as a convoy and share instruction fetches; every warp of the block then runs
+// the loop below with the same trip count, whether or not it has a stream or work left (`live`).
+#if HMP3_COOP && defined(HMP3_RATE_BARRIER)
+#define HMP3_FRAME_BARRIER() __syncthreads()
+#else
+#define HMP3_FRAME_BARRIER()
+#endif
+#if HMP3_COOP && defined(HMP3_RATE_BARRIER) && HMP3_RATE_BARRIER >= 2  // ... and the second granule of the call too
+#define HMP3_GRANULE_BARRIER() __syncthreads()
+#else
+#define HMP3_GRANULE_BARRIER()
+#endif
 // One emitted frame, as recorded by the serial stage.  The serial stage only does the bit ACCOUNTING; the bits
 // themselves (scale factors, Huffman codes, side info) are written afterwards by the packing pass
 // (pack_frame: one warp per frame, all frames in parallel) and the final byte layout (header | side | slice of
@@ -69,7 +82,7 @@ struct RateState {
     LongRate L;
     ShortRate S;
     alignas(16) QLine ix[2][576];  // quantised lines in transmission order (persist between granules)
-    unsigned char signx[2][576];
+    unsigned signx[2][18];    // sign bit of line k of a channel = bit (k & 31) of word (k >> 5); persists like ix
     GrSide gr[2][2];          // [granule][channel]
     ScaleFac sf[2][2];
     int scfsi[2];
@@ -499,7 +512,7 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, const
     GrSide *gr = R->gr[igr];
     ScaleFac *sf_out = R->sf[igr];
     QLine *ix = &R->ix[0][0];
-    unsigned char *sg = &R->signx[0][0];
+    unsigned *sg = &R->signx[0][0];
     const int bt = gr[0].block_type;
     const int init = T->cfg.initial_mnr;
     L->block_type = bt;
@@ -616,7 +629,7 @@ HMP3_HD void set_block_info(const EncTables *T, RateState *R, int igr, const Gra
 // Record what the packing pass needs of granule-channel (igr, ch): quantised lines, signs, scale factors, side info.
 HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
     const QLine *ix = R->ix[ch];
-    const unsigned char *sg = R->signx[ch];
+    const unsigned *sg = R->signx[ch];
 #if HMP3_COOP
     const int lane = HMP3_LANE;
     HMP3_SYNC();
@@ -624,14 +637,11 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
     const GrSide *g = &R->gr[igr][ch];
     const int extent = g->aux_not_null ? 2 * (g->aux_nreg[0] + g->aux_nreg[1] + g->aux_nreg[2]) + 4 * g->aux_nquads : 0;
     const int nwords = imin_(18, (extent + 31) >> 5);
-    for (int w = 0; w < nwords; w++) {
-        unsigned bits = 0;
-        for (int h = 0; h < 32 / HMP3_W; h++) {
-            const int k = 32 * w + HMP3_W * h + lane;
-            out->ix[k] = ix[k];
-            bits |= gballot(sg[k] & 1) << (HMP3_W * h);
-        }
-        if (lane == 0) out->sign[w] = bits;
+    {   // the coded lines, two per 32-bit word (both arrays are 4-byte aligned), and their sign words
+        const unsigned *src = (const unsigned *)ix;
+        unsigned *dst = (unsigned *)out->ix;
+        for (int k = lane; k < 16 * nwords; k += HMP3_W) dst[k] = src[k];
+        for (int w = lane; w < nwords; w += HMP3_W) out->sign[w] = sg[w];
     }
     const ScaleFac *sf = &R->sf[igr][ch];
     for (int k = lane; k < 23; k += HMP3_W) out->sf[k] = (unsigned char)sf->l[k];
@@ -642,11 +652,7 @@ HMP3_FN void record_gc(const RateState *R, int igr, int ch, PackGc *out) {
     HMP3_SYNC();
 #else
     for (int k = 0; k < 576; k++) out->ix[k] = ix[k];
-    for (int w = 0; w < 18; w++) {
-        unsigned m = 0;
-        for (int k = 0; k < 32; k++) m |= (unsigned)(sg[32 * w + k] & 1) << k;
-        out->sign[w] = m;
-    }
+    for (int w = 0; w < 18; w++) out->sign[w] = sg[w];
     const ScaleFac *sf = &R->sf[igr][ch];
     for (int i = 0; i < 23; i++) out->sf[i] = (unsigned char)sf->l[i];
     for (int w = 0; w < 3; w++)
@@ -689,6 +695,7 @@ HMP3_FN int encode_frame_mpeg1(const EncTables *T, RateState *R, GranuleIn *g0, 
     const int ms = g0->ms;  // frame decision (both granules carry it)
     int total = 0;
     for (int igr = 0; igr < 2; igr++) {
+        if (igr) HMP3_GRANULE_BARRIER();
         granule_allocate(T, R, gs[igr]->xr, gs[igr]->sm, gs[igr]->prep, igr, nch, ba_min, target, ba_max, bit_pool, ms);
         for (int ch = 0; ch < nch; ch++) {
             GrSide *g = &R->gr[igr][ch];
@@ -861,12 +868,15 @@ namespace hmp3 {
 // test/tomp3.cpp:1015-1036), checked at call boundaries.
 HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, int ngran, int ngran_real,
                             const GranuleInfo *gi, float *xr, const SigMask *sm, PrepGranule *prep,
-                            const signed char *ms, PackGc *pack, FrameRec *frames) {
-    const bool m1 = T->cfg.h_id == 1;
+                            const signed char *ms, PackGc *pack, FrameRec *frames, bool live = true) {
+    const bool m1 = live && T->cfg.h_id == 1;
     const int frames_real = m1 ? ngran_real / 2 : ngran_real;
-    for (int K = K0; K + 1 < K0 + NG && K + 1 < ngran; K += 2) {
-        if (R->finished) return;
-        if (K < R->next_granule) continue;
+    for (int K = K0; K + 1 < K0 + NG; K += 2) {
+        HMP3_FRAME_BARRIER();
+        if (!live || K + 1 >= ngran || R->finished || K < R->next_granule) {
+            HMP3_GRANULE_BARRIER();
+            continue;
+        }
         GranuleIn g[2];
         for (int q = 0; q < 2; q++) {
             const int o = K - K0 + q;
@@ -880,6 +890,7 @@ HMP3_FN void rate_run_chunk(const EncTables *T, RateState *R, int K0, int NG, in
         if (m1) encode_one_frame(T, R, frames, 0, &g[0], &g[1], pk, K);
         else {
             encode_one_frame(T, R, frames, 0, &g[0], nullptr, pk, K);
+            HMP3_GRANULE_BARRIER();
             encode_one_frame(T, R, frames, 1, &g[1], nullptr, pk + 2, K + 1);
         }
         R->next_granule = K + 2;

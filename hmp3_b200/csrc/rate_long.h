@@ -28,6 +28,8 @@ struct LongRate {
     int gzero[2][22], gmin[2][22], gsf[2][22];
     int G[2], preemp[2], sf_scale[2];
     RegionPlan plan[2];
+    int gsave[2][22];     // long_more_bits: the steps before the trial pass
+    int peak[22], peak10[22];  // long_trade_peaks: quantised band maxima of the channel in hand
     float (*x34)[576];  // |x|^(3/4) of the granule in flight: points into its PrepGranule
     const float *exx[2];  // band energies of the spectra the loop works on (left/right, or mid/side), same place
     int n_exx[2];         // bands they cover
@@ -132,7 +134,16 @@ HMP3_FN void long_flatten_targets(const EncTables *T, LongRate *L) {
 // Take over what the parallel prepare pass computed for this granule (prepare.h): band energies, step bounds,
 // the |x|^(3/4) array (by reference) and the signs (expanded into the persistent sign array for the lines that
 // were rewritten, so that lines beyond them keep their old value like the reference's signx buffer).
-HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P, unsigned char *signx, int n_energy,
+// Merge the sign bits of the first nl lines (packed 32 per word) into the persistent sign words: lines beyond nl keep
+// their old value like the reference's signx buffer.
+HMP3_HD void merge_sign_word(unsigned *dst, unsigned src, int w, int nl) {
+    if (32 * w + 32 <= nl) *dst = src;
+    else if (32 * w < nl) {
+        const unsigned m = (1u << (nl - 32 * w)) - 1u;
+        *dst = (*dst & ~m) | (src & m);
+    }
+}
+HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P, unsigned *signw /*[2][18]*/, int n_energy,
                                  const int *n_bounds /*[2]*/) {
     L->x34 = P->x34;
 #if HMP3_COOP
@@ -146,7 +157,7 @@ HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P
             L->gmin[ch][i] = P->gmin[ch][i];
         }
         const int nl = P->nlines[ch];
-        for (int k = HMP3_LANE; k < nl; k += HMP3_W) signx[576 * ch + k] = (unsigned char)((P->sign[ch][k >> 5] >> (k & 31)) & 1u);
+        for (int w = HMP3_LANE; w < 18; w += HMP3_W) merge_sign_word(signw + 18 * ch + w, P->sign[ch][w], w, nl);
     }
     HMP3_SYNC();
 #else
@@ -158,14 +169,14 @@ HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P
             L->gzero[ch][i] = P->gzero[ch][i];
             L->gmin[ch][i] = P->gmin[ch][i];
         }
-        for (int k = 0; k < P->nlines[ch]; k++) signx[576 * ch + k] = (unsigned char)((P->sign[ch][k >> 5] >> (k & 31)) & 1u);
+        for (int w = 0; w < 18; w++) merge_sign_word(signw + 18 * ch + w, P->sign[ch][w], w, P->nlines[ch]);
     }
 #endif
 }
 
 // left/right granule (bitallo3.cpp:816-898): noise targets from the prepared band energies.
 HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, const SigMask *sm /*[2][36]*/, PrepGranule *P,
-                             unsigned char *signx /*[2][576]*/) {
+                             unsigned *signx /*[2][18]*/) {
     const int mnr = L->mnr + 100;
     long_adopt_prepared(T, L, P, signx, -1, T->cfg.nsf3);
     for (int ch = 0; ch < 2; ch++) {
@@ -193,7 +204,7 @@ HMP3_FN void long_startup_lr(const EncTables *T, LongRate *L, const SigMask *sm 
 
 // mid/side granule (bitallo3.cpp:902-1065): noise targets from the prepared energies (the spectra were rotated to
 // |L+R|, |L-R| without 1/sqrt2 by the prepare pass; the global gain is lowered by 2 steps on output instead).
-HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm, PrepGranule *P, unsigned char *signx) {
+HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm, PrepGranule *P, unsigned *signx) {
     if (T->cfg.vbr_flag == 0 && L->calls > 10 && (L->target - L->min_target) < 100)
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
@@ -298,9 +309,9 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
 #if HMP3_COOP
 // One 576-float row of shared memory per stream of the block: per-line scratch of the line-parallel sections
 // (step search, sparse-band refit); nothing is kept in it between sections.
+extern __shared__ float s_rate_rows[];  // [streams of the block][576], dynamic (a 32-warp block needs 72 KB)
 __device__ __forceinline__ float *rate_scratch_row() {
-    __shared__ float s_row[kRateWarpsPerBlock * (32 / HMP3_W)][576];
-    return s_row[(threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W))];
+    return s_rate_rows + 576 * ((threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W)));
 }
 // max of v over the lanes named in `seg` (a lane mask inside the group, the caller's lane included); lanes with
 // different masks may execute this together
@@ -461,12 +472,14 @@ HMP3_HD float db_of(float x) { return (float)(10.0 * log10((double)x)); }
 HMP3_FN void long_trade_peaks(const EncTables *T, LongRate *L) {
     for (int ch = 0; ch < L->nchan; ch++) {
         const int nsf = T->cfg.nsf[ch];
-        int peak[22], peak10[22];
-        for (int i = 0; i < nsf; i++) {
+        int *peak = L->peak, *peak10 = L->peak10;
+        HMP3_SYNC();
+        HMP3_FOR_LANES(i, nsf) {
             peak[i] = quant_tuned_peak(T, L->x34max[ch][i], L->gsf[ch][i]);
             peak10[i] = quant_tuned_peak10(T, L->x34max[ch][i], L->gsf[ch][i]);
             L->ixmax[ch][i] = peak[i];
         }
+        HMP3_SYNC();
         int i;
         for (i = nsf - 1; i >= 11; i--) {
             if (peak10[i] > 16) break;
@@ -925,10 +938,11 @@ HMP3_FN int long_count(const EncTables *T, LongRate *L, const QLine *ix, const i
 HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, QLine *ix, int bits0, bool ms) {  // :2569-2721
     const int thres = L->min_target - (L->min_target >> 4);
     if (bits0 > thres) return bits0;
-    int g[2][21];
+    int(*g)[22] = L->gsave;
     int bits = bits0;
+    HMP3_SYNC();
     for (int ch = 0; ch < L->nchan; ch++)
-        for (int i = 0; i < T->cfg.nsf[ch]; i++) g[ch][i] = L->gsf[ch][i];
+        HMP3_FOR_LANES(i, T->cfg.nsf[ch]) g[ch][i] = L->gsf[ch][i];
     const int hf = T->cfg.hf_flag;
     for (int pass = 0; pass < 11; pass++) {
         const bool undo = (pass == 10) || (pass > 0 && bits >= thres);
@@ -936,12 +950,12 @@ HMP3_FN int long_more_bits(const EncTables *T, LongRate *L, QLine *ix, int bits0
             // finished stepping down; if that overshot the ceiling go back one step
             if (!(bits > L->max_target)) break;
             for (int ch = 0; ch < L->nchan; ch++)
-                for (int i = 0; i < T->cfg.nsf[ch]; i++) L->gsf[ch][i] = g[ch][i] + 1;
+                HMP3_FOR_LANES(i, T->cfg.nsf[ch]) L->gsf[ch][i] = g[ch][i] + 1;
         } else {
             for (int ch = 0; ch < L->nchan; ch++)
-                for (int i = 0; i < T->cfg.nsf[ch]; i++)
-                    L->gsf[ch][i] = g[ch][i] = imax_(g[ch][i] - 1, L->gmin[ch][i]);
+                HMP3_FOR_LANES(i, T->cfg.nsf[ch]) L->gsf[ch][i] = g[ch][i] = imax_(g[ch][i] - 1, L->gmin[ch][i]);
         }
+        HMP3_SYNC();
         if (ms) {
             L->hf_quant = 0;
             L->ixmax[0][21] = 0;
@@ -975,8 +989,9 @@ HMP3_FN int long_fewer_bits(const EncTables *T, LongRate *L, const float *xr, QL
     L->delta_mnr = 0;
     for (int k = 0; k < 10; k++) {
         L->delta_mnr += dN;
+        HMP3_SYNC();
         for (int ch = 0; ch < L->nchan; ch++)
-            for (int i = 0; i < T->cfg.nsf[ch]; i++) L->nt[ch][i] += dN;
+            HMP3_FOR_LANES(i, T->cfg.nsf[ch]) L->nt[ch][i] += dN;
         long_seek_actual(T, L, xr);
         long_scale_factors(T, L, false);
         long_quantise(T, L, ix, false);
@@ -991,7 +1006,8 @@ HMP3_FN int long_cap_bits(const EncTables *T, LongRate *L, QLine *ix, bool per_c
     for (int k = 0; k < 100; k++) {
         for (int ch = 0; ch < L->nchan; ch++)
             if (!per_channel || L->huff_bits[ch] > kPart23Max)
-                for (int i = 0; i < T->cfg.nsf[ch]; i++) L->gsf[ch][i] = imin_(127, L->gsf[ch][i] + 1);
+                HMP3_FOR_LANES(i, T->cfg.nsf[ch]) L->gsf[ch][i] = imin_(127, L->gsf[ch][i] + 1);
+        HMP3_SYNC();
         long_scale_factors(T, L, false);
         long_quantise(T, L, ix, false);
         bits = long_count(T, L, ix, T->cfg.nsf2);

@@ -19,6 +19,7 @@ struct ShortRate {
     float x34[2][3][192];
     alignas(16) QLine ix[2][3][192];
     unsigned char sign[2][3][192];
+    unsigned char sign_t[2][576];     // the signs in transmission order (one byte per line), before they are packed
     alignas(16) QLine quad_scratch[580];
 };
 
@@ -526,7 +527,7 @@ HMP3_FN void short_allocate(const EncTables *T, ShortRate *S, const float *xr) {
 // (bitallos.cpp:202-372).
 HMP3_FN int short_granule(const EncTables *T, ShortRate *S, float *xr, const SigMask *sm, int nchan, int min_bits,
                           int target_bits, int max_bits, int pool_bits, ScaleFac *sf_out, GrSide *gr, QLine *ix_out,
-                          unsigned char *sign_out, int ms, int mnr) {
+                          unsigned *sign_out /*[2][18]*/, int ms, int mnr) {
     S->mnr = mnr;
     if (T->cfg.h_id == 0) S->mnr = imin_(S->mnr, 850);
     S->ms = ms;
@@ -594,19 +595,52 @@ HMP3_FN int short_granule(const EncTables *T, ShortRate *S, float *xr, const Sig
             for (int i = 0; i < 12; i++) sf_out[ch].s[w][i] = S->sf[ch][w][i];
         }
     }
-    // lines in transmission order: [band][window][line] (bitallos.cpp:329-366)
+    // lines in transmission order: [band][window][line] (bitallos.cpp:329-366); the signs of the lines written are
+    // merged into the persistent sign words
     for (int ch = 0; ch < nchan; ch++) {
         QLine *dst = ix_out + 576 * ch;
-        unsigned char *ds = sign_out + 576 * ch;
+        unsigned *ds = sign_out + 18 * ch;
+        const int ncb = S->plan[ch].cb[2];
+        const int total = 3 * T->startBand_s[ncb];
+#if HMP3_COOP
+        const int lane = HMP3_LANE;
+        HMP3_SYNC();
+        for (int k = lane; k < 576; k += HMP3_W) dst[k] = 0;
+        HMP3_SYNC();
+        for (int it = lane; it < 3 * ncb; it += HMP3_W) {  // one (band, window) per lane
+            const int i = it / 3, w = it - 3 * i;
+            const int n = T->nBand_s[i], s0 = T->startBand_s[i], base = 3 * s0 + w * n;
+            for (int j = 0; j < n; j++) {
+                dst[base + j] = S->ix[ch][w][s0 + j];
+                S->sign_t[ch][base + j] = S->sign[ch][w][s0 + j];
+            }
+        }
+        HMP3_SYNC();
+        for (int w = 0; 32 * w < total; w++) {
+            unsigned bits = 0;
+            for (int h = 0; h < 32 / HMP3_W; h++) {
+                const int k = 32 * w + HMP3_W * h + lane;
+                bits |= gballot(k < total ? (S->sign_t[ch][k] & 1) : 0) << (HMP3_W * h);
+            }
+            if (lane == 0) merge_sign_word(ds + w, bits, w, total);
+        }
+        HMP3_SYNC();
+#else
         for (int k = 0; k < 576; k++) dst[k] = 0;
         int k = 0;
-        for (int i = 0; i < S->plan[ch].cb[2]; i++)
+        for (int i = 0; i < ncb; i++)
             for (int w = 0; w < 3; w++)
                 for (int j = T->startBand_s[i]; j < T->startBand_s[i + 1]; j++) {
                     dst[k] = S->ix[ch][w][j];
-                    ds[k] = S->sign[ch][w][j];
+                    S->sign_t[ch][k] = S->sign[ch][w][j];
                     k++;
                 }
+        for (int w = 0; 32 * w < total; w++) {
+            unsigned bits = 0;
+            for (int b = 0; b < 32 && 32 * w + b < total; b++) bits |= (unsigned)(S->sign_t[ch][32 * w + b] & 1) << b;
+            merge_sign_word(ds + w, bits, w, total);
+        }
+#endif
     }
     return S->feedback_bits;
 }
