@@ -170,8 +170,8 @@ int main(int argc, char **argv) {
             list = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : nullptr);
             continue;
         }
-        if ((a[1] == 'g' || a[1] == 'G') && (a[2] == 'p' || a[2] == 'P')) {  // -GPU<n>: device index (extension)
-            device = atoi(a + 4);
+        if ((a[1] == 'g' || a[1] == 'G') && (a[2] == 'p' || a[2] == 'P') && (a[3] == 'u' || a[3] == 'U')) {
+            device = atoi(a + 4);  // -GPU<n>: device index (extension)
             continue;
         }
         if (a[1] == 'x' || a[1] == 'X') {

@@ -26,7 +26,7 @@
 #if defined(__CUDA_ARCH__)
 #define HMP3_COOP 1
 #ifndef HMP3_W
-#define HMP3_W 16
+#define HMP3_W 32
 #endif
 #define HMP3_LANE ((int)(threadIdx.x & (unsigned)(HMP3_W - 1)))
 #define HMP3_GSHIFT (threadIdx.x & 31u & ~(unsigned)(HMP3_W - 1))

@@ -1,11 +1,12 @@
 // Serial-stage kernels + launchers (see kernels_rate.cuh).  This translation unit is compiled for code
 // SIZE (the rate loop is tens of thousands of instructions of branchy scalar code executed once per
 // granule: instruction fetch, not arithmetic, bounds it).
+#include <atomic>
 #include "kernels_rate.cuh"
 
 // lanes per stream of the serial stage (HMP3_W is only defined in device code)
 #ifndef HMP3_W_HOST_VALUE
-#define HMP3_W_HOST_VALUE 16
+#define HMP3_W_HOST_VALUE 32
 #endif
 static constexpr int HMP3_W_HOST = HMP3_W_HOST_VALUE;
 // one 576-float scratch row per stream of a block (rate_scratch_row)
@@ -49,11 +50,10 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
     // 1.63 s -> 1.55 s; 20 % costs occupancy, >= 50 % is the driver's choice again; giving the Phase A kernels the same
     // preference starves them of shared memory and is slower; halving the step search's scratch to reach the 64 KB
     // configuration gains nothing net: the two half passes cost what the extra L1 saves).
-    static unsigned long long configured = 0;  // one bit per device: function attributes are per device
+    static std::atomic<unsigned long long> configured{0};  // one bit per device: function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!((configured >> (dev & 63)) & 1ull)) {
-        configured |= 1ull << (dev & 63);
+    if (!((configured.fetch_or(1ull << (dev & 63)) >> (dev & 63)) & 1ull)) {
         const char *e = getenv("HMP3_RATE_CARVEOUT");
         const int pct = e ? atoi(e) : 40;
         if (pct >= 0) cudaFuncSetAttribute(k_rate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);

@@ -19,9 +19,10 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
     rate_state_init(tabs + st[s].cfg, rs + s);
 }
 
-// ---- K6: the serial stage over one chunk of granules, one GROUP of HMP3_W lanes per stream (two streams per
-// warp): the scalar control flow of the rate loop runs uniformly on the lanes of a group, the per-line /
-// per-band loops are split across them (HMP3_COOP sections of rate_*.h).
+// ---- K6: the serial stage over one chunk of granules, one GROUP of HMP3_W lanes per stream (HMP3_W = 32: one warp
+// per stream, the shipped configuration; 16 = two streams per warp, an experiment that loses once the streams
+// differ): the scalar control flow of the rate loop runs uniformly on the lanes of a group, the per-line / per-band
+// loops are split across them (HMP3_COOP sections of rate_*.h).
 __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
            unsigned char *main_buf, FrameRec *frames, int K0, int nstreams, long long *cycles) {

@@ -25,6 +25,7 @@ using namespace hmp3;
 namespace {
 
 thread_local std::string g_err;
+thread_local int g_create_status = 0;  // why the last hmp3_batch_create* of this thread failed (HMP3_ERR_*)
 void set_err(const std::string &s) { g_err = s; }
 
 #define CK(call)                                                                               \
@@ -221,6 +222,11 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         return HMP3_ERR_NO_DEVICE;
     }
     CK(cudaSetDevice(device));
+    for (int i = 0; i < n; i++)
+        if (nsamples[i] < 0) {
+            set_err("negative sample count");
+            return HMP3_ERR_ARG;
+        }
     b->device = device;
     b->n = n;
     b->status.assign(n, HMP3_OK);
@@ -446,7 +452,21 @@ int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_pre
     return HMP3_OK;
 }
 
-int run_plan(hmp3_batch *b) {
+int run_plan_impl(hmp3_batch *b);
+// Errors after work has been queued: nothing may still be reading the caller's PCM or writing the caller's output
+// buffers when the call returns, so the device is drained first.
+int drain_on_error(hmp3_batch *b, int r) {
+    if (r != HMP3_OK && b) {
+        const std::string keep = g_err;
+        cudaSetDevice(b->device);
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return r;
+}
+int run_plan(hmp3_batch *b) { return drain_on_error(b, run_plan_impl(b)); }
+int run_plan_impl(hmp3_batch *b) {
     const int n = b->n;
     CK(cudaSetDevice(b->device));
     b->launches = 0;
@@ -712,6 +732,7 @@ hmp3_batch *hmp3_batch_create_ex(const hmp3_control *controls, const int64_t *nu
     if (ng < 2) ng = 2;
     ng &= ~1;
     int r = plan_create(b, controls, ns.data(), n, device, ng, false, false, pcm_formats);
+    g_create_status = r;
     if (r != HMP3_OK) {
         delete b;
         return nullptr;
@@ -721,8 +742,8 @@ hmp3_batch *hmp3_batch_create_ex(const hmp3_control *controls, const int64_t *nu
 
 void hmp3_batch_destroy(hmp3_batch *b) { delete b; }
 
-int16_t *hmp3_batch_device_pcm(hmp3_batch *b) { return b->d_pcm; }
-int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i) { return b->st_h[i].pcm_off; }
+int16_t *hmp3_batch_device_pcm(hmp3_batch *b) { return b ? b->d_pcm : nullptr; }
+int64_t hmp3_batch_pcm_offset(const hmp3_batch *b, int i) { return (b && i >= 0 && i < b->n) ? b->st_h[i].pcm_off : -1; }
 
 int hmp3_batch_set_tail(hmp3_batch *b, int i, float value) {
     if (!b || i < 0 || i >= b->n || b->fmt[i] != HMP3_PCM_F32) {
@@ -734,12 +755,12 @@ int hmp3_batch_set_tail(hmp3_batch *b, int i, float value) {
     CK(cudaMemcpy(b->d_st + i, &b->st_h[i], sizeof(StreamDev), cudaMemcpyHostToDevice));
     return HMP3_OK;
 }
-uint8_t *hmp3_batch_device_out(hmp3_batch *b) { return b->d_out; }
-int64_t hmp3_batch_out_capacity(const hmp3_batch *b) { return b->out_cap; }
+uint8_t *hmp3_batch_device_out(hmp3_batch *b) { return b ? b->d_out : nullptr; }
+int64_t hmp3_batch_out_capacity(const hmp3_batch *b) { return b ? b->out_cap : 0; }
 
 namespace {
 int upload_any(hmp3_batch *b, int i, const void *pcm, int64_t num_samples, int want_fmt) {
-    if (i < 0 || i >= b->n || num_samples != b->st_h[i].nsamples || b->fmt[i] != want_fmt) {
+    if (!b || !pcm || i < 0 || i >= b->n || num_samples != b->st_h[i].nsamples || b->fmt[i] != want_fmt) {
         set_err("upload: stream index, length or sample format does not match the plan");
         return HMP3_ERR_ARG;
     }
@@ -759,12 +780,14 @@ int hmp3_batch_upload_f32(hmp3_batch *b, int i, const float *pcm, int64_t num_sa
 }
 
 int hmp3_batch_wait_uploads(hmp3_batch *b) {
+    if (!b) return HMP3_ERR_ARG;
     CK(cudaSetDevice(b->device));
     CK(cudaStreamSynchronize(b->stream));
     return HMP3_OK;
 }
 
 int hmp3_batch_set_timing(hmp3_batch *b, int on) {
+    if (!b) return HMP3_ERR_ARG;
     b->timing = on != 0;
     return HMP3_OK;
 }
@@ -779,16 +802,17 @@ int hmp3_batch_set_serialize(hmp3_batch *b, int on) {
 }
 
 int hmp3_batch_run(hmp3_batch *b, int async) {
+    if (!b) return HMP3_ERR_ARG;
     int r = run_plan(b);
     if (r != HMP3_OK) return r;
     return async ? HMP3_OK : sync_plan(b);
 }
 
-int hmp3_batch_sync(hmp3_batch *b) { return sync_plan(b); }
+int hmp3_batch_sync(hmp3_batch *b) { return b ? sync_plan(b) : HMP3_ERR_ARG; }
 
 int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames, int64_t *out_offsets,
                        int32_t *status) {
-    if (!b->results_valid) {
+    if (!b || !b->results_valid) {
         set_err("results: no completed run");
         return HMP3_ERR_ARG;
     }
@@ -805,7 +829,7 @@ int hmp3_batch_results(hmp3_batch *b, int64_t *out_bytes, int32_t *out_frames, i
 }
 
 int hmp3_batch_download(hmp3_batch *b, int i, uint8_t *out, int64_t cap) {
-    if (!b->results_valid || i < 0 || i >= b->n) {
+    if (!b || !out || !b->results_valid || i < 0 || i >= b->n) {
         set_err("download: no completed run or bad index");
         return HMP3_ERR_ARG;
     }
@@ -838,7 +862,7 @@ int hmp3_batch_download_all(hmp3_batch *b, uint8_t *out, int64_t cap, int64_t *t
 
 // Per-call output log of one stream, rebuilt from its frame records (one D2H copy of the records).
 int hmp3_batch_call_log(hmp3_batch *b, int i, int32_t *frames_after_call, int64_t *bytes_after_call, int cap) {
-    if (!b->results_valid || i < 0 || i >= b->n || b->status[i] != HMP3_OK) {
+    if (!b || !b->results_valid || i < 0 || i >= b->n || b->status[i] != HMP3_OK) {
         set_err("call_log: no completed run or bad index");
         return HMP3_ERR_ARG;
     }
@@ -862,9 +886,9 @@ int hmp3_batch_call_log(hmp3_batch *b, int i, int32_t *frames_after_call, int64_
     return ncalls;
 }
 
-int hmp3_batch_last_launches(const hmp3_batch *b) { return b->launches; }
-int hmp3_batch_chunk_granules(const hmp3_batch *b) { return b->NG; }
-float hmp3_batch_last_run_ms(const hmp3_batch *b) { return b->last_run_ms; }
+int hmp3_batch_last_launches(const hmp3_batch *b) { return b ? b->launches : 0; }
+int hmp3_batch_chunk_granules(const hmp3_batch *b) { return b ? b->NG : 0; }
+float hmp3_batch_last_run_ms(const hmp3_batch *b) { return b ? b->last_run_ms : 0.0f; }
 
 int hmp3_batch_phase_ms(const hmp3_batch *b, const char **names, float *ms, int *launches, int cap) {
     int k = 0;
@@ -888,7 +912,17 @@ bool is_pinned(const void *p) {
 }
 }  // namespace
 
+static int encode_host_impl(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+                            int64_t *out_bytes, int32_t *out_frames, int32_t *status);
 int hmp3_batch_encode_host(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
+                           int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
+    if (!b || !pcm || !out || !out_cap) {
+        set_err("bad arguments");
+        return HMP3_ERR_ARG;
+    }
+    return drain_on_error(b, encode_host_impl(b, pcm, out, out_cap, out_bytes, out_frames, status));
+}
+static int encode_host_impl(hmp3_batch *b, const void *const *pcm, uint8_t *const *out, const int64_t *out_cap,
                            int64_t *out_bytes, int32_t *out_frames, int32_t *status) {
     CK(cudaSetDevice(b->device));
     const bool trace = getenv("HMP3_TRACE_HOST") != nullptr;
@@ -1056,9 +1090,10 @@ int hmp3_encode_batch(hmp3_stream_desc *streams, int n, int device) {
         cap[i] = streams[i].out_capacity;
     }
     hmp3_batch *b = hmp3_batch_create_ex(ctl.data(), ns.data(), fmts.data(), n, device);
-    if (!b) {
-        int ndev = hmp3_device_count();
-        return ndev <= device ? HMP3_ERR_NO_DEVICE : HMP3_ERR_BAD_CONTROL;
+    if (!b) {  // the reason plan_create gave: no device, bad control, allocation failure ...
+        const int ndev = hmp3_device_count();
+        if (ndev <= device) return HMP3_ERR_NO_DEVICE;
+        return g_create_status != HMP3_OK ? g_create_status : HMP3_ERR_BAD_CONTROL;
     }
     int r = hmp3_batch_encode_host(b, pcm.data(), out.data(), cap.data(), nb.data(), nf.data(), st.data());
     if (r == HMP3_OK)
