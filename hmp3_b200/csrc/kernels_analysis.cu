@@ -2,12 +2,33 @@
 #define HMP3_W 32  // cooperative sections in this translation unit are warp-wide
 #include "kernels_analysis.cuh"
 
+#include <atomic>
+#include <stdlib.h>
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
+
+// HMP3_PHASEA_CARVEOUT=pct (experiments): shared-memory carve-out preference of the Phase A kernels.  With the serial
+// stage's own preference (40) their blocks can share an SM with resident serial-stage blocks.
+static void phase_a_configure() {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((configured.fetch_or(1ull << (dev & 63)) >> (dev & 63)) & 1ull) return;
+    const char *e = getenv("HMP3_PHASEA_CARVEOUT");
+    if (!e) return;
+    const int pct = atoi(e);
+    cudaFuncSetAttribute(k_polyphase, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_attack, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_hybrid, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_psy_stage1, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_psy_stage2, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_prepare, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
 
 void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, const float *pcmf, ChunkBufs cb,
                       int K0, int n, cudaStream_t stream) {
     const int G = cb.NG + 3;
+    phase_a_configure();
     k_polyphase<<<dim3((unsigned)((G + kPolyRun - 1) / kPolyRun), (unsigned)n), 256, 0, stream>>>(tabs, st, pcm, pcmf, cb,
                                                                                                  K0, n);
 }

@@ -58,6 +58,8 @@ void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so
         const int pct = e ? atoi(e) : 40;
         if (pct >= 0) cudaFuncSetAttribute(k_rate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRateSmem);
+        if (getenv("HMP3_PHASEA_CARVEOUT"))
+            cudaFuncSetAttribute(k_pack, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("HMP3_PHASEA_CARVEOUT")));
     }
     k_rate<<<blocks_for((long long)n * HMP3_W_HOST, 32 * kRateWarpsPerBlock), 32 * kRateWarpsPerBlock, kRateSmem, stream>>>(
         tabs, st, so, rs, cb, main_buf, frames, K0, n, cycles);
