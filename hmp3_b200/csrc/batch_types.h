@@ -83,6 +83,12 @@ void launch_psy_stage2(const EncTables *tabs, const StreamDev *st, PsyState *psy
                        cudaStream_t stream);
 void launch_prepare(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0, int n, cudaStream_t stream);
 int fp32_peak(int device, float *ffma_tflops, float *nonfused_tflops);
+// contraction form of the polyphase on the tensor cores (kernels_polymm.cu; not bit-exact, off by default):
+// parts = 3 (3xTF32) or 1 (plain TF32); wmat = build_polymm_matrix's output on the device
+void launch_polyphase_mm(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, const float *wmat, ChunkBufs cb,
+                         int K0, int n, int parts, cudaStream_t stream);
+void build_polymm_matrix(const EncTables *T, float *out);
+size_t polymm_matrix_floats();
 void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream);
 size_t sizeof_prep_granule();
 size_t sizeof_psy_state();

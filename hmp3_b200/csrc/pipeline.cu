@@ -93,6 +93,8 @@ struct hmp3_batch {
     float *d_pcmf = nullptr;            // float PCM: float inputs and the DC-filtered copies of the streams with -S1
     std::vector<int> fmt;               // per stream: 0 = int16 input, 1 = float32 input (scaled to +-32768)
     float *d_dc = nullptr;              // [n][2] filter state
+    int poly_mode = 0;                  // 0 = exact polyphase; 3 / 1 = tensor-core contraction, 3xTF32 / TF32 (HMP3_POLY_MODE)
+    float *d_polyw = nullptr;           // its coefficient blocks
     bool any_filter = false;
     int *d_msmem = nullptr;             // [n] M/S hysteresis memory (scan carry)
     PsyState *d_psy = nullptr;          // [n][2] psychoacoustic stage-2 carry
@@ -176,6 +178,7 @@ struct hmp3_batch {
         cudaFree(d_msmem);
         cudaFree(d_pcmf);
         cudaFree(d_dc);
+        cudaFree(d_polyw);
         cudaFree(d_psy);
         if (stream_c) cudaStreamDestroy(stream_c);
         for (int k = 0; k < kMaxSets; k++)
@@ -319,6 +322,16 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMemset(b->d_pcmf, 0, sizeof(float) * std::max<long long>(pcmf_off, 1)));
         CK(cudaMalloc(&b->d_dc, sizeof(float) * 2 * n));
     }
+    if (const char *pm = getenv("HMP3_POLY_MODE")) {  // experiments: the filterbank as a tensor-core contraction
+        b->poly_mode = !strcmp(pm, "3xtf32") ? 3 : (!strcmp(pm, "tf32") ? 1 : 0);
+        if (b->any_filter || any_float) b->poly_mode = 0;  // that kernel reads int16 PCM only
+        if (b->poly_mode) {
+            std::vector<float> w(polymm_matrix_floats());
+            build_polymm_matrix(&b->tabs_h[0], w.data());
+            CK(cudaMalloc(&b->d_polyw, sizeof(float) * w.size()));
+            CK(cudaMemcpy(b->d_polyw, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+        }
+    }
     CK(cudaMalloc(&b->d_msmem, sizeof(int) * n));
     CK(cudaMalloc(&b->d_psy, sizeof_psy_state() * n * 2));
     CK(cudaMalloc(&b->d_sw, sizeof(SwitchState) * n));
@@ -421,7 +434,8 @@ int launch_analysis(hmp3_batch *b, int K0, int k, cudaStream_t st, bool with_pre
     if (b->any_filter)
         launch_dc_filter(b->d_tabs, b->d_st, b->d_pcm, b->d_pcmf, b->d_dc, 576LL * K0, 576LL * (K0 + cb.NG), n, st);
     mark(b, PH_POLY, st);
-    launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, b->d_pcmf, cb, K0, n, st);
+    if (b->poly_mode) launch_polyphase_mm(b->d_tabs, b->d_st, b->d_pcm, b->d_polyw, cb, K0, n, b->poly_mode, st);
+    else launch_polyphase(b->d_tabs, b->d_st, b->d_pcm, b->d_pcmf, cb, K0, n, st);
     mark(b, -1, st);
     mark(b, PH_ATTACK, st);
     launch_attack(b->d_tabs, b->d_st, cb, K0, n, st);
