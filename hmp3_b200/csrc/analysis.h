@@ -65,6 +65,11 @@ HMP3_HD void polyphase_item_f(const EncTables *T, const float *pcmf, long len, i
 // Block-type scan step for encode granule K (channels share the decision).  e_new[ch][9] are the
 // attack energies of P[K-1].
 HMP3_HD GranuleInfo switch_step(const EncTables *T, SwitchState *s, const int *e_new0, const int *e_new1) {
+    if (T->cfg.allocator == 1) {  // the CBitAllo1 drivers never select a block type: always long (mp3enc.cpp:1236-1321)
+        GranuleInfo z;
+        z.block_type = z.block_type_prev = z.short_cur = z.short_next = 0;
+        return z;
+    }
     const int mpeg2 = (T->cfg.h_id == 0);
     const int nch = T->cfg.nchan;
     int flag = 0;

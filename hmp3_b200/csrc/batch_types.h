@@ -96,6 +96,9 @@ void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs,
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream,
                  long long *cycles = nullptr);
+// the twin of launch_rate for the streams whose configuration selects CBitAllo1 (each kernel skips the other's streams)
+void launch_rate_a1(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+                    unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);
 // packing pass of the frames the serial stage recorded in this chunk; `flags[s]` is set if a frame's written
 // bits ever differ from the accounted ones
 // Incremental output (host entry with pinned buffers): after the packing pass of a chunk, the frames that became

@@ -687,11 +687,8 @@ int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
     ec.vbr_delta_mnr = imin(ec.vbr_delta_mnr, 50);
     ec.vbr_delta_mnr = imax(ec.vbr_delta_mnr, -40);
 
-    // ---- allocator selection (mp3enc.cpp:696-766): only the CBitAllo3 drivers are built
-    if (h_mode == 2 || (h_mode == 1 && C.is_flag)) {
-        if (unsupported) *unsupported = 1;
-        return 0;
-    }
+    // ---- allocator selection (mp3enc.cpp:696-766): dual channel and intensity stereo take CBitAllo1
+    C.allocator = (h_mode == 2 || (h_mode == 1 && C.is_flag)) ? 1 : 0;
     C.hf_flag = ec.hf_flag;
     int mnr_bias = 10 * ec.vbr_delta_mnr;
     C.nt_flatten = ec.test1 < 0 ? 6 : ec.test1;
@@ -755,6 +752,64 @@ int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
     for (int i = 0; i < 12; i++) {
         float db = (float)(10.0 * log10((double)(float)T.nBand_s[i]));
         T.log_cbw_s[i] = (int)(100.0f * db);
+    }
+    // ---- CBitAllo1::BitAlloInit (bitallo1.cpp:107-203): estimators, intensity positions, constants
+    {
+        T.a1_bits[0] = 0;
+        for (int ixm = 1; ixm < 256; ixm++)
+            T.a1_bits[ixm] = (int)(16 * (1.4427 * log((double)(ixm + 1)) + (ixm - 0.6) / ixm));
+        double cum = 0.0f;
+        for (int ix = 0; ix < 256; ix++) {
+            double t = ix + 0.5;
+            const double xh = t * pow(t, 1.0 / 3.0);
+            t = ix;
+            const double x0 = t * pow(t, 1.0 / 3.0);
+            t = ix - 0.5;
+            const double xl = t * pow(fabs(t), 1.0 / 3.0);
+            const double dh = xh - x0, dl = xl - x0;
+            const double eps = (dh * dh * dh - dl * dl * dl) / (3.0 * (xh - xl));
+            cum += eps;
+            const double ave = cum / (ix + 1);
+            T.a1_f_ix[ix] = (float)eps;
+            T.a1_f_ixmax[ix] = (float)(10.0 * log10(ave));
+        }
+        cum = 0.0;
+        for (int i = 0; i < 256; i++) {
+            const int ix = 32 * i + 16;
+            double t = ix + 0.5;
+            const double xh = t * pow(t, 1.0 / 3.0);
+            t = ix;
+            const double x0 = t * pow(t, 1.0 / 3.0);
+            t = ix - 0.5;
+            const double xl = t * pow(fabs(t), 1.0 / 3.0);
+            const double dh = xh - x0, dl = xl - x0;
+            const double eps = (dh * dh * dh - dl * dl * dl) / (3.0 * (xh - xl));
+            cum += eps;
+            const double ave = cum / (i + 1);
+            T.a1_f_big_ix[i] = (float)(eps);
+            T.a1_f_big_ixmax[i] = (float)(10.0 * log10(ave));
+        }
+        if (h_id) {
+            const double pi = 4.0 * atan(1.0);
+            for (int i = 0; i < 34; i++) T.a1_is_pos[i] = (int)(((12.0 / pi) * atan(sqrt(i / 32.0))) + .25);
+        } else {
+            for (int i = 0; i < 34; i++) {
+                int k = (int)(-log((i + .0001) / 32.0) / log(2.0) + 0.5);
+                if (k < 0) k = 0;
+                if (k > 3) k = 3;
+                T.a1_is_pos[i] = k + k;
+            }
+        }
+        for (int i = 0; i < 21; i++) T.a1_log_cbw[i] = (float)(10.0 * log10((double)T.nBand_l_iso[i]));
+        static const float sparse1[21] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.10f, 0.10f, 0.10f, 0.10f, 0.10f, 0.10f,
+                                          0.20f, 0.30f, 0.40f, 0.50f, 0.60f, 0.70f, 0.80f, 0.90f, 1.0f, 1.5f};
+        static const float sparse2[21] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.10f, 0.10f, 0.10f, 0.10f, 0.10f, 0.10f,
+                                          0.20f, 0.30f, 0.40f, 0.50f, 0.50f, 0.60f, 0.70f, 0.80f, 0.90f};
+        for (int i = 0; i < 21; i++) T.a1_sparse[i] = h_id ? sparse1[i] : sparse2[i];
+        T.a1_gz_con1 = (float)(16.0 / (3.0 * log(2.0)));
+        T.a1_gz_con2 = (float)(1 - (16.0 / (3.0 * log(2.0))) * log(.5946) + 8);
+        T.a1_gz_con0 = (float)(exp((0.99 - T.a1_gz_con2) / T.a1_gz_con1));
+        T.a1_con707 = (float)(1.0 / sqrt(2.0));
     }
     // noise-target taper (bitallo3.cpp:411-446); quick = -1 (default) is "truthy" => no taper
     for (int i = 0; i < 22; i++) T.taperNT[i] = 0;

@@ -205,6 +205,7 @@ struct EncConfig {
     int nsf[2], nsf2[2], nsf3[2], nbmax[2], nbmax2[2], nbmax3[2];
     int nsf_s[2], nbmax_s[2];
     int ill_is_pos;
+    int allocator;           // 0 = CBitAllo3 + CBitAlloShort; 1 = CBitAllo1 (dual channel, intensity stereo: long blocks only)
     unsigned char head[4];
     int granules_per_frame;  // 2 MPEG-1, 1 MPEG-2
     // info (ec_global, mp3enc.cpp:841-866)
@@ -260,6 +261,14 @@ struct EncTables {
     // lines of the same band, and flags: 1 = first such lane of the chunk, 2 = the band ends inside this chunk
     uint32_t line_seg_l[576];
     unsigned char line_segflag_l[576];
+    // ---- CBitAllo1 (bitallo1.cpp:107-203, 441-542): estimators and constants of the allocator-1 configurations
+    int a1_bits[256];                              // look_bits: estimated bits (x16) per line at band maximum ixmax
+    float a1_f_ix[256], a1_f_ixmax[256];           // quantisation-noise estimators per value / per band maximum
+    float a1_f_big_ix[256], a1_f_big_ixmax[256];   // ... for values above 255, in steps of 32
+    int a1_is_pos[34];                             // intensity position from the channel energy ratio
+    float a1_log_cbw[21];                          // 10 log10(band width)
+    float a1_sparse[21];                           // Ssb: side-channel sparsing thresholds
+    float a1_gz_con0, a1_gz_con1, a1_gz_con2, a1_con707;
 };
 
 // ------------------------------------------------------------------ scalar table functions

@@ -6,12 +6,20 @@
 #include "batch_types.h"
 #include "rate_driver.h"
 
+#ifdef HMP3_RATE_ALLOCATOR1
+#define HMP3_RATE_KERNEL k_rate_a1
+#define HMP3_RATE_WANT 1
+#else
+#define HMP3_RATE_KERNEL k_rate
+#define HMP3_RATE_WANT 0
+#endif
 #ifndef HMP3_RATE_MIN_BLOCKS
 #define HMP3_RATE_MIN_BLOCKS (32 / HMP3_RATE_WARPS)  // 32 warps (1024 threads) per SM => 64 registers per thread
 #endif
 
 namespace hmp3 {
 
+#ifndef HMP3_RATE_ALLOCATOR1
 // ---- K6: state reset, one thread per stream
 __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int nstreams) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -19,14 +27,17 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
     rate_state_init(tabs + st[s].cfg, rs + s);
 }
 
+#endif
 // ---- K6: the serial stage over one chunk of granules, one GROUP of HMP3_W lanes per stream (HMP3_W = 32: one warp
 // per stream, the shipped configuration; 16 = two streams per warp, an experiment that loses once the streams
 // differ): the scalar control flow of the rate loop runs uniformly on the lanes of a group, the per-line / per-band
 // loops are split across them (HMP3_COOP sections of rate_*.h).
 __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
-    k_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
-           unsigned char *main_buf, FrameRec *frames, int K0, int nstreams, long long *cycles) {
+    HMP3_RATE_KERNEL(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+                     unsigned char *main_buf, FrameRec *frames, int K0, int nstreams, long long *cycles) {
     const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) / HMP3_W);
+    // a stream belongs to this kernel or to its twin for the other allocator (kernels_rate_a1.cu)
+    if (s < nstreams && tabs[st[s].cfg].cfg.allocator != HMP3_RATE_WANT) return;
 #ifdef HMP3_RATE_BARRIER
     if (s >= nstreams || K0 >= st[s].ngran) {  // no stream / nothing left: still a member of the block's barriers
         if (s < nstreams && HMP3_LANE == 0) {
@@ -59,6 +70,7 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     }
 }
 
+#ifndef HMP3_RATE_ALLOCATOR1
 // ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)
 __global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
     k_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
@@ -152,4 +164,5 @@ __global__ void k_advance_inc(const EncTables *tabs, const StreamDev *st, const 
     done_lo[s] = hi;
 }
 
+#endif
 }  // namespace hmp3

@@ -93,6 +93,7 @@ struct hmp3_batch {
     float *d_pcmf = nullptr;            // float PCM: float inputs and the DC-filtered copies of the streams with -S1
     std::vector<int> fmt;               // per stream: 0 = int16 input, 1 = float32 input (scaled to +-32768)
     float *d_dc = nullptr;              // [n][2] filter state
+    bool any_allo0 = false, any_allo1 = false;  // which serial-stage kernels the plan's streams need (CBitAllo3 / CBitAllo1)
     int poly_mode = 0;                  // 0 = exact polyphase; 3 / 1 = tensor-core contraction, 3xTF32 / TF32 (HMP3_POLY_MODE)
     float *d_polyw = nullptr;           // its coefficient blocks
     bool any_filter = false;
@@ -305,6 +306,11 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         set_err("no stream has a valid control block");
         return HMP3_ERR_BAD_CONTROL;
     }
+    for (int i = 0; i < n; i++)
+        if (b->status[i] == HMP3_OK) {
+            if (b->tabs_h[b->st_h[i].cfg].cfg.allocator == 1) b->any_allo1 = true;
+            else b->any_allo0 = true;
+        }
     b->pcm_elems = pcm_off;
     b->max_gran = max_gran;
     b->max_frames = max_frames;
@@ -574,8 +580,13 @@ int run_plan_impl(hmp3_batch *b) {
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
         if (c >= nb) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
-        launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
-                    (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
+        if (b->any_allo0)
+            launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
+                        (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
+        if (b->any_allo1) {
+            launch_rate_a1(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream);
+            b->launches++;
+        }
         if (b->d_cycles && c < kCycleLaunches) b->cycle_launches = c + 1;
         mark(b, -1, b->stream);
         CK(cudaEventRecord(b->ev_r[k], b->stream));
@@ -1238,7 +1249,8 @@ hmp3_in_out encoder_step(hmp3_encoder *e, const void *pcm, unsigned char *bs_out
         return io;
     }
     if (launch_analysis(b, K0, 0, b->stream) != HMP3_OK) return io;
-    launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
+    if (b->any_allo1) launch_rate_a1(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
+    else launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->cb2[0], b->d_main, b->d_frames, K0, 1, b->stream);
     launch_pack(b->d_tabs, b->d_st, b->d_so, b->cb2[0], b->d_main, b->d_frames, b->d_flags, K0, 1, b->stream);
     launch_finish(b->d_tabs, b->d_st, b->d_so, b->d_rs, b->d_frames, b->d_res, b->d_out_off, b->d_main, b->d_out, 48, 1,
                   b->stream, nullptr, e->win_frames_out, e->win_bytes_out);

@@ -82,6 +82,7 @@ HMP3_FN void long_prepare_bounds(const EncTables *T, PrepGranule *P, int ch, int
 // The state-free part of CBitAllo3::startup (ms == 0) / startup_ms2 (ms != 0) for one long-block granule.
 // xr [2][576] is modified in place exactly as the reference does (magnitudes; mid/side without 1/sqrt2).
 HMP3_FN void long_prepare(const EncTables *T, int ms, float *xr, PrepGranule *P) {
+    if (T->cfg.allocator == 1) return;  // CBitAllo1 strips signs / rotates for itself (smr_adj, bitallo1.cpp:640-908)
     const int nch = T->cfg.nchan;
     for (int ch = 0; ch < 2; ch++)
 #if HMP3_COOP

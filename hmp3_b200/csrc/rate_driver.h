@@ -7,6 +7,14 @@
 #pragma once
 #include "analysis.h"
 #include "rate_short.h"
+// The CBitAllo1 drivers (dual channel, intensity stereo) are compiled into the host build and into their own device
+// kernel (k_rate_a1, kernels_rate_a1.cu): the default serial-stage kernel stays exactly the code of the common path.
+#include "rate_allo1.h"
+#if !HMP3_COOP || defined(HMP3_RATE_ALLOCATOR1)
+#define HMP3_WITH_ALLO1 1
+#else
+#define HMP3_WITH_ALLO1 0
+#endif
 
 namespace hmp3 {
 
@@ -81,6 +89,7 @@ HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros
 struct RateState {
     LongRate L;
     ShortRate S;
+    Allo1 A1;                 // state of the CBitAllo1 configurations (dual channel, intensity stereo)
     alignas(16) QLine ix[2][576];  // quantised lines in transmission order (persist between granules)
     unsigned signx[2][18];    // sign bit of line k of a channel = bit (k & 31) of word (k >> 5); persists like ix
     GrSide gr[2][2];          // [granule][channel]
@@ -102,6 +111,7 @@ HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {
     for (unsigned i = 0; i < sizeof(RateState); i++) p[i] = 0;
     long_rate_init(T, &R->L);
     short_rate_init(&R->S);
+    allo1_init(T, &R->A1);
     R->padcount = T->cfg.pad_divisor;
 }
 
@@ -217,6 +227,57 @@ HMP3_FN int plan_sf_mpeg2(const ScaleFac *sf, int block_type, int *bits) {
     if (block_type == 2) *bits = 9 * (sl[0] + sl[1] + sl[2] + sl[3]);
     else *bits = 6 * sl[0] + 5 * (sl[1] + sl[2] + sl[3]);
     return sl[3] + (sl[2] << 2) + ((sl[1] + 5 * sl[0]) << 4);
+}
+// MPEG-2, right channel of an intensity-stereo frame (long blocks): three partitions of seven bands, an "illegal"
+// position (999 from the allocator = no intensity coding in that band) becomes the largest value of its partition's
+// field, and a legal position must not collide with it (l3pack.c:576-712).  Rewrites sf->l for the packing pass.
+HMP3_FN int plan_sf_mpeg2_is(ScaleFac *sf, int nsf_stereo, int *bits) {
+    int m1 = 0, m2 = 0, m3 = 0, ip1 = 0, ip2 = 0, ip3 = 0, is2 = -1, is3 = -1;
+    int i;
+    for (i = 0; i < 7; i++) {
+        if (sf->l[i] >= 999) ip1 = 1;
+        else if (sf->l[i] > m1) m1 = sf->l[i];
+    }
+    for (; i < 14; i++) {
+        if (sf->l[i] >= 999) {
+            ip2 = 1;
+            continue;
+        }
+        if (sf->l[i] > m2) m2 = sf->l[i];
+        if (i < nsf_stereo) continue;
+        if (sf->l[i] > is2) is2 = sf->l[i];
+    }
+    for (; i < 21; i++) {
+        if (sf->l[i] >= 999) {
+            ip3 = 1;
+            continue;
+        }
+        if (sf->l[i] > m3) m3 = sf->l[i];
+        if (i < nsf_stereo) continue;
+        if (sf->l[i] > is3) is3 = sf->l[i];
+    }
+    int s1 = slen_for(m1, 4), s2 = slen_for(m2, 4), s3 = slen_for(m3, 3);
+    if (is2 == ((1 << s2) - 1)) s2++;
+    if (is3 == ((1 << s3) - 1)) s3++;
+    if (ip1)
+        for (i = 0; i < 7; i++)
+            if (sf->l[i] >= 999) sf->l[i] = (1 << s1) - 1;
+    if (ip2)
+        for (i = 7; i < 14; i++)
+            if (sf->l[i] >= 999) sf->l[i] = (1 << s2) - 1;
+    if (ip3)
+        for (i = 14; i < 21; i++)
+            if (sf->l[i] >= 999) sf->l[i] = (1 << s3) - 1;
+    *bits = 7 * (s1 + s2 + s3);
+    const int sfc = s3 + 6 * s2 + 36 * s1;
+    return sfc + sfc + 1;  // intensity_scale bit
+}
+HMP3_FN void write_sf_mpeg2_is(BitSink *b, const unsigned char *sf, int sfc) {
+    const int v = sfc >> 1;
+    const int s1 = v / 36, s2 = (v % 36) / 6, s3 = v % 6;
+    for (int i = 0; i < 7; i++) sink_put(b, sf_byte(sf, i), s1);
+    for (int i = 7; i < 14; i++) sink_put(b, sf_byte(sf, i), s2);
+    for (int i = 14; i < 21; i++) sink_put(b, sf_byte(sf, i), s3);
 }
 HMP3_FN void write_sf_mpeg2(BitSink *b, const unsigned char *sf, int block_type, int sfc) {
     int sl[4];
@@ -487,7 +548,8 @@ HMP3_FN int pack_frame(const EncTables *T, FrameRec *fr, const PackGc *gc, unsig
         const GrSide *g = &p->gr;
         const long long start = b.total_bits;
         if (g->aux_not_null) {
-            if (!m1) write_sf_mpeg2(&b, p->sf, g->block_type, g->scalefac_compress);
+            if (!m1 && T->cfg.is_flag && (k % nch) == 1) write_sf_mpeg2_is(&b, p->sf, g->scalefac_compress);
+            else if (!m1) write_sf_mpeg2(&b, p->sf, g->block_type, g->scalefac_compress);
             else if (fr->short_frame) write_sf_mpeg1_plain(&b, p->sf, g->block_type, g->scalefac_compress);
             else write_sf_mpeg1_scfsi(&b, p->sf, (k / nch) ? fr->scfsi[k % nch] : 0, g->scalefac_compress);
             pack_huffman(T, &b, g, p->ix, p->sign);
@@ -765,6 +827,108 @@ HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, Granul
     return ms;
 }
 
+
+#if HMP3_WITH_ALLO1
+// ------------------------------------------------------------------ the CBitAllo1 drivers
+// encode_jointA / encode_singleA and their MPEG-2 forms (mp3enc.cpp:1236-1321, 1601-1671, 1753-1828, 1911-1973):
+// long blocks only, M/S decided per frame (MPEG-1) or granule (MPEG-2) from the allocator's own correlation measure
+// without hysteresis, dual channel allocated one channel at a time.
+HMP3_FN void allo1_io(RateState *R, GranuleIn *g, int ch0, int nch, Allo1Io *io) {
+    float(*x34)[576] = (float(*)[576]) & R->S.x34[0][0][0];  // the short-block work area is free: no short blocks here
+    for (int c = 0; c < nch; c++) {
+        const int ch = ch0 + c;
+        io->xr[c] = g->xr + 576 * ch;
+        io->x34[c] = x34[ch];
+        io->ix[c] = &R->ix[ch][0];
+        io->sign[c] = &R->signx[ch][0];
+        io->sm[c] = g->sm + 36 * ch;
+    }
+}
+HMP3_FN int encode_frame_a1(const EncTables *T, RateState *R, int igr_arg, GranuleIn *g0, GranuleIn *g1, PackGc *pack,
+                            int *frame_bits) {
+    const EncConfig &C = T->cfg;
+    const int nch = C.nchan;
+    const bool m1 = C.h_id == 1, joint = C.h_mode == 1;
+    Allo1 *A = &R->A1;
+    GranuleIn *gs[2] = {g0, g1};
+    const int ngr = m1 ? 2 : 1;
+    int bit_max, bit_min;
+    if (m1) {
+        const int sh = (joint || nch != 2) ? 2 : 1;
+        bit_max = R->byte_max << sh;
+        bit_min = R->byte_min << sh;
+    } else {
+        const int sh = (joint || nch != 2) ? 3 : 2;
+        bit_max = R->byte_max << sh;
+        bit_min = R->byte_min << sh;
+        if (joint && R->byte_pool > 245) bit_min += 40;
+    }
+    int ba_bit_max = bit_max > 4095 ? 4095 : bit_max, ba_bit_min = bit_min;
+    const int sf_bits = joint ? 2 * C.sf_bit_max : C.sf_bit_max;
+    ba_bit_max -= sf_bits;
+    ba_bit_min -= sf_bits;
+    int ba_min = ba_bit_min, ba_max = ba_bit_max;
+    int ms = 0;
+    if (joint && C.ms_flag) {
+        int m = allo1_ms_measure(T, g0->xr, g0->xr + 576);
+        if (m1) m += allo1_ms_measure(T, g1->xr, g1->xr + 576);
+        if (m >= 0) ms = 1;
+    }
+    int total = 0;
+    for (int q = 0; q < ngr; q++) {
+        const int igr = m1 ? q : igr_arg;
+        GranuleIn *g = gs[q];
+        set_block_info(T, R, igr, g);
+        Allo1Io io;
+        if (joint) {
+            allo1_io(R, g, 0, 2, &io);
+            allo1_granule(T, A, &io, 0, 2, ba_min, 2 * C.ave_target_bits, ba_max, &R->sf[igr][0], &R->gr[igr][0], ms);
+        }
+        for (int ch = 0; ch < nch; ch++) {
+            GrSide *gr = &R->gr[igr][ch];
+            if (!joint) {
+                allo1_io(R, g, ch, 1, &io);
+                allo1_granule(T, A, &io, ch, 1, ba_min, C.ave_target_bits, ba_max, &R->sf[igr][ch], gr, C.ms_flag);
+            }
+            int bits = 0, sfb = 0;
+            gr->scalefac_compress = 0;
+            if (m1 && joint) {
+                gr->scalefac_compress =
+                    plan_sf_mpeg1_scfsi(&R->sf[igr][ch], R->sf_save[ch], igr, &R->scfsi[ch], gr->aux_not_null, &sfb);
+                if (gr->aux_not_null) bits = sfb + gr->aux_bits;
+            } else if (m1) {
+                if (gr->aux_bits) {
+                    gr->scalefac_compress = plan_sf_mpeg1_plain(&R->sf[igr][ch], gr->block_type, &sfb);
+                    bits = sfb + gr->aux_bits;
+                }
+            } else if (joint ? gr->aux_not_null : gr->aux_bits) {
+                if (joint && (ch & C.is_flag)) gr->scalefac_compress = plan_sf_mpeg2_is(&R->sf[igr][ch], C.nsf_stereo, &sfb);
+                else gr->scalefac_compress = plan_sf_mpeg2(&R->sf[igr][ch], R->gr[igr][0].block_type, &sfb);
+                bits = sfb + gr->aux_bits;
+            }
+            if (joint) {
+                if (m1) {
+                    ba_min -= bits;
+                    ba_max -= bits;
+                }
+            } else {
+                ba_min += ba_bit_min + C.sf_bit_max - bits;
+                ba_max += ba_bit_max + C.sf_bit_max - bits;
+            }
+            gr->part2_3_length = bits;
+            total += bits;
+            record_gc(R, igr, ch, pack + (q * nch + ch));
+        }
+        if (joint && m1) {
+            ba_min += ba_bit_min + sf_bits;
+            ba_max += ba_bit_max + sf_bits;
+        }
+    }
+    *frame_bits = total;
+    return ms;
+}
+#endif
+
 // ------------------------------------------------------------------ frame driver + reservoir
 // Records one frame: header, its main-data slot and where its own data goes in the stream's main-data
 // stream (mp3enc.cpp:2106-2593).
@@ -806,7 +970,12 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, FrameRec *frames
     }
     const int main_data_begin = R->byte_pool;
     int frame_bits = 0;
+#if HMP3_WITH_ALLO1
+    const int ms = C.allocator == 1 ? encode_frame_a1(T, R, igr, g0, g1, pack, &frame_bits)
+                   : (m1 ? encode_frame_mpeg1(T, R, g0, g1, pack, &frame_bits) : encode_frame_mpeg2(T, R, igr, g0, pack, &frame_bits));
+#else
     const int ms = m1 ? encode_frame_mpeg1(T, R, g0, g1, pack, &frame_bits) : encode_frame_mpeg2(T, R, igr, g0, pack, &frame_bits);
+#endif
     const int mode_ext = ms + ms + C.is_flag;
     int bytes = (frame_bits + 7) >> 3;
     int ibr = 0;
@@ -842,6 +1011,7 @@ HMP3_FN void encode_one_frame(const EncTables *T, RateState *R, FrameRec *frames
     fr->igr0 = (short)igr;
     fr->main_data_begin = (short)main_data_begin;
     fr->short_frame = (short)(m1 ? ((g0->info.block_type == 2) | (g1->info.block_type == 2)) : 0);
+    if (C.allocator == 1 && m1 && C.h_mode != 1) fr->short_frame = 1;  // encode_singleA codes the scale factors without scfsi
     fr->scfsi[0] = (short)R->scfsi[0];
     fr->scfsi[1] = (short)R->scfsi[1];
     frame_header(T, fr->head, pad, mode_ext, ibr);

@@ -16,6 +16,28 @@
 //
 // The reference is NOT re-entrant (file-scope statics): one live encoder per process.
 
+// The reference reads at least one heap member before writing it (CBitAllo1::alpha_nmr: bitallo1.cpp:318 after the early
+// return of fnc_noise_seek at :1312-1317; found with MALLOC_PERTURB_ -- the dual-channel / intensity-stereo output
+// changes with the previous contents of the heap).  In a fresh process (the CLI) such memory is zero; inside a
+// long-lived test process it is not.  Every allocation of this library is therefore zero-filled (-Bsymbolic binds the
+// reference's `new` to these), which pins the oracle to the fresh-process behaviour.
+#include <cstdlib>
+#include <new>
+void *operator new(std::size_t n) {
+    void *p = std::calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void *operator new[](std::size_t n) {
+    void *p = std::calloc(1, n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void operator delete(void *p) noexcept { std::free(p); }
+void operator delete[](void *p) noexcept { std::free(p); }
+void operator delete(void *p, std::size_t) noexcept { std::free(p); }
+void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
+
 #include <cstring>
 #include <cstdlib>
 #include <cstdint>
@@ -211,8 +233,18 @@ void ref_xform_tables(float *win_out, float *csa_out, float *w18, float *w2_9, f
     memcpy(coef87, b->coef, sizeof(float));
 }
 
+// spd_smrLongEcho reads one element of a local array that it has not written when the partition count is odd
+// (spdsmr.c:193, 283: stab[npart]); what it finds there is whatever earlier calls left on the stack.  In the CLI that
+// is zero.  The harness zeroes the stack below itself before every encode call so that a call made from deep inside
+// a Python process sees the same thing.
+static void __attribute__((noinline)) scrub_stack() {
+    volatile unsigned char pad[192 * 1024];
+    for (unsigned i = 0; i < sizeof(pad); i++) pad[i] = 0;
+}
+
 // One encode call.  pcm = nchan*1152 floats, interleaved, scaled to +-32768 (pub/mp3enc.h:90-98).
 int ref_encode(const float *pcm, unsigned char *out, void *trace) {
+    scrub_stack();
     RefCall *t = (RefCall *)trace;
     g_call = t;
     g_granule = 0;
@@ -252,6 +284,7 @@ unsigned int ref_frames() { return g_enc ? g_enc->L3_audio_encode_get_frames() :
 // One call of CMp3Enc::L3_audio_encode_Packet (mp3enc.cpp:3445-3440): standard bitstream (out may be NULL) plus the
 // reformatted packet(s) of this call.  Returns out_bytes.
 int ref_encode_packet(const float *pcm, unsigned char *out, unsigned char *packet, int *nbytes_out) {
+    scrub_stack();
     g_call = nullptr;
     IN_OUT x = g_enc->L3_audio_encode_Packet(const_cast<float *>(pcm), out, packet, nbytes_out);
     return x.out_bytes;

@@ -289,6 +289,12 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
                 t[1360] = R->L.mnr;
                 t[1361] = R->byte_pool;
                 t[1362] = frames[R->frames - 1].head[3];
+                t[1363] = R->A1.bitadjust_save[0];
+                t[1364] = R->A1.bitadjust_save[1];
+                t[1365] = R->A1.call_count;
+                memcpy(&t[1366], &R->A1.ave_alpha_nmr, 4);
+                memcpy(&t[1367], &R->A1.alpha_nmr, 4);
+                for (int i = 0; i < 21; i++) t[1368 + i] = R->A1.gsf_save[1][i];
             }
     }
     if (bad) { delete R; delete T; return -3; }

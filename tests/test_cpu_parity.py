@@ -109,8 +109,8 @@ def test_control_resolution_matches_golden(name, seed, sr, nch, kw):
 @need_sim
 def test_rejected_and_unsupported_controls():
     assert simmod.resolve(capi.control(samprate=44100, nch=2, bitrate=16))["bytes_in"] == 0      # reference: init -> 0
-    r = simmod.resolve(capi.control(samprate=44100, nch=2, bitrate=64, mode=2))                  # dual channel
-    assert r["bytes_in"] == 0 and r["unsupported"] == 1
+    r = simmod.resolve(capi.control(samprate=44100, nch=2, bitrate=64, mode=2))                  # dual channel: CBitAllo1
+    assert r["bytes_in"] == 2 * 4 * 1152 and r["unsupported"] == 0
 
 
 @need_sim
@@ -147,6 +147,26 @@ def test_control_sweep_host_build_matches_oracle():
         pcm = synth_pcm(4000 + k, 2.0, sr, nch)
         ref, _ = refmod.ref_encode_clip(ecr, pcm)
         got, _, _ = simmod.encode_clip(ec, pcm)
-        assert ref.size == got.size and np.array_equal(ref, got), (sr, nch, kw)
+        if info["iencode"] in (0, 2, 4, 6):      # CBitAllo1: identical up to the reference's negative-scale-factor defect
+            assert refmod.same_bytes_or_sf_defect(ref, got), (sr, nch, kw)
+        else:
+            assert ref.size == got.size and np.array_equal(ref, got), (sr, nch, kw)
         n_ok += 1
-    assert n_ok >= 220
+    assert n_ok >= 280
+
+
+@need_sim
+@need_ref
+def test_allocator1_negative_scale_factor_defect_is_the_only_difference():
+    """The one known deviation from byte identity, pinned: a clip on which the reference's CBitAllo1 emits a negative
+    scale factor (refmod.same_bytes_or_sf_defect).  The host build shows the negative value in its trace, the streams
+    differ in a handful of bytes where the reference has all ones, and nowhere else."""
+    pcm = synth_pcm(9003, 4.0, 32000, 2)
+    kw = dict(bitrate=64, mode=2)
+    ref, _ = refmod.ref_encode_clip(refmod.make_ec(samprate=32000, nch=2, **kw), pcm)
+    got, _, tr = simmod.encode_clip(capi.control(samprate=32000, nch=2, **kw), pcm, max_trace_granules=400)
+    neg = [K for K in range(tr.shape[0]) for ch in range(2) if tr[K][54 + 23 * ch:54 + 23 * ch + 21].min() < 0]
+    assert neg, "expected a negative scale factor on this clip"
+    d = np.nonzero(ref != got)[0]
+    assert 0 < d.size <= 8 and refmod.same_bytes_or_sf_defect(ref, got)
+    assert np.all(ref[d] == 0xFF)
