@@ -96,6 +96,10 @@ void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs,
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream,
                  long long *cycles = nullptr);
+// launch_rate in its phase-scheduled form (kernels_rate_ph.cu): a block owns a set of streams and its warps run the
+// phase machine of rate_phased.h for them, phase by phase
+void launch_rate_ph(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
+                    FrameRec *frames, int K0, int n, cudaStream_t stream);
 // the twin of launch_rate for the streams whose configuration selects CBitAllo1 (each kernel skips the other's streams)
 void launch_rate_a1(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                     unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream);

@@ -41,6 +41,16 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
+// The serial stage runs phase-scheduled (kernels_rate_ph.cu) unless HMP3_RATE_MODE=nested asks for the one-warp-per-
+// stream kernel with the nested drivers (same bytes; kept for A/B measurements and the per-stream clock diagnostics).
+bool rate_mode_phased() {
+    static const bool v = [] {
+        const char *e = getenv("HMP3_RATE_MODE");
+        return !(e && strcmp(e, "nested") == 0);
+    }();
+    return v;
+}
+
 enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_MS, PH_PSY2, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
 const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "ms_scan",
                                      "psy_stage2", "prepare", "rate_loop", "pack", "assemble"};
@@ -580,9 +590,13 @@ int run_plan_impl(hmp3_batch *b) {
         CK(cudaStreamWaitEvent(b->stream, b->ev_a[k], 0));
         if (c >= nb) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
-        if (b->any_allo0)
-            launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
-                        (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
+        if (b->any_allo0) {
+            if (rate_mode_phased() && !b->d_cycles)
+                launch_rate_ph(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_frames, K0_this, n, b->stream);
+            else
+                launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,
+                            (b->d_cycles && c < kCycleLaunches) ? b->d_cycles + (long long)c * n : nullptr);
+        }
         if (b->any_allo1) {
             launch_rate_a1(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream);
             b->launches++;

@@ -85,6 +85,37 @@ HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros
     return (b->total_bits + 7) >> 3;
 }
 
+// ---- the phase machine's per-stream record (rate_phased.h restates the drivers below as phases)
+enum RatePhase {
+    RP_FRAME = 0,  // pair / frame prologue: reservoir bounds, budget of the frame
+    RP_GSTART,     // granule prologue: budget, noise targets, initial steps (or digital silence)
+    RP_SHORT,      // a short-block granule, whole (rare)
+    RP_SEEK,       // per-band step search
+    RP_MID,        // peak trading / HF decision, scale factors, low-band coarsening
+    RP_ADJ,        // one step of a budget loop: move the steps, scale factors
+    RP_QC,         // quantise + region planning + bit count, then the budget decision
+    RP_GEND,       // sparse-band refit, CBR feedback, coded scale factors, side info, scale-factor plan, records
+    RP_FEND,       // frame epilogue: frame size, reservoir, frame record
+    RP_IDLE,       // nothing (left) to do in this chunk
+    RP_NPHASES
+};
+enum RateLoop { RL_NONE = 0, RL_MORE, RL_FEWER, RL_CAP, RL_CAPCH };
+
+// Everything of a stream that lives across phase boundaries (in RateState: persistent like the rest).
+struct RateCtl {
+    int phase;
+    int K;       // first encode granule of the pair in hand (a pair = one encode call: 2 granules)
+    int sub;     // MPEG-2: frame of the pair (0, 1) = granule parity; MPEG-1: 0
+    int igr;     // MPEG-1: granule of the frame in hand
+    // ---- frame scope (encode_one_frame / encode_frame_mpeg{1,2})
+    int pad, mf_bytes, main_data_begin, frame_bits, short_frame, ms;
+    int bit_pool, ba_bit_min, ba_bit_max, ba_min, ba_max, dba_max, target, sf_bits;
+    // ---- granule scope (granule_allocate / long_allocate and its loops)
+    int gkind;   // 0 long, 1 digital silence, 2 short
+    int ga_ms;   // the ms flag the allocator was given
+    int loop, pass, undo, bits, bits0, thres, dN, f;
+};
+
 // Persistent per-stream state of the serial stage.
 struct RateState {
     LongRate L;
@@ -104,6 +135,7 @@ struct RateState {
     int byte_pool, byte_min, byte_max;
     int next_granule;         // encode granule to process next
     int finished;             // all real frames are complete
+    RateCtl ctl;              // the stream's place in the phase machine (rate_phased.h)
 };
 
 HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {

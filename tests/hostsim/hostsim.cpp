@@ -169,7 +169,7 @@ int sim_analysis(const hmp3_control *ec, const int16_t *pcm_any, long nsamples, 
 
 }  // extern "C"
 
-#include "../../hmp3_b200/csrc/rate_driver.h"
+#include "../../hmp3_b200/csrc/rate_phased.h"
 
 extern "C" {
 
@@ -261,6 +261,7 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
     }
     RateState *R = new RateState;
     rate_state_init(T, R);
+    const bool nested = getenv("HMP3_SIM_NESTED") && atoi(getenv("HMP3_SIM_NESTED")) != 0;
     std::vector<unsigned char> mainbuf((size_t)(ngran + 4) * 2100, 0);
     std::vector<FrameRec> frames(ngran + 4);
     // run granule pair by pair so that traces can be taken after each call; the packing pass of the frames a
@@ -269,8 +270,13 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
     int bad = 0;
     for (int K = 0; K + 1 < ngran && !R->finished; K += 2) {
         const int f0 = R->frames;
-        rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &smk[(size_t)K * 72], &prep[K],
-                       &msf[K], pack.data(), frames.data());
+        // allocator 0 runs the phase machine (what the device kernel schedules); HMP3_SIM_NESTED=1 the nested drivers
+        if (T->cfg.allocator == 0 && !nested)
+            rate_run_chunk_phased(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &smk[(size_t)K * 72],
+                                  &prep[K], &msf[K], pack.data(), frames.data());
+        else
+            rate_run_chunk(T, R, K, 2, ngran, ngran_real, &gi[K], &xr[(size_t)K * 2 * 576], &smk[(size_t)K * 72], &prep[K],
+                           &msf[K], pack.data(), frames.data());
         for (int f = f0; f < R->frames; f++)
             bad |= pack_frame(T, &frames[f], pack.data() + (size_t)(frames[f].granule0 - K) * 2, mainbuf.data());
         if (trace)
