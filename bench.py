@@ -8,7 +8,7 @@ step     one pass of the whole hot path (polyphase -> ... -> packed frames) over
 input    every stream is its own clip: a seeded mix of two of N_BASE synthetic base clips (seeded gains and window
          positions), so no two streams are equal; the e2e leg reads every stream from its own region of one pinned
          host buffer (25 GB per GPU at the default size)
-value    whole-job throughput with the PCM already resident in HBM
+value    whole-job throughput with the PCM already resident in HBM (default: 9472 clips per GPU = 64 streams per SM)
 e2e      the same through the C-ABI host entry (hmp3_batch_encode_host): pinned host PCM -> H2D ->
          kernels -> D2H of the MP3 frames, every step
 roofline the dominant kernel (k_rate, the serial stage), algorithmic bytes / CUDA-event launch time
@@ -62,6 +62,21 @@ def rate_traffic_per_gc():
     if best:
         return float(best[0]["dram_bytes_per_gc"]), best[1]
     return (24.749032e9 + 25.115575e9) / (4736 * 256 * 2), "profiles/r1h_rate_ncu_details.txt"
+
+
+def rate_issue_counters():
+    """Issue-slot utilisation and instruction-cache behaviour of the serial stage from the newest committed counter
+    capture (profiles/*_rate_counters.json, written by tools/rate_counters.py from an ncu --metrics run)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_rate_counters.json")))
+    if not files:
+        return None
+    try:
+        d = json.load(open(files[-1]))
+        d["source"] = os.path.relpath(files[-1], ROOT)
+        return d
+    except (OSError, ValueError):
+        return None
 
 
 # algorithmic work per granule-channel of every kernel (DESIGN.md section 4): (bound, bytes or flop per gc)
@@ -454,7 +469,8 @@ def run_gpu(args, rank, local_rank, world):
         avg_launch_s = rate_ms / max(rate_launches, 1) / 1e3
         achieved = bytes_per_launch / avg_launch_s / 1e9
         traffic_gc, traffic_src = rate_traffic_per_gc()
-        roof = {"kernel": "k_rate (serial stage of the rate loop, one warp per stream)",
+        roof = {"kernel": "k_rate_ph (serial stage of the rate loop, phase-scheduled: a block owns %d streams, its warps "
+                          "claim streams that need the block's current phase)" % -(-B // 148),
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak,
                 "traffic": args.rate_traffic if args.rate_traffic is not None else traffic_gc * gc_per_launch,
@@ -464,7 +480,8 @@ def run_gpu(args, rank, local_rank, world):
                 "share_note": "wall share of the step during which this kernel is running (Phase A and the packing "
                               "pass run concurrently on other streams)",
                 "note": "latency / instruction-supply bound serial code, not a bandwidth kernel (DESIGN.md 4, 7.2): "
-                        "its issue-slot utilisation from ncu is the meaningful fraction, see profiles/"}
+                        "its issue-slot utilisation from ncu is the meaningful fraction, see profiles/",
+                "issue": rate_issue_counters()}
         # every kernel against its own ceiling, from the serialised step (launch times without overlap)
         roof_all = {}
         for name, (bound, per_gc) in KERNEL_WORK.items():
@@ -529,8 +546,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips-per-gpu", type=int, default=4736,
-                    help="streams per GPU (default: one full wave of the serial-stage kernel, 148 SMs x 32 warps)")
+    ap.add_argument("--clips-per-gpu", type=int, default=9472,
+                    help="streams per GPU (default: 64 streams per SM for the phase-scheduled serial stage, 148 SMs; "
+                         "BASELINE config 5 puts 10000 on one GPU)")
     ap.add_argument("--total-clips", type=int, default=0,
                     help="strong scaling: this many clips in all, split over the GPUs (BASELINE config 5: 10000)")
     ap.add_argument("--parity-streams", type=int, default=8,

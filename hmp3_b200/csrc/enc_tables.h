@@ -31,7 +31,10 @@
 #define HMP3_LANE ((int)(threadIdx.x & (unsigned)(HMP3_W - 1)))
 #define HMP3_GSHIFT (threadIdx.x & 31u & ~(unsigned)(HMP3_W - 1))
 #define HMP3_GMASK ((HMP3_W == 32) ? 0xffffffffu : (((1u << (HMP3_W & 31)) - 1u) << HMP3_GSHIFT))
-#define HMP3_SYNC() __syncwarp(HMP3_GMASK)
+// (inline PTX, not __syncwarp(): the serial stage is compiled with the front end at -O1, which leaves the CUDA header
+// wrappers as real function calls -- lanes that arrive at such a call in separate groups synchronise inside it and
+// return in separate groups again, whereas the barrier instruction in line reconverges them here)
+#define HMP3_SYNC() asm volatile("bar.warp.sync %0;" ::"r"(HMP3_GMASK) : "memory")
 // independent items i = 0..n-1 dealt over the lanes of the group (sequential on the host)
 #define HMP3_FOR_LANES(i, n) for (int i = HMP3_LANE; i < (n); i += HMP3_W)
 #else

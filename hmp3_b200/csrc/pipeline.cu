@@ -44,11 +44,8 @@ inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items +
 // The serial stage runs phase-scheduled (kernels_rate_ph.cu) unless HMP3_RATE_MODE=nested asks for the one-warp-per-
 // stream kernel with the nested drivers (same bytes; kept for A/B measurements and the per-stream clock diagnostics).
 bool rate_mode_phased() {
-    static const bool v = [] {
-        const char *e = getenv("HMP3_RATE_MODE");
-        return !(e && strcmp(e, "nested") == 0);
-    }();
-    return v;
+    const char *e = getenv("HMP3_RATE_MODE");
+    return !(e && strcmp(e, "nested") == 0);
 }
 
 enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_MS, PH_PSY2, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };

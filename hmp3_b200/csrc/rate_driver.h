@@ -88,13 +88,16 @@ HMP3_HD long long sink_close(BitSink *b) {  // pad to a byte boundary with zeros
 // ---- the phase machine's per-stream record (rate_phased.h restates the drivers below as phases)
 enum RatePhase {
     RP_FRAME = 0,  // pair / frame prologue: reservoir bounds, budget of the frame
-    RP_GSTART,     // granule prologue: budget, noise targets, initial steps (or digital silence)
+    RP_GSTART,     // granule prologue: budget, noise targets (or digital silence)
     RP_SHORT,      // a short-block granule, whole (rare)
-    RP_SEEK,       // per-band step search
-    RP_MID,        // peak trading / HF decision, scale factors, low-band coarsening
-    RP_ADJ,        // one step of a budget loop: move the steps, scale factors
-    RP_QC,         // quantise + region planning + bit count, then the budget decision
-    RP_GEND,       // sparse-band refit, CBR feedback, coded scale factors, side info, scale-factor plan, records
+    RP_SEEK,       // initial steps + per-band step search
+    RP_TRADE,      // left/right granules: peak trading, HF decision
+    RP_SF,         // scale factors (after a budget loop's move of the steps, when in one)
+    RP_COARSE,     // low-band coarsening (first pass)
+    RP_QUANT,      // quantiser pass
+    RP_COUNT,      // region planning + bit count, then the budget decision
+    RP_REFIT,      // sparse-band refit
+    RP_GFIN,       // CBR feedback, coded scale factors, side info, scale-factor plan, records
     RP_FEND,       // frame epilogue: frame size, reservoir, frame record
     RP_IDLE,       // nothing (left) to do in this chunk
     RP_NPHASES

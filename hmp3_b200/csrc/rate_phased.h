@@ -203,7 +203,7 @@ HMP3_FN int phase_gstart(const RateCtx *x) {
             for (int j = 0; j < 21; j++) sf_out[ch].l[j] = 0;
         }
         c->gkind = 1;
-        return RP_GEND;
+        return RP_GFIN;
     }
     c->gkind = 0;
     // head of long_allocate
@@ -216,7 +216,6 @@ HMP3_FN int phase_gstart(const RateCtx *x) {
         } else long_hf_reset_lr(L);
         long_clear_hf_lines(T, ix, L->nchan);
     }
-    long_seek_initial(T, L);
     c->loop = RL_NONE;
     return RP_SEEK;
 }
@@ -238,49 +237,46 @@ HMP3_FN int phase_short(const RateCtx *x) {
     } else mnr0 = init + 400;
     short_granule(T, &R->S, x->xr + (long long)o * 2 * 576, x->sm + (long long)o * 72, C.nchan, c->ba_min, c->target,
                   c->ba_max, c->bit_pool, R->sf[igr], R->gr[igr], &R->ix[0][0], &R->signx[0][0], c->ga_ms, mnr0);
-    return RP_GEND;
+    return RP_GFIN;
 }
 
-// ---- RP_SEEK
+// ---- RP_SEEK: initial steps (first search of the granule) + the per-band step search
 HMP3_FN int phase_seek(const RateCtx *x) {
     RateState *R = x->R;
     RateCtl *c = &R->ctl;
     const int o = ctl_granule(x->T, c) - x->K0;
+    if (c->loop == RL_NONE) long_seek_initial(x->T, &R->L);
     long_seek_actual(x->T, &R->L, x->xr + (long long)o * 2 * 576);
-    return c->loop == RL_FEWER ? RP_ADJ : RP_MID;
+    if (c->loop == RL_FEWER) return RP_SF;
+    return c->ga_ms ? RP_SF : RP_TRADE;
 }
 
-// ---- RP_MID: long_allocate between the step search and the first quantiser pass
-HMP3_FN int phase_mid(const RateCtx *x) {
+// ---- RP_TRADE: left/right granules, between the step search and the scale factors (bitallo3.cpp:2990-3000)
+HMP3_FN int phase_trade(const RateCtx *x) {
     const EncTables *T = x->T;
-    RateState *R = x->R;
-    RateCtl *c = &R->ctl;
-    LongRate *L = &R->L;
-    const int hf = T->cfg.hf_flag;
-    const bool ms = c->ga_ms != 0;
-    const int o = ctl_granule(T, c) - x->K0;
-    if (ms) {
-        if (hf) long_hf_decide(T, L, 0, true);
-    } else {
-        long_trade_peaks(T, L);
-        if (hf & 2) long_hf_adjust_lr(T, L);
-    }
-    long_scale_factors(T, L, ms);
-    long_coarsen_low_bands(T, L, x->xr + (long long)o * 2 * 576);
-    return RP_QC;
+    LongRate *L = &x->R->L;
+    long_trade_peaks(T, L);
+    if (T->cfg.hf_flag & 2) long_hf_adjust_lr(T, L);
+    return RP_SF;
 }
 
-// ---- RP_ADJ: the part of a budget-loop pass that precedes its quantiser pass
-HMP3_FN int phase_adj(const RateCtx *x) {
+// ---- RP_SF: scale factors -- of the first pass, or of one pass of a budget loop after that loop's move of the
+// steps (long_more_bits bitallo3.cpp:2569-2721, long_fewer_bits :2814-2852, long_cap_bits :2725-2772)
+HMP3_FN int phase_sf(const RateCtx *x) {
     const EncTables *T = x->T;
     RateState *R = x->R;
     RateCtl *c = &R->ctl;
     LongRate *L = &R->L;
     QLine *ix = &R->ix[0][0];
     const bool ms = c->ga_ms != 0;
-    if (c->loop == RL_MORE) {  // long_more_bits, one pass (bitallo3.cpp:2569-2721)
+    const int hf = T->cfg.hf_flag;
+    if (c->loop == RL_NONE) {
+        if (ms && hf) long_hf_decide(T, L, 0, true);
+        long_scale_factors(T, L, ms);
+        return RP_COARSE;
+    }
+    if (c->loop == RL_MORE) {
         int(*g)[22] = L->gsave;
-        const int hf = T->cfg.hf_flag;
         HMP3_SYNC();
         if (c->undo) {
             for (int ch = 0; ch < L->nchan; ch++)
@@ -304,9 +300,9 @@ HMP3_FN int phase_adj(const RateCtx *x) {
             }
             long_scale_factors(T, L, false);
         }
-    } else if (c->loop == RL_FEWER) {  // long_fewer_bits after its step search (bitallo3.cpp:2814-2852)
+    } else if (c->loop == RL_FEWER) {
         long_scale_factors(T, L, false);
-    } else {  // long_cap_bits (bitallo3.cpp:2725-2772)
+    } else {
         const bool per_channel = c->loop == RL_CAPCH;
         for (int ch = 0; ch < L->nchan; ch++)
             if (!per_channel || L->huff_bits[ch] > kPart23Max)
@@ -314,10 +310,17 @@ HMP3_FN int phase_adj(const RateCtx *x) {
         HMP3_SYNC();
         long_scale_factors(T, L, false);
     }
-    return RP_QC;
+    return RP_QUANT;
 }
 
-// ---- RP_QC: quantise, plan, count; then what long_allocate and its loops decide from the count
+// ---- RP_COARSE: coarser steps on the low bands while the noise allows (first pass only)
+HMP3_FN int phase_coarse(const RateCtx *x) {
+    RateState *R = x->R;
+    const int o = ctl_granule(x->T, &R->ctl) - x->K0;
+    long_coarsen_low_bands(x->T, &R->L, x->xr + (long long)o * 2 * 576);
+    return RP_QUANT;
+}
+
 HMP3_FN void fewer_step(const EncTables *T, LongRate *L, RateCtl *c) {  // head of one long_fewer_bits pass
     L->delta_mnr += c->dN;
     HMP3_SYNC();
@@ -325,7 +328,23 @@ HMP3_FN void fewer_step(const EncTables *T, LongRate *L, RateCtl *c) {  // head 
         HMP3_FOR_LANES(i, T->cfg.nsf[ch]) L->nt[ch][i] += c->dN;
     HMP3_SYNC();
 }
-HMP3_FN int phase_qc(const RateCtx *x) {
+// ---- RP_QUANT: the quantiser pass
+HMP3_FN int phase_quant(const RateCtx *x) {
+    const EncTables *T = x->T;
+    RateState *R = x->R;
+    RateCtl *c = &R->ctl;
+    LongRate *L = &R->L;
+    QLine *ix = &R->ix[0][0];
+    const bool ms = c->ga_ms != 0;
+    if (c->loop == RL_NONE || c->loop == RL_MORE) {
+        long_quantise(T, L, ix, true);
+        if (ms) L->ixmax[0][21] = 0;
+        if (L->hf_quant) long_quantise_hf(T, L, ix, ms);
+    } else long_quantise(T, L, ix, false);
+    return RP_COUNT;
+}
+// ---- RP_COUNT: region planning + bit count, then what long_allocate and its loops decide from the count
+HMP3_FN int phase_count(const RateCtx *x) {
     const EncTables *T = x->T;
     RateState *R = x->R;
     RateCtl *c = &R->ctl;
@@ -334,15 +353,8 @@ HMP3_FN int phase_qc(const RateCtx *x) {
     const bool ms = c->ga_ms != 0;
     const int hf = T->cfg.hf_flag;
     int bits;
-    if (c->loop == RL_NONE || c->loop == RL_MORE) {
-        long_quantise(T, L, ix, true);
-        if (ms) L->ixmax[0][21] = 0;
-        if (L->hf_quant) long_quantise_hf(T, L, ix, ms);
-        bits = long_count(T, L, ix, ms ? T->cfg.nsf2 : T->cfg.nsf3);
-    } else {
-        long_quantise(T, L, ix, false);
-        bits = long_count(T, L, ix, T->cfg.nsf2);
-    }
+    if (c->loop == RL_NONE || c->loop == RL_MORE) bits = long_count(T, L, ix, ms ? T->cfg.nsf2 : T->cfg.nsf3);
+    else bits = long_count(T, L, ix, T->cfg.nsf2);
     const int nclr = ms ? 1 : L->nchan;
     // the decisions, in the order of long_allocate (bitallo3.cpp:3050-3149)
     switch (c->loop) {
@@ -359,7 +371,7 @@ HMP3_FN int phase_qc(const RateCtx *x) {
                 c->pass = 0;
                 c->undo = 0;
                 c->bits = bits;
-                return RP_ADJ;
+                return RP_SF;
             }
         }
         break;
@@ -369,7 +381,7 @@ HMP3_FN int phase_qc(const RateCtx *x) {
             const int undo = (c->pass == 10) || (bits >= c->thres);
             if (!undo || bits > L->max_target) {
                 c->undo = undo;
-                return RP_ADJ;
+                return RP_SF;
             }
         }
         break;
@@ -383,12 +395,12 @@ HMP3_FN int phase_qc(const RateCtx *x) {
         goto after_fewer;
     case RL_CAP:
         c->pass++;
-        if (bits > L->max_bits && c->pass < 100) return RP_ADJ;
+        if (bits > L->max_bits && c->pass < 100) return RP_SF;
         goto after_cap;
     default:  // RL_CAPCH
         c->pass++;
-        if (!((L->huff_bits[0] <= kPart23Max) && (L->huff_bits[1] <= kPart23Max)) && c->pass < 100) return RP_ADJ;
-        return RP_GEND;
+        if (!((L->huff_bits[0] <= kPart23Max) && (L->huff_bits[1] <= kPart23Max)) && c->pass < 100) return RP_SF;
+        return RP_REFIT;
     }
     // after the first count / the more-bits loop
     if (ms) {
@@ -411,7 +423,7 @@ after_fewer:
         long_clear_hf_lines(T, ix, nclr);
         c->loop = RL_CAP;
         c->pass = 0;
-        return RP_ADJ;
+        return RP_SF;
     }
 after_cap:
     if (bits > kPart23Max)
@@ -420,13 +432,21 @@ after_cap:
                 long_clear_hf_lines(T, ix, nclr);
                 c->loop = RL_CAPCH;
                 c->pass = 0;
-                return RP_ADJ;
+                return RP_SF;
             }
-    return RP_GEND;
+    return RP_REFIT;
 }
 
-// ---- RP_GEND: tail of long_allocate and granule_allocate, then the frame driver's per-channel accounting
-HMP3_FN int phase_gend(const RateCtx *x) {
+// ---- RP_REFIT: tail of long_allocate
+HMP3_FN int phase_refit(const RateCtx *x) {
+    RateState *R = x->R;
+    const int o = ctl_granule(x->T, &R->ctl) - x->K0;
+    long_refit_sparse_bands(x->T, &R->L, x->xr + (long long)o * 2 * 576, &R->ix[0][0]);
+    return RP_GFIN;
+}
+
+// ---- RP_GFIN: tail of granule_allocate, then the frame driver's per-channel accounting and the records
+HMP3_FN int phase_gfin(const RateCtx *x) {
     const EncTables *T = x->T;
     RateState *R = x->R;
     RateCtl *c = &R->ctl;
@@ -435,12 +455,10 @@ HMP3_FN int phase_gend(const RateCtx *x) {
     const bool m1 = C.h_id == 1;
     const int nch = C.nchan;
     const int igr = c->igr;
-    const int o = ctl_granule(T, c) - x->K0;
     GrSide *gr = R->gr[igr];
     if (c->gkind == 0) {
         const bool ms = c->ga_ms != 0;
         const int bt = L->block_type;
-        long_refit_sparse_bands(T, L, x->xr + (long long)o * 2 * 576, &R->ix[0][0]);
         if (C.vbr_flag == 0) long_mnr_feedback(T, L, L->active_lines, c->bits0, bt);
         ScaleFac *sf_out = R->sf[igr];
         for (int ch = 0; ch < nch; ch++) {
@@ -598,10 +616,13 @@ HMP3_HD int rate_run_phase(const RateCtx *x, int phase) {
     case RP_GSTART: return phase_gstart(x);
     case RP_SHORT: return phase_short(x);
     case RP_SEEK: return phase_seek(x);
-    case RP_MID: return phase_mid(x);
-    case RP_ADJ: return phase_adj(x);
-    case RP_QC: return phase_qc(x);
-    case RP_GEND: return phase_gend(x);
+    case RP_TRADE: return phase_trade(x);
+    case RP_SF: return phase_sf(x);
+    case RP_COARSE: return phase_coarse(x);
+    case RP_QUANT: return phase_quant(x);
+    case RP_COUNT: return phase_count(x);
+    case RP_REFIT: return phase_refit(x);
+    case RP_GFIN: return phase_gfin(x);
     case RP_FEND: return phase_fend(x);
     default: return RP_IDLE;
     }

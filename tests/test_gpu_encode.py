@@ -51,6 +51,33 @@ def test_mixed_batch_matches_reference():
         assert o.size == r.size and np.array_equal(o, r), "stream %d differs" % k
 
 
+@pytest.mark.parametrize("slots,warps,opts", [(8, 3, 0), (16, 16, 8), (5, 2, 0)])
+def test_phase_scheduler_with_many_streams_per_block(monkeypatch, slots, warps, opts):
+    """The phase-scheduled serial stage with several streams per block and several warps per block (the shape it has at
+    scale: a warp claims a stream that needs the block's current phase, another warp runs that stream's next phase),
+    on a mixed ragged batch; nested-driver kernel and reference as the checks."""
+    ctl, pcms = [], []
+    for k in range(44):
+        name, seed, sr, nch, kw = CONFIGS[k % len(CONFIGS)]
+        secs = 0.6 + 0.37 * (k % 7)
+        pcms.append(synth_pcm(seed + 300 + k, secs, sr, nch))
+        ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+    monkeypatch.setenv("HMP3_RATE_PH_SLOTS", str(slots))
+    monkeypatch.setenv("HMP3_RATE_PH_WARPS", str(warps))
+    monkeypatch.setenv("HMP3_RATE_PH_OPTS", str(opts))
+    outs = capi.encode_batch(ctl, pcms)
+    outs2 = capi.encode_batch(ctl, pcms)
+    monkeypatch.setenv("HMP3_RATE_MODE", "nested")
+    outs3 = capi.encode_batch(ctl, pcms)
+    for k in range(len(pcms)):
+        assert np.array_equal(outs[k], outs2[k]), "stream %d: run-to-run difference" % k
+        assert np.array_equal(outs[k], outs3[k]), "stream %d: differs from the nested-driver kernel" % k
+    for k in range(0, len(pcms), 3):
+        name, seed, sr, nch, kw = CONFIGS[k % len(CONFIGS)]
+        ref = ref_encode(sr, nch, kw, pcms[k])
+        assert outs[k].size == ref.size and np.array_equal(outs[k], ref), "stream %d differs from the reference" % k
+
+
 def test_plan_reuse_and_device_resident_run():
     """A plan encodes repeatedly with identical results; the device-resident leg equals the host leg."""
     name, seed, sr, nch, kw = CONFIGS[0]
