@@ -63,22 +63,29 @@ def test_c5_style_batch_properties_and_spot_parity():
 
 
 def test_control_sweep_in_one_mixed_batch():
-    """Every accepted control of the sweep as ONE batch of 228 streams with 228 different tables: each stream's bytes
+    """Every accepted control of the sweep as ONE batch of 288 streams with 288 different tables: each stream's bytes
     equal the reference's."""
     from sweep_cases import sweep_cases
-    ctl, pcms, refs = [], [], []
+    ctl, pcms, refs, allo1 = [], [], [], []
     for k, sr, nch, kw in sweep_cases():
         ecr = refmod.make_ec(samprate=sr, nch=nch, **kw)
-        if refmod.ref_info(ecr) is None:
+        info = refmod.ref_info(ecr)
+        if info is None:
             continue
         pcm = synth_pcm(4000 + k, 2.0, sr, nch)
         ctl.append(capi.control(samprate=sr, nch=nch, **kw))
         pcms.append(pcm)
         refs.append(refmod.ref_encode_clip(ecr, pcm)[0])
-    assert len(ctl) >= 220
+        allo1.append(info["iencode"] in (0, 2, 4, 6))
+    assert len(ctl) >= 280 and sum(allo1) >= 24
     outs = capi.encode_batch(ctl, pcms)
-    bad = [i for i, (o, r) in enumerate(zip(outs, refs)) if o.size != r.size or not np.array_equal(o, r)]
+    # CBitAllo1 streams: identical up to the reference's negative-scale-factor defect (refmod.same_bytes_or_sf_defect,
+    # pinned in tests/test_cpu_parity.py); every other stream byte for byte
+    bad = [i for i, (o, r, a1) in enumerate(zip(outs, refs, allo1))
+           if not (refmod.same_bytes_or_sf_defect(r, o) if a1 else (o.size == r.size and np.array_equal(o, r)))]
     assert not bad, bad
+    exact = sum(1 for o, r in zip(outs, refs) if o.size == r.size and np.array_equal(o, r))
+    assert exact >= len(outs) - 2
 
 
 @pytest.mark.gpu
