@@ -92,7 +92,7 @@ size_t polymm_matrix_floats();
 void launch_prepare_init(int *msmem, PsyState *psy, int n, cudaStream_t stream);
 size_t sizeof_prep_granule();
 size_t sizeof_psy_state();
-void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream);
+void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, void *cold, int n, cudaStream_t stream);
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream,
                  long long *cycles = nullptr);
@@ -122,6 +122,7 @@ void launch_finish(const EncTables *tabs, const StreamDev *st, const StreamOut *
 void launch_handle_rebase(RateState *rs, FrameRec *frames, unsigned char *main_buf, int dK, StreamResult *res,
                           cudaStream_t stream);
 size_t sizeof_rate_state();
+size_t sizeof_rate_cold();
 size_t sizeof_frame_rec();
 size_t sizeof_pack_gc();
 

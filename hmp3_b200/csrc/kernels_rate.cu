@@ -40,8 +40,8 @@ __global__ void k_out_offsets(const StreamResult *res, long long *out_off, int n
 }
 
 
-void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int n, cudaStream_t stream) {
-    k_rate_init<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, rs, n);
+void launch_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, void *cold, int n, cudaStream_t stream) {
+    k_rate_init<<<blocks_for(n, 64), 64, 0, stream>>>(tabs, st, rs, (RateCold *)cold, n);
 }
 void launch_rate(const EncTables *tabs, const StreamDev *st, const StreamOut *so, RateState *rs, ChunkBufs cb,
                  unsigned char *main_buf, FrameRec *frames, int K0, int n, cudaStream_t stream, long long *cycles) {
@@ -137,6 +137,7 @@ void launch_handle_rebase(RateState *rs, FrameRec *frames, unsigned char *main_b
     k_handle_rebase<<<1, 32, 0, stream>>>(rs, frames, main_buf, dK, res);
 }
 size_t sizeof_rate_state() { return sizeof(RateState); }
+size_t sizeof_rate_cold() { return sizeof(RateCold); }
 size_t sizeof_frame_rec() { return sizeof(FrameRec); }
 size_t sizeof_pack_gc() { return sizeof(PackGc); }
 }  // namespace hmp3

@@ -21,10 +21,10 @@ namespace hmp3 {
 
 #ifndef HMP3_RATE_ALLOCATOR1
 // ---- K6: state reset, one thread per stream
-__global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, int nstreams) {
+__global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, RateCold *cold, int nstreams) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nstreams) return;
-    rate_state_init(tabs + st[s].cfg, rs + s);
+    rate_state_init(tabs + st[s].cfg, rs + s, cold + s);
 }
 
 #endif

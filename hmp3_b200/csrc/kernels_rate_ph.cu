@@ -10,7 +10,6 @@
 //
 // Compiled for code size like kernels_rate.cu, with HMP3_RATE_WARPS = 24 (the scratch rows are dealt by it).
 #include <atomic>
-#include <stdio.h>
 #include "analysis.h"
 #include "batch_types.h"
 #include "rate_phased.h"
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(32 * MAXW, 1)
               int K0, int nstreams, int S, int opts) {
     __shared__ unsigned s_ready[RP_NPHASES][kPhWords];  // bit j of a phase's mask: the stream in slot j waits for that phase
     __shared__ int s_age[RP_NPHASES];
-    __shared__ int s_cur, s_active, s_abort;
+    __shared__ int s_cur, s_active;
     __shared__ RateCtx s_ctx[kPhMaxSlots];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = blockIdx.x * S;
@@ -116,7 +115,6 @@ __global__ void __launch_bounds__(32 * MAXW, 1)
     if (threadIdx.x == 0) {
         s_cur = RP_FRAME;
         s_active = 0;
-        s_abort = 0;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < S; j += blockDim.x) {
@@ -190,24 +188,11 @@ __global__ void __launch_bounds__(32 * MAXW, 1)
                 if (w_lane0(sm_ld(&s_active)) == 0) break;  // every stream of the block is through the chunk
                 nap_ns(nap);
                 if (nap < 8192) nap <<= 1;
-                // watchdog: a launch lasts a fraction of a second; a scheduler that waits for ten is broken, and a
-                // failed launch is better than a hung device
-                else if (w_lane0((int)(clock_now() - t_start > 6000000000ll))) {
-                    if (opts & 4) {  // diagnostics: say what the block was waiting for and let the launch end
-                        if (lane == 0 && sm_exch(&s_abort, 1) == 0 && blockIdx.x < 4) {
-                            printf("[k_rate_ph] block %d warp %d: cur %d active %d\n", blockIdx.x, warp, s_cur, s_active);
-                            for (int p = 0; p < RP_IDLE; p++)
-                                if (s_ready[p][0] | s_ready[p][1]) printf("   phase %d ready %08x %08x\n", p, s_ready[p][0], s_ready[p][1]);
-                            for (int j = 0; j < S; j++) {
-                                const RateCtl *c = &s_ctx[j].R->ctl;
-                                printf("   slot %d: phase %d K %d sub %d igr %d loop %d pass %d gkind %d\n", j, c->phase, c->K, c->sub, c->igr, c->loop, c->pass, c->gkind);
-                            }
-                        }
-                        break;
-                    }
+                // watchdog: a launch lasts a fraction of a second (a few under a profiler's replay passes); a scheduler
+                // that has waited for a minute is broken, and a failed launch is better than a hung device
+                else if (!(opts & 16) && w_lane0((int)(clock_now() - t_start > 120000000000ll))) {
                     __trap();
                 }
-                if (w_lane0(sm_ld(&s_abort))) break;
                 continue;
             }
             const int best = top & 31;
@@ -224,10 +209,18 @@ __global__ void __launch_bounds__(32 * MAXW, 1)
         nap = 256;
         const RateCtx *x = &s_ctx[found];
         int ran = cur, next = rate_run_phase(x, cur);
-        if (next == RP_FRAME && !(opts & 1)) {
+        // phases that run on in the same warp (the stream is not handed back to the block in between): the two halves
+        // of the frame bookkeeping always; with opts & 32 / 64 also the pairs that the coarser phase set had as one
+        for (;;) {
+            bool on = (next == RP_FRAME && !(opts & 1));
+            if (opts & 32) on = on || (ran == RP_QUANT && next == RP_COUNT);
+            if (opts & 64)
+                on = on || (ran == RP_SEEK && next == RP_TRADE) || (ran == RP_SF && next == RP_COARSE) ||
+                     (ran == RP_REFIT && next == RP_GFIN);
+            if (!on) break;
             w_sync();
-            ran = RP_FRAME;
-            next = rate_run_phase(x, RP_FRAME);
+            ran = next;
+            next = rate_run_phase(x, ran);
         }
         if (ran == RP_FRAME && next == RP_GSTART && !(opts & 2)) {  // the inputs of the frame's granules
             const int o = x->R->ctl.K - K0;
@@ -284,9 +277,10 @@ void launch_rate_ph(const EncTables *tabs, const StreamDev *st, const StreamOut 
     if (W > 24) W = 24;
     if (W > S) W = S;
     const unsigned blocks = (unsigned)((n + S - 1) / S);
-    int opts = 0;  // diagnostics: 1 = no chaining of the frame phases, 2 = no prefetch, 4 = report instead of trap, 8 = pipeline-order policy
+    int opts = 0;  // diagnostics: 1 = no chaining of the frame phases, 2 = no prefetch, 8 = pipeline-order policy, 16 = no watchdog, 32 / 64 = run quantise+count / seek+trade, sf+coarsen, refit+finish as one phase
     if (const char *e = getenv("HMP3_RATE_PH_OPTS")) opts = atoi(e);
-    if (W > 16) k_rate_ph<24><<<blocks, 32 * W, kRatePhRow * W, stream>>>(tabs, st, so, rs, cb, frames, K0, n, S, opts);
+    // (HMP3_RATE_PH_REGS80=1: the 80-register instance whatever the warp count -- leaves registers for Phase A blocks)
+    if (W > 16 || getenv("HMP3_RATE_PH_REGS80")) k_rate_ph<24><<<blocks, 32 * W, kRatePhRow * W, stream>>>(tabs, st, so, rs, cb, frames, K0, n, S, opts);
     else k_rate_ph<16><<<blocks, 32 * W, kRatePhRow * W, stream>>>(tabs, st, so, rs, cb, frames, K0, n, S, opts);
 }
 

@@ -48,6 +48,35 @@ bool rate_mode_phased() {
     return !(e && strcmp(e, "nested") == 0);
 }
 
+// The serial stage's hot per-stream state (RateState, ~7 KB per stream) is read and written by every granule of its
+// stream, while ~14 KB of granule inputs and records per stream stream through L2 between two visits: left alone, the
+// state is evicted and comes back from HBM every granule (profiles/r2o: L2 hit rate 60 %, long_scoreboard the top
+// stall).  An access-policy window on the serial stage's CUDA stream marks the state array as persisting; the L2
+// set-aside is HMP3_RATE_L2_PERSIST_MB (default 0 = off: see below).
+void keep_rate_state_in_l2(cudaStream_t stream, void *base, size_t bytes, int device) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    size_t want = 0;  // measured (profiles/r2p): DRAM writes of the serial stage halve, its time does not change -> off
+    if (const char *e = getenv("HMP3_RATE_L2_PERSIST_MB")) want = (size_t)atoll(e) << 20;
+    if (want == 0 || max_persist <= 0 || max_window <= 0) return;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    size_t cur = 0;
+    cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+    if (cur < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof(a));
+    a.accessPolicyWindow.base_ptr = base;
+    a.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)a.accessPolicyWindow.num_bytes);
+    a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+}
+
 enum { PH_POLY = 0, PH_ATTACK, PH_SWITCH, PH_HYBRID, PH_PSY, PH_MS, PH_PSY2, PH_PREP, PH_RATE, PH_PACK, PH_ASSEMBLE, PH_COUNT };
 const char *kPhaseNames[PH_COUNT] = {"polyphase", "attack", "switch_scan", "hybrid_mdct", "psy_stage1", "ms_scan",
                                      "psy_stage2", "prepare", "rate_loop", "pack", "assemble"};
@@ -77,6 +106,7 @@ struct hmp3_batch {
     SwitchState *d_sw = nullptr;
     SwitchState *d_sw_init = nullptr;
     RateState *d_rs = nullptr;
+    void *d_rs_cold = nullptr;   // RateCold[n]: short-block / CBitAllo1 state, kept out of the hot array
     unsigned char *d_main = nullptr;
     FrameRec *d_frames = nullptr;
     StreamResult *d_res = nullptr;
@@ -151,6 +181,7 @@ struct hmp3_batch {
         cudaFree(d_sw);
         cudaFree(d_sw_init);
         cudaFree(d_rs);
+        cudaFree(d_rs_cold);
         cudaFree(d_main);
         cudaFree(d_frames);
         cudaFree(d_res);
@@ -395,6 +426,8 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMalloc(&b->d_so, sizeof(StreamOut) * n));
         CK(cudaMemcpy(b->d_so, b->so_h.data(), sizeof(StreamOut) * n, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&b->d_rs, sizeof_rate_state() * n));
+        CK(cudaMalloc(&b->d_rs_cold, sizeof_rate_cold() * n));
+        keep_rate_state_in_l2(b->stream, b->d_rs, sizeof_rate_state() * (size_t)n, device);
         CK(cudaMalloc(&b->d_main, std::max<long long>(main_off, 16)));
         CK(cudaMalloc(&b->d_frames, sizeof_frame_rec() * std::max<long long>(frames_off, 1)));
         CK(cudaMalloc(&b->d_res, sizeof(StreamResult) * n));
@@ -506,7 +539,7 @@ int run_plan_impl(hmp3_batch *b) {
     CK(cudaEventRecord(b->ev_run0, b->stream));
     int r = plan_reset_state(b);
     if (r != HMP3_OK) return r;
-    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, n, b->stream);
+    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, b->d_rs_cold, n, b->stream);
     b->launches++;
     // Phase A runs on its own stream one chunk ahead of the serial stage, the packing pass on a third stream
     // one chunk behind it (two chunk buffer sets):
@@ -1205,7 +1238,7 @@ int encoder_init(hmp3_encoder *e, const hmp3_control *ec, bool float_in) {
     cudaSetDevice(e->device);
     if (plan_reset_state(b) != HMP3_OK) return 0;
     cudaMemsetAsync(b->d_flags, 0, sizeof(int), b->stream);
-    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, 1, b->stream);
+    launch_rate_init(b->d_tabs, b->d_st, b->d_rs, b->d_rs_cold, 1, b->stream);
     if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
         set_err("device initialisation failed");
         return 0;

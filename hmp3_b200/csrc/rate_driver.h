@@ -119,11 +119,17 @@ struct RateCtl {
     int loop, pass, undo, bits, bits0, thres, dN, f;
 };
 
-// Persistent per-stream state of the serial stage.
-struct RateState {
-    LongRate L;
+// Persistent per-stream state of the serial stage.  The part that every granule touches (RateState, ~7 KB) and the
+// part that only short-block granules and the CBitAllo1 configurations touch (RateCold, ~17 KB) live in separate
+// arrays: the hot array of a full batch fits in L2 next to the granule inputs streaming through it, and the pipeline
+// asks for it to stay there (access-policy window, pipeline.cu).
+struct RateCold {
     ShortRate S;
     Allo1 A1;                 // state of the CBitAllo1 configurations (dual channel, intensity stereo)
+};
+struct RateState {
+    LongRate L;
+    RateCold *cold;
     alignas(16) QLine ix[2][576];  // quantised lines in transmission order (persist between granules)
     unsigned signx[2][18];    // sign bit of line k of a channel = bit (k & 31) of word (k >> 5); persists like ix
     GrSide gr[2][2];          // [granule][channel]
@@ -141,12 +147,13 @@ struct RateState {
     RateCtl ctl;              // the stream's place in the phase machine (rate_phased.h)
 };
 
-HMP3_FN void rate_state_init(const EncTables *T, RateState *R) {
+HMP3_FN void rate_state_init(const EncTables *T, RateState *R, RateCold *cold) {
     unsigned char *p = (unsigned char *)R;
     for (unsigned i = 0; i < sizeof(RateState); i++) p[i] = 0;
+    R->cold = cold;
     long_rate_init(T, &R->L);
-    short_rate_init(&R->S);
-    allo1_init(T, &R->A1);
+    short_rate_init(&cold->S);
+    allo1_init(T, &cold->A1);
     R->padcount = T->cfg.pad_divisor;
 }
 
@@ -636,7 +643,7 @@ HMP3_FN void granule_allocate(const EncTables *T, RateState *R, float *xr, const
             mnr0 = L->mnr - (imax_(L->mnr - init, 0) >> 1) - (imax_(L->mnr - init - 400, 0) >> 2);
             mnr0 = imax_(init + 400, mnr0);
         } else mnr0 = init + 400;
-        short_granule(T, &R->S, xr, sm, nchan, min_bits, target_bits, max_bits, pool_bits, sf_out, gr, ix, sg, ms, mnr0);
+        short_granule(T, &R->cold->S, xr, sm, nchan, min_bits, target_bits, max_bits, pool_bits, sf_out, gr, ix, sg, ms, mnr0);
         return;  // (the CBR feedback is a no-op for short blocks, bitallo3.cpp:2905-2909)
     }
     L->ms = ms;
@@ -869,7 +876,7 @@ HMP3_FN int encode_frame_mpeg2(const EncTables *T, RateState *R, int igr, Granul
 // long blocks only, M/S decided per frame (MPEG-1) or granule (MPEG-2) from the allocator's own correlation measure
 // without hysteresis, dual channel allocated one channel at a time.
 HMP3_FN void allo1_io(RateState *R, GranuleIn *g, int ch0, int nch, Allo1Io *io) {
-    float(*x34)[576] = (float(*)[576]) & R->S.x34[0][0][0];  // the short-block work area is free: no short blocks here
+    float(*x34)[576] = (float(*)[576]) & R->cold->S.x34[0][0][0];  // the short-block work area is free: no short blocks here
     for (int c = 0; c < nch; c++) {
         const int ch = ch0 + c;
         io->xr[c] = g->xr + 576 * ch;
@@ -884,7 +891,7 @@ HMP3_FN int encode_frame_a1(const EncTables *T, RateState *R, int igr_arg, Granu
     const EncConfig &C = T->cfg;
     const int nch = C.nchan;
     const bool m1 = C.h_id == 1, joint = C.h_mode == 1;
-    Allo1 *A = &R->A1;
+    Allo1 *A = &R->cold->A1;
     GranuleIn *gs[2] = {g0, g1};
     const int ngr = m1 ? 2 : 1;
     int bit_max, bit_min;

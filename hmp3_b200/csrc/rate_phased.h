@@ -235,7 +235,7 @@ HMP3_FN int phase_short(const RateCtx *x) {
         mnr0 = L->mnr - (imax_(L->mnr - init, 0) >> 1) - (imax_(L->mnr - init - 400, 0) >> 2);
         mnr0 = imax_(init + 400, mnr0);
     } else mnr0 = init + 400;
-    short_granule(T, &R->S, x->xr + (long long)o * 2 * 576, x->sm + (long long)o * 72, C.nchan, c->ba_min, c->target,
+    short_granule(T, &R->cold->S, x->xr + (long long)o * 2 * 576, x->sm + (long long)o * 72, C.nchan, c->ba_min, c->target,
                   c->ba_max, c->bit_pool, R->sf[igr], R->gr[igr], &R->ix[0][0], &R->signx[0][0], c->ga_ms, mnr0);
     return RP_GFIN;
 }

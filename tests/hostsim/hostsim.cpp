@@ -260,7 +260,8 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
         }
     }
     RateState *R = new RateState;
-    rate_state_init(T, R);
+    RateCold *Rcold = new RateCold;
+    rate_state_init(T, R, Rcold);
     const bool nested = getenv("HMP3_SIM_NESTED") && atoi(getenv("HMP3_SIM_NESTED")) != 0;
     std::vector<unsigned char> mainbuf((size_t)(ngran + 4) * 2100, 0);
     std::vector<FrameRec> frames(ngran + 4);
@@ -295,15 +296,15 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
                 t[1360] = R->L.mnr;
                 t[1361] = R->byte_pool;
                 t[1362] = frames[R->frames - 1].head[3];
-                t[1363] = R->A1.bitadjust_save[0];
-                t[1364] = R->A1.bitadjust_save[1];
-                t[1365] = R->A1.call_count;
-                memcpy(&t[1366], &R->A1.ave_alpha_nmr, 4);
-                memcpy(&t[1367], &R->A1.alpha_nmr, 4);
-                for (int i = 0; i < 21; i++) t[1368 + i] = R->A1.gsf_save[1][i];
+                t[1363] = Rcold->A1.bitadjust_save[0];
+                t[1364] = Rcold->A1.bitadjust_save[1];
+                t[1365] = Rcold->A1.call_count;
+                memcpy(&t[1366], &Rcold->A1.ave_alpha_nmr, 4);
+                memcpy(&t[1367], &Rcold->A1.alpha_nmr, 4);
+                for (int i = 0; i < 21; i++) t[1368 + i] = Rcold->A1.gsf_save[1][i];
             }
     }
-    if (bad) { delete R; delete T; return -3; }
+    if (bad) { delete R; delete Rcold; delete T; return -3; }
     long total = 0;
     const int nf = R->frames_done;
     for (int f = 0; f < nf; f++) {
@@ -316,7 +317,7 @@ long sim_encode_clip_any(const hmp3_control *ec, const void *pcm_any, int is_flo
         total += sz;
     }
     if (nframes_out) *nframes_out = nf;
-    delete R;
+    delete R; delete Rcold;
     delete T;
     return total;
 }
