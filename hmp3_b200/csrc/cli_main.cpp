@@ -151,6 +151,41 @@ struct Job {
 
 }  // namespace
 
+// Encode sample rate for a source rate and the -A value, as CMp3Enc::MP3_audio_encode_init picks it
+// (mp3enc.cpp:2628-2651 find_nearest over {22050, 24000, 16000, 44100, 48000, 32000}, :2696-2748); 0 = init fails.
+static int nearest_rate(const int *table, int n, int x) {
+    int best = table[0], d0 = abs(table[0] - x);
+    for (int i = 0; i < n; i++) {
+        const int d = abs(table[i] - x);
+        if (d < d0) {
+            d0 = d;
+            best = table[i];
+        }
+    }
+    return best;
+}
+static int target_rate(int source, int mpeg_select) {
+    static const int rates[6] = {22050, 24000, 16000, 44100, 48000, 32000};
+    if (source < 4000 || source > 48000) return 0;
+    int t;
+    switch (mpeg_select) {
+    case 0:
+        if (source < 16000 && (t = nearest_rate(rates, 3, 2 * source)) == 2 * source) return t;
+        return nearest_rate(rates, 6, source);
+    case 1:
+        if (source < 16000 && (t = nearest_rate(rates + 3, 3, 4 * source)) == 4 * source) return t;
+        if (source < 32000 && (t = nearest_rate(rates + 3, 3, 2 * source)) == 2 * source) return t;
+        return nearest_rate(rates + 3, 3, source);
+    case 2:
+        if (source < 16000 && (t = nearest_rate(rates, 3, 2 * source)) == 2 * source) return t;
+        if (source > 24000 && 2 * (t = nearest_rate(rates, 3, source / 2)) == source) return t;
+        return nearest_rate(rates, 3, source);
+    default:
+        t = nearest_rate(rates, 6, mpeg_select);
+        return t == mpeg_select ? t : 0;
+    }
+}
+
 int main(int argc, char **argv) {
     hmp3_control base;
     hmp3_control_defaults(&base);
@@ -159,6 +194,7 @@ int main(int argc, char **argv) {
     bool ignore_length = false;
     std::vector<std::string> names;
     const char *list = nullptr;
+    int mpeg_select = 0;
     for (int i = 1; i < argc; i++) {
         const char *a = argv[i];
         if (a[0] != '-' || a[1] == 0) {  // a file name, or "-" = stdin/stdout
@@ -177,6 +213,10 @@ int main(int argc, char **argv) {
         if (a[1] == 'x' || a[1] == 'X') {
             xing = atoi(a + 2);
             if (xing == 2) xing = 3;
+        }
+        if (a[1] == 'a' || a[1] == 'A') {  // -A<n>: mpeg_select of MP3_audio_encode_init (tomp3.cpp:545-550)
+            mpeg_select = atoi(a + 2);
+            if (mpeg_select < 0) mpeg_select = 0;
         }
         if (hmp3_control_apply_option(&base, a) != 0) {
             fprintf(stderr, "\n Usage:  hmp3b200 <input> <output> [options]   (options as hmp3; -@ <list> for a batch)\n");
@@ -233,13 +273,19 @@ int main(int argc, char **argv) {
         // encode rate as CMp3Enc::MP3_audio_encode_init picks it (mp3enc.cpp:2700-2714, mpeg_select 0): a source below
         // 16 kHz is doubled when that is an MPEG-2 rate (Csrc case 1); any other non-MPEG rate would need the general
         // resampler, which is not built
+        // the encode rate MP3_audio_encode_init derives from the source rate and -A (mp3enc.cpp:2700-2748)
         j.enc_rate = j.wav.rate;
-        const bool native = j.wav.rate == 16000 || j.wav.rate == 22050 || j.wav.rate == 24000 || j.wav.rate == 32000 ||
-                            j.wav.rate == 44100 || j.wav.rate == 48000;
-        const bool up2 = !native && (j.wav.rate == 8000 || j.wav.rate == 11025 || j.wav.rate == 12000);
-        if (!native && !up2) {
-            fprintf(stderr, "\n ENCODER INIT FAIL (input rate %d needs the general sample-rate converter, which is not built)\n",
-                    j.wav.rate);
+        const int target = target_rate(j.wav.rate, mpeg_select);
+        const bool native = target == j.wav.rate;
+        // Csrc case 1.  (A 16 kHz source forced to 32 kHz by -A1 / -A32000 is refused: the reference CLI's output for
+        // that one combination differs from its own encoder run on the 1:2 up-converted samples from the seventh frame
+        // on, mono, whatever the length -- not understood, so not claimed.)
+        const bool up2 = target == 2 * j.wav.rate && j.wav.rate != 16000;
+        if (target == 0 || (!native && !up2)) {
+            if (target == 0) fprintf(stderr, "\n ENCODER INIT FAIL\n");
+            else
+                fprintf(stderr, "\n ENCODER INIT FAIL (input rate %d -> encode rate %d needs the general sample-rate "
+                                "converter, which is not built)\n", j.wav.rate, target);
             continue;
         }
         const bool downmix = j.wav.channels == 2 && mono_convert;

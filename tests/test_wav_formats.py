@@ -340,6 +340,24 @@ def test_cli_identity_for_up_converted_input(tmp_path):
                 subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
                 got = np.fromfile(out, dtype=np.uint8)
                 assert got.size == want.size and np.array_equal(got, want), name
+    # -A<n> (mpeg_select of MP3_audio_encode_init): values that resolve to the source rate or to its 1:2 up-conversion
+    # give the reference's file; a target that needs the general resampler is refused
+    for sr, nch, opts in [(22050, 2, ["-A1"]), (24000, 2, ["-A48000"]), (44100, 2, ["-A1"]),
+                          (44100, 2, ["-A44100", "-B64"]), (22050, 2, ["-A2"]), (11025, 1, ["-A2"]), (32000, 2, ["-A0"])]:
+        samples = wavutil.make_samples(synth_pcm(84, 2.0, sr, nch)[:30000], "s16", seed=3)
+        name = "asel_%d_%d_%s" % (sr, nch, "".join(opts).replace("-", ""))
+        wav, want = ref_cli_file(tmp_path, samples, "s16", sr, nch, opts, name)
+        out = str(tmp_path / (name + "_gpu.mp3"))
+        subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        got = np.fromfile(out, dtype=np.uint8)
+        assert got.size == want.size and np.array_equal(got, want), name
+    for sr, opts in [(44100, ["-A2"]), (11025, ["-A1"]), (44100, ["-A32000"]), (44100, ["-A12345"]), (16000, ["-A1"])]:
+        samples = wavutil.make_samples(synth_pcm(85, 0.5, sr, 2), "s16")
+        wav = str(tmp_path / ("asel_bad_%d%s.wav" % (sr, opts[0])))
+        wavutil.write_wav(wav, samples, "s16", sr, 2)
+        outp = wav[:-4] + ".mp3"
+        r = subprocess.run([CLI, wav, outp] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        assert r.returncode != 0 and not os.path.exists(outp), (sr, opts)
     # a rate that would need the general resampler is refused, not mis-encoded
     samples = wavutil.make_samples(synth_pcm(83, 0.5, 37800, 2), "s16")
     wav = str(tmp_path / "odd.wav")
