@@ -292,11 +292,71 @@ __device__ __forceinline__ int ms_measure_long_warp(const EncTables *T, const fl
     return __reduce_add_sync(0xffffffffu, cm);
 }
 
+// Short blocks, lane-parallel (same per-item operations and orders as psy_short_stage1 / ms_measure_short of
+// psy_core.h): the partition energies are 3 x 32 independent ordered sums, the spreading 3 x npart/2 independent pairs
+// of ordered sums, the M/S measure 3 x nsf independent bands with integer votes.  (On one lane a short granule cost
+// several long ones and held its whole block back.)
+__device__ __forceinline__ void psy_short_stage1_warp(const EncTables *T, const float *xr /*[3][192]*/, PsyRaw *R,
+                                                      float *e /*[96] scratch*/, int lane) {
+    const int nmap = T->psy_emap_n_s;
+    const int npart = T->psy_npart_s;
+    const float *w = T->w_spd_s;
+    for (int it = lane; it < 96; it += 32) {
+        const int win = it >> 5, j = it & 31;
+        float s = 0.0f;
+        if (j < nmap) {
+            const int n = T->psy_nsum_s[j];
+            const float *x = xr + 192 * win + T->psy_start_s[j];
+            for (int q = 0; q < n; q++) s += x[q] * x[q];
+        }
+        e[it] = s;
+    }
+    __syncwarp();
+    const int mpart = (npart + 1) >> 1;
+    for (int it = lane; it < 3 * mpart; it += 32) {
+        const int win = it / mpart, m = it - win * mpart, i = 2 * m;
+        int k = 0;  // first weight of partition i: the weights of all partitions follow each other
+        for (int q = 0; q < i; q++) k += T->spd_cnt_s[q];
+        const float *ew = e + 32 * win;
+        int p = T->spd_off_s[i], n = T->spd_cnt_s[i];
+        float s0 = 0.5f;
+        for (int j = 0; j < n; j++, k++) s0 += w[k] * ew[p + j];
+        p = T->spd_off_s[i + 1];
+        n = T->spd_cnt_s[i + 1];
+        float t0 = 0.5f;
+        for (int j = 0; j < n; j++, k++) t0 += w[k] * ew[p + j];
+        R->thr[16 * win + m] = s0 + t0;
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ int ms_measure_short_warp(const EncTables *T, const float *x0, const float *x1, int lane) {
+    const int nsf = T->cfg.nsf_s[0];
+    int d = 0;
+    for (int it = lane; it < 3 * nsf; it += 32) {
+        const int win = it / nsf, i = it - win * nsf;
+        const int k0 = 192 * win + T->startBand_s[i], n = T->nBand_s[i];
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int k = k0; k < k0 + n; k++) {
+            float a = x0[k] * x0[k];
+            const float b = x1[k] * x1[k];
+            s0 += (a + b);
+            a = a - b;
+            if (a < 0.0f) a = -a;
+            s1 += a;
+        }
+        if ((double)s1 > 0.80 * (double)s0) d++;
+        if ((double)s1 > 0.95 * (double)s0) d += 2;
+    }
+    d = __reduce_add_sync(0xffffffffu, d);
+    return (nsf - d) << 10;
+}
+
 __global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
                                                     int nstreams) {
     __shared__ float s_x[4][2][576];
     __shared__ float s_xtab[4][44];
     __shared__ int s_mbe[4][44], s_snr[4][44];
+    __shared__ float s_e[4][96];
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int q = (int)(wid % cb.NG), s = (int)(wid / cb.NG);
@@ -313,14 +373,13 @@ __global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const
     for (int c = 0; c < sd.nch; c++) {
         PsyRaw *R = cb.raw + o * 2 + c;
         if (bt != 2) psy_long_stage1_warp(T, s_x[wl][c], R, s_xtab[wl], s_mbe[wl], s_snr[wl], lane);
-        else if (lane == 0) psy_short_stage1(T, s_x[wl][c], R);
+        else psy_short_stage1_warp(T, s_x[wl][c], R, s_e[wl], lane);
         __syncwarp();
     }
     int m = 0;
     if (sd.nch == 2) {
         if (bt != 2) m = ms_measure_long_warp(T, s_x[wl][0], s_x[wl][1], lane);
-        else if (lane == 0) m = ms_measure_short(T, s_x[wl][0], s_x[wl][1]);
-        if (bt == 2) m = __shfl_sync(0xffffffffu, m, 0);
+        else m = ms_measure_short_warp(T, s_x[wl][0], s_x[wl][1], lane);
     }
     if (lane == 0) cb.ms_raw[o] = m;
 }
