@@ -54,6 +54,22 @@ HMP3_HD void long_band_sums(const EncTables *T, const float *v, int nbands, floa
     }
     HMP3_SYNC();
 }
+// Two rows at once: a band's ordered sum is a dependent chain as long as the band (up to ~100 lines for one lane
+// while the others wait), so two independent chains per pass halve the passes; each sum keeps its own order.
+HMP3_HD void long_band_sums2(const EncTables *T, const float *v0, const float *v1, int nbands, float *out0, float *out1) {
+    HMP3_SYNC();
+    for (int i = HMP3_LANE; i < nbands; i += HMP3_W) {
+        const int k0 = T->startBand_l[i], n = T->nBand_l[i];
+        float a = 0.0f, b = 0.0f;
+        for (int k = k0; k < k0 + n; k++) {
+            a += v0[k];
+            b += v1[k];
+        }
+        out0[i] = a;
+        out1[i] = b;
+    }
+    HMP3_SYNC();
+}
 #endif
 
 // band maxima of |x|^(3/4) and the step range [gmin, gzero] (bitallo3.cpp:881-896)
@@ -147,8 +163,7 @@ HMP3_FN void long_prepare(const EncTables *T, int ms, float *xr, PrepGranule *P)
         sq0[k] = xr[k] * xr[k];
         sq1[k] = xr[576 + k] * xr[576 + k];
     }
-    long_band_sums(T, sq0, nsf0, P->xsxx[0]);
-    long_band_sums(T, sq1, nsf0, P->xsxx[1]);
+    long_band_sums2(T, sq0, sq1, nsf0, P->xsxx[0], P->xsxx[1]);
     for (int w = 0; 32 * w < nrot; w++) {
         unsigned bm = 0, bd = 0;
         for (int h = 0; h < 32 / HMP3_W; h++) {
@@ -172,8 +187,7 @@ HMP3_FN void long_prepare(const EncTables *T, int ms, float *xr, PrepGranule *P)
             P->sign[1][w] = bd;
         }
     }
-    long_band_sums(T, sq0, nsf0, P->e2[0]);
-    long_band_sums(T, sq1, nsf0, P->e2[1]);
+    long_band_sums2(T, sq0, sq1, nsf0, P->e2[0], P->e2[1]);
     HMP3_SYNC();
     for (int ch = 0; ch < 2; ch++)
         for (int k = HMP3_LANE; k < T->cfg.nbmax2[ch]; k += HMP3_W) P->x34[ch][k] = pow34(T, xr[576 * ch + k]);
@@ -208,6 +222,31 @@ HMP3_FN void long_prepare(const EncTables *T, int ms, float *xr, PrepGranule *P)
     }
     for (int ch = 0; ch < 2; ch++)
         for (int k = 0; k < T->cfg.nbmax2[ch]; k++) P->x34[ch][k] = pow34(T, xr[576 * ch + k]);
+#endif
+#if HMP3_COOP
+    if (nch == 2 && T->cfg.nsf2[0] == T->cfg.nsf2[1]) {  // both channels' band maxima in one pass (two chains per lane)
+        HMP3_SYNC();
+        for (int i = HMP3_LANE; i < T->cfg.nsf2[0]; i += HMP3_W) {
+            const int k0 = T->startBand_l[i], n = T->nBand_l[i];
+            const float *y0 = P->x34[0] + k0, *y1 = P->x34[1] + k0;
+            float m0 = 0.0f, m1 = 0.0f;
+            for (int k = 0; k < n; k++) {
+                if (y0[k] > m0) m0 = y0[k];
+                if (y1[k] > m1) m1 = y1[k];
+            }
+            for (int ch = 0; ch < 2; ch++) {
+                const float m = ch ? m1 : m0;
+                P->x34max[ch][i] = m;
+                float t = (0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f));
+                int g0 = round_away(t);
+                if (g0 < 0) g0 = 0;
+                P->gzero[ch][i] = g0;
+                P->gmin[ch][i] = (g0 - kGminOffset) > 0 ? (g0 - kGminOffset) : 0;
+            }
+        }
+        HMP3_SYNC();
+        return;
+    }
 #endif
     for (int ch = 0; ch < nch; ch++) long_prepare_bounds(T, P, ch, T->cfg.nsf2[ch]);
 }
