@@ -8,6 +8,20 @@
 
 namespace hmp3 {
 
+// Asynchronous global -> shared copies (LDGSTS).  The staging loops of these kernels used to load a value and store
+// it to shared memory at once: one line in flight per warp, and 55-75 % of the kernel's stall samples on that store
+// (profiles/r2z).  cp.async puts a warp's whole tile in flight without holding registers; .cg = past L1, the data is
+// used once.  stage_row copies n floats (n a multiple of 4, both pointers 16-byte aligned) with the lanes of a warp.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void stage_row(float *smem, const float *gmem, int n, int lane) {
+    for (int k = 4 * lane; k < n; k += 128) cp_async16(smem + k, gmem + k);
+}
+
 // ---- K1: polyphase analysis.  One block = kPolyRun consecutive polyphase granules of one stream, both channels:
 // the PCM span they need (576 * run + 480 samples per channel) is staged once in shared memory as float
 // (coalesced 32-bit reads of the interleaved int16 input, zero outside the clip), then one thread per
@@ -70,17 +84,23 @@ __global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const 
         }
     } else if (nch == 2) {
         const unsigned *src2 = (const unsigned *)src;  // pcm_off is even-aligned: one 32-bit word = (left, right)
-        for (int p = threadIdx.x; p < kPolySpan; p += 256) {
-            const long long n = n0 + p;
-            float l = 0.0f, r = 0.0f;
-            if (n >= 0 && n < sd.nsamples) {
-                const unsigned w = src2[n];
-                l = (float)(short)(w & 0xffffu);
-                r = (float)(short)(w >> 16);
+        for (int p0 = threadIdx.x; p0 < kPolySpan; p0 += 6 * 256) {  // six loads in flight, then the six stores
+            unsigned w[6];
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int p = p0 + 256 * u;
+                const long long n = n0 + p;
+                w[u] = (p < kPolySpan && n >= 0 && n < sd.nsamples) ? src2[n] : 0u;
             }
-            const int q = p + (p >> 5);
-            s_pcm[0][q] = l;
-            s_pcm[1][q] = r;
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int p = p0 + 256 * u;
+                if (p < kPolySpan) {
+                    const int q = p + (p >> 5);
+                    s_pcm[0][q] = (float)(short)(w[u] & 0xffffu);
+                    s_pcm[1][q] = (float)(short)(w[u] >> 16);
+                }
+            }
         }
     } else {
         for (int p = threadIdx.x; p < kPolySpan; p += 256) {
@@ -155,7 +175,7 @@ __global__ void k_switch_scan(const EncTables *tabs, const StreamDev *st, Switch
 // consecutive values per sub-band -- would otherwise touch 32 different cache lines per instruction).
 __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
                                                 int nstreams) {
-    __shared__ float s_buf[4][3][576];
+    __shared__ __align__(16) float s_buf[4][3][576];
     const int G = cb.NG + 3;
     long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -173,10 +193,9 @@ __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const Str
     const float *cur = cb.P + (((long long)s * G + q + 1) * 2 + ch) * 576;   // P[K-2]
     float *xr = cb.xr + (((long long)s * cb.NG + q) * 2 + ch) * 576;
     float(*sb)[576] = s_buf[threadIdx.x >> 5];
-    for (int k = lane; k < 576; k += 32) {
-        sb[0][k] = prev[k];
-        sb[1][k] = cur[k];
-    }
+    stage_row(sb[0], prev, 576, lane);
+    stage_row(sb[1], cur, 576, lane);
+    cp_async_wait_all();
     __syncwarp();
     hybrid_item(T, sb[0], sb[1], bt, lane, sb[2]);
     __syncwarp();
@@ -353,7 +372,7 @@ __device__ __forceinline__ int ms_measure_short_warp(const EncTables *T, const f
 
 __global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
                                                     int nstreams) {
-    __shared__ float s_x[4][2][576];
+    __shared__ __align__(16) float s_x[4][2][576];
     __shared__ float s_xtab[4][44];
     __shared__ int s_mbe[4][44], s_snr[4][44];
     __shared__ float s_e[4][96];
@@ -367,8 +386,8 @@ __global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const
     const long long o = (long long)s * cb.NG + q;
     const int bt = cb.gi[o].block_type;
     const float *x0 = cb.xr + o * 2 * 576;
-    for (int c = 0; c < sd.nch; c++)
-        for (int k = lane; k < 576; k += 32) s_x[wl][c][k] = x0[576 * c + k];
+    for (int c = 0; c < sd.nch; c++) stage_row(s_x[wl][c], x0 + 576 * c, 576, lane);
+    cp_async_wait_all();
     __syncwarp();
     for (int c = 0; c < sd.nch; c++) {
         PsyRaw *R = cb.raw + o * 2 + c;
