@@ -184,7 +184,7 @@ __device__ __forceinline__ float gsum_ordered(float acc, float v, int m) {
 #endif
 constexpr int kRateWarpsPerBlock = HMP3_RATE_WARPS;
 // warps (= frames) per thread block of the packing kernel
-constexpr int kPackWarpsPerBlock = 8;
+constexpr int kPackWarpsPerBlock = 4;
 
 enum FrameDriver { FD_VBR_MPEG1 = 0, FD_CBR_MPEG1 = 1, FD_VBR_MPEG2 = 2, FD_CBR_MPEG2 = 3 };
 

@@ -19,7 +19,19 @@
 
 namespace hmp3 {
 
-#ifndef HMP3_RATE_ALLOCATOR1
+// Which kernels a translation unit gets: the serial stage (size-optimised build), or the parallel passes around it
+// (packing, assembly, results: ordinary -O3 build, kernels_pack.cu).  HMP3_RATE_ALLOCATOR1: only the CBitAllo1 twin.
+#if defined(HMP3_RATE_PART_PACK)
+#define HMP3_WANT_SERIAL 0
+#define HMP3_WANT_PACK 1
+#elif defined(HMP3_RATE_ALLOCATOR1)
+#define HMP3_WANT_SERIAL 1
+#define HMP3_WANT_PACK 0
+#else
+#define HMP3_WANT_SERIAL 1
+#define HMP3_WANT_PACK 0
+#endif
+#if HMP3_WANT_SERIAL && !defined(HMP3_RATE_ALLOCATOR1)
 // ---- K6: state reset, one thread per stream
 __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateState *rs, RateCold *cold, int nstreams) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,6 +40,7 @@ __global__ void k_rate_init(const EncTables *tabs, const StreamDev *st, RateStat
 }
 
 #endif
+#if HMP3_WANT_SERIAL
 // ---- K6: the serial stage over one chunk of granules, one GROUP of HMP3_W lanes per stream (HMP3_W = 32: one warp
 // per stream, the shipped configuration; 16 = two streams per warp, an experiment that loses once the streams
 // differ): the scalar control flow of the rate loop runs uniformly on the lanes of a group, the per-line / per-band
@@ -70,7 +83,8 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
     }
 }
 
-#ifndef HMP3_RATE_ALLOCATOR1
+#endif  // HMP3_WANT_SERIAL
+#if HMP3_WANT_PACK
 // ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)
 __global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
     k_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
@@ -84,7 +98,21 @@ __global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
     FrameRec *fr = frames + o.frames_off + f;
     const EncTables *T = tabs + st[s].cfg;
     const PackGc *gc = cb.pack + ((long long)s * cb.NG + (fr->granule0 - K0)) * 2;
-    if (pack_frame(T, fr, gc, main_buf + o.main_off) && (threadIdx.x & 31) == 0) flags[s] = 1;
+    // the frame's granule-channel records (up to 4 x 1396 bytes) go to shared memory first, all of them in flight at
+    // once: the Huffman loops then read their lines there instead of waiting for one global load per pair
+    __shared__ unsigned s_gc[kPackWarpsPerBlock][4 * (sizeof(PackGc) / 4)];
+    static_assert(sizeof(PackGc) % 4 == 0, "PackGc is copied in 32-bit words");
+    unsigned *dst = s_gc[(threadIdx.x >> 5) % kPackWarpsPerBlock];
+    {
+        const int lane = threadIdx.x & 31;
+        const int nwords = fr->ngr * T->cfg.nchan * (int)(sizeof(PackGc) / 4);
+        const unsigned *src = (const unsigned *)gc;
+        for (int k = lane; k < nwords; k += 32)
+            asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.ca.shared.global [a], [%1], 4; }" ::"l"(dst + k), "l"(src + k));
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    if (pack_frame(T, fr, (const PackGc *)dst, main_buf + o.main_off) && (threadIdx.x & 31) == 0) flags[s] = 1;
 }
 
 // ---- per-stream totals after the last chunk
