@@ -536,9 +536,135 @@ __global__ void __launch_bounds__(128) k_psy_stage2(const EncTables *tabs, const
 }
 
 // ---- K5d: prepare pass, one warp per (stream, granule): state-free part of the rate-loop prologue (long blocks)
+// long_prepare (prepare.h) with the granule staged in shared memory: x = the two spectra (rewritten in place to
+// magnitudes / mid-side like the global copy), q = per-line squares and then |x|^(3/4).  The ordered band sums and band
+// maxima -- dependent chains as long as a band, one band per lane -- read shared memory instead of global memory, and
+// the final contents of xr and PrepGranule are exactly long_prepare's (including the squares it leaves in x34 above the
+// last line it raises to the 3/4).
+__device__ __forceinline__ void band_sums2_sm(const EncTables *T, const float *v0, const float *v1, int nbands, float *out0,
+                                              float *out1, int lane) {
+    for (int i = lane; i < nbands; i += 32) {
+        const int k0 = T->startBand_l[i], n = T->nBand_l[i];
+        float a = 0.0f, b = 0.0f;
+        for (int k = k0; k < k0 + n; k++) {
+            a += v0[k];
+            b += v1[k];
+        }
+        out0[i] = a;
+        if (out1) out1[i] = b;
+    }
+}
+__device__ __forceinline__ void band_bounds_sm(const EncTables *T, PrepGranule *P, const float *y, int ch, int nbands, int lane) {
+    for (int i = lane; i < nbands; i += 32) {
+        const int k0 = T->startBand_l[i], n = T->nBand_l[i];
+        float m = 0.0f;
+        for (int k = k0; k < k0 + n; k++)
+            if (y[k] > m) m = y[k];
+        P->x34max[ch][i] = m;
+        const float t = (0.017716950f * mb_log(T, m) + (104.585000f - 100.0f + 8.0f));
+        int g0 = round_away(t);
+        if (g0 < 0) g0 = 0;
+        P->gzero[ch][i] = g0;
+        P->gmin[ch][i] = (g0 - kGminOffset) > 0 ? (g0 - kGminOffset) : 0;
+    }
+}
+__device__ __forceinline__ void long_prepare_warp(const EncTables *T, int ms, float *xr, PrepGranule *P, float (*x)[576],
+                                                  float (*q)[576], int lane) {
+    const int nch = T->cfg.nchan;
+    for (int ch = 0; ch < 2; ch++) stage_row(x[ch], xr + 576 * ch, 576, lane);  // (the buffer always has two rows)
+    for (int w = lane; w < 36; w += 32) (&P->sign[0][0])[w] = 0;
+    cp_async_wait_all();
+    __syncwarp();
+    if (!ms) {
+        for (int ch = 0; ch < nch; ch++) {
+            const int nb = T->cfg.nsf3[ch], nl = T->startBand_l[nb];
+            if (lane == 0) P->nlines[ch] = nl;
+            for (int w = 0; 32 * w < nl; w++) {
+                const int k = 32 * w + lane;
+                int sgn = 0;
+                if (k < nl) {
+                    float v = x[ch][k];
+                    if (!(v >= 0.0f)) {
+                        sgn = 1;
+                        v = -v;
+                        x[ch][k] = v;
+                        xr[576 * ch + k] = v;
+                    }
+                    q[ch][k] = v * v;
+                }
+                const unsigned bits = __ballot_sync(0xffffffffu, sgn);
+                if (lane == 0) P->sign[ch][w] = bits;
+            }
+            __syncwarp();
+            band_sums2_sm(T, q[ch], q[ch], nb, P->xsxx[ch], nullptr, lane);
+            __syncwarp();
+            const int nmax = T->cfg.nbmax3[ch];
+            for (int k = lane; k < (nl > nmax ? nl : nmax); k += 32) {
+                const float v = k < nmax ? pow34(T, x[ch][k]) : q[ch][k];
+                q[ch][k] = v;
+                P->x34[ch][k] = v;
+            }
+            __syncwarp();
+            band_bounds_sm(T, P, q[ch], ch, nb, lane);
+        }
+        return;
+    }
+    const int nsf0 = T->cfg.nsf[0];
+    const int nl = T->startBand_l[nsf0];
+    const int nrot = nl + (T->cfg.hf_flag ? T->nBand_l[21] : 0);
+    if (lane == 0) P->nlines[0] = P->nlines[1] = nrot;
+    for (int k = lane; k < nl; k += 32) {
+        q[0][k] = x[0][k] * x[0][k];
+        q[1][k] = x[1][k] * x[1][k];
+    }
+    __syncwarp();
+    band_sums2_sm(T, q[0], q[1], nsf0, P->xsxx[0], P->xsxx[1], lane);
+    __syncwarp();
+    for (int w = 0; 32 * w < nrot; w++) {
+        const int k = 32 * w + lane;
+        int sm_ = 0, sd_ = 0;
+        if (k < nrot) {
+            float m = (x[0][k] + x[1][k]);
+            float d = (x[0][k] - x[1][k]);
+            if (m < 0.0f) { sm_ = 1; m = -m; }
+            if (d < 0.0f) { sd_ = 1; d = -d; }
+            x[0][k] = m;
+            x[1][k] = d;
+            xr[k] = m;
+            xr[576 + k] = d;
+            q[0][k] = m * m;
+            q[1][k] = d * d;
+        }
+        const unsigned bm = __ballot_sync(0xffffffffu, sm_), bd = __ballot_sync(0xffffffffu, sd_);
+        if (lane == 0) {
+            P->sign[0][w] = bm;
+            P->sign[1][w] = bd;
+        }
+    }
+    __syncwarp();
+    band_sums2_sm(T, q[0], q[1], nsf0, P->e2[0], P->e2[1], lane);
+    __syncwarp();
+    for (int ch = 0; ch < 2; ch++) {
+        const int nmax = T->cfg.nbmax2[ch];
+        const int hi = nmax > nrot ? nmax : nrot;
+        for (int k = lane; k < hi; k += 32) {
+            float v;
+            if (k < nmax) v = pow34(T, x[ch][k]);
+            else v = q[ch][k];  // (k < nrot: the square long_prepare leaves there)
+            q[ch][k] = v;
+            P->x34[ch][k] = v;
+        }
+    }
+    __syncwarp();
+    for (int ch = 0; ch < nch; ch++) band_bounds_sm(T, P, q[ch], ch, T->cfg.nsf2[ch], lane);
+}
+
 __global__ void __launch_bounds__(128) k_prepare(const EncTables *tabs, const StreamDev *st, ChunkBufs cb, int K0,
                                                  int nstreams) {
+    __shared__ __align__(16) float s_x[4][2][576];
+    __shared__ __align__(16) float s_q[4][2][576];
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int q = (int)(wid % cb.NG), s = (int)(wid / cb.NG);
     if (s >= nstreams) return;
     const StreamDev sd = st[s];
@@ -546,9 +672,10 @@ __global__ void __launch_bounds__(128) k_prepare(const EncTables *tabs, const St
     const long long o = (long long)s * cb.NG + q;
     if (cb.gi[o].block_type == 2) return;
     const EncTables *T = tabs + sd.cfg;
+    if (T->cfg.allocator == 1) return;  // CBitAllo1 strips signs / rotates for itself
     // the flag the allocator is called with (mp3enc.cpp:1556 / :1880: MPEG-2 mono passes the configured ms_flag)
     const int ms = (T->cfg.h_id == 0 && sd.nch != 2) ? T->cfg.ms_flag : (int)cb.ms[o];
-    long_prepare(T, ms, cb.xr + o * 2 * 576, cb.prep + o);
+    long_prepare_warp(T, ms, cb.xr + o * 2 * 576, cb.prep + o, s_x[wl], s_q[wl], lane);
 }
 
 __global__ void k_prepare_init(int *msmem, PsyState *psy, int nstreams) {
