@@ -843,6 +843,17 @@ HMP3_FN void long_quantise(const EncTables *T, LongRate *L, QLine *ix, bool tune
         const float *x = L->x34[ch];
         QLine *q = ix + 576 * ch;
         const int nb = T->cfg.nsf[ch], nl = T->startBand_l[nb];
+#if HMP3_W == 32
+        {   // the channel's |x|^(3/4) row goes to the warp's scratch row first, all of it in flight at once (cp.async):
+            // the loop below would otherwise wait for one global load per 32 lines, 18 times in a row
+            float *row = rate_scratch_row();
+            for (int k = 2 * lane; k < nl; k += 64)
+                asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.ca.shared.global [a], [%1], 8; }" ::"l"(row + k), "l"(x + k));
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            HMP3_SYNC();
+            x = row;
+        }
+#endif
         float ig_own = 0.0f;  // W = 32: lane b holds the inverse step of band b
         if (HMP3_W == 32 && lane < nb) ig_own = T->igain34[L->gsf[ch][lane]];
         int carry_b = -1, carry_m = 0;

@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+O=gpurun_out
+timeout 300 python -m pytest tests/test_gpu_encode.py -x -q > $O/r3a_pytest.txt 2>&1; rc=$?; echo "pytest rc=$rc" >> $O/r3a_pytest.txt
+[ $rc = 0 ] || { echo "gpu tests failed"; tail -30 $O/r3a_pytest.txt; exit 1; }
+HMP3_SERIALIZE=1 timeout 200 python tools/quick_bench.py 9472 30 > $O/r3a_serial_9472.txt 2>&1
+timeout 200 python tools/quick_bench.py 9472 30 > $O/r3a_9472.txt 2>&1
+timeout 200 python tools/quick_bench.py 4736 30 > $O/r3a_4736.txt 2>&1
+echo done
