@@ -35,6 +35,15 @@ struct LongRate {
     int n_exx[2];         // bands they cover
 };
 
+#if HMP3_COOP
+// One 576-float row of shared memory per stream of the block: per-line scratch of the line-parallel sections
+// (step search, sparse-band refit); nothing is kept in it between sections.
+extern __shared__ float s_rate_rows[];  // [streams of the block][576], dynamic (a 32-warp block needs 72 KB)
+__device__ __forceinline__ float *rate_scratch_row() {
+    return s_rate_rows + 576 * ((threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W)));
+}
+#endif
+
 HMP3_FN void long_rate_init(const EncTables *T, LongRate *L) {  // bitallo3.cpp:288-480
     L->mnr = T->cfg.initial_mnr;
     L->pool_fraction = T->cfg.vbr_flag ? 614 : 0;
@@ -143,23 +152,39 @@ HMP3_HD void merge_sign_word(unsigned *dst, unsigned src, int w, int nl) {
         *dst = (*dst & ~m) | (src & m);
     }
 }
-HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P, unsigned *signw /*[2][18]*/, int n_energy,
-                                 const int *n_bounds /*[2]*/) {
+HMP3_FN const PrepGranule *long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P, unsigned *signw /*[2][18]*/,
+                                               int n_energy, const int *n_bounds /*[2]*/) {
     L->x34 = P->x34;
 #if HMP3_COOP
+    const PrepGranule *Q = P;
+#if HMP3_W == 32
+    {   // the granule's band records (signs, energies, maxima, step bounds: the kilobyte behind the two x34 rows) are
+        // touched here for the first time -- bring them to the warp's scratch row in one go (cp.async) instead of one
+        // cold global load per little loop below; Q addresses the staged copy with PrepGranule's own field offsets
+        float *row = rate_scratch_row();
+        const char *src = (const char *)&P->sign[0][0];
+        constexpr int kBytes = (int)(sizeof(PrepGranule) - sizeof(P->x34));
+        static_assert(kBytes % 8 == 0 && kBytes <= 2304, "band records of a PrepGranule fit the scratch row");
+        for (int o = 8 * HMP3_LANE; o < kBytes; o += 8 * 32)
+            asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.ca.shared.global [a], [%1], 8; }" ::"l"((char *)row + o), "l"(src + o));
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        Q = (const PrepGranule *)((const char *)row - sizeof(P->x34));
+    }
+#endif
     HMP3_SYNC();
     for (int ch = 0; ch < L->nchan; ch++) {
         const int ne = n_energy < 0 ? n_bounds[ch] : n_energy;
-        for (int i = HMP3_LANE; i < ne; i += HMP3_W) L->xsxx[ch][i] = P->xsxx[ch][i];
+        for (int i = HMP3_LANE; i < ne; i += HMP3_W) L->xsxx[ch][i] = Q->xsxx[ch][i];
         for (int i = HMP3_LANE; i < n_bounds[ch]; i += HMP3_W) {
-            L->x34max[ch][i] = P->x34max[ch][i];
-            L->gzero[ch][i] = P->gzero[ch][i];
-            L->gmin[ch][i] = P->gmin[ch][i];
+            L->x34max[ch][i] = Q->x34max[ch][i];
+            L->gzero[ch][i] = Q->gzero[ch][i];
+            L->gmin[ch][i] = Q->gmin[ch][i];
         }
-        const int nl = P->nlines[ch];
-        for (int w = HMP3_LANE; w < 18; w += HMP3_W) merge_sign_word(signw + 18 * ch + w, P->sign[ch][w], w, nl);
+        const int nl = Q->nlines[ch];
+        for (int w = HMP3_LANE; w < 18; w += HMP3_W) merge_sign_word(signw + 18 * ch + w, Q->sign[ch][w], w, nl);
     }
     HMP3_SYNC();
+    return Q;
 #else
     for (int ch = 0; ch < L->nchan; ch++) {
         const int ne = n_energy < 0 ? n_bounds[ch] : n_energy;
@@ -171,6 +196,7 @@ HMP3_FN void long_adopt_prepared(const EncTables *T, LongRate *L, PrepGranule *P
         }
         for (int w = 0; w < 18; w++) merge_sign_word(signw + 18 * ch + w, P->sign[ch][w], w, P->nlines[ch]);
     }
+    return P;
 #endif
 }
 
@@ -209,7 +235,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
         L->mnr = imin_(L->mnr + 50, 2050);
     const int mnr = L->mnr;
     const int nsf0 = T->cfg.nsf[0];
-    long_adopt_prepared(T, L, P, signx, nsf0, T->cfg.nsf2);
+    const PrepGranule *Q = long_adopt_prepared(T, L, P, signx, nsf0, T->cfg.nsf2);
     for (int ch = 0; ch < 2; ch++) {
         L->exx[ch] = P->e2[ch];
         L->n_exx[ch] = nsf0;
@@ -217,7 +243,7 @@ HMP3_FN void long_startup_ms(const EncTables *T, LongRate *L, const SigMask *sm,
     int lines = 0;
     HMP3_FOR_LANES(i, nsf0) {
         const int n = T->nBand_l[i];
-        const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = P->e2[0][i], ed = P->e2[1][i];
+        const float el = L->xsxx[0][i], er = L->xsxx[1][i], em = Q->e2[0][i], ed = Q->e2[1][i];
         const int cbw = T->log_cbw_l[i];
         int ntl, ntr;
         int n0l = mb_log(T, el) - cbw;
@@ -307,12 +333,6 @@ HMP3_FN int seek_coarser(const EncTables *T, const float *y34, const float *y, i
 }
 
 #if HMP3_COOP
-// One 576-float row of shared memory per stream of the block: per-line scratch of the line-parallel sections
-// (step search, sparse-band refit); nothing is kept in it between sections.
-extern __shared__ float s_rate_rows[];  // [streams of the block][576], dynamic (a 32-warp block needs 72 KB)
-__device__ __forceinline__ float *rate_scratch_row() {
-    return s_rate_rows + 576 * ((threadIdx.x / HMP3_W) % (kRateWarpsPerBlock * (32 / HMP3_W)));
-}
 // max of v over the lanes named in `seg` (a lane mask inside the group, the caller's lane included); lanes with
 // different masks may execute this together
 __device__ __forceinline__ int gmax_seg(int v, unsigned seg) {
