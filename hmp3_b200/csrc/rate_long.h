@@ -375,6 +375,11 @@ HMP3_FN void long_seek_actual(const EncTables *T, LongRate *L, const float *xr) 
         const int nl = T->startBand_l[T->cfg.nsf[c]];
         const float *y34 = L->x34[c];
         const float *y = xr + 576 * c;
+        // both rows of the channel on their way to L1 before the first round asks for them line by line
+        for (int o = 32 * lane; o < nl; o += 32 * HMP3_W) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(y34 + o));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(y + o));
+        }
         for (;;) {
             unsigned am = gballot(mode0 != 0);  // bit b = band b of the channel is still searching
             if (NS > 1) am |= gballot(mode1 != 0) << (HMP3_W & 31);
