@@ -486,7 +486,10 @@ def run_gpu(args, rank, local_rank, world):
         roof_all = {}
         for name, (bound, per_gc) in KERNEL_WORK.items():
             ms, ln = alone.get(name, (0.0, 0))
-            if ln == 0 or ms <= 0:
+            if ln == 0:
+                continue
+            if not ms > 0:   # (an event pair that could not be read; seen once for one kernel)
+                roof_all[name] = {"bound": bound, "ms_per_step_alone": None, "launches": ln, "note": "not measured in this run"}
                 continue
             halo = (NG + 3.0) / NG if name in ("polyphase", "attack") else 1.0   # these also redo a 3-granule halo per chunk
             work = per_gc * 2.0 * float(nf.sum()) * NCH * halo                     # per step
