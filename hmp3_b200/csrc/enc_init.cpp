@@ -1,7 +1,7 @@
 // Host-side resolution of a control block into the constants and tables the kernels read.
 // Pure integer/float host logic (double-precision libm at init, rounded to float tables) following the
 // reference's init rules; every block cites the rule it reproduces.  Compared table-by-table with the
-// oracle in tests/test_boundary.py.
+// oracle in tests/test_cpu_parity.py (resolved values, golden tables) and tests/test_cabi.py.
 #include "enc_init.h"
 
 #include <math.h>

@@ -8,18 +8,40 @@
 
 namespace hmp3 {
 
-// Asynchronous global -> shared copies (LDGSTS).  The staging loops of these kernels used to load a value and store
-// it to shared memory at once: one line in flight per warp, and 55-75 % of the kernel's stall samples on that store
-// (profiles/r2z).  cp.async puts a warp's whole tile in flight without holding registers; .cg = past L1, the data is
-// used once.  stage_row copies n floats (n a multiple of 4, both pointers 16-byte aligned) with the lanes of a warp.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+// Bulk asynchronous global -> shared copies by the TMA engine (cp.async.bulk, 1-D form: a granule row is 2304
+// contiguous bytes).  The staging loops of these kernels used to load a value and store it to shared memory at
+// once: one line in flight per warp, and 55-75 % of the kernel's stall samples on that store (profiles/r2z).  Now
+// one lane of the warp hands the whole tile to the copy engine (one or two instructions, no registers), the bytes land
+// in shared memory past L1, and the warp waits on its own mbarrier for the transaction count.
+struct WarpTma {
+    unsigned bar;  // shared-memory address of the warp's mbarrier
+};
+__device__ __forceinline__ unsigned smem_u32_(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ WarpTma tma_begin(unsigned long long *bar, int lane, unsigned bytes) {
+    WarpTma t;
+    t.bar = smem_u32_(bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t.bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t.bar), "r"(bytes) : "memory");
+    }
+    __syncwarp();
+    return t;
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+// bytes: a multiple of 16; both addresses 16-byte aligned.  Issued by lane 0 only.
+__device__ __forceinline__ void tma_row(const WarpTma &t, void *smem, const void *gmem, unsigned bytes, int lane) {
+    if (lane == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32_(smem)),
+                     "l"(gmem), "r"(bytes), "r"(t.bar)
+                     : "memory");
 }
-__device__ __forceinline__ void stage_row(float *smem, const float *gmem, int n, int lane) {
-    for (int k = 4 * lane; k < n; k += 128) cp_async16(smem + k, gmem + k);
+__device__ __forceinline__ void tma_wait(const WarpTma &t) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@!p bra W_%=;\n\t}" ::"r"(t.bar)
+        : "memory");
 }
 
 // ---- K1: polyphase analysis.  One block = kPolyRun consecutive polyphase granules of one stream, both channels:
@@ -193,10 +215,13 @@ __global__ void __launch_bounds__(128) k_hybrid(const EncTables *tabs, const Str
     const float *cur = cb.P + (((long long)s * G + q + 1) * 2 + ch) * 576;   // P[K-2]
     float *xr = cb.xr + (((long long)s * cb.NG + q) * 2 + ch) * 576;
     float(*sb)[576] = s_buf[threadIdx.x >> 5];
-    stage_row(sb[0], prev, 576, lane);
-    stage_row(sb[1], cur, 576, lane);
-    cp_async_wait_all();
-    __syncwarp();
+    {
+        __shared__ unsigned long long s_bar[4];
+        const WarpTma t = tma_begin(&s_bar[threadIdx.x >> 5], lane, 2 * 2304);
+        tma_row(t, sb[0], prev, 2304, lane);
+        tma_row(t, sb[1], cur, 2304, lane);
+        tma_wait(t);
+    }
     hybrid_item(T, sb[0], sb[1], bt, lane, sb[2]);
     __syncwarp();
     if (bt != 2) alias_item(T, lane, sb[2]);
@@ -386,9 +411,12 @@ __global__ void __launch_bounds__(128) k_psy_stage1(const EncTables *tabs, const
     const long long o = (long long)s * cb.NG + q;
     const int bt = cb.gi[o].block_type;
     const float *x0 = cb.xr + o * 2 * 576;
-    for (int c = 0; c < sd.nch; c++) stage_row(s_x[wl][c], x0 + 576 * c, 576, lane);
-    cp_async_wait_all();
-    __syncwarp();
+    {
+        __shared__ unsigned long long s_bar[4];
+        const WarpTma t = tma_begin(&s_bar[wl], lane, 2304u * sd.nch);
+        tma_row(t, s_x[wl][0], x0, 2304u * sd.nch, lane);  // the granule's rows lie one after the other
+        tma_wait(t);
+    }
     for (int c = 0; c < sd.nch; c++) {
         PsyRaw *R = cb.raw + o * 2 + c;
         if (bt != 2) psy_long_stage1_warp(T, s_x[wl][c], R, s_xtab[wl], s_mbe[wl], s_snr[wl], lane);
@@ -536,7 +564,7 @@ __global__ void __launch_bounds__(128) k_psy_stage2(const EncTables *tabs, const
 }
 
 // ---- K5d: prepare pass, one warp per (stream, granule): state-free part of the rate-loop prologue (long blocks)
-// long_prepare (prepare.h) with the granule staged in shared memory: x = the two spectra (rewritten in place to
+// long_prepare (prepare.h) with the granule staged in shared memory (TMA bulk copy): x = the two spectra (rewritten in place to
 // magnitudes / mid-side like the global copy), q = per-line squares and then |x|^(3/4).  The ordered band sums and band
 // maxima -- dependent chains as long as a band, one band per lane -- read shared memory instead of global memory, and
 // the final contents of xr and PrepGranule are exactly long_prepare's (including the squares it leaves in x34 above the
@@ -569,12 +597,12 @@ __device__ __forceinline__ void band_bounds_sm(const EncTables *T, PrepGranule *
     }
 }
 __device__ __forceinline__ void long_prepare_warp(const EncTables *T, int ms, float *xr, PrepGranule *P, float (*x)[576],
-                                                  float (*q)[576], int lane) {
+                                                  float (*q)[576], unsigned long long *bar, int lane) {
     const int nch = T->cfg.nchan;
-    for (int ch = 0; ch < 2; ch++) stage_row(x[ch], xr + 576 * ch, 576, lane);  // (the buffer always has two rows)
+    const WarpTma t = tma_begin(bar, lane, 2 * 2304);
+    tma_row(t, x[0], xr, 2 * 2304, lane);  // both rows (the buffer always has two, one after the other)
     for (int w = lane; w < 36; w += 32) (&P->sign[0][0])[w] = 0;
-    cp_async_wait_all();
-    __syncwarp();
+    tma_wait(t);
     if (!ms) {
         for (int ch = 0; ch < nch; ch++) {
             const int nb = T->cfg.nsf3[ch], nl = T->startBand_l[nb];
@@ -663,6 +691,7 @@ __global__ void __launch_bounds__(128) k_prepare(const EncTables *tabs, const St
                                                  int nstreams) {
     __shared__ __align__(16) float s_x[4][2][576];
     __shared__ __align__(16) float s_q[4][2][576];
+    __shared__ unsigned long long s_bar[4];
     const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int q = (int)(wid % cb.NG), s = (int)(wid / cb.NG);
@@ -675,7 +704,7 @@ __global__ void __launch_bounds__(128) k_prepare(const EncTables *tabs, const St
     if (T->cfg.allocator == 1) return;  // CBitAllo1 strips signs / rotates for itself
     // the flag the allocator is called with (mp3enc.cpp:1556 / :1880: MPEG-2 mono passes the configured ms_flag)
     const int ms = (T->cfg.h_id == 0 && sd.nch != 2) ? T->cfg.ms_flag : (int)cb.ms[o];
-    long_prepare_warp(T, ms, cb.xr + o * 2 * 576, cb.prep + o, s_x[wl], s_q[wl], lane);
+    long_prepare_warp(T, ms, cb.xr + o * 2 * 576, cb.prep + o, s_x[wl], s_q[wl], &s_bar[wl], lane);
 }
 
 __global__ void k_prepare_init(int *msmem, PsyState *psy, int nstreams) {
