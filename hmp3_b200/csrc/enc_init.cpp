@@ -417,6 +417,20 @@ int control_apply_option(hmp3_control *ec, const char *opt) {
     return 0;
 }
 
+void fixed_polyphase_tables(float *polyA, float *polyB, float *dct32) {
+    for (int i = 0; i < 256; i++) {
+        polyA[i] = bits_f(kPolyA_bits[i]);
+        polyB[i] = bits_f(kPolyB_bits[i]);
+    }
+    const double pi = 4.0 * atan(1.0);  // 32-point DCT twiddles (sbt.c:113-131), as in build_tables
+    int n = 16, kk = 0;
+    for (int i = 0; i < 5; i++, n = n / 2)
+        for (int p = 0; p < n; p++, kk++) {
+            const double t = (pi / (4 * n)) * (2 * p + 1);
+            dct32[kk] = (float)(2.0 * cos(t));
+        }
+}
+
 int build_tables(const hmp3_control *ec_arg, EncTables *Tp, int *unsupported) {
     EncTables &T = *Tp;
     memset(&T, 0, sizeof(T));

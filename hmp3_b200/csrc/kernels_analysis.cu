@@ -3,7 +3,9 @@
 #include "kernels_analysis.cuh"
 
 #include <atomic>
+#include <mutex>
 #include <stdlib.h>
+#include "enc_init.h"
 namespace hmp3 {
 static inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
@@ -25,10 +27,26 @@ static void phase_a_configure() {
     cudaFuncSetAttribute(k_prepare, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 
+// the configuration-independent polyphase tables -> constant memory, once per device
+static void polyphase_constants() {
+    static std::mutex mu;
+    static unsigned long long done = 0;  // one bit per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if ((done >> (dev & 63)) & 1ull) return;
+    done |= 1ull << (dev & 63);
+    float A[256], B[256], D[31];
+    fixed_polyphase_tables(A, B, D);
+    cudaMemcpyToSymbol(c_polyA, A, sizeof(A));
+    cudaMemcpyToSymbol(c_polyB, B, sizeof(B));
+    cudaMemcpyToSymbol(c_dct32, D, sizeof(D));
+}
 void launch_polyphase(const EncTables *tabs, const StreamDev *st, const int16_t *pcm, const float *pcmf, ChunkBufs cb,
                       int K0, int n, cudaStream_t stream) {
     const int G = cb.NG + 3;
     phase_a_configure();
+    polyphase_constants();
     k_polyphase<<<dim3((unsigned)((G + kPolyRun - 1) / kPolyRun), (unsigned)n), 256, 0, stream>>>(tabs, st, pcm, pcmf, cb,
                                                                                                  K0, n);
 }

@@ -44,6 +44,54 @@ __device__ __forceinline__ void tma_wait(const WarpTma &t) {
         : "memory");
 }
 
+// The polyphase tables do not depend on the configuration: they live in constant memory, and with the window fold
+// fully unrolled every coefficient is an instruction operand (no load) and every sample a shared-memory load at an
+// immediate offset.  Filled once per device by launch_polyphase (fixed_polyphase_tables, enc_init.cpp).
+__constant__ float c_polyA[32][8];
+__constant__ float c_polyB[32][8];
+__constant__ float c_dct32[31];
+// kPolyIa / kPolyIb of tables_data.h as functions of k (checked against the tables when the constants are filled)
+__host__ __device__ constexpr int poly_ia(int k) { return k <= 16 ? 16 + k : 80 - k; }
+__host__ __device__ constexpr int poly_ib(int k) { return (k == 0 || k == 16) ? 0 : (k < 16 ? 16 - k : 16 + k); }
+// polyphase_slot (dsp_core.h) for the staged PCM row: rb = the row at this slot's origin (33 * slot with the row
+// padding), sample i (0 = newest) at rb[(511 - i) + ((511 - i) >> 5)].  Same sums, same order.
+__device__ __forceinline__ void polyphase_slot_c(const float *rb, float *out, int stride) {
+    float a[32], b[32];
+#define HMP3_PCM(i) rb[(511 - (i)) + ((511 - (i)) >> 5)]
+    {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += c_polyA[0][j] * HMP3_PCM(poly_ia(0) + 64 * j);
+        b[0] = s;
+    }
+#pragma unroll
+    for (int k = 1; k < 32; k++) {
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            s1 += c_polyA[k][j] * HMP3_PCM(poly_ia(k) + 64 * j);
+            s2 += c_polyB[k][j] * HMP3_PCM(poly_ib(k) + 64 * j);
+        }
+        b[k] = s1 + s2;
+    }
+#undef HMP3_PCM
+    const float *c = c_dct32;
+    dct32_split<32, 1>(b, a);
+    dct32_split<16, 2>(a, b);
+    dct32_split<8, 4>(b, a);
+    dct32_split<4, 8>(a, b);
+    dct32_merge<2, 16>(b, a, c + 16 + 8 + 4 + 2);
+    dct32_merge<4, 8>(a, b, c + 16 + 8 + 4);
+    dct32_merge<8, 4>(b, a, c + 16 + 8);
+    dct32_merge<16, 2>(a, b, c + 16);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const float tw = c[k] * b[k + 16];
+        out[stride * k] = b[k] + tw;
+        out[stride * (31 - k)] = b[k] - tw;
+    }
+}
+
 // ---- K1: polyphase analysis.  One block = kPolyRun consecutive polyphase granules of one stream, both channels:
 // the PCM span they need (576 * run + 480 samples per channel) is staged once in shared memory as float
 // (coalesced 32-bit reads of the interleaved int16 input, zero outside the clip), then one thread per
@@ -136,14 +184,10 @@ __global__ void __launch_bounds__(256) k_polyphase(const EncTables *tabs, const 
     const int jr = slot / 18, t = slot - 18 * jr;
     const int jj = jj0 + jr;
     if (jj >= G || j0 + jr >= sd.ngran) return;
-    const float *row = s_pcm[ch];
-    const int newest = 32 * slot + 31 + 480;  // position of this slot's newest sample in the staged span
-    auto fetch = [&](int i) -> float {
-        const int p = newest - i;
-        return row[p + (p >> 5)];
-    };
+    // this slot's newest sample sits at position p = 32 * slot + 511 of the staged span, i.e. at padded index
+    // p + (p >> 5) = 33 * slot + 511 + 15
     float col[32];
-    polyphase_slot(T, fetch, col, 1);
+    polyphase_slot_c(s_pcm[ch] + 33 * slot, col, 1);
     float *out = cb.P + (((long long)s * G + jj) * 2 + ch) * 576;
     const int nsb = T->cfg.nsb_hybrid;
 #pragma unroll
