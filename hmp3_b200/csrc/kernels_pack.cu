@@ -34,7 +34,7 @@ __global__ void k_out_offsets(const StreamResult *res, long long *out_off, int n
 
 void launch_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
                  FrameRec *frames, int *flags, int K0, int n, cudaStream_t stream) {
-    k_pack<<<blocks_for((long long)n * cb.NG * 32, 32 * kPackWarpsPerBlock), 32 * kPackWarpsPerBlock, 0, stream>>>(
+    k_pack<<<(unsigned)((long long)n * cb.NG), 128, 0, stream>>>(
         tabs, st, so, cb, main_buf, frames, flags, K0, n);
 }
 void launch_assemble_inc(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, int *done_lo,

@@ -85,12 +85,16 @@ __global__ void __launch_bounds__(32 * kRateWarpsPerBlock, HMP3_RATE_MIN_BLOCKS)
 
 #endif  // HMP3_WANT_SERIAL
 #if HMP3_WANT_PACK
-// ---- K7a: packing pass, one warp per frame recorded in this chunk (every warp runs the same short code)
-__global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
+// ---- K7a: packing pass, one BLOCK per frame recorded in this chunk, one warp per granule-channel of the frame.  The
+// frame's records are staged in shared memory (cp.async), every warp ORs its granule-channel's scale-factor and
+// Huffman bits into the frame's shared bit buffer at the position the part2_3_lengths before it imply, and the block
+// writes the bytes out together.  (One warp per frame packed the four granule-channels one after the other: a chain of
+// dependent table look-ups and warp scans four times as long, on a kernel that is bound by exactly that latency.)
+constexpr int kFrameWords = 576;  // 18432 bits: four part2_3_lengths (12-bit fields, the reference can overflow them a little)
+__global__ void __launch_bounds__(128)
     k_pack(const EncTables *tabs, const StreamDev *st, const StreamOut *so, ChunkBufs cb, unsigned char *main_buf,
            FrameRec *frames, int *flags, int K0, int nstreams) {
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int s = (int)(wid / cb.NG), j = (int)(wid % cb.NG);  // at most NG frames per stream per chunk (MPEG-2)
+    const int s = (int)(blockIdx.x / (unsigned)cb.NG), j = (int)(blockIdx.x % (unsigned)cb.NG);  // <= NG frames per stream per chunk
     if (s >= nstreams) return;
     const int f = cb.fr0[s] + j;
     if (f >= cb.fr1[s]) return;
@@ -98,21 +102,38 @@ __global__ void __launch_bounds__(32 * kPackWarpsPerBlock)
     FrameRec *fr = frames + o.frames_off + f;
     const EncTables *T = tabs + st[s].cfg;
     const PackGc *gc = cb.pack + ((long long)s * cb.NG + (fr->granule0 - K0)) * 2;
-    // the frame's granule-channel records (up to 4 x 1396 bytes) go to shared memory first, all of them in flight at
-    // once: the Huffman loops then read their lines there instead of waiting for one global load per pair
-    __shared__ unsigned s_gc[kPackWarpsPerBlock][4 * (sizeof(PackGc) / 4)];
+    __shared__ unsigned s_bits[kFrameWords];
+    __shared__ unsigned s_gc[4][sizeof(PackGc) / 4];
+    __shared__ int s_bad;
     static_assert(sizeof(PackGc) % 4 == 0, "PackGc is copied in 32-bit words");
-    unsigned *dst = s_gc[(threadIdx.x >> 5) % kPackWarpsPerBlock];
-    {
-        const int lane = threadIdx.x & 31;
-        const int nwords = fr->ngr * T->cfg.nchan * (int)(sizeof(PackGc) / 4);
-        const unsigned *src = (const unsigned *)gc;
-        for (int k = lane; k < nwords; k += 32)
-            asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.ca.shared.global [a], [%1], 4; }" ::"l"(dst + k), "l"(src + k));
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngc = fr->ngr * T->cfg.nchan;
+    for (int k = threadIdx.x; k < kFrameWords; k += 128) s_bits[k] = 0;
+    if (threadIdx.x == 0) s_bad = 0;
+    if (w < ngc) {
+        const unsigned *src = (const unsigned *)(gc + w);
+        for (int k = lane; k < (int)(sizeof(PackGc) / 4); k += 32)
+            asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.ca.shared.global [a], [%1], 4; }" ::"l"(&s_gc[w][k]), "l"(src + k));
     }
-    if (pack_frame(T, fr, (const PackGc *)dst, main_buf + o.main_off) && (threadIdx.x & 31) == 0) flags[s] = 1;
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const PackGc *rec = (const PackGc *)&s_gc[0][0];
+    if (w < ngc) {
+        int start = 0;
+        for (int k = 0; k < w; k++) start += rec[k].gr.part2_3_length;
+        const PackGc *p = rec + w;
+        int bits = 0;
+        if (p->gr.aux_not_null && start + p->gr.part2_3_length <= kFrameWords * 32 - 96) bits = pack_gc_bits(T, fr, p, w, s_bits, start);
+        if (bits != p->gr.part2_3_length && lane == 0) s_bad = 1;
+    }
+    __syncthreads();
+    unsigned char *dst = main_buf + o.main_off + fr->data_start;
+    for (int i = threadIdx.x; i < fr->data_bytes; i += 128)
+        dst[i] = i < kFrameWords * 4 ? (unsigned char)(s_bits[i >> 2] >> (24 - 8 * (i & 3))) : (unsigned char)0;
+    if (w == 0) {
+        pack_side(T, fr, rec, fr->side);
+        if (s_bad && lane == 0) flags[s] = 1;
+    }
 }
 
 // ---- per-stream totals after the last chunk

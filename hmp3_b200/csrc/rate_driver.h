@@ -495,10 +495,133 @@ HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const
     b->total_bits += pos - p0;
     PK_SYNC();
 }
+
+// One granule-channel of a frame into the frame's shared bit buffer W at bit position pos0: scale factors (one field
+// per lane, in transmission order, as write_sf_* emit them) and then the Huffman data exactly as pack_huffman lays it
+// out.  Returns the bits written.  The four granule-channels of a frame are packed by four warps at once: where
+// each one starts follows from the part2_3_length of those before it, the fields are OR-ed in with shared-memory
+// atomics, so neighbours may share a word.  k = index of the granule-channel in the frame.
+HMP3_FN int pack_gc_bits(const EncTables *T, const FrameRec *fr, const PackGc *p, int k, unsigned *W, int pos0) {
+    const GrSide *g = &p->gr;
+    const int lane = PK_LANE;
+    const int nch = T->cfg.nchan;
+    const bool m1 = T->cfg.h_id == 1;
+    int pos = pos0;
+    {
+        const int sfc = g->scalefac_compress;
+        const bool shortb = g->block_type == 2;
+        const bool is_right = !m1 && T->cfg.is_flag && (k % nch) == 1;
+        const bool scfsi_mode = m1 && !fr->short_frame;
+        const int scfsi = (scfsi_mode && (k / nch)) ? fr->scfsi[k % nch] : 0;
+        int s1 = 0, s2 = 0, s3 = 0, sl0 = 0, sl1 = 0, sl2 = 0, sl3 = 0;
+        if (m1) sfc_slens(sfc, &s1, &s2);
+        else if (is_right) {
+            const int v = sfc >> 1;
+            s1 = v / 36;
+            s2 = (v % 36) / 6;
+            s3 = v % 6;
+        } else {
+            sl3 = sfc & 3;
+            sl2 = (sfc >> 2) & 3;
+            sl1 = (sfc >> 4) % 5;
+            sl0 = (sfc >> 4) / 5;
+        }
+        for (int h = 0; h < 2; h++) {  // 21 fields (long) or 36 (short, in (band, window) order): two rounds of 32
+            const int t = lane + 32 * h;
+            unsigned v = 0;
+            int l = 0;
+            if (shortb && !is_right) {
+                if (t < 36) {
+                    const int i = t / 3, w = t - 3 * i;
+                    v = (unsigned)sf_byte_s(p->sf, w, i);
+                    const int q = i / 3;
+                    l = m1 ? (i < 6 ? s1 : s2) : (q == 0 ? sl0 : (q == 1 ? sl1 : (q == 2 ? sl2 : sl3)));
+                }
+            } else if (t < 21) {
+                v = (unsigned)sf_byte(p->sf, t);
+                const int grp = t < 6 ? 0 : (t < 11 ? 1 : (t < 16 ? 2 : 3));  // kSfGroupEdge = 0, 6, 11, 16, 21
+                if (is_right) l = t < 7 ? s1 : (t < 14 ? s2 : s3);
+                else if (!m1) l = grp == 0 ? sl0 : (grp == 1 ? sl1 : (grp == 2 ? sl2 : sl3));
+                else if (scfsi_mode) l = (scfsi & (8 >> grp)) ? 0 : (grp < 2 ? s1 : s2);
+                else l = t < 11 ? s1 : s2;
+            }
+            if (l > 0) v &= (1u << l) - 1u;
+            else v = 0;
+            int tot;
+            const int off = warp_scan_excl(l, &tot);
+            bitbuf_or(W, pos + off, v, l);
+            pos += tot;
+            if (h == 0 && !shortb) break;  // long blocks: 21 fields, one round
+        }
+    }
+    int k0 = 0;
+    for (int r = 0; r < 3; r++) {
+        const int n = g->aux_nreg[r];
+        const int t = g->table_select[r];
+        const int book = T->huff_sel_book[t];
+        if (book != 0) {
+            const uint32_t *bk = T->huff_book[book];
+            const int lb = T->huff_linbits[t];
+            const bool esc = t >= 16;
+            const short *ix = p->ix;
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int j = j0 + lane;
+                unsigned long long v = 0;
+                int len = 0;
+                if (j < n) {
+                    const int kk = k0 + 2 * j;
+                    const int x0 = ix[kk], y0 = ix[kk + 1];
+                    int x = x0, y = y0;
+                    if (esc) {
+                        if (x > 15) x = 15;
+                        if (y > 15) y = 15;
+                    }
+                    const uint32_t e = bk[(x & 15) * 16 + (y & 15)];
+                    v = e & 0xFFFFFFu;
+                    len = (int)(e >> 24);
+                    if (esc && x >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(x0 - 15) & ((1u << lb) - 1u)); len += lb; }
+                    if (x) { v = (v << 1) | sign_bit(p->sign, kk); len++; }
+                    if (esc && y >= 15 && lb > 0) { v = (v << lb) | ((unsigned)(y0 - 15) & ((1u << lb) - 1u)); len += lb; }
+                    if (y) { v = (v << 1) | sign_bit(p->sign, kk + 1); len++; }
+                }
+                int tot;
+                const int off = warp_scan_excl(len, &tot);
+                bitbuf_or(W, pos + off, v, len);
+                pos += tot;
+            }
+        }
+        k0 += 2 * n;
+    }
+    {
+        const int nq = g->aux_nquads;
+        const bool tabB = g->count1table_select == 1;
+        const short *ix = p->ix;
+        for (int j0 = 0; j0 < nq; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned long long v = 0;
+            int len = 0;
+            if (j < nq) {
+                const int kk = k0 + 4 * j;
+                const unsigned x = (unsigned)((ix[kk] << 3) + (ix[kk + 1] << 2) + (ix[kk + 2] << 1) + ix[kk + 3]) & 15u;
+                if (tabB) { v = x ^ 15u; len = 4; }
+                else { v = kQuadCodeA[x]; len = kQuadLenA[x]; }
+                for (int q = 0; q < 4; q++)
+                    if (x & (8u >> q)) { v = (v << 1) | sign_bit(p->sign, kk + q); len++; }
+            }
+            int tot;
+            const int off = warp_scan_excl(len, &tot);
+            bitbuf_or(W, pos + off, v, len);
+            pos += tot;
+        }
+    }
+    return pos - pos0;
+}
 #else
 HMP3_FN void pack_huffman(const EncTables *T, BitSink *b, const GrSide *g, const short *ix, const unsigned *sign) {
     pack_huffman_seq(T, b, g, ix, sign);
 }
+// (device only; the host build packs a frame with the sequential writer)
+HMP3_FN int pack_gc_bits(const EncTables *, const FrameRec *, const PackGc *, int, unsigned *, int) { return 0; }
 #endif
 
 // ------------------------------------------------------------------ side information (l3pack.c:1123-1244)
