@@ -80,8 +80,9 @@ def rate_issue_counters():
 
 
 # algorithmic work per granule-channel of every kernel: (bound, bytes or flop per gc)
+# (k_attack reads sub-bands 4..17 of P and writes nine energies)
 KERNEL_WORK = {
-    "polyphase": ("fp32_nonfused", 23.9e3), "attack": ("hbm", 14 * 18 * 4 + 36),   # sub-bands 4..17 of P in, nine energies out "hybrid_mdct": ("hbm", 4608 + 2304),
+    "polyphase": ("fp32_nonfused", 23.9e3), "attack": ("hbm", 14 * 18 * 4 + 36), "hybrid_mdct": ("hbm", 4608 + 2304),
     "psy_stage1": ("hbm", 2304 + 372), "psy_stage2": ("hbm", 368 + 288), "prepare": ("hbm", 4608 + 2304 + 2816),
     "rate_loop": ("hbm", K6_BYTES_PER_GC), "pack": ("hbm", 1396 + 105),
 }
