@@ -353,8 +353,21 @@ HMP3_FN int phase_count(const RateCtx *x) {
     const bool ms = c->ga_ms != 0;
     const int hf = T->cfg.hf_flag;
     int bits;
-    if (c->loop == RL_NONE || c->loop == RL_MORE) bits = long_count(T, L, ix, ms ? T->cfg.nsf2 : T->cfg.nsf3);
-    else bits = long_count(T, L, ix, T->cfg.nsf2);
+    const QLine *ixc = ix;
+#if HMP3_COOP && HMP3_W == 32
+    {   // the quantised lines of both channels (2 x 576 int16 = one scratch row) are read pair by pair by the planner
+        // and the counters: bring them over in one go (cp.async) instead of waiting for one load per 64 lines
+        char *row = (char *)rate_scratch_row();
+        const char *src = (const char *)ix;
+        for (int o = 16 * HMP3_LANE; o < 2304; o += 16 * 32)
+            asm volatile("{ .reg .u64 a; cvta.to.shared.u64 a, %0; cp.async.cg.shared.global [a], [%1], 16; }" ::"l"(row + o), "l"(src + o));
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        HMP3_SYNC();
+        ixc = (const QLine *)row;
+    }
+#endif
+    if (c->loop == RL_NONE || c->loop == RL_MORE) bits = long_count(T, L, ixc, ms ? T->cfg.nsf2 : T->cfg.nsf3);
+    else bits = long_count(T, L, ixc, T->cfg.nsf2);
     const int nclr = ms ? 1 : L->nchan;
     // the decisions, in the order of long_allocate (bitallo3.cpp:3050-3149)
     switch (c->loop) {
