@@ -155,6 +155,17 @@ class Batch:
     def sync_stream(self):
         self._ck(lib().hmp3_batch_wait_uploads(self.h), "wait_uploads")
 
+    def set_rate_tap(self, stream, ngran):
+        """Diagnostics: have every run copy what the serial stage hands the packing pass for `stream` (hmp3_debug_set_
+        rate_tap).  Returns the structured array [ngran][2] that the runs fill: ix, sign, sf, gr per granule-channel."""
+        L = lib()
+        L.hmp3_debug_set_rate_tap.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
+        dt = np.dtype([("ix", "<i2", 576), ("sign", "<u4", 18), ("sf", "u1", 64), ("gr", "<i4", 27)])
+        assert dt.itemsize == L.hmp3_debug_rate_tap_record_bytes()
+        self._tap = np.zeros((ngran, 2), dt)
+        self._ck(L.hmp3_debug_set_rate_tap(self.h, stream, vp(self._tap), 2 * ngran), "set_rate_tap")
+        return self._tap
+
     def set_timing(self, on):
         lib().hmp3_batch_set_timing(self.h, 1 if on else 0)
 

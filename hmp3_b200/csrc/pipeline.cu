@@ -152,6 +152,9 @@ struct hmp3_batch {
     cudaStream_t stream_o = nullptr;    // D2H copies of finished output (copy engine)
     int chunks_run = 0;
     std::vector<std::array<float, 3>> timeline;
+    int tap_stream = -1;                // hmp3_debug_set_rate_tap: stream whose pack records are copied out, -1 = off
+    unsigned char *tap_out = nullptr;
+    long long tap_cap = 0;
     long long *d_cycles = nullptr;      // [kCycleLaunches][n] serial-stage clocks per launch (diagnostics, on request)
     int cycle_launches = 0;
     std::vector<int> flags_h;
@@ -633,6 +636,13 @@ int run_plan_impl(hmp3_batch *b) {
         }
         if (b->d_cycles && c < kCycleLaunches) b->cycle_launches = c + 1;
         mark(b, -1, b->stream);
+        if (b->tap_stream >= 0 && b->tap_out && 2LL * K0_this < b->tap_cap) {  // diagnostics: the chunk's records of one stream
+            const size_t rec = sizeof_pack_gc();
+            const long long nrec = std::min<long long>(2LL * ng_c, b->tap_cap - 2LL * K0_this);
+            CK(cudaMemcpyAsync(b->tap_out + rec * 2 * K0_this,
+                               (const unsigned char *)view.pack + rec * 2 * ((long long)b->tap_stream * ng_c), rec * nrec,
+                               cudaMemcpyDeviceToHost, b->stream));
+        }
         CK(cudaEventRecord(b->ev_r[k], b->stream));
         CK(cudaStreamWaitEvent(b->stream_p, b->ev_r[k], 0));
         mark(b, PH_PACK, b->stream_p);
@@ -1575,6 +1585,15 @@ int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap) {
         for (int j = 0; j < 3; j++) rows[3 * k + j] = b->timeline[k][j];
     return k;
 }
+
+int hmp3_debug_set_rate_tap(hmp3_batch *b, int stream, void *records, long long cap_records) {
+    if (!b || (records && (stream < 0 || stream >= b->n || cap_records <= 0))) return HMP3_ERR_ARG;
+    b->tap_stream = records ? stream : -1;
+    b->tap_out = (unsigned char *)records;
+    b->tap_cap = records ? cap_records : 0;
+    return HMP3_OK;
+}
+int hmp3_debug_rate_tap_record_bytes(void) { return (int)sizeof_pack_gc(); }
 
 int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches) {
     // first call (cycles == NULL or nothing recorded yet): switch recording on for the following runs

@@ -21,6 +21,16 @@ int hmp3_debug_analysis(const hmp3_control *ec, const int16_t *pcm, long long ns
  * buffer copies cycles[launch][stream] (SM clocks each stream's warp spent in that k_rate launch, up to 64 launches)
  * and returns the number of launches recorded. */
 int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches);
+/* Tap of the serial stage (the device's rate loop, whichever kernel runs it): while set, every hmp3_batch_run copies
+ * what the serial stage handed the packing pass for stream `stream` -- one record per granule-channel, record
+ * 2 * K + ch for encode granule K -- into `records` (room for `cap_records`; granules beyond are dropped).  A record
+ * is hmp3_debug_rate_tap_record_bytes() bytes: int16 ix[576] (quantised magnitudes in transmission order; only the
+ * coded extent, 2 * big_values + 4 * count1 lines, is meaningful), uint32 sign[18], uint8 sf[64] (long: l[0..22];
+ * short: s[w][i] at 23 + 13 w + i), int32 gr[27] (the granule's side information in the order of GR, pub/l3e.h:71-96,
+ * followed by the packer's region sizes).  Compares with the reference's ix / scale factors / GR after
+ * CBitAllo3::BitAllo and the frame driver (bitallo3.cpp:484-678, mp3enc.cpp:1492-2027).  records == NULL clears it. */
+int hmp3_debug_set_rate_tap(hmp3_batch *b, int stream, void *records, long long cap_records);
+int hmp3_debug_rate_tap_record_bytes(void);
 /* Kernel timeline of the last run with timing on (hmp3_batch_set_timing): rows of (phase index as in
  * hmp3_batch_phase_ms, begin ms, end ms) since the run began; returns the number of rows. */
 int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap);

@@ -78,6 +78,59 @@ def test_phase_scheduler_with_many_streams_per_block(monkeypatch, slots, warps, 
         assert outs[k].size == ref.size and np.array_equal(outs[k], ref), "stream %d differs from the reference" % k
 
 
+@pytest.mark.parametrize("name,seed,sr,nch,kw", [CONFIGS[0], CONFIGS[2], CONFIGS[3]])
+def test_serial_stage_tap_on_the_device(name, seed, sr, nch, kw):
+    """Stage parity of the device's rate loop itself (not only of the bytes it leads to): the quantised lines, scale
+    factors and side information the serial stage hands the packing pass, granule by granule, against the host build of
+    the same routines -- whose taps are pinned to the reference's (tests/test_cpu_parity.py) -- and, for C1, against
+    the reference's own dump of the first granules (tests/golden/c1_head.npz)."""
+    import os
+    import simmod
+    pcm = synth_pcm(seed, 10.0, sr, nch)[:int(4.0 * sr)]
+    ctl = capi.control(samprate=sr, nch=nch, **kw)
+    G = 2 * (pcm.shape[0] // 1152)
+    b = capi.Batch([ctl], [pcm.shape[0]])
+    tap = b.set_rate_tap(0, G)
+    outs, _ = b.encode_host([pcm])
+    got = tap.copy()
+    b.close()
+    ref_bytes, _, tr = simmod.encode_clip(ctl, pcm, max_trace_granules=G)
+    assert np.array_equal(outs[0], ref_bytes)
+    shorts = 0
+    for K in range(G):
+        for c in range(nch):
+            gr = got[K, c]["gr"]
+            assert np.array_equal(gr[:24], tr[K, 27 * c:27 * c + 24]), "side information of granule %d ch %d" % (K, c)
+            if gr[20] == 0:      # aux_not_null: nothing coded, scale factors and lines are not transmitted
+                continue
+            if gr[5] == 2:       # short block: s[w][i]
+                shorts += 1
+                want = tr[K, 100 + 39 * c:100 + 39 * c + 39].reshape(3, 13)[:, :12]
+                have = got[K, c]["sf"][23:23 + 39].reshape(3, 13)[:, :12]
+            else:
+                want = tr[K, 54 + 23 * c:54 + 23 * c + 21]
+                have = got[K, c]["sf"][:21]
+            assert np.array_equal(have.astype(np.int32), want), "scale factors of granule %d ch %d" % (K, c)
+            if K & 1:            # the host build's trace keeps the lines of the call's last granule
+                extent = 2 * int(gr[21] + gr[22] + gr[23]) + 4 * int(gr[18])
+                want_ix = tr[K, 200 + 576 * c:200 + 576 * c + extent]
+                assert np.array_equal(got[K, c]["ix"][:extent].astype(np.int32), want_ix), "lines of granule %d ch %d" % (K, c)
+    if name == CONFIGS[2][0]:
+        assert shorts > 0    # the 48 kHz clip switches blocks
+    if name == CONFIGS[0][0]:
+        h = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_head.npz"))
+        for k in np.nonzero(h["valid"] > 0)[0]:
+            if k >= G:
+                continue
+            for c in range(nch):
+                assert np.array_equal(got[k, c]["gr"][:24], h["gr"][k, c, :24]), "reference side info, granule %d ch %d" % (k, c)
+                assert np.array_equal(got[k, c]["sf"][:21].astype(np.int32), h["sf_l"][k, c, :21])
+                gr = got[k, c]["gr"]
+                extent = 2 * int(gr[21] + gr[22] + gr[23]) + 4 * int(gr[18]) if gr[20] else 0
+                assert np.array_equal(got[k, c]["ix"][:extent].astype(np.int32), h["ix"][k, c, :extent]), \
+                    "reference lines, granule %d ch %d" % (k, c)
+
+
 def test_plan_reuse_and_device_resident_run():
     """A plan encodes repeatedly with identical results; the device-resident leg equals the host leg."""
     name, seed, sr, nch, kw = CONFIGS[0]
