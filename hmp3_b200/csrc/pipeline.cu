@@ -41,11 +41,15 @@ bool same_control(const hmp3_control &a, const hmp3_control &b) { return memcmp(
 
 inline unsigned blocks_for(long long items, int bs) { return (unsigned)((items + bs - 1) / bs); }
 
-// The serial stage runs phase-scheduled (kernels_rate_ph.cu) unless HMP3_RATE_MODE=nested asks for the one-warp-per-
-// stream kernel with the nested drivers (same bytes; kept for A/B measurements and the per-stream clock diagnostics).
-bool rate_mode_phased() {
+// Which kernel runs the serial stage.  Phase-scheduled (kernels_rate_ph.cu) when the batch gives every SM enough
+// streams to schedule by phase, the one-warp-per-stream kernel with the nested drivers otherwise (same bytes).
+// Measured (tools/gpu_call_r3f.sh, x realtime nested / phased): 1250 streams 65.9k / 60.6k, 2500: 82.7k / 78.0k,
+// 4736: equal, 9472: 87.5k / 116.7k.  HMP3_RATE_MODE=nested | phased overrides.
+bool rate_mode_phased(int nstreams, int sm_count) {
     const char *e = getenv("HMP3_RATE_MODE");
-    return !(e && strcmp(e, "nested") == 0);
+    if (e && strcmp(e, "nested") == 0) return false;
+    if (e && strcmp(e, "phased") == 0) return true;
+    return nstreams > 24 * (sm_count > 0 ? sm_count : 148);
 }
 
 // The serial stage's hot per-stream state (RateState, ~7 KB per stream) is read and written by every granule of its
@@ -152,6 +156,7 @@ struct hmp3_batch {
     cudaStream_t stream_o = nullptr;    // D2H copies of finished output (copy engine)
     int chunks_run = 0;
     std::vector<std::array<float, 3>> timeline;
+    int sm_count = 0;                   // multiprocessors of the plan's device
     int tap_stream = -1;                // hmp3_debug_set_rate_tap: stream whose pack records are copied out, -1 = off
     unsigned char *tap_out = nullptr;
     long long tap_cap = 0;
@@ -431,6 +436,7 @@ int plan_create(hmp3_batch *b, const hmp3_control *controls, const long long *ns
         CK(cudaMalloc(&b->d_rs, sizeof_rate_state() * n));
         CK(cudaMalloc(&b->d_rs_cold, sizeof_rate_cold() * n));
         keep_rate_state_in_l2(b->stream, b->d_rs, sizeof_rate_state() * (size_t)n, device);
+        cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device);
         CK(cudaMalloc(&b->d_main, std::max<long long>(main_off, 16)));
         CK(cudaMalloc(&b->d_frames, sizeof_frame_rec() * std::max<long long>(frames_off, 1)));
         CK(cudaMalloc(&b->d_res, sizeof(StreamResult) * n));
@@ -624,7 +630,7 @@ int run_plan_impl(hmp3_batch *b) {
         if (c >= nb) CK(cudaStreamWaitEvent(b->stream, b->ev_p[k], 0));
         mark(b, PH_RATE, b->stream);
         if (b->any_allo0) {
-            if (rate_mode_phased() && !b->d_cycles)
+            if (rate_mode_phased(n, b->sm_count) && !b->d_cycles)
                 launch_rate_ph(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_frames, K0_this, n, b->stream);
             else
                 launch_rate(b->d_tabs, b->d_st, b->d_so, b->d_rs, view, b->d_main, b->d_frames, K0_this, n, b->stream,

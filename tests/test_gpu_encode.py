@@ -62,6 +62,7 @@ def test_phase_scheduler_with_many_streams_per_block(monkeypatch, slots, warps, 
         secs = 0.6 + 0.37 * (k % 7)
         pcms.append(synth_pcm(seed + 300 + k, secs, sr, nch))
         ctl.append(capi.control(samprate=sr, nch=nch, **kw))
+    monkeypatch.setenv("HMP3_RATE_MODE", "phased")   # (a batch this small would get the nested kernel by itself)
     monkeypatch.setenv("HMP3_RATE_PH_SLOTS", str(slots))
     monkeypatch.setenv("HMP3_RATE_PH_WARPS", str(warps))
     monkeypatch.setenv("HMP3_RATE_PH_OPTS", str(opts))
@@ -78,14 +79,16 @@ def test_phase_scheduler_with_many_streams_per_block(monkeypatch, slots, warps, 
         assert outs[k].size == ref.size and np.array_equal(outs[k], ref), "stream %d differs from the reference" % k
 
 
+@pytest.mark.parametrize("mode", ["phased", "nested"])
 @pytest.mark.parametrize("name,seed,sr,nch,kw", [CONFIGS[0], CONFIGS[2], CONFIGS[3]])
-def test_serial_stage_tap_on_the_device(name, seed, sr, nch, kw):
+def test_serial_stage_tap_on_the_device(monkeypatch, name, seed, sr, nch, kw, mode):
     """Stage parity of the device's rate loop itself (not only of the bytes it leads to): the quantised lines, scale
     factors and side information the serial stage hands the packing pass, granule by granule, against the host build of
     the same routines -- whose taps are pinned to the reference's (tests/test_cpu_parity.py) -- and, for C1, against
     the reference's own dump of the first granules (tests/golden/c1_head.npz)."""
     import os
     import simmod
+    monkeypatch.setenv("HMP3_RATE_MODE", mode)   # both forms of the serial stage: phase-scheduled and one warp per stream
     pcm = synth_pcm(seed, 10.0, sr, nch)[:int(4.0 * sr)]
     ctl = capi.control(samprate=sr, nch=nch, **kw)
     G = 2 * (pcm.shape[0] // 1152)

@@ -62,10 +62,12 @@ def test_c5_style_batch_properties_and_spot_parity():
         assert outs[i].size == ref.size and np.array_equal(outs[i], ref), i
 
 
-def test_control_sweep_in_one_mixed_batch():
+@pytest.mark.parametrize("mode", ["phased", "nested"])
+def test_control_sweep_in_one_mixed_batch(monkeypatch, mode):
     """Every accepted control of the sweep as ONE batch of 288 streams with 288 different tables: each stream's bytes
     equal the reference's."""
     from sweep_cases import sweep_cases
+    monkeypatch.setenv("HMP3_RATE_MODE", mode)   # the serial stage phase-scheduled (as at scale) and one warp per stream
     ctl, pcms, refs, allo1 = [], [], [], []
     for k, sr, nch, kw in sweep_cases():
         ecr = refmod.make_ec(samprate=sr, nch=nch, **kw)
