@@ -11,6 +11,7 @@
 #include <string>
 #include <array>
 #include <chrono>
+#include <limits>
 #include <vector>
 
 #include "../../include/hmp3_b200.h"
@@ -19,6 +20,7 @@
 #include "analysis.h"
 #include "batch_types.h"
 #include "rate_driver.h"
+#include "resample.h"
 
 using namespace hmp3;
 
@@ -1213,6 +1215,8 @@ struct hmp3_encoder {
     int src_bits = 16, src_float = 0;
     int src_chan = 0;           // channels of the caller's PCM (2 with nch == 1: down-mix to mono, Csrc kfilter 2)
     bool up2 = false;           // 1:2 up-conversion (Csrc case 1)
+    bool resample = false;      // general conversion (Csrc cases 2-4, resample.h)
+    hmp3::Resampler rs;
     int frames_in = 1152;       // sample frames of the caller's PCM consumed per call
     std::vector<float> conv;    // the call's samples after sr_convert's type conversion
     int capacity_seconds = 20;
@@ -1380,20 +1384,57 @@ int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds) {
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert) {
     if (!e || !ec) return 0;
-    // in scope: 8/16/24/32-bit integer or 32-bit float PCM at a native MPEG rate, or at half of an MPEG-2 rate (1:2
-    // up-conversion, Csrc case 1); the general resampler (cases 2-4) is not built
-    const int rates[6] = {16000, 22050, 24000, 32000, 44100, 48000};
-    bool native = false;
-    for (int r : rates) native |= (ec->samprate == r);
-    const bool up2 = !native && (ec->samprate == 8000 || ec->samprate == 11025 || ec->samprate == 12000) &&
-                     (mpeg_select == 0 || mpeg_select == 2 || mpeg_select == 2 * ec->samprate);
+    // the encode rate as CMp3Enc::MP3_audio_encode_init picks it from the source rate and mpeg_select
+    // (mp3enc.cpp:2628-2651, 2683-2748): track the input / an MPEG-1 rate / an MPEG-2 rate / the rate given
+    auto nearest = [](const int *t, int n, int x) {
+        int best = t[0], d0 = abs(t[0] - x);
+        for (int i = 0; i < n; i++)
+            if (abs(t[i] - x) < d0) {
+                d0 = abs(t[i] - x);
+                best = t[i];
+            }
+        return best;
+    };
+    static const int rates[6] = {22050, 24000, 16000, 44100, 48000, 32000};
+    const int source = ec->samprate;
+    if (source < 4000 || source > 48000) return 0;
+    if (mpeg_select < 0) mpeg_select = 0;
+    int target = 0, t2;
+    switch (mpeg_select) {
+    case 0:
+        if (source < 16000 && (t2 = nearest(rates, 3, 2 * source)) == 2 * source) target = t2;
+        else target = nearest(rates, 6, source);
+        break;
+    case 1:
+        if (source < 16000 && (t2 = nearest(rates + 3, 3, 4 * source)) == 4 * source) target = t2;
+        else if (source < 32000 && (t2 = nearest(rates + 3, 3, 2 * source)) == 2 * source) target = t2;
+        else target = nearest(rates + 3, 3, source);
+        break;
+    case 2:
+        if (source < 16000 && (t2 = nearest(rates, 3, 2 * source)) == 2 * source) target = t2;
+        else if (source > 24000 && 2 * (t2 = nearest(rates, 3, source / 2)) == source) target = t2;
+        else target = nearest(rates, 3, source);
+        break;
+    default:
+        target = nearest(rates, 6, mpeg_select);
+        if (target != mpeg_select) return 0;
+    }
+    const bool native = target == source;
+    const bool up2 = target == 2 * source;
     const bool fmt_ok = source_is_float ? (source_bits == 32)
                                         : (source_bits == 8 || source_bits == 16 || source_bits == 24 || source_bits == 32);
-    if (!fmt_ok || (!native && !up2) ||
-        (native && ((mpeg_select > 2 && mpeg_select != ec->samprate) || (mpeg_select == 1 && ec->samprate < 32000) ||
-                    (mpeg_select == 2 && ec->samprate > 24000)))) {
-        set_err("MP3_audio_encode_init: only PCM at a native MPEG rate (or half of an MPEG-2 rate) is in scope");
+    // Csrc::sr_convert_init's own limits (srcc.cpp:741-756)
+    if (!fmt_ok || source < 8000 || target < 5000 || target > 50400) {
+        set_err("MP3_audio_encode_init: sample format or rate outside what the converter takes");
         return 0;
+    }
+    e->resample = false;
+    if (!native && !up2) {  // general conversion (Csrc cases 2-4)
+        if (e->rs.init(source, target) <= 0 || e->rs.ncase < 2) {
+            set_err("MP3_audio_encode_init: no conversion from this source rate to the encode rate");
+            return 0;
+        }
+        e->resample = true;
     }
     // channels as CMp3Enc::MP3_audio_encode_init derives them (mp3enc.cpp:2689-2696): the source has two unless the
     // mode is mono; mono_convert encodes a two-channel source as mono (Csrc kfilter 2)
@@ -1402,20 +1443,24 @@ int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int sour
     const bool downmix = mono_convert && e->src_chan == 2;
     if (downmix) ec2.mode = 3;
     e->up2 = up2;
-    if (up2) {  // encode rate and band limit of the up-converted signal (mp3enc.cpp:2700-2714, 2765-2787)
-        ec2.samprate = 2 * ec->samprate;
-        const int cutoff = (int)(0.90f * ec->samprate / 2);
-        int nsb = (64 * cutoff + ec2.samprate / 2) / ec2.samprate;
+    ec2.samprate = target;
+    if (source < target) {  // band limit of an up-converted signal (mp3enc.cpp:2765-2787; cutoff: srcc.cpp:780-781)
+        const int cutoff = (int)(0.90f * source / 2);
+        int nsb = (64 * cutoff + target / 2) / target;
         if (nsb > 30) nsb = 30;
         if (ec2.nsb_limit <= 0) ec2.nsb_limit = 30;
         if (ec2.nsb_limit > nsb) ec2.nsb_limit = nsb;
     }
     e->src_bits = source_bits;
     e->src_float = source_is_float;
-    const int bytes_in = encoder_init(e, &ec2, up2 || downmix || !(source_bits == 16 && !source_is_float));
+    const int bytes_in = encoder_init(e, &ec2, up2 || e->resample || downmix || !(source_bits == 16 && !source_is_float));
     if (!bytes_in) return 0;
     // what Csrc::sr_convert_init returns: the sample frames that must be buffered for a call (srcc.cpp:185-187, 769-773):
     // the 1152 (576 when up-converting) it consumes plus one
+    if (e->resample) {  // the converter's own figure: the source frames a call may look at
+        e->frames_in = e->rs.minbuf;
+        return e->frames_in * e->src_chan * (source_bits / 8);
+    }
     e->frames_in = up2 ? 576 : 1152;
     return (e->frames_in + 1) * e->src_chan * (source_bits / 8);
 }
@@ -1434,9 +1479,12 @@ hmp3_in_out mp3_encode_call(hmp3_encoder *e, const unsigned char *pcm, unsigned 
     }
     // sample conversion of Csrc::sr_convert (hmp3/src/srcc.cpp:804-834): everything becomes float on a +-32768 scale.
     // Up-conversion looks one sample frame past the 576 it consumes (the caller buffers frames_in + 1, see init).
-    const int nfr = e->frames_in + (e->up2 ? 1 : 0);
-    const int n = nfr * e->src_chan;
     const bool downmix = e->src_chan == 2 && e->nch == 1;
+    const hmp3::Resampler::Layout lay = e->src_chan == 1 ? hmp3::Resampler::MONO
+                                        : (downmix ? hmp3::Resampler::TO_MONO : hmp3::Resampler::DUAL);
+    // the frames this call reads: the general converter looks as far as the reference's does (Resampler::reach)
+    const int nfr = e->resample ? e->rs.reach(lay) : e->frames_in + (e->up2 ? 1 : 0);
+    const int n = nfr * e->src_chan;
     if ((int)e->conv.size() < n) e->conv.resize(n);
     float *d = e->conv.data();
     if (e->src_float) {
@@ -1459,6 +1507,12 @@ hmp3_in_out mp3_encode_call(hmp3_encoder *e, const unsigned char *pcm, unsigned 
     }
     if ((int)e->stage.size() < 1152 * e->nch) e->stage.resize((size_t)1152 * e->nch);
     float *y = e->stage.data();
+    if (e->resample) {  // Csrc cases 2-4: 1152 frames at the encode rate from as many source frames as that takes
+        const int used = e->rs.run(lay, d, y);
+        io = encoder_step(e, y, bs_out, want_bs, packet, nbytes_out);
+        if (io.in_bytes) io.in_bytes = used * e->src_chan * (e->src_bits / 8);
+        return io;
+    }
     if (!e->up2) {
         if (downmix)  // src_filter_to_mono_case0 (hmp3/src/srccf.cpp:458-468)
             for (int i = 0; i < 1152; i++) y[i] = (float)((d[2 * i] + d[2 * i + 1]) * 0.5);
@@ -1590,6 +1644,25 @@ int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap) {
     for (; k < (int)b->timeline.size() && k < cap; k++)
         for (int j = 0; j < 3; j++) rows[3 * k + j] = b->timeline[k][j];
     return k;
+}
+
+int hmp3_debug_resample(int source, int target, int layout, const float *x, int ncalls, float *y, int *used) {
+    // the handle's sample-rate converter on its own (host code, no device): tests compare it with the reference's Csrc
+    hmp3::Resampler r;
+    const int minbuf = r.init(source, target);
+    if (minbuf <= 0 || r.ncase < 2) return minbuf <= 0 ? 0 : -r.ncase;
+    const int fw = layout == 0 ? 1 : 2, ow = layout == 1 ? 2 : 1;
+    long off = 0;
+    std::vector<float> stage;
+    for (int k = 0; k < ncalls; k++) {
+        // staged the way the handle stages a call: reach() frames and not one more (what lies behind them is poisoned)
+        const int nfr = r.reach((hmp3::Resampler::Layout)layout);
+        stage.assign((size_t)(nfr + 64) * fw, std::numeric_limits<float>::quiet_NaN());
+        memcpy(stage.data(), x + off * fw, sizeof(float) * nfr * fw);
+        used[k] = r.run((hmp3::Resampler::Layout)layout, stage.data(), y + (long)k * 1152 * ow);
+        off += used[k];
+    }
+    return minbuf;
 }
 
 int hmp3_debug_set_rate_tap(hmp3_batch *b, int stream, void *records, long long cap_records) {

@@ -31,6 +31,11 @@ int hmp3_debug_rate_cycles(hmp3_batch *b, long long *cycles, int max_launches);
  * CBitAllo3::BitAllo and the frame driver (bitallo3.cpp:484-678, mp3enc.cpp:1492-2027).  records == NULL clears it. */
 int hmp3_debug_set_rate_tap(hmp3_batch *b, int stream, void *records, long long cap_records);
 int hmp3_debug_rate_tap_record_bytes(void);
+/* The CMp3Enc mirror's sample-rate converter on its own (host code; Csrc cases 2-4, srcc.cpp / srccf.cpp): `ncalls`
+ * calls, each producing 1152 frames at `target` Hz from float frames at `source` Hz (layout 0 mono, 1 two channels,
+ * 2 two channels mixed down to one); used[c] = source frames call c consumed.  Returns the frames a call may look at
+ * (what sr_convert_init's byte count is made of), 0 if the rates are refused, -1 / 0 for the 1:2 / 1:1 cases. */
+int hmp3_debug_resample(int source, int target, int layout, const float *x, int ncalls, float *y, int *used);
 /* Kernel timeline of the last run with timing on (hmp3_batch_set_timing): rows of (phase index as in
  * hmp3_batch_phase_ms, begin ms, end ms) since the run began; returns the number of rows. */
 int hmp3_debug_timeline(const hmp3_batch *b, float *rows, int cap);

@@ -52,6 +52,7 @@ void operator delete[](void *p, std::size_t) noexcept { std::free(p); }
 
 extern "C" {
 #include "xhead.h"
+#include "srcc.h"
 }
 
 namespace {
@@ -334,6 +335,28 @@ long ref_encode_clip(const int *ec_words, const float *pcm, long nsamples_per_ch
     free(buf);
     if (ncalls_out) *ncalls_out = call;
     return total;
+}
+
+
+// The reference's sample-rate converter on its own (Csrc, srcc.cpp / srccf.cpp): `ncalls` calls of sr_convert over the
+// raw PCM bytes at `in` (the caller pads the buffer: a call reads more frames than it consumes).  out receives
+// 1152 * target_channels floats per call, used[c] the bytes call c consumed.  Returns sr_convert_init's value
+// (bytes to buffer per call; <= 0 = refused); *cutoff = the encoder cutoff frequency it reports.
+int ref_src_convert(int source, int channels, int bits, int is_float, int target, int target_channels,
+                    const unsigned char *in, int ncalls, float *out, int *used, int *cutoff) {
+    Csrc c;
+    int co = 0;
+    const int minb = c.sr_convert_init(source, channels, bits, is_float, target, target_channels, &co);
+    if (cutoff) *cutoff = co;
+    if (minb <= 0) return minb;
+    const int tch = target_channels < channels ? target_channels : channels;
+    long off = 0;
+    for (int k = 0; k < ncalls; k++) {
+        IN_OUT x = c.sr_convert((unsigned char *)in + off, out + (long)k * 1152 * (tch < 1 ? 1 : tch));
+        used[k] = x.in_bytes;
+        off += x.in_bytes;
+    }
+    return minb;
 }
 
 }  // extern "C"
