@@ -4,8 +4,9 @@
 // per-channel kbit/s, -V<n> VBR, -HF<n>, -F<hz>, -M<mode>, -X<flag> ...), the WAV is encoded through the C ABI and
 // the output file is the Xing/Info frame followed by the audio frames -- byte-identical to what `hmp3` writes.
 // Extension: `-@ <list>` encodes many files in ONE batch on the GPU (each line of <list>: input<TAB or space>output).
-// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at a native MPEG rate, or at 8 / 11.025 / 12 kHz (up-converted
-// 1:2 as the reference does; no general sample-rate conversion).  "-" as
+// Input: 8/16/24/32-bit integer or 32-bit float PCM WAV at any rate from 8 to 48 kHz; -A<n> picks the encode rate as
+// the reference does.  A file at its encode rate or at half of it joins the batch (1:2 up-conversion is done here);
+// any other pair of rates goes through the handle, whose MP3_audio_encode converts call by call (Csrc cases 2-4).  "-" as
 // input reads the WAV from stdin and, like -IL, ignores the header's data length (tomp3.cpp:721-745); "-" as output
 // writes to stdout, where -- as with the reference, which cannot re-read its own stdout -- the Xing/Info frame stays
 // the placeholder written before encoding (tomp3.cpp:1055-1072).
@@ -147,6 +148,7 @@ struct Job {
     hmp3_control ec;
     int enc_rate = 0;  // sample rate handed to the encoder (twice the file's for 8 / 11.025 / 12 kHz input)
     bool ok = false;
+    bool via_handle = false;  // needs the general sample-rate converter: encoded through the CMp3Enc mirror, call by call
 };
 
 }  // namespace
@@ -184,6 +186,117 @@ static int target_rate(int source, int mpeg_select) {
         t = nearest_rate(rates, 6, mpeg_select);
         return t == mpeg_select ? t : 0;
     }
+}
+
+
+// Writes one encoded stream the way ff_encode leaves the file: the Xing/Info frame (tomp3.cpp:871-896, 1055-1072), then
+// the audio frames.  frames_after_call / bytes_after_call: the main loop's calls (the seek table), nsamples_enc: the
+// stream length at the encode rate (for the closing report only).
+static bool write_stream(const Job &j, const hmp3_control &eff, const hmp3_mpeg_head &head, int xing, const uint8_t *audio,
+                         int64_t nb, int32_t nf, const int32_t *fa, const int64_t *ba, int nc, int64_t nsamples_enc) {
+    uint8_t tag[2048];
+    int tag_bytes = 0;
+    const bool to_pipe = (j.out == "-");
+    if (xing && to_pipe) {
+        tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, nsamples_enc, nullptr, 0, 0, nullptr,
+                                    nullptr, 0, tag, (int)sizeof(tag));
+    } else if (xing) {
+        const int64_t samples_audio = (int64_t)(j.wav.audio_bytes / ((size_t)j.wav.channels * (j.wav.bits / 8)));
+        tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, samples_audio, audio, nb, (uint32_t)nf,
+                                    fa, ba, nc, tag, (int)sizeof(tag));
+    }
+    FILE *f = to_pipe ? stdout : fopen(j.out.c_str(), "wb");
+    if (!f) {
+        fprintf(stderr, "\n CANNOT CREATE OUTPUT FILE %s\n", j.out.c_str());
+        return false;
+    }
+    if (tag_bytes) fwrite(tag, 1, (size_t)tag_bytes, f);
+    fwrite(audio, 1, (size_t)nb, f);
+    if (to_pipe) fflush(f);
+    else fclose(f);
+    const double secs = (double)nsamples_enc / j.enc_rate;
+    fprintf(stderr, "\n %s: %d frames, %lld bytes, %.2f kbps", j.out.c_str(), nf, (long long)(nb + tag_bytes),
+            secs > 0 ? 8e-3 * (double)nb / secs : 0.0);
+    return true;
+}
+
+// A file whose rate has to be converted by more than 1:2 (Csrc cases 2-4): the reference CLI's own loop over the
+// CMp3Enc mirror (ff_encode, tomp3.cpp:908-1036).  At the end of the data 4 x bytes_in_init zero bytes are appended
+// and calls go on while bytes_in_init bytes are buffered; then zero input is fed until the frame count has caught up
+// with the calls made.
+static bool encode_with_handle(Job &j, int mpeg_select, bool mono_convert, int device, int xing) {
+    hmp3_encoder *e = hmp3_encoder_new(device);
+    if (!e) {
+        fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
+        return false;
+    }
+    struct Closer {
+        hmp3_encoder *e;
+        ~Closer() { hmp3_encoder_delete(e); }
+    } closer{e};
+    const int ch = j.wav.channels;
+    const bool f32 = j.wav.use_float;
+    const int fb = ch * (f32 ? 4 : 2);
+    hmp3_control ec = j.ec;
+    ec.samprate = j.wav.rate;
+    // 16-bit samples go in as read.  Every other type was converted by the reader to float on the +-32768 scale, the
+    // way Csrc::sr_convert converts it; handed over as float on the +-1 scale it reaches the converter with those values.
+    const int bytes_in = hmp3_MP3_audio_encode_init(e, &ec, f32 ? 32 : 16, f32 ? 1 : 0, mpeg_select, mono_convert ? 1 : 0);
+    if (!bytes_in) {
+        fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
+        return false;
+    }
+    const size_t minfr = (size_t)bytes_in / fb, nfr = j.wav.total() / ch;
+    // The CLI appends its 4 x bytes_in_init zero bytes only if they fit what it takes for the free part of its PCM
+    // buffer (tomp3.cpp:268, 802, 925; pcmhpm.c:450): with wide samples and a converter that buffers a lot (two-stage
+    // down-conversion of 24/32-bit stereo) they do not, and the tail of the file shorter than one call is dropped.
+    const size_t src_bii = minfr * (size_t)ch * (size_t)(j.wav.bits / 8);
+    const size_t psf = (size_t)ch * (size_t)((j.wav.bits * 7) / 8);
+    const bool padded = 4 * src_bii < (((size_t)(2u * 128u * 4u * 2304u) / psf) & ~(size_t)1);
+    const size_t tot = nfr + (padded ? 4 * minfr : 0);  // the data, then the CLI's padding
+    // ... and what a call may look at past that: an up-converting call reads a frame or two more than bytes_in_init, in
+    // the CLI's buffer leftovers of earlier reads when the last call starts with exactly that much buffered; zero here
+    const size_t room = tot + minfr + 8;
+    std::vector<uint8_t> src(room * fb);
+    if (f32) {
+        float *d = (float *)src.data();
+        const float pad = j.wav.bits == 8 ? -1.0f : 0.0f;  // what the zero bytes decode to
+        for (size_t i = 0; i < room * ch; i++) d[i] = i < nfr * ch ? j.wav.pcmf[i] * (1.0f / 32768.0f) : pad;
+    } else {
+        memcpy(src.data(), j.wav.pcm.data(), nfr * fb);
+    }
+    std::vector<uint8_t> out, bs(65536), zeros((4 * minfr + 8) * fb, 0);
+    if (f32 && j.wav.bits == 8)
+        for (size_t i = 0; i < zeros.size() / 4; i++) ((float *)zeros.data())[i] = -1.0f;
+    std::vector<int32_t> fa;
+    std::vector<int64_t> ba;
+    size_t pos = 0;
+    unsigned calls = 0;
+    while (tot - pos >= minfr) {
+        const hmp3_in_out x = hmp3_MP3_audio_encode(e, src.data() + pos * fb, bs.data());
+        if (x.in_bytes <= 0) {
+            fprintf(stderr, "\n ENCODE FAILED: %s\n", hmp3_get_last_error());
+            return false;
+        }
+        pos += (size_t)x.in_bytes / fb;
+        out.insert(out.end(), bs.begin(), bs.begin() + x.out_bytes);
+        const hmp3_int_pair p = hmp3_L3_audio_encode_get_frames_bytes(e);
+        fa.push_back(p.a);
+        ba.push_back(p.b);
+        calls++;
+    }
+    hmp3_control eff;
+    hmp3_mpeg_head head;
+    hmp3_L3_audio_encode_info_ec(e, &eff);
+    hmp3_L3_audio_encode_info_head(e, &head);
+    const unsigned expected = eff.samprate < 32000 ? 2 * calls : calls;
+    for (int guard = 0; hmp3_L3_audio_encode_get_frames(e) < expected && guard < 64; guard++) {
+        const hmp3_in_out x = hmp3_MP3_audio_encode(e, zeros.data(), bs.data());
+        out.insert(out.end(), bs.begin(), bs.begin() + x.out_bytes);
+    }
+    const int32_t nf = (int32_t)hmp3_L3_audio_encode_get_frames(e);
+    const int64_t ns_enc = (int64_t)((double)nfr * j.enc_rate / j.wav.rate);
+    return write_stream(j, eff, head, xing, out.data(), (int64_t)out.size(), nf, fa.data(), ba.data(), (int)fa.size(), ns_enc);
 }
 
 int main(int argc, char **argv) {
@@ -270,22 +383,22 @@ int main(int argc, char **argv) {
         if (j.wav.channels == 1) j.ec.mode = 3;
         j.wav.use_float = !(j.wav.type == 1 && j.wav.bits == 16);
         j.wav.enc_channels = j.wav.channels;
-        // encode rate as CMp3Enc::MP3_audio_encode_init picks it (mp3enc.cpp:2700-2714, mpeg_select 0): a source below
-        // 16 kHz is doubled when that is an MPEG-2 rate (Csrc case 1); any other non-MPEG rate would need the general
-        // resampler, which is not built
         // the encode rate MP3_audio_encode_init derives from the source rate and -A (mp3enc.cpp:2700-2748)
         j.enc_rate = j.wav.rate;
         const int target = target_rate(j.wav.rate, mpeg_select);
         const bool native = target == j.wav.rate;
-        // Csrc case 1.  (A 16 kHz source forced to 32 kHz by -A1 / -A32000 is refused: the reference CLI's output for
-        // that one combination differs from its own encoder run on the 1:2 up-converted samples from the seventh frame
-        // on, mono, whatever the length -- not understood, so not claimed.)
-        const bool up2 = target == 2 * j.wav.rate && j.wav.rate != 16000;
-        if (target == 0 || (!native && !up2)) {
-            if (target == 0) fprintf(stderr, "\n ENCODER INIT FAIL\n");
-            else
-                fprintf(stderr, "\n ENCODER INIT FAIL (input rate %d -> encode rate %d needs the general sample-rate "
-                                "converter, which is not built)\n", j.wav.rate, target);
+        // Csrc case 1 (1:2) is done here, ahead of the batch; any other pair of rates (Csrc cases 2-4) runs through the
+        // handle, whose MP3_audio_encode converts call by call exactly as the reference's does
+        const bool up2 = target == 2 * j.wav.rate;
+        if (target == 0) {
+            fprintf(stderr, "\n ENCODER INIT FAIL\n");
+            continue;
+        }
+        if (!native && !up2) {
+            j.via_handle = true;
+            j.enc_rate = target;
+            if (j.wav.channels == 2 && j.ec.mode == 3) j.ec.mode = 1;  // tomp3.cpp:813-815; the down-mix is mono_convert's
+            j.ok = true;
             continue;
         }
         const bool downmix = j.wav.channels == 2 && mono_convert;
@@ -353,73 +466,63 @@ int main(int argc, char **argv) {
         fmts.push_back(j.wav.use_float ? HMP3_PCM_F32 : HMP3_PCM_S16);
         idx.push_back((int)k);
     }
-    if (ctl.empty()) return 1;
-    // ---- one batch on the GPU
-    hmp3_batch *b = hmp3_batch_create_ex(ctl.data(), ns.data(), fmts.data(), (int)ctl.size(), device);
-    if (!b) {
-        fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
-        return 1;
-    }
-    const int n = (int)ctl.size();
-    for (int i = 0; i < n; i++)  // the reference flushes with zero BYTES, which 8-bit samples decode to -32768
-        if (jobs[idx[i]].wav.bits == 8) hmp3_batch_set_tail(b, i, -32768.0f);
-    std::vector<const void *> pcm(n);
-    std::vector<std::vector<uint8_t>> out(n);
-    std::vector<uint8_t *> outp(n);
-    std::vector<int64_t> cap(n), nb(n);
-    std::vector<int32_t> nf(n), st(n);
-    for (int i = 0; i < n; i++) {
-        pcm[i] = fmts[i] == HMP3_PCM_F32 ? (const void *)jobs[idx[i]].wav.pcmf.data() : (const void *)jobs[idx[i]].wav.pcm.data();
-        cap[i] = hmp3_batch_out_bound(&ctl[i], ns[i]);
-        out[i].resize((size_t)cap[i]);
-        outp[i] = out[i].data();
-    }
-    if (hmp3_batch_encode_host(b, pcm.data(), outp.data(), cap.data(), nb.data(), nf.data(), st.data()) != HMP3_OK) {
-        fprintf(stderr, "\n ENCODE FAILED: %s\n", hmp3_get_last_error());
-        return 1;
-    }
     int rc = 0;
-    for (int i = 0; i < n; i++) {
-        Job &j = jobs[idx[i]];
-        if (st[i] != HMP3_OK) {
-            fprintf(stderr, "\n ENCODE FAILED (%d) for %s\n", st[i], j.in.c_str());
-            rc = 1;
-            continue;
+    const bool mono_convert_all = (base.mode == 3);
+    if (!ctl.empty()) {
+        // ---- one batch on the GPU
+        hmp3_batch *b = hmp3_batch_create_ex(ctl.data(), ns.data(), fmts.data(), (int)ctl.size(), device);
+        if (!b) {
+            fprintf(stderr, "\n ENCODER INIT FAIL: %s\n", hmp3_get_last_error());
+            return 1;
         }
-        hmp3_control eff;
-        hmp3_mpeg_head head;
-        hmp3_effective_control(&ctl[i], &eff, &head);
-        uint8_t tag[2048];
-        int tag_bytes = 0;
-        const bool to_pipe = (j.out == "-");
-        if (xing && to_pipe) {
-            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, ns[i], nullptr, 0, 0, nullptr,
-                                        nullptr, 0, tag, (int)sizeof(tag));
-        } else if (xing) {
+        const int n = (int)ctl.size();
+        for (int i = 0; i < n; i++)  // the reference flushes with zero BYTES, which 8-bit samples decode to -32768
+            if (jobs[idx[i]].wav.bits == 8) hmp3_batch_set_tail(b, i, -32768.0f);
+        std::vector<const void *> pcm(n);
+        std::vector<std::vector<uint8_t>> out(n);
+        std::vector<uint8_t *> outp(n);
+        std::vector<int64_t> cap(n), nb(n);
+        std::vector<int32_t> nf(n), st(n);
+        for (int i = 0; i < n; i++) {
+            pcm[i] = fmts[i] == HMP3_PCM_F32 ? (const void *)jobs[idx[i]].wav.pcmf.data() : (const void *)jobs[idx[i]].wav.pcm.data();
+            cap[i] = hmp3_batch_out_bound(&ctl[i], ns[i]);
+            out[i].resize((size_t)cap[i]);
+            outp[i] = out[i].data();
+        }
+        if (hmp3_batch_encode_host(b, pcm.data(), outp.data(), cap.data(), nb.data(), nf.data(), st.data()) != HMP3_OK) {
+            fprintf(stderr, "\n ENCODE FAILED: %s\n", hmp3_get_last_error());
+            return 1;
+        }
+        for (int i = 0; i < n; i++) {
+            Job &j = jobs[idx[i]];
+            if (st[i] != HMP3_OK) {
+                fprintf(stderr, "\n ENCODE FAILED (%d) for %s\n", st[i], j.in.c_str());
+                rc = 1;
+                continue;
+            }
+            hmp3_control eff;
+            hmp3_mpeg_head head;
+            hmp3_effective_control(&ctl[i], &eff, &head);
             const int ncalls_main = (int)calls_main(ns[i]);
             std::vector<int32_t> fa(ncalls_main + 64);
             std::vector<int64_t> ba(ncalls_main + 64);
-            int nc = hmp3_batch_call_log(b, i, fa.data(), ba.data(), (int)fa.size());
-            if (nc > ncalls_main) nc = ncalls_main;
-            const int64_t samples_audio = (int64_t)(j.wav.audio_bytes / ((size_t)j.wav.channels * (j.wav.bits / 8)));
-            tag_bytes = hmp3_info_frame(&eff, head.mode, xing, j.wav.rate, j.wav.channels, samples_audio, out[i].data(), nb[i],
-                                        (uint32_t)nf[i], fa.data(), ba.data(), nc, tag, (int)sizeof(tag));
+            int nc = 0;
+            if (xing && j.out != "-") {
+                nc = hmp3_batch_call_log(b, i, fa.data(), ba.data(), (int)fa.size());
+                if (nc > ncalls_main) nc = ncalls_main;
+            }
+            if (!write_stream(j, eff, head, xing, out[i].data(), nb[i], nf[i], fa.data(), ba.data(), nc, ns[i])) rc = 1;
         }
-        FILE *f = to_pipe ? stdout : fopen(j.out.c_str(), "wb");
-        if (!f) {
-            fprintf(stderr, "\n CANNOT CREATE OUTPUT FILE %s\n", j.out.c_str());
-            rc = 1;
-            continue;
-        }
-        if (tag_bytes) fwrite(tag, 1, (size_t)tag_bytes, f);
-        fwrite(out[i].data(), 1, (size_t)nb[i], f);
-        if (to_pipe) fflush(f);
-        else fclose(f);
-        const double secs = (double)ns[i] / j.enc_rate;
-        fprintf(stderr, "\n %s: %d frames, %lld bytes, %.2f kbps", j.out.c_str(), nf[i], (long long)(nb[i] + tag_bytes),
-                secs > 0 ? 8e-3 * (double)nb[i] / secs : 0.0);
+        hmp3_batch_destroy(b);
     }
+    // ---- files that need the general sample-rate converter: one at a time through the handle
+    bool any = !ctl.empty();
+    for (Job &j : jobs) {
+        if (!j.ok || !j.via_handle) continue;
+        any = true;
+        if (!encode_with_handle(j, mpeg_select, mono_convert_all, device, xing)) rc = 1;
+    }
+    if (!any) return 1;
     fprintf(stderr, "\n");
-    hmp3_batch_destroy(b);
     return rc;
 }

@@ -186,11 +186,14 @@ void hmp3_encoder_delete(hmp3_encoder *e);
 int hmp3_encoder_set_capacity_seconds(hmp3_encoder *e, int seconds);
 
 /* CMp3Enc::MP3_audio_encode_init (hmp3/src/mp3enc.cpp:2655-2808): returns, like the reference, the bytes the
- * caller must have buffered for a call (what Csrc::sr_convert_init returns: 1153 sample frames, 577 when the source
- * is up-converted; a call consumes 1152 / 576 of them, reported in hmp3_in_out.in_bytes), 0 = failure.
- * In scope: 8/16/24/32-bit integer and 32-bit float PCM at a native MPEG rate or at 8 / 11.025 / 12 kHz (1:2
- * up-conversion, Csrc case 1); mono_convert down-mixes a two-channel source.  Other rates would need the general
- * resampler (Csrc cases 2-4), which is not built: init fails. */
+ * caller must have buffered for a call (what Csrc::sr_convert_init returns; a call consumes what hmp3_in_out.in_bytes
+ * reports), 0 = failure.  ec->samprate is the SOURCE rate (4000 < rate <= 48000; the converter takes 8000 and up);
+ * mpeg_select picks the encode rate as the reference does: 0 = the nearest MPEG rate (twice the source below 16 kHz),
+ * 1 = an MPEG-1 rate, 2 = an MPEG-2 rate, any other value = that rate, which must be one of the six.
+ * 8/16/24/32-bit integer and 32-bit float PCM; mono_convert down-mixes a two-channel source.  The sample-rate
+ * converter is Csrc's (hmp3/src/srcc.cpp, srccf.cpp), every case: none, 1:2 up, m:n up (linear interpolation),
+ * down through a polyphase FIR, down in two stages.  Like the reference's, an up-converting call may look one or two
+ * sample frames past the bytes this function returns. */
 int hmp3_MP3_audio_encode_init(hmp3_encoder *e, const hmp3_control *ec, int source_bits, int source_is_float,
                                int mpeg_select, int mono_convert);
 /* CMp3Enc::MP3_audio_encode (hmp3/src/mp3enc.cpp:2812-2828). */

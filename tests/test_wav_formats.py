@@ -24,10 +24,10 @@ CASES = [(44100, 2, ["-B64"], dict(bitrate=64)), (22050, 1, ["-B32"], dict(bitra
          (48000, 2, ["-V100", "-HF2", "-F19000", "-S1"], dict(vbr_mnr=100, hf=2, freq_limit=19000, filter_select=1))]
 
 
-def ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name="a"):
+def ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name="a", binary=None):
     wav, mp3 = str(tmp_path / (name + ".wav")), str(tmp_path / (name + "_ref.mp3"))
     wavutil.write_wav(wav, samples, kind, sr, nch)
-    subprocess.run([REF_BIN, wav, mp3] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    subprocess.run([binary or REF_BIN, wav, mp3] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
     return wav, np.fromfile(mp3, dtype=np.uint8)
 
 
@@ -341,7 +341,7 @@ def test_cli_identity_for_up_converted_input(tmp_path):
                 got = np.fromfile(out, dtype=np.uint8)
                 assert got.size == want.size and np.array_equal(got, want), name
     # -A<n> (mpeg_select of MP3_audio_encode_init): values that resolve to the source rate or to its 1:2 up-conversion
-    # give the reference's file; a target that needs the general resampler is refused
+    # give the reference's file (other targets: test_cli_identity_with_general_rate_conversion); no MPEG rate is refused
     for sr, nch, opts in [(22050, 2, ["-A1"]), (24000, 2, ["-A48000"]), (44100, 2, ["-A1"]),
                           (44100, 2, ["-A44100", "-B64"]), (22050, 2, ["-A2"]), (11025, 1, ["-A2"]), (32000, 2, ["-A0"])]:
         samples = wavutil.make_samples(synth_pcm(84, 2.0, sr, nch)[:30000], "s16", seed=3)
@@ -351,19 +351,54 @@ def test_cli_identity_for_up_converted_input(tmp_path):
         subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
         got = np.fromfile(out, dtype=np.uint8)
         assert got.size == want.size and np.array_equal(got, want), name
-    for sr, opts in [(44100, ["-A2"]), (11025, ["-A1"]), (44100, ["-A32000"]), (44100, ["-A12345"]), (16000, ["-A1"])]:
+    # no MPEG rate; below the range; rates the reference's converter has no filter for (its init fails as well)
+    for sr, opts in [(44100, ["-A12345"]), (3000, []), (44100, ["-A8000"]), (22255, []), (33075, [])]:
         samples = wavutil.make_samples(synth_pcm(85, 0.5, sr, 2), "s16")
-        wav = str(tmp_path / ("asel_bad_%d%s.wav" % (sr, opts[0])))
+        wav = str(tmp_path / ("asel_bad_%d%s.wav" % (sr, "".join(opts))))
         wavutil.write_wav(wav, samples, "s16", sr, 2)
         outp = wav[:-4] + ".mp3"
         r = subprocess.run([CLI, wav, outp] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         assert r.returncode != 0 and not os.path.exists(outp), (sr, opts)
-    # a rate that would need the general resampler is refused, not mis-encoded
-    samples = wavutil.make_samples(synth_pcm(83, 0.5, 37800, 2), "s16")
-    wav = str(tmp_path / "odd.wav")
-    wavutil.write_wav(wav, samples, "s16", 37800, 2)
-    r = subprocess.run([CLI, wav, str(tmp_path / "odd.mp3")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
-    assert r.returncode != 0 and not os.path.exists(str(tmp_path / "odd.mp3"))
+
+
+RESAMPLE_CLI_CASES = [(37800, 2, ["-B64"], "s16"), (47250, 2, [], "s16"), (44100, 2, ["-A2"], "s16"), (11025, 1, ["-A1", "-B48"], "s16"),
+                      (44100, 2, ["-A32000", "-B96"], "s24"), (48000, 2, ["-A22050", "-M3", "-B40"], "f32"),
+                      (32000, 1, ["-A44100"], "u8"), (16000, 2, ["-A1", "-B48"], "s16"), (16000, 1, ["-A32000", "-B48"], "s16"),
+                      (44100, 1, ["-A24000", "-B32"], "s32"), (44000, 2, [], "s16"), (30000, 1, ["-B48"], "s24")]
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_identity_with_general_rate_conversion(tmp_path):
+    """Source rates that are no MPEG rate, and -A targets that need more than 1:2 (Csrc cases 2-4: up by m:n, down
+    through a polyphase FIR, down in two stages), for every sample type; one batch list mixing such files with native-
+    rate ones.  The reference is oracle/_ref/hmp3_zi (the unmodified sources, automatic variables zero-initialised): with
+    the converter running inside the encode call the plain build reads the converter's leftovers through its one
+    uninitialised local (spdsmr.c:193, 283; tests/test_resample.py, tests/test_gpu_boundary.py)."""
+    zi = os.path.join(os.path.dirname(REF_BIN), "hmp3_zi")
+    if not os.path.exists(zi):
+        pytest.skip("oracle/_ref/hmp3_zi not built")
+    for k, (sr, nch, opts, kind) in enumerate(RESAMPLE_CLI_CASES):
+        samples = wavutil.make_samples(synth_pcm(90 + k, 2.5, sr, nch)[:int(2.2 * sr) + 7 * k], kind, seed=4)
+        name = "rs%d" % k
+        wav, want = ref_cli_file(tmp_path, samples, kind, sr, nch, opts, name, binary=zi)
+        out = str(tmp_path / (name + "_gpu.mp3"))
+        subprocess.run([CLI, wav, out] + opts, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        got = np.fromfile(out, dtype=np.uint8)
+        assert want.size > 2000 and got.size == want.size and np.array_equal(got, want), (sr, nch, opts, kind)
+    # a list: two files that go through the converter between two that do not
+    lst, wants = str(tmp_path / "mixed.txt"), []
+    with open(lst, "w") as f:
+        for k, sr in enumerate([44100, 37800, 32000, 47250]):
+            samples = wavutil.make_samples(synth_pcm(120 + k, 1.5, sr, 2), "s16")
+            name = "mx%d" % k
+            wav, want = ref_cli_file(tmp_path, samples, "s16", sr, 2, ["-B64"], name, binary=zi)
+            wants.append((name, want))
+            f.write("%s %s\n" % (wav, tmp_path / (name + "_gpu.mp3")))
+    subprocess.run([CLI, "-@", lst, "-B64"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    for name, want in wants:
+        got = np.fromfile(str(tmp_path / (name + "_gpu.mp3")), dtype=np.uint8)
+        assert got.size == want.size and np.array_equal(got, want), name
 
 
 @pytest.mark.gpu
