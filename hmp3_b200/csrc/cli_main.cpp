@@ -332,6 +332,9 @@ int main(int argc, char **argv) {
             if (mpeg_select < 0) mpeg_select = 0;
         }
         if (hmp3_control_apply_option(&base, a) != 0) {
+            // -h (anything but -HF) prints the usage text and ends; a letter that is no option is passed over in
+            // silence, as the reference's switch does (tomp3.cpp:402-556)
+            if (a[1] != 'h' && a[1] != 'H') continue;
             fprintf(stderr, "\n Usage:  hmp3b200 <input> <output> [options]   (options as hmp3; -@ <list> for a batch)\n");
             return 0;
         }

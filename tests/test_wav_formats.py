@@ -475,3 +475,13 @@ def test_option_strings_through_the_parser_against_the_reference_cli(tmp_path):
                 whole = np.fromfile(mp3, dtype=np.uint8)
                 head = whole.size - got.size
                 assert head >= 0 and np.array_equal(whole[head:], got), (opts, sr, nch)
+
+
+def test_cli_passes_over_unknown_option_letters_like_the_reference():
+    """tomp3.cpp's option switch has no default: a letter that is no option is ignored, -h prints the usage text."""
+    if not os.path.exists(CLI):
+        pytest.skip("CLI not built")
+    r = subprocess.run([CLI, "in.wav", "out.mp3", "-Y9", "-k"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "Usage" not in r.stdout            # (goes on to open the input, or to report that there is no device)
+    r = subprocess.run([CLI, "in.wav", "out.mp3", "-h"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert "Usage" in r.stdout and r.returncode == 0
