@@ -109,3 +109,22 @@ def test_zero_initialised_reference_build_is_the_reference(tmp_path, opts, sr, n
     subprocess.run([zi, wav, b] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     ga = open(a, "rb").read()
     assert len(ga) > 2000 and ga == open(b, "rb").read()
+
+
+@needs_ref
+@pytest.mark.parametrize("source,target,layout", [(32000, 44100, 0), (37800, 44100, 1), (48000, 22050, 2), (44100, 32000, 1),
+                                                  (11025, 32000, 0), (47250, 48000, 1)])
+def test_converter_matches_reference_over_a_long_stream(source, target, layout):
+    """400 calls (about ten seconds at the encode rate): every phase counter wraps many times."""
+    channels = 1 if layout == 0 else 2
+    target_channels = 2 if layout == 1 else 1
+    ncalls = 400
+    need = int(ncalls * 1152 * source / target) + 8000
+    base = synth_pcm(700 + layout, 4.0, source, channels)
+    pcm = np.concatenate([base] * (need // base.shape[0] + 1))[:need]
+    pcm = np.concatenate([pcm, np.zeros((4096, channels), np.int16)])
+    r_ref, y_ref, u_ref, _ = ref_convert(source, channels, target, target_channels, pcm, ncalls)
+    r_our, y_our, u_our = our_convert(source, target, layout, pcm, ncalls)
+    assert r_ref > 0 and r_our * channels * 2 == r_ref
+    assert np.array_equal(u_our * channels * 2, u_ref)
+    assert np.array_equal(y_our.view(np.uint32), y_ref.reshape(y_our.shape).view(np.uint32))
