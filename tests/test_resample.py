@@ -128,3 +128,24 @@ def test_converter_matches_reference_over_a_long_stream(source, target, layout):
     assert r_ref > 0 and r_our * channels * 2 == r_ref
     assert np.array_equal(u_our * channels * 2, u_ref)
     assert np.array_equal(y_our.view(np.uint32), y_ref.reshape(y_our.shape).view(np.uint32))
+
+
+def test_zero_initialised_reference_build_over_the_option_sets(tmp_path):
+    """... and for the option strings of the CLI tests at three native rates (48 encodes with each build)."""
+    from test_wav_formats import OPTION_SETS
+    plain, zi = os.path.join(REFDIR, "hmp3"), os.path.join(REFDIR, "hmp3_zi")
+    if not (os.path.exists(plain) and os.path.exists(zi)):
+        pytest.skip("oracle/_ref not built")
+    wav, a, b = str(tmp_path / "in.wav"), str(tmp_path / "a.mp3"), str(tmp_path / "b.mp3")
+    for it, opts in enumerate(OPTION_SETS):
+        for sr, nch in [(44100, 2), (32000, 1), (24000, 2)]:
+            write_wav(wav, synth_pcm(900 + it, 1.5, sr, nch), "s16", sr, nch)
+            for f in (a, b):
+                if os.path.exists(f):
+                    os.remove(f)
+            subprocess.run([plain, wav, a] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            subprocess.run([zi, wav, b] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            if not os.path.exists(a):                    # a combination the reference's init refuses
+                assert not os.path.exists(b), (opts, sr, nch)
+                continue
+            assert open(a, "rb").read() == open(b, "rb").read(), (opts, sr, nch)
