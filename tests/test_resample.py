@@ -149,3 +149,50 @@ def test_zero_initialised_reference_build_over_the_option_sets(tmp_path):
                 assert not os.path.exists(b), (opts, sr, nch)
                 continue
             assert open(a, "rb").read() == open(b, "rb").read(), (opts, sr, nch)
+
+
+@needs_ref
+@pytest.mark.parametrize("sr,nch,opts,kw,target,to_mono", [
+    (37800, 2, ["-B64"], dict(bitrate=64), 32000, False), (37800, 2, ["-A44100"], dict(), 44100, False), (48000, 2, ["-A32000", "-B64"], dict(bitrate=64), 32000, False),
+    (44100, 1, ["-A24000", "-B32"], dict(bitrate=32), 24000, False), (32000, 1, ["-A44100", "-B64"], dict(bitrate=64), 44100, False),
+    (48000, 2, ["-A22050", "-M3", "-B40"], dict(bitrate=40), 22050, True), (44100, 2, ["-A2"], dict(), 22050, False),
+    (47250, 2, [], dict(), 48000, False)])
+def test_converter_and_host_encoder_reproduce_reference_cli_audio(tmp_path, sr, nch, opts, kw, target, to_mono):
+    """The whole MP3_audio_encode path on the CPU: the handle's converter, then the host build of the kernel bodies at
+    the encode rate (with the sub-band limit of an up-converted signal, mp3enc.cpp:2765-2787), against the audio frames
+    the reference CLI (hmp3_zi) writes for the same WAV -- the composition the GPU tests check through the C ABI."""
+    import simmod
+    zi = os.path.join(REFDIR, "hmp3_zi")
+    if not (os.path.exists(zi) and simmod.available()):
+        pytest.skip("oracle/_ref/hmp3_zi or the host build missing")
+    N = int(2.3 * sr)
+    pcm = synth_pcm(1300 + sr // 100, 2.5, sr, nch)[:N]
+    wav, mp3 = str(tmp_path / "in.wav"), str(tmp_path / "ref.mp3")
+    write_wav(wav, pcm, "s16", sr, nch)
+    subprocess.run([zi, wav, mp3] + opts, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, check=True)
+    whole = np.fromfile(mp3, dtype=np.uint8)
+    # the CLI's main loop (tomp3.cpp:908-942): 4 x bytes_in_init zero bytes after the data, a call while bytes_in_init
+    # bytes are buffered
+    layout = 0 if nch == 1 else (2 if to_mono else 1)
+    padded = np.concatenate([pcm.reshape(N, nch), np.zeros((40000, nch), np.int16)])
+    ncalls = int(N * target / sr / 1152) + 8
+    minfr, y, used = our_convert(sr, target, layout, padded, ncalls)
+    assert minfr > 0
+    pos = np.concatenate([[0], np.cumsum(used)])
+    calls = int(np.sum(N + 4 * minfr - pos[:ncalls] >= minfr))
+    assert 0 < calls < ncalls
+    y = y[:calls].reshape(calls * 1152, -1)
+    # the same calls from the host encoder's own loop: a stream of n samples makes (n + 3 * 1153 + 1152) // 1152 calls
+    # and everything behind n is the zero tail, so n must lie behind the last sample that is not zero
+    n = 1152 * (calls - 1) - 3 * 1153
+    nz = np.nonzero(np.any(y != 0, axis=1))[0]
+    extent = int(nz[-1]) + 1 if nz.size else 0
+    n = max(n, extent)
+    assert (n + 3 * 1153 + 1152) // 1152 == calls, "clip length lands on a call boundary: pick another"
+    ctl = dict(kw)
+    if sr < target:
+        ctl["nsb_limit"] = min(30, (64 * int(0.90 * sr / 2) + target // 2) // target)
+    ec = capi.control(samprate=target, nch=y.shape[1], **ctl)
+    got, _, _ = simmod.encode_clip(ec, np.ascontiguousarray(y[:n]), tail=0.0)
+    head = whole.size - got.size
+    assert head > 0 and np.array_equal(whole[head:], got), (sr, target, opts)
